@@ -1,0 +1,227 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see types.h).  parity unpinned.
+// Restates src/odomEstimationClass.cpp:7-343 line by line (quirks Q1-Q4, Q10-Q12 of SURVEY.md §0 kept verbatim).
+#include "floam_oracle.h"
+#include <algorithm>
+#include <cctype>
+#include <cstdio>
+
+namespace fo {
+
+CloudI VelToIntensityCopy(const CloudIRT& c) {  // :308-318
+  CloudI out(c.size());
+  for (size_t i = 0; i < c.size(); ++i) out[i] = make_xyzi(c[i].x, c[i].y, c[i].z, c[i].intensity);
+  return out;
+}
+
+void OdomEstimation::init(const LidarParam& lidar_param, double map_resolution, const std::string& loss_function) {
+  laserCloudCornerMap.clear();
+  laserCloudSurfMap.clear();
+  leaf_edge_ = (float)map_resolution;        // setLeafSize(float,float,float): implicit double->float
+  leaf_surf_ = (float)(map_resolution * 2);
+  odom = iso_identity();
+  last_odom = iso_identity();
+  optimization_count = 2;
+  loss_function_ = loss_function;
+  std::transform(loss_function_.begin(), loss_function_.end(), loss_function_.begin(), [](unsigned char ch) { return std::tolower(ch); });
+  lidar_param_ = lidar_param;
+  kf_first_ = true;
+}
+
+void OdomEstimation::initMapWithPoints(const CloudI& edge_in, const CloudI& surf_in) {
+  laserCloudCornerMap.insert(laserCloudCornerMap.end(), edge_in.begin(), edge_in.end());
+  laserCloudSurfMap.insert(laserCloudSurfMap.end(), surf_in.begin(), surf_in.end());
+  optimization_count = 12;
+}
+
+void OdomEstimation::UpdatePointsToMapSelector(CloudIRT& edge_in, CloudIRT& surf_in, bool deskew) {
+  if (!deskew) {
+    updatePointsToMap(edge_in, surf_in, VANILLA);
+  } else {
+    updatePointsToMap(edge_in, edge_in, INITIAL_ITERATION);  // Q3: edge cloud as both edge and surf
+    Vec3 velocity = GetVelocity();
+    CompensateVelocity(edge_in, velocity);
+    CompensateVelocity(surf_in, velocity);
+    updatePointsToMap(edge_in, surf_in, REFINEMENT_AND_UPDATE);
+  }
+}
+
+void OdomEstimation::updatePointsToMap(const CloudIRT& edge_in, const CloudIRT& surf_in, UpdateType t) {
+  CloudI e = VelToIntensityCopy(edge_in);
+  CloudI s = VelToIntensityCopy(surf_in);
+  updatePointsToMap(e, s, t);
+}
+
+void OdomEstimation::updatePointsToMap(const CloudI& edge_in, const CloudI& surf_in, UpdateType update_type) {
+  if (optimization_count > 2) optimization_count--;
+
+  Iso3 odom_prediction = iso_mul(odom, iso_mul(iso_inverse(last_odom), odom));
+  // `update_type == VANILLA || UpdateType::INITIAL_ITERATION` : second operand is the constant 1 -> always true (Q2)
+  last_odom = odom;
+  odom = odom_prediction;
+
+  Quat q_w_curr = quat_from_matrix(odom.R);
+  parameters[0] = q_w_curr.x; parameters[1] = q_w_curr.y; parameters[2] = q_w_curr.z; parameters[3] = q_w_curr.w;
+  parameters[4] = odom.t.x; parameters[5] = odom.t.y; parameters[6] = odom.t.z;
+
+  CloudI downsampledEdgeCloud, downsampledSurfCloud;
+  downSamplingToMap(edge_in, downsampledEdgeCloud, surf_in, downsampledSurfCloud);
+  if (debug) { debug->outer_iterations = 0; debug->residuals.clear(); debug->lm = LmSummary(); }
+
+  if (laserCloudCornerMap.size() > 10 && laserCloudSurfMap.size() > 50) {
+    if (use_kdtree) {  // full rebuild every call (Q12)
+      kdtreeEdgeMap.setInputCloud(laserCloudCornerMap);
+      kdtreeSurfMap.setInputCloud(laserCloudSurfMap);
+    }
+    LossKind loss = (loss_function_ == "huber") ? LOSS_HUBER : (loss_function_ == "cauchy_true" ? LOSS_CAUCHY_TRUE : LOSS_TRIVIAL);  // Q1
+    for (int iterCount = 0; iterCount < optimization_count; iterCount++) {
+      std::vector<Residual> problem;
+      const bool tap = debug && (iterCount == optimization_count - 1);
+      addEdgeCostFactor(downsampledEdgeCloud, laserCloudCornerMap, problem, tap);
+      addSurfCostFactor(downsampledSurfCloud, laserCloudSurfMap, problem, tap);
+      LmSummary sm;
+      ceres_solve_pose(problem, loss, parameters, &sm, 4);
+      if (debug) { debug->outer_iterations++; if (tap) { debug->residuals = problem; debug->lm = sm; } }
+    }
+  } else {
+    // printf("not enough points in map to associate, map error");
+  }
+  Quat qf{parameters[0], parameters[1], parameters[2], parameters[3]};
+  odom = iso_identity();
+  odom.R = quat_to_matrix(qf);
+  odom.t = Vec3{parameters[4], parameters[5], parameters[6]};
+  bool kf = false;
+  if (update_type == VANILLA || update_type == REFINEMENT_AND_UPDATE) {
+    kf = KeyFrameUpdate(odom);
+    if (kf) addPointsToMap(downsampledEdgeCloud, downsampledSurfCloud);
+  }
+  if (debug) { debug->ds_edge = downsampledEdgeCloud; debug->ds_surf = downsampledSurfCloud; debug->keyframe = kf; }
+}
+
+void OdomEstimation::pointAssociateToMap(const PointXYZI& pi, PointXYZI& po) const {
+  Quat q{parameters[0], parameters[1], parameters[2], parameters[3]};
+  Vec3 point_w = quat_rotate(q, Vec3{pi.x, pi.y, pi.z}) + Vec3{parameters[4], parameters[5], parameters[6]};
+  po = make_xyzi((float)point_w.x, (float)point_w.y, (float)point_w.z, pi.intensity);
+}
+
+void OdomEstimation::downSamplingToMap(const CloudI& e_in, CloudI& e_out, const CloudI& s_in, CloudI& s_out) const {
+  voxel_grid_filter(e_in, leaf_edge_, e_out, total_order);
+  voxel_grid_filter(s_in, leaf_surf_, s_out, total_order);
+}
+
+void OdomEstimation::addEdgeCostFactor(const CloudI& pc_in, const CloudI& map_in, std::vector<Residual>& problem, bool tap) {
+  if (tap) { debug->edge_knn.assign(pc_in.size() * 5, -1); debug->edge_d2.assign(pc_in.size() * 5, 0.f); debug->edge_ok.assign(pc_in.size(), 0); }
+  for (int i = 0; i < (int)pc_in.size(); i++) {
+    PointXYZI point_temp;
+    pointAssociateToMap(pc_in[i], point_temp);
+    int pointSearchInd[8];
+    float pointSearchSqDis[8];
+    if (use_kdtree) kdtreeEdgeMap.nearestKSearch(point_temp, 5, pointSearchInd, pointSearchSqDis);
+    else knn_bruteforce(map_in, point_temp, 5, pointSearchInd, pointSearchSqDis);
+    stat_knn_queries++;
+    if (tap) for (int j = 0; j < 5; ++j) { debug->edge_knn[i * 5 + j] = pointSearchInd[j]; debug->edge_d2[i * 5 + j] = pointSearchSqDis[j]; }
+    if (pointSearchSqDis[4] < 1.0) {
+      Vec3 nearCorners[5];
+      Vec3 center{0, 0, 0};
+      for (int j = 0; j < 5; j++) {
+        Vec3 tmp{map_in[pointSearchInd[j]].x, map_in[pointSearchInd[j]].y, map_in[pointSearchInd[j]].z};
+        center = center + tmp;
+        nearCorners[j] = tmp;
+      }
+      center = center / 5.0;
+      Mat3 covMat = {{{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}};
+      for (int j = 0; j < 5; j++) {
+        Vec3 d = nearCorners[j] - center;
+        const double dv[3] = {d.x, d.y, d.z};
+        for (int a = 0; a < 3; ++a)
+          for (int b = 0; b < 3; ++b) covMat.m[a][b] = covMat.m[a][b] + dv[a] * dv[b];
+      }
+      Eigen3 saes = self_adjoint_eigen3(covMat);
+      Vec3 unit_direction{saes.vectors[0][2], saes.vectors[1][2], saes.vectors[2][2]};
+      Vec3 curr_point{pc_in[i].x, pc_in[i].y, pc_in[i].z};
+      if (saes.values[2] > 3 * saes.values[1]) {
+        Vec3 point_on_line = center;
+        Vec3 point_a = 0.1 * unit_direction + point_on_line;
+        Vec3 point_b = -0.1 * unit_direction + point_on_line;
+        problem.push_back(Residual{0, curr_point, point_a, point_b});
+        if (tap) debug->edge_ok[i] = 1;
+      }
+    }
+  }
+}
+
+void OdomEstimation::addSurfCostFactor(const CloudI& pc_in, const CloudI& map_in, std::vector<Residual>& problem, bool tap) {
+  if (tap) { debug->surf_knn.assign(pc_in.size() * 5, -1); debug->surf_d2.assign(pc_in.size() * 5, 0.f); debug->surf_ok.assign(pc_in.size(), 0); }
+  for (int i = 0; i < (int)pc_in.size(); i++) {
+    PointXYZI point_temp;
+    pointAssociateToMap(pc_in[i], point_temp);
+    int pointSearchInd[8];
+    float pointSearchSqDis[8];
+    if (use_kdtree) kdtreeSurfMap.nearestKSearch(point_temp, 5, pointSearchInd, pointSearchSqDis);
+    else knn_bruteforce(map_in, point_temp, 5, pointSearchInd, pointSearchSqDis);
+    stat_knn_queries++;
+    if (tap) for (int j = 0; j < 5; ++j) { debug->surf_knn[i * 5 + j] = pointSearchInd[j]; debug->surf_d2[i * 5 + j] = pointSearchSqDis[j]; }
+    double matA0[15];
+    const double matB0[5] = {-1, -1, -1, -1, -1};
+    if (pointSearchSqDis[4] < 1.0) {
+      for (int j = 0; j < 5; j++) {
+        matA0[j * 3 + 0] = map_in[pointSearchInd[j]].x;
+        matA0[j * 3 + 1] = map_in[pointSearchInd[j]].y;
+        matA0[j * 3 + 2] = map_in[pointSearchInd[j]].z;
+      }
+      double nv[3];
+      colpiv_qr_solve_nx3(matA0, matB0, 5, nv);
+      Vec3 nrm{nv[0], nv[1], nv[2]};
+      double nn = norm(nrm);
+      double negative_OA_dot_norm = 1 / nn;
+      nrm = nrm / nn;  // norm.normalize(): *this /= norm()
+      bool planeValid = true;
+      for (int j = 0; j < 5; j++) {
+        if (std::fabs(nrm.x * map_in[pointSearchInd[j]].x + nrm.y * map_in[pointSearchInd[j]].y + nrm.z * map_in[pointSearchInd[j]].z +
+                      negative_OA_dot_norm) > 0.2) {
+          planeValid = false;
+          break;
+        }
+      }
+      Vec3 curr_point{pc_in[i].x, pc_in[i].y, pc_in[i].z};
+      if (planeValid) {
+        problem.push_back(Residual{1, curr_point, nrm, Vec3{negative_OA_dot_norm, 0, 0}});
+        if (tap) debug->surf_ok[i] = 1;
+      }
+    }
+  }
+}
+
+void OdomEstimation::addPointsToMap(const CloudI& ds_edge, const CloudI& ds_surf) {
+  for (const PointXYZI& p : ds_edge) { PointXYZI t; pointAssociateToMap(p, t); laserCloudCornerMap.push_back(t); }
+  for (const PointXYZI& p : ds_surf) { PointXYZI t; pointAssociateToMap(p, t); laserCloudSurfMap.push_back(t); }
+  const float mn[3] = {(float)(odom.t.x - 100), (float)(odom.t.y - 100), (float)(odom.t.z - 100)};
+  const float mx[3] = {(float)(odom.t.x + 100), (float)(odom.t.y + 100), (float)(odom.t.z + 100)};
+  CloudI tmpCorner, tmpSurf;
+  crop_box_filter(laserCloudSurfMap, mn, mx, tmpSurf);
+  crop_box_filter(laserCloudCornerMap, mn, mx, tmpCorner);
+  voxel_grid_filter(tmpSurf, leaf_surf_, laserCloudSurfMap, total_order);
+  voxel_grid_filter(tmpCorner, leaf_edge_, laserCloudCornerMap, total_order);
+}
+
+void OdomEstimation::getMap(CloudI& out) const {
+  out.insert(out.end(), laserCloudSurfMap.begin(), laserCloudSurfMap.end());
+  out.insert(out.end(), laserCloudCornerMap.begin(), laserCloudCornerMap.end());
+}
+
+bool OdomEstimation::KeyFrameUpdate(const Iso3& pose) {
+  if (kf_first_) {
+    kf_first_ = false;
+    kf_last_pose_ = pose;
+    return true;
+  }
+  const Iso3 delta = iso_mul(iso_inverse(kf_last_pose_), pose);
+  const double delta_movement = norm(delta.t);
+  const double delta_rot = rotation_angle(delta.R);
+  if (delta_movement > keyframe_min_transl_ || delta_rot > keyframe_min_rot_) {
+    kf_last_pose_ = pose;
+    return true;
+  }
+  return false;
+}
+
+}  // namespace fo
