@@ -300,3 +300,9 @@ double fo_replay_sequence(const PointXYZIRT* scans, const long long* offsets, in
 }
 
 }  // extern "C"
+
+extern "C" void fo_householder_qr_solve(const double* A_rowmajor, const double* b, int rows, int cols, double* x) {
+  std::vector<double> A((size_t)rows * cols), rhs(b, b + rows);
+  for (int r = 0; r < rows; ++r) for (int c = 0; c < cols; ++c) A[(size_t)c * rows + r] = A_rowmajor[(size_t)r * cols + c];
+  householder_qr_solve(A.data(), rhs.data(), rows, cols, x);
+}

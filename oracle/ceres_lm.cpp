@@ -5,6 +5,8 @@
 // TrustRegionMinimizer, LevenbergMarquardtStrategy, DenseQRSolver, ResidualBlock::Evaluate, Corrector, HuberLoss).
 #include "floam_oracle.h"
 #include <cstring>
+#include <cstdio>
+#include <cstdlib>
 #include <limits>
 
 namespace fo {
@@ -275,6 +277,7 @@ void ceres_solve_pose(const std::vector<Residual>& blocks, LossKind loss, double
       }
       model_cost_change = -model_cost_change;
     }
+    if (getenv("FO_LM_DEBUG")) fprintf(stderr, "it %d radius %g step %g %g %g %g %g %g finite %d model %g\n", iteration, radius, step[0], step[1], step[2], step[3], step[4], step[5], (int)step_finite, model_cost_change);
     if (!step_finite || !(model_cost_change > 0.0)) {  // HandleInvalidStep
       radius *= 0.5;
       reuse_diagonal = true;
@@ -289,6 +292,7 @@ void ceres_solve_pose(const std::vector<Residual>& blocks, LossKind loss, double
     if (!evaluate_program(blocks, loss, candidate_x, &candidate_cost, nullptr, nullptr, nullptr))
       candidate_cost = std::numeric_limits<double>::max();
 
+    if (getenv("FO_LM_DEBUG")) fprintf(stderr, "it %d radius %g step %g %g %g %g %g %g delta %g %g %g %g %g %g model %g cost %g cand %g\n", iteration, radius, step[0], step[1], step[2], step[3], step[4], step[5], delta[0], delta[1], delta[2], delta[3], delta[4], delta[5], model_cost_change, x_cost, candidate_cost);
     // ParameterToleranceReached
     double diff[7];
     for (int j = 0; j < 7; ++j) diff[j] = x[j] - candidate_x[j];

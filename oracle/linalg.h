@@ -372,7 +372,7 @@ inline void householder_qr_solve(double* A_colmajor, double* b, int rows, int co
   for (int k = 0; k < cols; ++k) detail::apply_householder_left(&b[k], rows - k, &A_colmajor[(size_t)k * rows + k + 1], h[k]);
   for (int i = cols - 1; i >= 0; --i) {
     double s = b[i];
-    for (int j = i + 1; j < cols; ++j) s -= A_colmajor[(size_t)j * rows + i] * b[j];
+    for (int j = i + 1; j < cols; ++j) s -= A_colmajor[(size_t)j * rows + i] * x_out[j];
     x_out[i] = s / A_colmajor[(size_t)i * rows + i];
   }
 }
