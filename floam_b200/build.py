@@ -14,7 +14,9 @@ CUDA_LIB = os.path.join(LIB_DIR, "libfloam_b200.so")
 SYNTH_LIB = os.path.join(LIB_DIR, "libfloam_synth.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
-              "-Xcompiler", "-Wall", "--expt-relaxed-constexpr"]
+              "-Xcompiler", "-Wall", "--expt-relaxed-constexpr",
+              # no FMA contraction: float/double arithmetic must round like the reference's x86 build
+              "-fmad=false"]
 
 
 def _stale(target, sources):
@@ -47,7 +49,7 @@ def build_cuda(force=False, verbose=False):
     os.makedirs(LIB_DIR, exist_ok=True)
     if force or _stale(CUDA_LIB, deps):
         cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-            ["-I", os.path.join(ROOT, "include"), "-I", CSRC, "-shared", "-o", CUDA_LIB] + srcs + ["-lcudart"]
+            ["-I", os.path.join(ROOT, "include"), "-I", CSRC, "-shared", "-o", CUDA_LIB] + srcs
         subprocess.check_call(cmd)
     return CUDA_LIB
 

@@ -1,0 +1,122 @@
+// Shared device/host definitions for the B200-native FLOAM odometry path (sm_100a only).
+// Data layout and kernel inventory are described in DESIGN.md.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+
+#include "floam_b200.h"
+
+#define FLOAM_CUDA_OK(expr)                                                                          \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    if (_e != cudaSuccess) {                                                                         \
+      std::fprintf(stderr, "[floam_b200] CUDA error %s at %s:%d: %s\n", #expr, __FILE__, __LINE__, cudaGetErrorString(_e)); \
+      return FLOAM_ERR_CUDA;                                                                         \
+    }                                                                                                \
+  } while (0)
+
+namespace floam {
+
+constexpr int kNumSMs = 148;  // B200
+
+// kernels launched by the calling host thread (bench.py's gpu_launches); defined in sort_scan.cu
+extern thread_local long long g_launches;
+inline void count_launch(int n = 1) { g_launches += n; }
+
+// 32-byte scan/feature point, byte-identical to vel_point::PointXYZIRT (reference include/lidar.h:14-32).
+struct __align__(16) PointIRT {
+  float x, y, z, pad0;
+  float intensity;
+  unsigned short ring, pad1;
+  float time;
+  float pad2;
+};
+static_assert(sizeof(PointIRT) == 32, "PointXYZIRT layout");
+
+// Odometry-side clouds are kept as float4 (x, y, z, intensity): half the bytes of pcl::PointXYZI, same information.
+typedef float4 P4;
+
+// 32-byte pcl::PointXYZI for the boundary
+struct __align__(16) PointI {
+  float x, y, z, pad0;
+  float intensity, p1, p2, p3;
+};
+static_assert(sizeof(PointI) == 32, "PointXYZI layout");
+
+// ---- arithmetic that must match the reference's non-contracted x86 code bit for bit (SURVEY.md §7 FP discipline) ----
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
+
+// order-preserving float <-> uint mapping for atomicMin/atomicMax on floats
+__device__ __forceinline__ unsigned int float_flip(float f) {
+  unsigned int u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float float_unflip(unsigned int u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+__device__ __forceinline__ int warp_incl_scan(int v) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane_id() >= o) v += t;
+  }
+  return v;
+}
+
+// Block-wide exclusive scan of one int per thread (blockDim.x <= 1024, multiple of 32). smem: 33 ints. Returns exclusive
+// prefix; *total receives the block sum (valid in every thread).
+__device__ __forceinline__ int block_excl_scan(int v, int* smem, int* total) {
+  int incl = warp_incl_scan(v);
+  const int w = warp_id(), l = lane_id(), nw = blockDim.x >> 5;
+  __syncthreads();
+  if (l == 31) smem[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    int s = (l < nw) ? smem[l] : 0;
+    int si = warp_incl_scan(s);
+    smem[l] = si - s;
+    if (l == 31) smem[32] = si;
+  }
+  __syncthreads();
+  int r = incl - v + smem[w];
+  *total = smem[32];
+  return r;
+}
+
+// ---- device-wide primitives (sort_scan.cu). All sizes are read from device memory so a frame needs no host sync. ----
+struct SortWorkspace {
+  unsigned int* keys_alt;   // capacity n_max
+  int* vals_alt;            // capacity n_max
+  int* hist;                // 256 * max_blocks
+  int max_blocks;
+  int n_max;
+};
+size_t sort_workspace_bytes(int n_max);
+void sort_workspace_bind(SortWorkspace& ws, void* mem, int n_max);
+// Stable LSD radix sort of (key,value) pairs, 8 bits per pass; passes beyond *d_nbits (device) degrade to copies so that
+// the sorted result always lands back in keys/vals. n is read from *d_n; launch geometry is sized for n_max.
+void radix_sort_pairs(unsigned int* keys, int* vals, const int* d_n, const int* d_nbits, int n_max, SortWorkspace& ws, const int* d_skip, cudaStream_t s);
+
+// in-place exclusive scan of a small device array (n known on the host) by a single CTA
+void exclusive_scan_small(int* data, int n, cudaStream_t s);
+
+struct ScanWorkspace {
+  int* block_sums;  // capacity ceil(n_max / 4096) + 1
+  int n_max;
+};
+size_t scan_workspace_bytes(int n_max);
+void scan_workspace_bind(ScanWorkspace& ws, void* mem, int n_max);
+// out[i] = sum_{j<i} in[j] for i in [0, n]; out has n+1 entries (out[n] = total). n read from *d_n (or n_fixed if d_n==nullptr).
+void exclusive_scan_i32(const int* in, int* out, const int* d_n, int n_fixed, int n_max, ScanWorkspace& ws, const int* d_skip, cudaStream_t s);
+
+}  // namespace floam

@@ -1,0 +1,316 @@
+// Subsystem (1): LaserProcessingClass::featureExtraction on the device.
+// Replaces reference src/laserProcessingClass.cpp:11-22 (RingExtractionVelodyne), :72-118 (curvature + sectors) and
+// :121-231 (featureExtractionFromSector) with six kernels and no host round trip:
+//   ring_count -> scan -> ring_scatter   : stable bucketing by ring with the range gate (order inside a ring preserved)
+//   sector                               : one CTA per (ring, sector): ring segment staged in shared memory, curvature in the
+//                                          reference's exact float/double operation order, bitonic sort by (value, id),
+//                                          greedy edge pick with the +-5 neighbour suppression, surf = the rest
+//   offsets -> gather                    : sector counts -> output offsets, points copied out as 2x float4
+#include "feature.cuh"
+
+namespace floam {
+namespace {
+
+constexpr int kTile = 1024;         // points per CTA in the bucketing kernels (32 warps, one point per thread)
+constexpr int kMaxRings = 128;
+constexpr int kSectorThreads = 256;
+constexpr int kSectorCap = 1024;    // max curvature entries per sector (ring <= ~6150 points)
+constexpr int kHalo = 10;
+
+__device__ __forceinline__ bool range_gate(const PointIRT& p, double min_d, double max_d, int num_lines) {
+  // double distance = sqrt(x*x + y*y) with float products/sum and the float sqrt overload (laserProcessingClass.cpp:14-15)
+  const float d = __fsqrt_rn(fadd(fmul(p.x, p.x), fmul(p.y, p.y)));
+  const double dd = (double)d;
+  if (dd < min_d || dd > max_d) return false;
+  return (int)p.ring < num_lines;
+}
+
+__device__ __forceinline__ PointIRT load_point(const PointIRT* __restrict__ pts, int i) {
+  const float4* q = reinterpret_cast<const float4*>(pts + i);
+  float4 a = __ldg(q), b = __ldg(q + 1);
+  PointIRT p;
+  *reinterpret_cast<float4*>(&p) = a;
+  *(reinterpret_cast<float4*>(&p) + 1) = b;
+  return p;
+}
+__device__ __forceinline__ void store_point(PointIRT* pts, int i, const PointIRT& p) {
+  float4* q = reinterpret_cast<float4*>(pts + i);
+  q[0] = *reinterpret_cast<const float4*>(&p);
+  q[1] = *(reinterpret_cast<const float4*>(&p) + 1);
+}
+
+// tile_cnt[ring * ntiles + tile] = number of gated points of that ring in the tile
+__global__ void __launch_bounds__(kTile) ring_count_kernel(const PointIRT* __restrict__ pts, const int* __restrict__ d_n, FeatureParams prm,
+                                                            int ntiles, int* __restrict__ tile_cnt, int* __restrict__ d_flags) {
+  __shared__ int s_cnt[kMaxRings];
+  const int n = *d_n;
+  if (threadIdx.x < kMaxRings) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const int i = blockIdx.x * kTile + threadIdx.x;
+  unsigned int ring = 0xffffffffu;
+  if (i < n) {
+    PointIRT p = load_point(pts, i);
+    if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) atomicOr(d_flags, 1);  // Q9: undefined in the reference
+    if (range_gate(p, prm.min_distance, prm.max_distance, prm.num_lines)) ring = p.ring;
+  }
+  const unsigned int m = __match_any_sync(0xffffffffu, ring);
+  if (ring != 0xffffffffu && (__ffs(m) - 1) == lane_id()) atomicAdd(&s_cnt[ring], __popc(m));
+  __syncthreads();
+  if (threadIdx.x < prm.num_lines) tile_cnt[threadIdx.x * ntiles + blockIdx.x] = s_cnt[threadIdx.x];
+  if (blockIdx.x == 0 && threadIdx.x == 0) tile_cnt[prm.num_lines * ntiles] = 0;  // becomes the grand total after the scan
+}
+
+__global__ void __launch_bounds__(kTile) ring_scatter_kernel(const PointIRT* __restrict__ pts, const int* __restrict__ d_n, FeatureParams prm,
+                                                              int ntiles, const int* __restrict__ tile_off, PointIRT* __restrict__ ring_pts,
+                                                              int* __restrict__ ring_src) {
+  __shared__ int s_cnt[32][kMaxRings];  // per-warp counts -> exclusive prefix over warps
+  const int n = *d_n;
+  if (blockIdx.x * kTile >= n) return;
+  for (int k = threadIdx.x; k < 32 * kMaxRings; k += kTile) (&s_cnt[0][0])[k] = 0;
+  __syncthreads();
+  const int i = blockIdx.x * kTile + threadIdx.x;
+  const int w = warp_id(), l = lane_id();
+  unsigned int ring = 0xffffffffu;
+  PointIRT p;
+  if (i < n) {
+    p = load_point(pts, i);
+    if (range_gate(p, prm.min_distance, prm.max_distance, prm.num_lines)) ring = p.ring;
+  }
+  const unsigned int m = __match_any_sync(0xffffffffu, ring);
+  const int rank = __popc(m & ((1u << l) - 1u));
+  if (ring != 0xffffffffu && rank == 0) s_cnt[w][ring] = __popc(m);
+  __syncthreads();
+  if (threadIdx.x < prm.num_lines) {
+    int run = tile_off[threadIdx.x * ntiles + blockIdx.x];
+    for (int ww = 0; ww < 32; ++ww) { const int c = s_cnt[ww][threadIdx.x]; s_cnt[ww][threadIdx.x] = run; run += c; }
+  }
+  __syncthreads();
+  if (ring != 0xffffffffu) {
+    const int pos = s_cnt[w][ring] + rank;
+    p.pad0 = 1.0f; p.pad1 = 0; p.pad2 = 0.0f;
+    store_point(ring_pts, pos, p);
+    ring_src[pos] = i;
+  }
+}
+
+struct SortKey {
+  double v;
+  int id;
+};
+__device__ __forceinline__ bool key_less(double va, int ia, double vb, int ib) { return va < vb || (va == vb && ia < ib); }
+
+// One CTA per (ring, sector).
+__global__ void __launch_bounds__(kSectorThreads) sector_kernel(const PointIRT* __restrict__ ring_pts, const int* __restrict__ tile_off, int ntiles,
+                                                                FeatureParams prm, int* __restrict__ edge_tmp, int* __restrict__ surf_tmp,
+                                                                int* __restrict__ edge_cnt, int* __restrict__ surf_cnt, int* __restrict__ d_flags) {
+  __shared__ float sx[kSectorCap + kHalo], sy[kSectorCap + kHalo], sz[kSectorCap + kHalo];
+  __shared__ double sval[kSectorCap];
+  __shared__ short sid[kSectorCap];
+  __shared__ unsigned char spicked[kSectorCap + kHalo], sgap[kSectorCap + kHalo];
+  __shared__ int s_scan[33];
+  __shared__ int s_nedge;
+
+  const int ring = blockIdx.x / 6, sec = blockIdx.x % 6;
+  const int ring_start = tile_off[ring * ntiles];
+  const int ring_n = tile_off[(ring + 1) * ntiles] - ring_start;
+  const int tid = threadIdx.x;
+  if (ring_n < 131) {  // laserProcessingClass.cpp:89-91
+    if (tid == 0) { edge_cnt[blockIdx.x] = 0; surf_cnt[blockIdx.x] = 0; }
+    return;
+  }
+  const int total_points = ring_n - 10;
+  const int sector_length = total_points / 6;
+  const int sector_start = sector_length * sec;
+  const int sector_end = (sec == 5) ? (total_points - 1) : (sector_length * (sec + 1) - 1);  // exclusive end (Q5)
+  const int m = sector_end - sector_start;
+  if (m > kSectorCap) {
+    if (tid == 0) { atomicOr(d_flags, 2); edge_cnt[blockIdx.x] = 0; surf_cnt[blockIdx.x] = 0; }
+    return;
+  }
+  // stage ring points [sector_start, sector_end + 10): local index q <-> ring index sector_start + q;
+  // curvature entry c (0 <= c < m) is ring point j = sector_start + c + 5 = local c + 5
+  const int nload = m + kHalo;
+  const PointIRT* base = ring_pts + ring_start + sector_start;
+  for (int q = tid; q < nload; q += kSectorThreads) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(base + q));
+    sx[q] = a.x; sy[q] = a.y; sz[q] = a.z;
+    spicked[q] = 0;
+  }
+  __syncthreads();
+  int mpad = 32;
+  while (mpad < m) mpad <<= 1;
+  for (int c = tid; c < mpad; c += kSectorThreads) {
+    if (c < m) {
+      const int j = c + 5;
+      // float left-to-right: p[j-5]+...+p[j-1] - 10*p[j] + p[j+1]+...+p[j+5]  (laserProcessingClass.cpp:96-98)
+      float dx = fadd(sx[j - 5], sx[j - 4]); dx = fadd(dx, sx[j - 3]); dx = fadd(dx, sx[j - 2]); dx = fadd(dx, sx[j - 1]);
+      dx = fsub(dx, fmul(10.0f, sx[j]));
+      dx = fadd(dx, sx[j + 1]); dx = fadd(dx, sx[j + 2]); dx = fadd(dx, sx[j + 3]); dx = fadd(dx, sx[j + 4]); dx = fadd(dx, sx[j + 5]);
+      float dy = fadd(sy[j - 5], sy[j - 4]); dy = fadd(dy, sy[j - 3]); dy = fadd(dy, sy[j - 2]); dy = fadd(dy, sy[j - 1]);
+      dy = fsub(dy, fmul(10.0f, sy[j]));
+      dy = fadd(dy, sy[j + 1]); dy = fadd(dy, sy[j + 2]); dy = fadd(dy, sy[j + 3]); dy = fadd(dy, sy[j + 4]); dy = fadd(dy, sy[j + 5]);
+      float dz = fadd(sz[j - 5], sz[j - 4]); dz = fadd(dz, sz[j - 3]); dz = fadd(dz, sz[j - 2]); dz = fadd(dz, sz[j - 1]);
+      dz = fsub(dz, fmul(10.0f, sz[j]));
+      dz = fadd(dz, sz[j + 1]); dz = fadd(dz, sz[j + 2]); dz = fadd(dz, sz[j + 3]); dz = fadd(dz, sz[j + 4]); dz = fadd(dz, sz[j + 5]);
+      const double X = dx, Y = dy, Z = dz;
+      sval[c] = dadd(dadd(dmul(X, X), dmul(Y, Y)), dmul(Z, Z));
+      sid[c] = (short)c;
+    } else {
+      sval[c] = __longlong_as_double(0x7ff0000000000000LL);  // +inf padding sorts last
+      sid[c] = (short)c;
+    }
+  }
+  // gap flag between local points q and q+1: squared distance (double, float differences) > 0.05  (:151-168)
+  for (int q = tid; q < nload - 1; q += kSectorThreads) {
+    const double ax = (double)fsub(sx[q + 1], sx[q]), ay = (double)fsub(sy[q + 1], sy[q]), az = (double)fsub(sz[q + 1], sz[q]);
+    sgap[q] = dadd(dadd(dmul(ax, ax), dmul(ay, ay)), dmul(az, az)) > 0.05 ? 1 : 0;
+  }
+  __syncthreads();
+  // bitonic sort ascending by (value, id): the total order that stands in for std::sort's tie behaviour (Q8)
+  for (int k = 2; k <= mpad; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < mpad; i += kSectorThreads) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const double va = sval[i], vb = sval[ixj];
+          const short ia = sid[i], ib = sid[ixj];
+          const bool up = ((i & k) == 0);
+          const bool a_gt_b = key_less(vb, ib, va, ia);
+          if (a_gt_b == up) { sval[i] = vb; sval[ixj] = va; sid[i] = ib; sid[ixj] = ia; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // greedy pick from the largest curvature down (:132-170); local point index of entry c is c + 5
+  if (tid == 0) {
+    int largestPickedNum = 0, nedge = 0;
+    for (int i = m - 1; i >= 0; --i) {
+      const int c = sid[i];
+      const int q = c + 5;
+      if (spicked[q]) continue;
+      if (sval[i] <= 0.1) break;
+      largestPickedNum++;
+      spicked[q] = 1;
+      if (largestPickedNum <= 20) {
+        edge_tmp[blockIdx.x * 20 + nedge] = ring_start + sector_start + q;
+        nedge++;
+      } else {
+        break;  // the 21st candidate stays picked: neither edge nor surf (Q6)
+      }
+      for (int k = 1; k <= 5; ++k) {
+        if (sgap[q + k - 1]) break;
+        spicked[q + k] = 1;
+      }
+      for (int k = -1; k >= -5; --k) {
+        if (sgap[q + k]) break;
+        spicked[q + k] = 1;
+      }
+    }
+    s_nedge = nedge;
+  }
+  __syncthreads();
+  // surf = every non-picked entry in ascending curvature order (:220-227): stable compaction of the sorted list
+  int written = 0;
+  int* surf_out = surf_tmp + ring_start + sector_start + 5;
+  for (int b0 = 0; b0 < m; b0 += kSectorThreads) {
+    const int i = b0 + tid;
+    int keep = 0, q = 0;
+    if (i < m) { q = sid[i] + 5; keep = spicked[q] ? 0 : 1; }
+    int tot;
+    const int ex = block_excl_scan(keep, s_scan, &tot);
+    if (keep) surf_out[written + ex] = ring_start + sector_start + q;
+    written += tot;
+    __syncthreads();
+  }
+  if (tid == 0) { edge_cnt[blockIdx.x] = s_nedge; surf_cnt[blockIdx.x] = written; }
+}
+
+// exclusive offsets over <= 1024 sectors; totals to d_ne / d_ns
+__global__ void __launch_bounds__(1024) feature_offsets_kernel(const int* __restrict__ edge_cnt, const int* __restrict__ surf_cnt, int nsectors,
+                                                                int* __restrict__ edge_off, int* __restrict__ surf_off, int* d_ne, int* d_ns) {
+  __shared__ int smem[33];
+  const int t = threadIdx.x;
+  int e = t < nsectors ? edge_cnt[t] : 0, s = t < nsectors ? surf_cnt[t] : 0;
+  int te, ts;
+  const int ee = block_excl_scan(e, smem, &te);
+  __syncthreads();
+  const int se = block_excl_scan(s, smem, &ts);
+  if (t < nsectors) { edge_off[t] = ee; surf_off[t] = se; }
+  if (t == 0) { *d_ne = te; *d_ns = ts; }
+}
+
+__global__ void __launch_bounds__(256) feature_gather_kernel(const PointIRT* __restrict__ ring_pts, const int* __restrict__ ring_src,
+                                                              const int* __restrict__ tile_off, int ntiles, const int* __restrict__ edge_tmp,
+                                                              const int* __restrict__ surf_tmp, const int* __restrict__ edge_cnt,
+                                                              const int* __restrict__ surf_cnt, const int* __restrict__ edge_off,
+                                                              const int* __restrict__ surf_off, PointIRT* __restrict__ edge_out,
+                                                              PointIRT* __restrict__ surf_out, int* __restrict__ edge_src, int* __restrict__ surf_src) {
+  const int sector = blockIdx.x;
+  const int ne = edge_cnt[sector], ns = surf_cnt[sector];
+  if (ne == 0 && ns == 0) return;
+  const int ring = sector / 6, sec = sector % 6;
+  const int ring_start = tile_off[ring * ntiles];
+  const int ring_n = tile_off[(ring + 1) * ntiles] - ring_start;
+  const int sector_start = ((ring_n - 10) / 6) * sec;
+  const int eo = edge_off[sector], so = surf_off[sector];
+  // each point is two float4: even threads move the first half, odd threads the second
+  const int half = threadIdx.x & 1;
+  for (int k = threadIdx.x >> 1; k < ne; k += 128) {
+    const int src = edge_tmp[sector * 20 + k];
+    reinterpret_cast<float4*>(edge_out + eo + k)[half] = __ldg(reinterpret_cast<const float4*>(ring_pts + src) + half);
+    if (!half) edge_src[eo + k] = ring_src[src];
+  }
+  const int* st = surf_tmp + ring_start + sector_start + 5;
+  for (int k = threadIdx.x >> 1; k < ns; k += 128) {
+    const int src = st[k];
+    reinterpret_cast<float4*>(surf_out + so + k)[half] = __ldg(reinterpret_cast<const float4*>(ring_pts + src) + half);
+    if (!half) surf_src[so + k] = ring_src[src];
+  }
+}
+
+}  // namespace
+
+size_t feature_workspace_bytes(int max_scan_points, int num_lines) {
+  const int ntiles = (max_scan_points + kTile - 1) / kTile;
+  size_t b = 0;
+  b += (size_t)max_scan_points * sizeof(PointIRT);      // ring_pts
+  b += (size_t)max_scan_points * 4 * 2;                 // ring_src, surf_tmp
+  b += ((size_t)num_lines * ntiles + 1) * 4;            // tile_cnt/off
+  b += (size_t)num_lines * 6 * (20 + 4) * 4;            // edge_tmp, counts, offsets
+  return b + 1024;
+}
+
+void feature_workspace_bind(FeatureWorkspace& ws, void* mem, int max_scan_points, int num_lines) {
+  char* p = (char*)mem;
+  auto take = [&](size_t bytes) { void* r = p; p += (bytes + 255) / 256 * 256; return r; };
+  ws.max_scan_points = max_scan_points;
+  ws.ntiles = (max_scan_points + kTile - 1) / kTile;
+  ws.nsectors = num_lines * 6;
+  ws.ring_pts = (PointIRT*)take((size_t)max_scan_points * sizeof(PointIRT));
+  ws.ring_src = (int*)take((size_t)max_scan_points * 4);
+  ws.surf_tmp = (int*)take((size_t)max_scan_points * 4);
+  ws.tile_off = (int*)take(((size_t)num_lines * ws.ntiles + 1) * 4);
+  ws.edge_tmp = (int*)take((size_t)ws.nsectors * 20 * 4);
+  ws.edge_cnt = (int*)take((size_t)ws.nsectors * 4);
+  ws.surf_cnt = (int*)take((size_t)ws.nsectors * 4);
+  ws.edge_off = (int*)take((size_t)ws.nsectors * 4);
+  ws.surf_off = (int*)take((size_t)ws.nsectors * 4);
+}
+
+size_t feature_workspace_bytes_padded(int max_scan_points, int num_lines) { return feature_workspace_bytes(max_scan_points, num_lines) + 16 * 256; }
+
+void feature_extract_device(const PointIRT* d_scan, const int* d_n, const FeatureParams& prm, FeatureWorkspace& ws, PointIRT* d_edge, int* d_ne,
+                            PointIRT* d_surf, int* d_ns, int* d_edge_src, int* d_surf_src, int* d_flags, cudaStream_t s) {
+  const int ntiles = ws.ntiles;
+  ring_count_kernel<<<ntiles, kTile, 0, s>>>(d_scan, d_n, prm, ntiles, ws.tile_off, d_flags);
+  exclusive_scan_small(ws.tile_off, prm.num_lines * ntiles + 1, s);
+  ring_scatter_kernel<<<ntiles, kTile, 0, s>>>(d_scan, d_n, prm, ntiles, ws.tile_off, ws.ring_pts, ws.ring_src);
+  sector_kernel<<<ws.nsectors, kSectorThreads, 0, s>>>(ws.ring_pts, ws.tile_off, ntiles, prm, ws.edge_tmp, ws.surf_tmp, ws.edge_cnt, ws.surf_cnt, d_flags);
+  feature_offsets_kernel<<<1, 1024, 0, s>>>(ws.edge_cnt, ws.surf_cnt, ws.nsectors, ws.edge_off, ws.surf_off, d_ne, d_ns);
+  feature_gather_kernel<<<ws.nsectors, 256, 0, s>>>(ws.ring_pts, ws.ring_src, ws.tile_off, ntiles, ws.edge_tmp, ws.surf_tmp, ws.edge_cnt, ws.surf_cnt,
+                                                    ws.edge_off, ws.surf_off, d_edge, d_surf, d_edge_src, d_surf_src);
+  count_launch(5);
+}
+
+}  // namespace floam

@@ -1,0 +1,143 @@
+// IMU-aided deskew folded into the scan path: CenterTime (src/laserProcessingNode.cpp:65-78), dmapping::Compensate
+// (src/dataHandler.cpp:93-122) and the IMU alignment transform (src/laserProcessingNode.cpp:113-116) as ONE per-point kernel.
+// The per-point ImuHandler::Get (std::lower_bound over the whole history, :51-69) becomes a binary search over the device copy
+// of the samples restricted to the scan's time window.
+#include "imu.cuh"
+
+#include <algorithm>
+#include <cmath>
+
+#include "odom_math.cuh"
+
+namespace floam {
+
+void imu_push(ImuDevice& imu, double stamp, const double q_xyzw[4]) {
+  ImuSample s{stamp, {q_xyzw[0], q_xyzw[1], q_xyzw[2], q_xyzw[3]}};
+  if (imu.host.empty()) { imu.host.push_back(s); return; }
+  const double tdiff = stamp - imu.host.back().stamp;
+  if (tdiff > 0.00001) imu.host.push_back(s);
+}
+
+// index of the sample ImuHandler::Get returns for tStamp, or -1 when the validity rule (:57) fails
+static int imu_lookup(const std::vector<ImuSample>& v, double t) {
+  const int n = (int)v.size();
+  int lo = 0, hi = n;  // lower_bound: first stamp >= t
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (v[mid].stamp < t) lo = mid + 1; else hi = mid;
+  }
+  const int after = lo;
+  if (after == 0 || after == n) return -1;
+  const int before = after - 1;
+  if (before == 0) return -1;
+  return before;
+}
+
+bool imu_get(const ImuDevice& imu, double stamp, double q[4]) {
+  const int i = imu_lookup(imu.host, stamp);
+  if (i < 0) return false;
+  for (int k = 0; k < 4; ++k) q[k] = imu.host[i].q[k];
+  return true;
+}
+
+bool imu_time_contained(const ImuDevice& imu, double t) {
+  return !imu.host.empty() && t >= imu.host.front().stamp && t <= imu.host.back().stamp;
+}
+
+static double stamp_to_sec(uint64_t stamp_us) {  // pcl_conversions::fromPCL + ros::Time::toSec
+  const uint64_t ns = stamp_us * 1000ull;
+  return (double)(ns / 1000000000ull) + 1e-9 * (double)(ns % 1000000000ull);
+}
+static uint64_t sec_to_stamp(double t) {         // ros::Time(double) + pcl_conversions::toPCL (truncating to microseconds)
+  uint64_t sec = (uint64_t)std::floor(t);
+  uint64_t nsec = (uint64_t)std::llround((t - (double)sec) * 1e9);
+  sec += nsec / 1000000000ull;
+  nsec %= 1000000000ull;
+  return nsec / 1000ull + sec * 1000000ull;
+}
+
+void deskew_plan(const ImuDevice& imu, uint64_t stamp_us, float time_front, float time_back, const double extr[4], DeskewPlan* p) {
+  const double tScan = stamp_to_sec(stamp_us);
+  const double tEnd = tScan + time_back;
+  const double tBegin = tScan + time_front;
+  const double tCenter = tBegin + (tEnd - tBegin) / 2.0;
+  p->t_scan_old = tScan;
+  p->t_center = tCenter;
+  p->stamp_us_new = sec_to_stamp(tCenter);
+  p->t_scan_new = stamp_to_sec(p->stamp_us_new);
+  for (int k = 0; k < 4; ++k) p->extr[k] = extr[k];
+  // Compensate works on the re-centred times (float store of pnt.time + tScan - tCenter)
+  const float tf = (float)((double)time_front + tScan - tCenter), tb = (float)((double)time_back + tScan - tCenter);
+  const double t0 = (double)tf + p->t_scan_new, t1 = (double)tb + p->t_scan_new;
+  p->can_compensate = (imu_time_contained(imu, t0) && imu_time_contained(imu, t1)) ? 1 : 0;
+  double qi[4] = {0, 0, 0, 0};  // default sensor_msgs::Imu orientation when Get fails (:71-75)
+  imu_get(imu, p->t_scan_new, qi);
+  double q[4];
+  m::quat_mul(qi, extr, q);
+  const double n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+  if (n2 > 0) { p->q_init_inv[0] = -q[0] / n2; p->q_init_inv[1] = -q[1] / n2; p->q_init_inv[2] = -q[2] / n2; p->q_init_inv[3] = q[3] / n2; }
+  else { p->q_init_inv[0] = p->q_init_inv[1] = p->q_init_inv[2] = p->q_init_inv[3] = 0.0; }
+  m::quat_to_matrix(q, p->R_align);  // Eigen::Affine3d ImuNowT(q), q = Imu(stamp) * extrinsics
+}
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__global__ void __launch_bounds__(kThreads) deskew_align_kernel(PointIRT* __restrict__ pts, const int* __restrict__ d_n, DeskewPlan plan,
+                                                                 const ImuSample* __restrict__ samples, int n_samples) {
+  const int n = *d_n;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+    float4* raw = reinterpret_cast<float4*>(pts + i);
+    float4 a = raw[0], b = raw[1];  // b = intensity, ring|pad, time, pad
+    // CenterTime: pnt.time = pnt.time + tScan - tCenter (float + double - double, float store)
+    const float t_new = (float)(((double)b.z + plan.t_scan_old) - plan.t_center);
+    b.z = t_new;
+    if (plan.can_compensate) {
+      const double t_cur = plan.t_scan_new + (double)t_new;
+      // ImuHandler::Get: sample strictly before lower_bound(t_cur); invalid -> zero quaternion
+      int lo = 0, hi = n_samples;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(&samples[mid].stamp) < t_cur) lo = mid + 1; else hi = mid;
+      }
+      double qi[4] = {0.0, 0.0, 0.0, 0.0};
+      if (lo != 0 && lo != n_samples && lo - 1 != 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) qi[k] = __ldg(&samples[lo - 1].q[k]);
+      }
+      double q_now[4], q_diff[4];
+      m::quat_mul(qi, plan.extr, q_now);
+      m::quat_mul(plan.q_init_inv, q_now, q_diff);
+      const m::V3 pt = m::quat_rotate(q_diff, m::V3{(double)a.x, (double)a.y, (double)a.z});
+      // compensated cloud is stored as float, then pcl::transformPointCloud(Affine3d): double R*p + 0, float store
+      const double x = (double)(float)pt.x, y = (double)(float)pt.y, z = (double)(float)pt.z;
+      const double* R = plan.R_align;
+      a.x = (float)(R[0] * x + R[1] * y + R[2] * z + 0.0);
+      a.y = (float)(R[3] * x + R[4] * y + R[5] * z + 0.0);
+      a.z = (float)(R[6] * x + R[7] * y + R[8] * z + 0.0);
+      a.w = 1.0f;
+    }
+    raw[0] = a; raw[1] = b;
+  }
+}
+
+}  // namespace
+
+int deskew_align_device(ImuDevice& imu, const DeskewPlan& plan, PointIRT* d_pts, const int* d_n, int n_max, cudaStream_t s) {
+  const int total = (int)imu.host.size();
+  if (total > imu.dev_cap) return FLOAM_ERR_CAPACITY;
+  if (total > imu.dev_count) {
+    FLOAM_CUDA_OK(cudaMemcpyAsync(imu.d_samples + imu.dev_count, imu.host.data() + imu.dev_count, (size_t)(total - imu.dev_count) * sizeof(ImuSample),
+                                  cudaMemcpyHostToDevice, s));
+    imu.dev_count = total;
+  }
+  int g = (n_max + kThreads - 1) / kThreads;
+  if (g > kNumSMs * 8) g = kNumSMs * 8;
+  if (g < 1) g = 1;
+  deskew_align_kernel<<<g, kThreads, 0, s>>>(d_pts, d_n, plan, imu.d_samples, total);
+  count_launch(1);
+  return FLOAM_OK;
+}
+
+}  // namespace floam

@@ -1,0 +1,45 @@
+// dmapping::ImuHandler mirror and the IMU-aided deskew (CenterTime + dmapping::Compensate + IMU alignment) on the device.
+// Reference: src/dataHandler.cpp:24-122, src/laserProcessingNode.cpp:65-78,108-116. See imu.cu.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "common.cuh"
+
+namespace floam {
+
+struct ImuSample {   // device record
+  double stamp;
+  double q[4];       // x, y, z, w (Eigen coefficient order)
+};
+
+struct ImuDevice {
+  std::vector<ImuSample> host;   // time-sorted, same admission rule as ImuHandler::AddMsg (:24-40)
+  ImuSample* d_samples = nullptr;
+  int dev_count = 0;             // samples already uploaded
+  int dev_cap = 0;
+};
+
+// ImuHandler::AddMsg: keeps the sample iff it is the first or more than 10 us after the previous one
+void imu_push(ImuDevice& imu, double stamp, const double q_xyzw[4]);
+// ImuHandler::Get(t, data) (:51-69): zero-order hold with the reference's validity rule; false -> q untouched
+bool imu_get(const ImuDevice& imu, double stamp, double q_xyzw[4]);
+bool imu_time_contained(const ImuDevice& imu, double t);   // :76-81
+
+struct DeskewPlan {       // everything the per-point kernel needs, computed on the host from the scan header
+  double t_scan_old;      // stamp before CenterTime
+  double t_center;        // mid-scan time
+  double t_scan_new;      // stamp after CenterTime (microsecond-truncated like pcl_conversions)
+  double q_init_inv[4];   // (Imu(t_scan_new) * extrinsics)^-1
+  double extr[4];
+  double R_align[9];      // rotation matrix of Imu(t_scan_new) * extrinsics (row-major)
+  int can_compensate;     // dmapping::Compensate's return value
+  uint64_t stamp_us_new;
+};
+// ros::Time / pcl stamp conversions + CenterTime + the host part of Compensate (TimeContained, qInit) and of the alignment
+void deskew_plan(const ImuDevice& imu, uint64_t stamp_us, float time_front, float time_back, const double extr_xyzw[4], DeskewPlan* plan);
+// uploads new samples (if any) and runs the fused per-point kernel in place: time re-centring always; rotation-only deskew and
+// alignment only when plan.can_compensate
+int deskew_align_device(ImuDevice& imu, const DeskewPlan& plan, PointIRT* d_pts, const int* d_n, int n_max, cudaStream_t s);
+
+}  // namespace floam

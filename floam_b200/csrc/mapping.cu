@@ -1,0 +1,286 @@
+// LaserMappingClass on the device (reference src/laserMappingClass.cpp:7-32,106-200).
+//
+// The reference keeps a vector<vector<vector<cloud>>> of 50 m cells and, per frame, pushes the transformed scan into the cells and
+// runs an in-place pcl::VoxelGrid over each of the 5x5x5 cells around the sensor.  Here the global map is ONE flat cloud with a
+// packed cell id per point.  A frame
+//   1. splits the map into "rest" and "block" (points whose cell lies in the 5x5x5 block) with a stable partition,
+//   2. appends the float-transformed scan (z-based intensity, :165) to the block,
+//   3. voxelises the block with two stable radix sorts, (ky,kx) then (cell,kz) — i.e. per cell in ascending VoxelGrid index,
+//      accumulating in arrival order exactly like the 125 separate filters (old centroid first, then the new points),
+//   4. writes rest ++ block back.
+// getMap() (:188-200) orders cells x-major, y, z like the reference's triple loop with one more stable sort by cell id.
+// Points that fall outside the allocated 5x5x5 block make the reference index unallocated cells (undefined behaviour); here they
+// are dropped and counted in d_counts[4].
+#include "mapping.cuh"
+
+#include <cmath>
+
+namespace floam {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr double kCell = 50.0;     // LASER_CELL_WIDTH/HEIGHT/DEPTH, include/laserMappingClass.h:26-28
+constexpr int kRange = 2;          // LASER_CELL_RANGE_HORIZONTAL/VERTICAL, :32-33
+constexpr unsigned int kNoCell = 0xffffffffu;
+
+struct BlockGeom {
+  int cx, cy, cz;       // cell of the sensor position
+  int kx0, ky0, kz0;    // voxel coordinate origin of the block
+  int DX, DZ;           // key strides: key1 = kx + ky * DX ; key2 = kz + local_cell * DZ
+  float inv_leaf;
+  float R[9], t[3];     // pose.cast<float>()
+};
+
+inline int grid_for(int n_max) {
+  int g = (n_max + kThreads - 1) / kThreads;
+  const int cap = kNumSMs * 8;
+  return g < 1 ? 1 : (g > cap ? cap : g);
+}
+
+__host__ __device__ inline unsigned int pack_cell(int cx, int cy, int cz) {
+  return ((unsigned int)(cx + 512) << 20) | ((unsigned int)(cy + 512) << 10) | (unsigned int)(cz + 512);
+}
+__device__ __forceinline__ int local_cell(unsigned int packed, const BlockGeom& g) {  // 0..124 inside the block, 125 otherwise
+  if (packed == kNoCell) return 125;
+  const int dx = (int)(packed >> 20) - 512 - g.cx + kRange, dy = (int)((packed >> 10) & 1023u) - 512 - g.cy + kRange,
+            dz = (int)(packed & 1023u) - 512 - g.cz + kRange;
+  if (dx < 0 || dx > 2 * kRange || dy < 0 || dy > 2 * kRange || dz < 0 || dz > 2 * kRange) return 125;
+  return (dx * 5 + dy) * 5 + dz;
+}
+__device__ __forceinline__ int cell_coord(float v) { return (int)floor((double)v / kCell + 0.5); }  // :166-168
+
+__global__ void __launch_bounds__(kThreads) classify_old_kernel(const unsigned int* __restrict__ cell, const int* __restrict__ counts, BlockGeom g,
+                                                                 int* __restrict__ flags) {
+  const int n = counts[0];
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) flags[i] = local_cell(cell[i], g) < 125 ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(kThreads) partition_kernel(const P4* __restrict__ pts, const unsigned int* __restrict__ cell, const int* __restrict__ pos,
+                                                              int* __restrict__ counts, P4* __restrict__ rest, unsigned int* __restrict__ rest_cell,
+                                                              P4* __restrict__ work, unsigned int* __restrict__ work_cell) {
+  const int n = counts[0];
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+    const int p = pos[i];
+    const bool in_block = pos[i + 1] != p;
+    if (in_block) { work[p] = pts[i]; work_cell[p] = cell[i]; }
+    else { rest[i - p] = pts[i]; rest_cell[i - p] = cell[i]; }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const int nin = n > 0 ? pos[n] : 0;
+    counts[2] = nin;
+    counts[1] = n - nin;
+  }
+}
+
+// pcl::transformPointCloud(pose.cast<float>()) + intensity rewrite + cell id (:158-171)
+__global__ void __launch_bounds__(kThreads) transform_new_kernel(const char* __restrict__ in, int stride, const int* __restrict__ d_nin, int* __restrict__ counts,
+                                                                  BlockGeom g, int cap, P4* __restrict__ work, unsigned int* __restrict__ work_cell) {
+  const int nin = *d_nin, base = counts[2];
+  const bool fits = counts[1] + base + nin <= cap;
+  if (fits) {
+    for (int i = blockIdx.x * kThreads + threadIdx.x; i < nin; i += gridDim.x * kThreads) {
+      const float4 p = __ldg(reinterpret_cast<const float4*>(in + (size_t)i * stride));
+      const float x = fadd(fadd(fadd(fmul(g.R[0], p.x), fmul(g.R[1], p.y)), fmul(g.R[2], p.z)), g.t[0]);
+      const float y = fadd(fadd(fadd(fmul(g.R[3], p.x), fmul(g.R[4], p.y)), fmul(g.R[5], p.z)), g.t[1]);
+      const float z = fadd(fadd(fadd(fmul(g.R[6], p.x), fmul(g.R[7], p.y)), fmul(g.R[8], p.z)), g.t[2]);
+      const float inten = (float)fmin(1.0, fmax((double)p.z + 2.0, 0.0) / 5);
+      const int cx = cell_coord(x), cy = cell_coord(y), cz = cell_coord(z);
+      unsigned int pc = kNoCell;
+      if (abs(cx - g.cx) <= kRange && abs(cy - g.cy) <= kRange && abs(cz - g.cz) <= kRange) pc = pack_cell(cx, cy, cz);
+      else atomicAdd(&counts[4], 1);
+      work[base + i] = make_float4(x, y, z, inten);
+      work_cell[base + i] = pc;
+    }
+  }
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    counts[3] = fits ? base + nin : base;
+    if (!fits) counts[7] = 1;
+  }
+}
+
+__device__ __forceinline__ void voxel_of(const float4 p, const BlockGeom& g, int& kx, int& ky, int& kz) {
+  kx = (int)floorf(fmul(p.x, g.inv_leaf)) - g.kx0;
+  ky = (int)floorf(fmul(p.y, g.inv_leaf)) - g.ky0;
+  kz = (int)floorf(fmul(p.z, g.inv_leaf)) - g.kz0;
+}
+
+__global__ void __launch_bounds__(kThreads) keys1_kernel(const P4* __restrict__ work, const unsigned int* __restrict__ work_cell, const int* __restrict__ counts,
+                                                          BlockGeom g, unsigned int* __restrict__ keys, int* __restrict__ vals) {
+  const int n = counts[3];
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+    unsigned int key = 0;
+    if (work_cell[i] != kNoCell) {
+      int kx, ky, kz;
+      voxel_of(work[i], g, kx, ky, kz);
+      key = (unsigned int)(kx + ky * g.DX);
+    }
+    keys[i] = key;
+    vals[i] = i;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) keys2_kernel(const P4* __restrict__ work, const unsigned int* __restrict__ work_cell, const int* __restrict__ counts,
+                                                          BlockGeom g, const int* __restrict__ vals, unsigned int* __restrict__ keys) {
+  const int n = counts[3];
+  for (int j = blockIdx.x * kThreads + threadIdx.x; j < n; j += gridDim.x * kThreads) {
+    const int i = vals[j];
+    const int lc = local_cell(work_cell[i], g);
+    int kz = 0;
+    if (lc < 125) { int kx, ky; voxel_of(work[i], g, kx, ky, kz); }
+    keys[j] = (unsigned int)(kz + lc * g.DZ);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) heads_kernel(const P4* __restrict__ work, const unsigned int* __restrict__ work_cell, const int* __restrict__ counts,
+                                                          BlockGeom g, const int* __restrict__ vals, int* __restrict__ flags) {
+  const int n = counts[3];
+  for (int j = blockIdx.x * kThreads + threadIdx.x; j < n; j += gridDim.x * kThreads) {
+    const int i = vals[j];
+    const unsigned int c = work_cell[i];
+    int head = 0;
+    if (c != kNoCell) {
+      head = 1;
+      if (j > 0) {
+        const int ip = vals[j - 1];
+        if (work_cell[ip] == c) {
+          int ax, ay, az, bx, by, bz;
+          voxel_of(work[i], g, ax, ay, az);
+          voxel_of(work[ip], g, bx, by, bz);
+          if (ax == bx && ay == by && az == bz) head = 0;
+        }
+      }
+    }
+    flags[j] = head;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) reduce_kernel(const P4* __restrict__ work, const unsigned int* __restrict__ work_cell, int* __restrict__ counts,
+                                                           BlockGeom g, const int* __restrict__ vals, const int* __restrict__ seg, P4* __restrict__ out,
+                                                           unsigned int* __restrict__ out_cell) {
+  const int n = counts[3], base = counts[1];
+  for (int j = blockIdx.x * kThreads + threadIdx.x; j < n; j += gridDim.x * kThreads) {
+    if (seg[j + 1] == seg[j]) continue;  // not a voxel head (or a dropped point)
+    const unsigned int c = work_cell[vals[j]];
+    int hx, hy, hz;
+    voxel_of(work[vals[j]], g, hx, hy, hz);
+    float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+    int k = j;
+    do {  // pcl::CentroidPoint: float sums in run order, then / n
+      const float4 p = work[vals[k]];
+      sx = fadd(sx, p.x); sy = fadd(sy, p.y); sz = fadd(sz, p.z); si = fadd(si, p.w);
+      ++k;
+    } while (k < n && seg[k + 1] == seg[k] && work_cell[vals[k]] == c);
+    const float cnt = (float)(k - j);
+    out[base + seg[j]] = make_float4(__fdiv_rn(sx, cnt), __fdiv_rn(sy, cnt), __fdiv_rn(sz, cnt), __fdiv_rn(si, cnt));
+    out_cell[base + seg[j]] = c;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    counts[5] = n > 0 ? seg[n] : 0;
+    counts[6] = base + (n > 0 ? seg[n] : 0);  // new map size, committed by commit_kernel
+  }
+}
+
+__global__ void commit_kernel(int* counts) {
+  if (threadIdx.x == 0) counts[0] = counts[6];
+}
+
+__global__ void __launch_bounds__(kThreads) cell_keys_kernel(const unsigned int* __restrict__ cell, const int* __restrict__ counts, unsigned int* __restrict__ keys,
+                                                              int* __restrict__ vals) {
+  const int n = counts[0];
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) { keys[i] = cell[i]; vals[i] = i; }
+}
+__global__ void __launch_bounds__(kThreads) gather_kernel(const P4* __restrict__ pts, const int* __restrict__ vals, const int* __restrict__ counts,
+                                                           P4* __restrict__ out) {
+  const int n = counts[0];
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) out[i] = pts[vals[i]];
+}
+
+int bits_for(long long v) {
+  int b = 1;
+  while (b < 32 && (1ll << b) < v) ++b;
+  return b;
+}
+
+}  // namespace
+
+int mapping_device_init(MappingDevice& md, int cap, double map_resolution, VoxelWorkspace* vws, void* (*alloc)(void*, size_t), void* actx, cudaStream_t s) {
+  md.cap = cap;
+  md.leaf = (float)map_resolution;  // downSizeFilter.setLeafSize(map_resolution, ...) :31
+  md.vws = vws;
+  if (cap > vws->n_max) md.cap = vws->n_max;  // the sorts run in the shared voxel workspace
+  md.pts = (P4*)alloc(actx, (size_t)md.cap * 16);
+  md.pts_alt = (P4*)alloc(actx, (size_t)md.cap * 16);
+  md.work = (P4*)alloc(actx, (size_t)md.cap * 16);
+  md.cell = (unsigned int*)alloc(actx, (size_t)md.cap * 4);
+  md.cell_alt = (unsigned int*)alloc(actx, (size_t)md.cap * 4);
+  md.work_cell = (unsigned int*)alloc(actx, (size_t)md.cap * 4);
+  md.d_counts = (int*)alloc(actx, 64);
+  md.d_nbits = md.d_counts ? md.d_counts + 8 : nullptr;
+  if (!md.pts || !md.pts_alt || !md.work || !md.cell || !md.cell_alt || !md.work_cell || !md.d_counts) return FLOAM_ERR_CUDA;
+  FLOAM_CUDA_OK(cudaMemsetAsync(md.d_counts, 0, 64, s));
+  md.enabled = true;
+  return FLOAM_OK;
+}
+
+int mapping_update_device(MappingDevice& md, const void* d_in, int stride, const int* d_n, int n_max, const double T[16], cudaStream_t s) {
+  BlockGeom g;
+  g.cx = (int)std::floor(T[3] / kCell + 0.5);   // :150-152
+  g.cy = (int)std::floor(T[7] / kCell + 0.5);
+  g.cz = (int)std::floor(T[11] / kCell + 0.5);
+  if (std::abs(g.cx) > 500 || std::abs(g.cy) > 500 || std::abs(g.cz) > 500) return FLOAM_ERR_CAPACITY;
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) g.R[r * 3 + c] = (float)T[r * 4 + c];
+    g.t[r] = (float)T[r * 4 + 3];
+  }
+  g.inv_leaf = 1.0f / md.leaf;
+  // the block spans cells [c-2, c+2] -> coordinates [(c-2.5)*50, (c+2.5)*50); one metre of slack on each side
+  const double span = (2 * kRange + 1) * kCell + 2.0;
+  g.kx0 = (int)std::floor(((g.cx - kRange - 0.5) * kCell - 1.0) * g.inv_leaf) - 1;
+  g.ky0 = (int)std::floor(((g.cy - kRange - 0.5) * kCell - 1.0) * g.inv_leaf) - 1;
+  g.kz0 = (int)std::floor(((g.cz - kRange - 0.5) * kCell - 1.0) * g.inv_leaf) - 1;
+  const long long D = (long long)std::ceil(span * g.inv_leaf) + 4;
+  if (D * D >= (1ll << 32) || D * 126 >= (1ll << 32)) return FLOAM_ERR_ARG;  // leaf too small for 32-bit keys
+  g.DX = (int)D;
+  g.DZ = (int)D;
+  const int nbits[2] = {bits_for(D * D), bits_for(D * 126)};
+  FLOAM_CUDA_OK(cudaMemcpyAsync(md.d_nbits, nbits, 8, cudaMemcpyHostToDevice, s));
+
+  VoxelWorkspace& ws = *md.vws;
+  int* counts = md.d_counts;
+  const int gmap = grid_for(md.cap), gin = grid_for(n_max);
+  classify_old_kernel<<<gmap, kThreads, 0, s>>>(md.cell, counts, g, ws.flags);
+  exclusive_scan_i32(ws.flags, ws.flags, counts, 0, md.cap, ws.scan, nullptr, s);
+  partition_kernel<<<gmap, kThreads, 0, s>>>(md.pts, md.cell, ws.flags, counts, md.pts_alt, md.cell_alt, md.work, md.work_cell);
+  transform_new_kernel<<<gin, kThreads, 0, s>>>((const char*)d_in, stride, d_n, counts, g, md.cap, md.work, md.work_cell);
+  keys1_kernel<<<gmap, kThreads, 0, s>>>(md.work, md.work_cell, counts, g, ws.keys, ws.vals);
+  count_launch(4);
+  radix_sort_pairs(ws.keys, ws.vals, counts + 3, md.d_nbits, md.cap, ws.sort, nullptr, s);
+  keys2_kernel<<<gmap, kThreads, 0, s>>>(md.work, md.work_cell, counts, g, ws.vals, ws.keys);
+  count_launch(1);
+  radix_sort_pairs(ws.keys, ws.vals, counts + 3, md.d_nbits + 1, md.cap, ws.sort, nullptr, s);
+  heads_kernel<<<gmap, kThreads, 0, s>>>(md.work, md.work_cell, counts, g, ws.vals, ws.flags);
+  exclusive_scan_i32(ws.flags, ws.flags, counts + 3, 0, md.cap, ws.scan, nullptr, s);
+  reduce_kernel<<<gmap, kThreads, 0, s>>>(md.work, md.work_cell, counts, g, ws.vals, ws.flags, md.pts_alt, md.cell_alt);
+  commit_kernel<<<1, 32, 0, s>>>(counts);
+  count_launch(3);
+  std::swap(md.pts, md.pts_alt);
+  std::swap(md.cell, md.cell_alt);
+  return FLOAM_OK;
+}
+
+int mapping_get_map_device(MappingDevice& md, P4** d_out, int** d_out_n, cudaStream_t s) {
+  VoxelWorkspace& ws = *md.vws;
+  const int nbits = 30;
+  FLOAM_CUDA_OK(cudaMemcpyAsync(md.d_nbits + 2, &nbits, 4, cudaMemcpyHostToDevice, s));
+  const int g = grid_for(md.cap);
+  cell_keys_kernel<<<g, kThreads, 0, s>>>(md.cell, md.d_counts, ws.keys, ws.vals);
+  radix_sort_pairs(ws.keys, ws.vals, md.d_counts, md.d_nbits + 2, md.cap, ws.sort, nullptr, s);
+  gather_kernel<<<g, kThreads, 0, s>>>(md.pts, ws.vals, md.d_counts, md.pts_alt);
+  count_launch(2);
+  *d_out = md.pts_alt;
+  *d_out_n = md.d_counts;
+  return FLOAM_OK;
+}
+
+}  // namespace floam

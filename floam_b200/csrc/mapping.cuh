@@ -1,0 +1,34 @@
+// LaserMappingClass (src/laserMappingClass.cpp:7-200) on the device: the global map is one flat cloud plus a 50 m cell key per
+// point; a frame touches the 5x5x5 block of cells around the sensor exactly like the reference's 125 in-place VoxelGrid filters.
+// See mapping.cu.
+#pragma once
+#include "common.cuh"
+#include "voxel.cuh"
+
+namespace floam {
+
+struct MappingDevice {
+  P4* pts = nullptr;          // global map (cells of the last touched block at the tail, each in voxel order)
+  unsigned int* cell = nullptr;  // packed 50 m cell id per point: (cx+512) << 20 | (cy+512) << 10 | (cz+512)
+  P4* pts_alt = nullptr;      // ping-pong target of an update
+  unsigned int* cell_alt = nullptr;
+  P4* work = nullptr;         // points of the touched block: old in-block points followed by the new frame
+  unsigned int* work_cell = nullptr;
+  int* d_counts = nullptr;    // [0] map size, [1] rest, [2] old in block, [3] work size, [4] out-of-block drops, [5] voxels, [6] new count
+  int* flags = nullptr;       // predicate / scan buffer, cap + 1
+  unsigned int* keys = nullptr;
+  int* vals = nullptr;
+  int* d_nbits = nullptr;     // [0] bits of the (kx,ky) key, [1] bits of the (kz,cell) key
+  VoxelWorkspace* vws = nullptr;
+  int cap = 0;
+  float leaf = 0.4f;
+  bool enabled = false;
+};
+
+int mapping_device_init(MappingDevice& md, int cap, double map_resolution, VoxelWorkspace* vws, void* (*alloc)(void*, size_t), void* actx, cudaStream_t s);
+// updateCurrentPointsToMap :148-186 ; d_in = stride-32 PointXYZI cloud, pose row-major 4x4 (host)
+int mapping_update_device(MappingDevice& md, const void* d_in, int stride, const int* d_n, int n_max, const double pose16[16], cudaStream_t s);
+// getMap :188-200 : cells in (x, y, z) order, each cell in voxel order. Sorts into the alt buffers; *d_out_n = size.
+int mapping_get_map_device(MappingDevice& md, P4** d_out, int** d_out_n, cudaStream_t s);
+
+}  // namespace floam

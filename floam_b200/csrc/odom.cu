@@ -1,0 +1,855 @@
+// Subsystems (3) and (4) plus the pose / keyframe state machine of OdomEstimationClass, all device-resident.
+//
+//   reference                                            here
+//   ---------------------------------------------------  ------------------------------------------------------------
+//   updatePointsToMap :57-71 (prediction, Q2)            predict_kernel (1 thread)
+//   downSamplingToMap :137-142                           voxel_grid_device x2 (voxel.cu)
+//   kdtree setInputCloud :78-79 (rebuilt every call)     1 m uniform grid, rebuilt only when the map changed (Q12):
+//                                                         grid_bbox -> grid_dims -> grid_count -> scan -> grid_scatter
+//   addEdgeCostFactor/addSurfCostFactor :144-251         assoc_eval_kernel: pointAssociateToMap, exact 5-NN over the 27
+//                                                         neighbouring cells with (distance, index) order, PCA line fit /
+//                                                         5x3 QR plane fit, and the iteration-0 residual+Jacobian reduction
+//   ceres::Solve :100-108 (LM, <= 4 step attempts)       cand_eval_kernel x4: evaluates the candidate pose; the last CTA
+//                                                         to finish runs the trust-region bookkeeping (accept / reject,
+//                                                         radius law, tolerances, next step) on the device
+//   odom write-back, KeyFrameUpdate :114-118,320-343     finish_kernel (1 thread)
+//   addPointsToMap :253-294                              append_kernel -> crop_box_device -> voxel_grid_device -> grid rebuild,
+//                                                         all predicated on the device-side keyframe flag (no host sync)
+//
+// Compiled with -fmad=false: the float distance / pointAssociateToMap arithmetic must round exactly like the reference's
+// non-contracted x86 code so that neighbour ids are bit-exact.
+#include "odom.cuh"
+
+#include <cfloat>
+#include <cstddef>
+
+#include "odom_math.cuh"
+
+namespace floam {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kAssocBlocks = kNumSMs * 4;   // 592 CTAs x 128 threads, grid-stride over the query slots
+constexpr int kCandBlocks = kNumSMs;        // candidate evaluations touch 88 B per correspondence: one CTA per SM is plenty
+static_assert(kAssocBlocks <= 1024, "partials rows");
+
+inline int grid_for(int n_max) {
+  int g = (n_max + kThreads - 1) / kThreads;
+  const int cap = kNumSMs * 8;
+  return g < 1 ? 1 : (g > cap ? cap : g);
+}
+
+__device__ __forceinline__ float4 load_xyzi(const char* base, int stride, int i) {
+  const char* p = base + (size_t)i * stride;
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  if (stride == 16) return a;
+  return make_float4(a.x, a.y, a.z, __ldg(reinterpret_cast<const float*>(p + 16)));
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// state machine: prediction and write-back
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void state_init_kernel(PoseState* S) {
+  if (threadIdx.x != 0) return;
+  PoseState z;
+  memset(&z, 0, sizeof(z));
+  z.odom[0] = z.odom[4] = z.odom[8] = 1.0;
+  z.last_odom[0] = z.last_odom[4] = z.last_odom[8] = 1.0;
+  z.kf_pose[0] = z.kf_pose[4] = z.kf_pose[8] = 1.0;
+  z.x[3] = 1.0;
+  z.kf_first = 1;
+  z.not_keyframe = 1;
+  *S = z;
+}
+
+// updatePointsToMap :62-71. The motion prediction is unconditional (Q2).
+__global__ void predict_kernel(PoseState* S, const int* n_edge_map, const int* n_surf_map) {
+  if (threadIdx.x != 0) return;
+  double inv[12], rel[12], pred[12];
+  m::iso_inverse(S->last_odom, inv);
+  m::iso_mul(inv, S->odom, rel);
+  m::iso_mul(S->odom, rel, pred);
+  for (int i = 0; i < 12; ++i) { S->last_odom[i] = S->odom[i]; S->odom[i] = pred[i]; }
+  double q[4];
+  m::quat_from_matrix(pred, q);
+  S->x[0] = q[0]; S->x[1] = q[1]; S->x[2] = q[2]; S->x[3] = q[3];
+  S->x[4] = pred[9]; S->x[5] = pred[10]; S->x[6] = pred[11];
+  S->skip_solve = (*n_edge_map > 10 && *n_surf_map > 50) ? 0 : 1;  // :77 "not enough points in map to associate"
+  S->outer_iterations = 0;
+  S->not_keyframe = 1;
+  S->keyframe = 0;
+  S->lm_iterations_last = 0; S->lm_accepted_last = 0; S->lm_termination_last = 5; S->lm_final_cost_last = 0.0; S->initial_cost = 0.0;
+  for (int i = 0; i < 21; ++i) S->H0[i] = 0.0;
+  for (int i = 0; i < 6; ++i) S->g0[i] = 0.0;
+  S->n_corr = 0;
+}
+
+// :114-121 + KeyFrameUpdate :320-343 + the CropBox bounds of addPointsToMap :270-279
+__global__ void finish_kernel(PoseState* S, int update_type, double scan_period) {
+  if (threadIdx.x != 0) return;
+  double R[9];
+  m::quat_to_matrix(S->x, R);
+  for (int i = 0; i < 9; ++i) S->odom[i] = R[i];
+  S->odom[9] = S->x[4]; S->odom[10] = S->x[5]; S->odom[11] = S->x[6];
+  for (int a = 0; a < 3; ++a) S->velocity[a] = (S->odom[9 + a] - S->last_odom[9 + a]) / scan_period;  // GetVelocity()
+  int kf = 0;
+  if (update_type == FLOAM_VANILLA || update_type == FLOAM_REFINEMENT_AND_UPDATE) {
+    if (S->kf_first) {
+      S->kf_first = 0;
+      kf = 1;
+    } else {
+      double inv[12], delta[12];
+      m::iso_inverse(S->kf_pose, inv);
+      m::iso_mul(inv, S->odom, delta);
+      const double mov = sqrt(delta[9] * delta[9] + delta[10] * delta[10] + delta[11] * delta[11]);
+      const double rot = m::rotation_angle(delta);
+      if (mov > 0.07 || rot > 2.0 * M_PI / 180.0) kf = 1;
+    }
+    if (kf) {
+      for (int i = 0; i < 12; ++i) S->kf_pose[i] = S->odom[i];
+      for (int a = 0; a < 3; ++a) {
+        S->crop_bounds[a] = (float)(S->odom[9 + a] - 100.0);
+        S->crop_bounds[3 + a] = (float)(S->odom[9 + a] + 100.0);
+      }
+    }
+  }
+  S->keyframe = kf;
+  S->not_keyframe = kf ? 0 : 1;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// local map: append, uniform 1 m grid
+// ------------------------------------------------------------------------------------------------------------------
+// initMapWithPoints :28-32 / set_map: raw append of a strided cloud (no transform)
+__global__ void __launch_bounds__(kThreads) map_append_raw_kernel(const char* __restrict__ in, int stride, const int* __restrict__ d_nin, P4* __restrict__ map,
+                                                                   int* d_nmap, int cap, int replace, int* d_err) {
+  const int nin = *d_nin;
+  const int base = replace ? 0 : *d_nmap;
+  const bool fits = base + nin <= cap;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < nin && fits; i += gridDim.x * kThreads) map[base + i] = load_xyzi(in, stride, i);
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0 && !fits) atomicOr(d_err, 1);
+}
+__global__ void map_bump_kernel(int* d_nmap, const int* d_nin, int cap, int replace, const int* d_skip) {
+  if (d_skip && *d_skip) return;
+  if (threadIdx.x != 0) return;
+  const int base = replace ? 0 : *d_nmap;
+  if (base + *d_nin <= cap) *d_nmap = base + *d_nin;
+}
+
+// addPointsToMap :256-268: pointAssociateToMap (double transform, float store) and push_back
+__global__ void __launch_bounds__(kThreads) map_append_kernel(const P4* __restrict__ ds, const int* __restrict__ d_nds, P4* __restrict__ map,
+                                                               const int* __restrict__ d_nmap, int cap, PoseState* S, const int* d_skip) {
+  if (*d_skip) return;
+  const int nds = *d_nds, base = *d_nmap;
+  if (base + nds > cap) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&S->error_flags, 1);
+    return;
+  }
+  double x[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) x[k] = S->x[k];
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < nds; i += gridDim.x * kThreads) {
+    const float4 p = __ldg(ds + i);
+    const m::V3 w = m::add(m::quat_rotate(x, m::V3{(double)p.x, (double)p.y, (double)p.z}), m::V3{x[4], x[5], x[6]});
+    map[base + i] = make_float4((float)w.x, (float)w.y, (float)w.z, p.w);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) grid_bbox_kernel(const P4* __restrict__ pts, const int* __restrict__ d_n, unsigned int* __restrict__ bbox,
+                                                              const int* d_skip) {
+  if (d_skip && *d_skip) return;
+  const int n = *d_n;
+  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  bool any = false;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+    const float4 p = __ldg(pts + i);
+    mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
+    mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
+    any = true;
+  }
+  if (!__any_sync(0xffffffffu, any)) return;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+      mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+    }
+  }
+  if (lane_id() == 0) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      atomicMin(&bbox[a], float_flip(mn[a]));
+      atomicMax(&bbox[3 + a], float_flip(mx[a]));
+    }
+  }
+}
+
+// one thread: grid extent from the bounding box; re-arms the bbox accumulators for the next build
+__global__ void grid_dims_kernel(unsigned int* bbox, const int* d_n, GridDims* dims, int ncells_cap, PoseState* S, const int* d_skip) {
+  if (d_skip && *d_skip) return;
+  if (threadIdx.x != 0) return;
+  GridDims g;
+  g.ix0 = g.iy0 = g.iz0 = 0; g.nx = g.ny = g.nz = 0; g.ncells = 0;
+  if (*d_n > 0) {
+    const float mnx = float_unflip(bbox[0]), mny = float_unflip(bbox[1]), mnz = float_unflip(bbox[2]);
+    const float mxx = float_unflip(bbox[3]), mxy = float_unflip(bbox[4]), mxz = float_unflip(bbox[5]);
+    g.ix0 = (int)floorf(mnx); g.iy0 = (int)floorf(mny); g.iz0 = (int)floorf(mnz);
+    const long long nx = (long long)floorf(mxx) - g.ix0 + 1, ny = (long long)floorf(mxy) - g.iy0 + 1, nz = (long long)floorf(mxz) - g.iz0 + 1;
+    if (nx * ny * nz <= (long long)ncells_cap) {
+      g.nx = (int)nx; g.ny = (int)ny; g.nz = (int)nz; g.ncells = (int)(nx * ny * nz);
+    } else {
+      atomicOr(&S->error_flags, 2);  // grid capacity exceeded: every query of this map is rejected
+    }
+  }
+  *dims = g;
+  bbox[0] = bbox[1] = bbox[2] = 0xffffffffu;
+  bbox[3] = bbox[4] = bbox[5] = 0u;
+}
+
+__device__ __forceinline__ int cell_of(const GridDims& g, float x, float y, float z) {
+  const int cx = (int)floorf(x) - g.ix0, cy = (int)floorf(y) - g.iy0, cz = (int)floorf(z) - g.iz0;
+  return cx + g.nx * (cy + g.ny * cz);
+}
+
+__global__ void __launch_bounds__(kThreads) grid_count_kernel(const P4* __restrict__ pts, const int* __restrict__ d_n, const GridDims* __restrict__ dims,
+                                                               int* __restrict__ cell_count, const int* d_skip) {
+  if (d_skip && *d_skip) return;
+  const GridDims g = *dims;
+  if (g.ncells == 0) return;
+  const int n = *d_n;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+    const float4 p = __ldg(pts + i);
+    atomicAdd(&cell_count[cell_of(g, p.x, p.y, p.z)], 1);
+  }
+}
+
+// cell_count doubles as the fill cursor: it is counted down to zero here, which is also the state the next build expects.
+// The order of points inside a cell is arbitrary; the search orders candidates by (distance, index), so results do not depend on it.
+__global__ void __launch_bounds__(kThreads) grid_scatter_kernel(const P4* __restrict__ pts, const int* __restrict__ d_n, const GridDims* __restrict__ dims,
+                                                                 const int* __restrict__ cell_start, int* __restrict__ cell_count,
+                                                                 float4* __restrict__ cell_pts, const int* d_skip) {
+  if (d_skip && *d_skip) return;
+  const GridDims g = *dims;
+  if (g.ncells == 0) return;
+  const int n = *d_n;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+    const float4 p = __ldg(pts + i);
+    const int c = cell_of(g, p.x, p.y, p.z);
+    const int pos = cell_start[c] + atomicSub(&cell_count[c], 1) - 1;
+    cell_pts[pos] = make_float4(p.x, p.y, p.z, __int_as_float(i));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// exact 5-NN over the 27 cells around the query (pcl::KdTreeFLANN::nearestKSearch, k = 5, for d5^2 < 1)
+// ------------------------------------------------------------------------------------------------------------------
+struct Knn5 {
+  float d[5];
+  int id[5];
+};
+
+__device__ __forceinline__ void knn5_insert(Knn5& k, float dist, int idx) {
+  if (dist > k.d[4] || (dist == k.d[4] && idx > k.id[4])) return;
+  // replace the current worst, then bubble up by (distance, index); static indices keep the set in registers
+  k.d[4] = dist; k.id[4] = idx;
+#pragma unroll
+  for (int j = 4; j >= 1; --j) {
+    const bool lt = k.d[j] < k.d[j - 1] || (k.d[j] == k.d[j - 1] && k.id[j] < k.id[j - 1]);
+    if (lt) {
+      const float td = k.d[j]; k.d[j] = k.d[j - 1]; k.d[j - 1] = td;
+      const int ti = k.id[j]; k.id[j] = k.id[j - 1]; k.id[j - 1] = ti;
+    }
+  }
+}
+
+__device__ __forceinline__ void knn5_search(const GridDims& g, const int* __restrict__ cell_start, const float4* __restrict__ cell_pts, float qx, float qy,
+                                            float qz, Knn5& k) {
+#pragma unroll
+  for (int j = 0; j < 5; ++j) { k.d[j] = FLT_MAX; k.id[j] = 0x7fffffff; }
+  if (g.ncells == 0) return;
+  // float -> int conversion saturates, so far-away queries simply find no cell
+  const int cx = (int)floorf(qx) - g.ix0, cy = (int)floorf(qy) - g.iy0, cz = (int)floorf(qz) - g.iz0;
+  const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
+  if (x0 > x1) return;
+  for (int z = max(cz - 1, 0); z <= min(cz + 1, g.nz - 1); ++z) {
+    for (int y = max(cy - 1, 0); y <= min(cy + 1, g.ny - 1); ++y) {
+      const int row = g.nx * (y + g.ny * z);
+      const int b = __ldg(cell_start + row + x0), e = __ldg(cell_start + row + x1 + 1);  // the three x-cells are contiguous
+      for (int i = b; i < e; ++i) {
+        const float4 p = __ldg(cell_pts + i);
+        // flann::L2_Simple: ((0 + dx^2) + dy^2) + dz^2 in float, no contraction
+        const float dx = fsub(qx, p.x), dy = fsub(qy, p.y), dz = fsub(qz, p.z);
+        const float dist = fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
+        knn5_insert(k, dist, __float_as_int(p.w));
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// residuals, Jacobians and the 28-term reduction (21 H upper triangle, 6 g, cost)
+// ------------------------------------------------------------------------------------------------------------------
+struct Accum {
+  double v[kLmTerms];
+};
+
+__device__ __forceinline__ void loss_correct(int loss, double& r, double* J, double& cost_term) {
+  const double s = r * r;
+  if (loss == FLOAM_LOSS_TRIVIAL) { cost_term = 0.5 * s; return; }
+  double rho0, rho1;
+  if (loss == FLOAM_LOSS_HUBER) {  // ceres::HuberLoss(0.1)
+    const double a = 0.1, b = a * a;
+    if (s > b) {
+      const double rt = sqrt(s);
+      rho0 = 2.0 * a * rt - b;
+      rho1 = fmax(DBL_MIN, a / rt);
+    } else {
+      rho0 = s; rho1 = 1.0;
+    }
+  } else {  // ceres::CauchyLoss(0.2), opt-in only (Q1)
+    const double a = 0.2, b = a * a, c = 1.0 / b;
+    const double sum = 1.0 + s * c;
+    rho0 = b * log(sum);
+    rho1 = fmax(DBL_MIN, 1.0 / sum);
+  }
+  cost_term = 0.5 * rho0;
+  // Corrector with rho'' <= 0: residual and Jacobian scaled by sqrt(rho')
+  const double sr = sqrt(rho1);
+  r *= sr;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) J[j] *= sr;
+}
+
+// EdgeAnalyticCostFunction::Evaluate (src/lidarOptimization.cpp:12-43)
+__device__ __forceinline__ void eval_edge(const double* x, m::V3 p, m::V3 a, m::V3 b, double& r, double* J) {
+  const m::V3 lp = m::add(m::quat_rotate(x, p), m::V3{x[4], x[5], x[6]});
+  const m::V3 nu = m::cross(m::sub(lp, a), m::sub(lp, b));
+  const m::V3 de = m::sub(a, b);
+  const double de_norm = m::norm(de), nun = m::norm(nu);
+  r = nun / de_norm;
+  const m::V3 w{-nu.x / nun, -nu.y / nun, -nu.z / nun};
+  const m::V3 ws = m::cross(w, de);      // w^T * skew(de)
+  const m::V3 jr = m::cross(lp, ws);     // (w^T skew(de)) * (-skew(lp))
+  J[0] = jr.x / de_norm; J[1] = jr.y / de_norm; J[2] = jr.z / de_norm;
+  J[3] = ws.x / de_norm; J[4] = ws.y / de_norm; J[5] = ws.z / de_norm;
+}
+// SurfNormAnalyticCostFunction::Evaluate (:51-74)
+__device__ __forceinline__ void eval_surf(const double* x, m::V3 p, m::V3 n, double d, double& r, double* J) {
+  const m::V3 pw = m::add(m::quat_rotate(x, p), m::V3{x[4], x[5], x[6]});
+  r = m::dot(n, pw) + d;
+  const m::V3 jr = m::cross(pw, n);      // n^T * (-skew(pw))
+  J[0] = jr.x; J[1] = jr.y; J[2] = jr.z; J[3] = n.x; J[4] = n.y; J[5] = n.z;
+}
+
+__device__ __forceinline__ void accumulate(Accum& A, double r, const double* J, double cost_term) {
+  int k = 0;
+#pragma unroll
+  for (int a = 0; a < 6; ++a)
+#pragma unroll
+    for (int b = a; b < 6; ++b) A.v[k++] += J[a] * J[b];
+#pragma unroll
+  for (int a = 0; a < 6; ++a) A.v[21 + a] += J[a] * r;
+  A.v[27] += cost_term;
+}
+
+// PoseSE3Parameterization gradient projection used for gradient_max_norm: |x - Plus(x, -g)|_inf
+__device__ double gradient_max_norm(const double* x, const double* g) {
+  double ng[6], proj[7];
+  for (int j = 0; j < 6; ++j) ng[j] = -g[j];
+  m::se3_plus(x, ng, proj);
+  double mx = 0.0;
+  for (int j = 0; j < 7; ++j) mx = fmax(mx, fabs(x[j] - proj[j]));
+  return mx;
+}
+__device__ __forceinline__ double norm7(const double* a) {
+  double s = 0;
+  for (int i = 0; i < 7; ++i) s += a[i] * a[i];
+  return sqrt(s);
+}
+__device__ __forceinline__ int tri(int a, int b) {  // index of (a,b), a <= b, in the packed upper triangle
+  return a * 6 - a * (a - 1) / 2 + (b - a);
+}
+
+__device__ void lm_finish(PoseState& S, int termination) {
+  S.lm_done = 1;
+  S.termination = termination;
+  S.lm_iterations_last = S.iteration;
+  S.lm_accepted_last = S.accepted;
+  S.lm_termination_last = termination;
+  S.lm_final_cost_last = S.cost;
+  S.outer_iterations++;
+}
+
+// Ceres TrustRegionMinimizer loop head up to the point where a candidate has to be evaluated.
+// Everything is a function of H = J^T J, g = J^T r and the cost at the current point.
+__device__ void lm_next_candidate(PoseState& S) {
+  for (;;) {
+    if (S.iteration >= 4) { lm_finish(S, 0); return; }                                 // max_num_iterations
+    if (S.last_successful && S.gmax <= 1e-10) { lm_finish(S, 3); return; }             // gradient_tolerance
+    if (S.radius <= 1e-32) { lm_finish(S, 6); return; }                                // min_trust_region_radius
+    S.iteration++;
+    S.last_successful = 0;
+    if (!S.reuse_diag) {
+      for (int j = 0; j < 6; ++j) {
+        const double d = S.scale[j] * S.scale[j] * S.H[tri(j, j)];
+        S.diag[j] = fmin(fmax(d, 1e-6), 1e32);
+      }
+    }
+    double A[36], gs[6], y[6];
+    for (int a = 0; a < 6; ++a) {
+      gs[a] = S.scale[a] * S.g[a];
+      for (int b = 0; b < 6; ++b) {
+        const int lo = a < b ? a : b, hi = a < b ? b : a;
+        A[a * 6 + b] = S.scale[a] * S.scale[b] * S.H[tri(lo, hi)];
+      }
+    }
+    double Hs[36];
+    for (int i = 0; i < 36; ++i) Hs[i] = A[i];
+    for (int j = 0; j < 6; ++j) {
+      const double lm_diagonal = sqrt(S.diag[j] / S.radius);
+      A[j * 6 + j] += lm_diagonal * lm_diagonal;
+    }
+    const bool ok = m::cholesky6_solve(A, gs, y);
+    S.reuse_diag = 1;
+    double step[6], mcc = 0.0;
+    if (ok) {
+      for (int j = 0; j < 6; ++j) step[j] = -y[j];
+      double lin = 0.0, quad = 0.0;
+      for (int a = 0; a < 6; ++a) {
+        lin += step[a] * gs[a];
+        double t = 0.0;
+        for (int b = 0; b < 6; ++b) t += Hs[a * 6 + b] * step[b];
+        quad += step[a] * t;
+      }
+      mcc = -(lin + 0.5 * quad);
+    }
+    if (!ok || !(mcc > 0.0)) {  // HandleInvalidStep
+      S.radius *= 0.5;
+      continue;
+    }
+    S.model_cost_change = mcc;
+    double delta[6];
+    for (int j = 0; j < 6; ++j) delta[j] = step[j] * S.scale[j];
+    m::se3_plus(S.x, delta, S.x_cand);
+    return;  // candidate pending
+  }
+}
+
+// iteration 0: H, g, cost at the starting point are in place
+__device__ void lm_start(PoseState& S, const double* sums, int n_corr) {
+  S.lm_done = 0; S.iteration = 0; S.accepted = 0; S.termination = 0;
+  S.radius = 1e4; S.decrease_factor = 2.0; S.reuse_diag = 0; S.last_successful = 1;
+  for (int i = 0; i < 21; ++i) { S.H[i] = sums[i]; S.H0[i] = sums[i]; }
+  for (int i = 0; i < 6; ++i) { S.g[i] = sums[21 + i]; S.g0[i] = sums[21 + i]; }
+  S.cost = sums[27];
+  S.initial_cost = S.cost;
+  S.n_corr = n_corr;
+  if (n_corr == 0) { lm_finish(S, 5); return; }           // no residual blocks: Solve returns immediately
+  bool finite = isfinite(S.cost);
+  for (int i = 0; i < 27; ++i) finite = finite && isfinite(sums[i]);
+  if (!finite) { lm_finish(S, 4); return; }               // iteration-0 evaluation failure leaves x unchanged
+  for (int j = 0; j < 6; ++j) S.scale[j] = 1.0 / (1.0 + sqrt(S.H[tri(j, j)]));  // Jacobi scaling, computed once per solve
+  S.x_norm = norm7(S.x);
+  S.gmax = gradient_max_norm(S.x, S.g);
+  lm_next_candidate(S);
+}
+
+// the candidate's cost, H and g have been reduced
+__device__ void lm_after_candidate(PoseState& S, const double* sums) {
+  double cand_cost = sums[27];
+  bool finite = isfinite(cand_cost);
+  for (int i = 0; i < 27; ++i) finite = finite && isfinite(sums[i]);
+  if (!finite) cand_cost = DBL_MAX;
+  double diff[7];
+  for (int j = 0; j < 7; ++j) diff[j] = S.x[j] - S.x_cand[j];
+  if (norm7(diff) <= 1e-8 * (S.x_norm + 1e-8)) { lm_finish(S, 1); return; }        // parameter tolerance: candidate discarded
+  const double cost_change = S.cost - cand_cost;
+  if (fabs(cost_change) <= 1e-6 * S.cost) { lm_finish(S, 2); return; }              // function tolerance: candidate discarded
+  const double rel = cost_change / S.model_cost_change;
+  if (rel > 1e-3) {  // HandleSuccessfulStep
+    for (int j = 0; j < 7; ++j) S.x[j] = S.x_cand[j];
+    S.x_norm = norm7(S.x);
+    for (int i = 0; i < 21; ++i) S.H[i] = sums[i];
+    for (int i = 0; i < 6; ++i) S.g[i] = sums[21 + i];
+    S.cost = cand_cost;
+    S.gmax = gradient_max_norm(S.x, S.g);
+    S.last_successful = 1;
+    S.accepted++;
+    const double t = 2.0 * rel - 1.0;
+    S.radius = fmin(1e16, S.radius / fmax(1.0 / 3.0, 1.0 - t * t * t));
+    S.decrease_factor = 2.0;
+    S.reuse_diag = 0;
+  } else {           // HandleUnsuccessfulStep
+    S.radius = S.radius / S.decrease_factor;
+    S.decrease_factor *= 2.0;
+    S.reuse_diag = 1;
+  }
+  lm_next_candidate(S);
+}
+
+constexpr int kEvalThreads = 128;
+
+// Block reduction of the 28 accumulators into partials[blockIdx.x][*]; returns true in every thread of the last CTA to finish,
+// after which sums[] (shared) holds the grid totals, reduced in a fixed order (deterministic).
+__device__ bool reduce_terms(const Accum& A, double* __restrict__ partials, unsigned int* ticket, double* s_sums /*[kLmTerms]*/) {
+  __shared__ double s_part[kEvalThreads / 32][kLmTerms];
+  __shared__ int s_last;
+  const int w = warp_id(), l = lane_id();
+#pragma unroll
+  for (int k = 0; k < kLmTerms; ++k) {
+    double v = A.v[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (l == 0) s_part[w][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < kLmTerms) {
+    double v = 0.0;
+#pragma unroll
+    for (int ww = 0; ww < kEvalThreads / 32; ++ww) v += s_part[ww][threadIdx.x];
+    partials[(size_t)blockIdx.x * kLmTerms + threadIdx.x] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(ticket, 1u);
+    s_last = (t == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last) return false;
+  __threadfence();
+  // warp w sums terms w, w+4, ...; lane l takes rows l, l+32, ... then a shuffle tree
+  for (int k = w; k < kLmTerms; k += kEvalThreads / 32) {
+    double v = 0.0;
+    for (int r = l; r < (int)gridDim.x; r += 32) v += __ldcg(partials + (size_t)r * kLmTerms + k);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (l == 0) s_sums[k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *ticket = 0;
+  return true;
+}
+
+// One outer iteration's association (:144-251) fused with the iteration-0 evaluation of ceres::Solve.
+// Slots [0, nde) are edge queries against the edge map, [nde, nde+nds) surf queries against the surf map.
+__global__ void __launch_bounds__(kEvalThreads) assoc_eval_kernel(PoseState* __restrict__ S, const P4* __restrict__ ds_edge, const int* __restrict__ d_nde,
+                                                                   const P4* __restrict__ ds_surf, const int* __restrict__ d_nds, LocalMap emap, LocalMap smap,
+                                                                   int qcap, double* __restrict__ corr, unsigned char* __restrict__ corr_ok,
+                                                                   int* __restrict__ knn_ids, float* __restrict__ knn_d2, int loss,
+                                                                   double* __restrict__ partials, int tap) {
+  if (S->skip_solve) return;
+  __shared__ double s_sums[kLmTerms];
+  __shared__ int s_ncorr;
+  if (threadIdx.x == 0) s_ncorr = 0;
+  __syncthreads();
+  const int nde = *d_nde, nds = *d_nds;
+  double x[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) x[k] = S->x[k];
+  const GridDims ge = *emap.dims, gs = *smap.dims;
+  Accum A;
+#pragma unroll
+  for (int k = 0; k < kLmTerms; ++k) A.v[k] = 0.0;
+  int my_corr = 0;
+  const size_t cs = (size_t)2 * qcap;  // stride between the planes of corr
+  for (int slot = blockIdx.x * kEvalThreads + threadIdx.x; slot < nde + nds; slot += gridDim.x * kEvalThreads) {
+    const bool is_edge = slot < nde;
+    const int qi = is_edge ? slot : slot - nde;
+    const int out = is_edge ? qi : qcap + qi;
+    const float4 p = __ldg((is_edge ? ds_edge : ds_surf) + qi);
+    const m::V3 pc{(double)p.x, (double)p.y, (double)p.z};
+    // pointAssociateToMap :126-135: double transform, float store
+    const m::V3 pw = m::add(m::quat_rotate(x, pc), m::V3{x[4], x[5], x[6]});
+    const float qx = (float)pw.x, qy = (float)pw.y, qz = (float)pw.z;
+    Knn5 nn;
+    const LocalMap& map = is_edge ? emap : smap;
+    knn5_search(is_edge ? ge : gs, map.cell_start, map.cell_pts, qx, qy, qz, nn);
+    const bool near = nn.d[4] < 1.0f;  // pointSearchSqDis[4] < 1.0
+    if (tap) {
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        knn_ids[(size_t)out * 5 + j] = near ? nn.id[j] : -1;
+        knn_d2[(size_t)out * 5 + j] = near ? nn.d[j] : 0.f;
+      }
+    }
+    bool ok = false;
+    double r = 0.0, J[6], cost_term = 0.0;
+    if (near) {
+      m::V3 q[5];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        const float4 mp = __ldg(map.pts + nn.id[j]);
+        q[j] = m::V3{(double)mp.x, (double)mp.y, (double)mp.z};
+      }
+      if (is_edge) {
+        m::V3 c{0, 0, 0};
+#pragma unroll
+        for (int j = 0; j < 5; ++j) c = m::add(c, q[j]);
+        c = m::V3{c.x / 5.0, c.y / 5.0, c.z / 5.0};
+        double c00 = 0, c01 = 0, c02 = 0, c11 = 0, c12 = 0, c22 = 0;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          const m::V3 d = m::sub(q[j], c);
+          c00 += d.x * d.x; c01 += d.x * d.y; c02 += d.x * d.z; c11 += d.y * d.y; c12 += d.y * d.z; c22 += d.z * d.z;
+        }
+        double vals[3], u[3];
+        m::eigen3_sym(c00, c01, c11, c02, c12, c22, vals, u);
+        if (vals[2] > 3 * vals[1]) {
+          const m::V3 a{0.1 * u[0] + c.x, 0.1 * u[1] + c.y, 0.1 * u[2] + c.z};
+          const m::V3 b{-0.1 * u[0] + c.x, -0.1 * u[1] + c.y, -0.1 * u[2] + c.z};
+          corr[0 * cs + out] = a.x; corr[1 * cs + out] = a.y; corr[2 * cs + out] = a.z;
+          corr[3 * cs + out] = b.x; corr[4 * cs + out] = b.y; corr[5 * cs + out] = b.z;
+          eval_edge(x, pc, a, b, r, J);
+          ok = true;
+        }
+      } else {
+        double matA[15];  // column-major 5x3
+#pragma unroll
+        for (int j = 0; j < 5; ++j) { matA[0 * 5 + j] = q[j].x; matA[1 * 5 + j] = q[j].y; matA[2 * 5 + j] = q[j].z; }
+        const double matB[5] = {-1, -1, -1, -1, -1};
+        double nv[3];
+        m::colpiv_qr_solve_5x3(matA, matB, nv);
+        const double nn_ = sqrt(nv[0] * nv[0] + nv[1] * nv[1] + nv[2] * nv[2]);
+        const double d = 1 / nn_;
+        const m::V3 n{nv[0] / nn_, nv[1] / nn_, nv[2] / nn_};
+        bool valid = true;
+#pragma unroll
+        for (int j = 0; j < 5; ++j)
+          if (fabs(n.x * q[j].x + n.y * q[j].y + n.z * q[j].z + d) > 0.2) valid = false;
+        if (valid) {
+          corr[0 * cs + out] = n.x; corr[1 * cs + out] = n.y; corr[2 * cs + out] = n.z; corr[3 * cs + out] = d;
+          eval_surf(x, pc, n, d, r, J);
+          ok = true;
+        }
+      }
+    }
+    corr_ok[out] = ok ? 1 : 0;
+    if (ok) {
+      loss_correct(loss, r, J, cost_term);
+      accumulate(A, r, J, cost_term);
+      my_corr++;
+    }
+  }
+  // correspondences count (needed for the "no residual blocks" exit): warp sum -> shared -> global via the partials' spare slot
+  for (int o = 16; o > 0; o >>= 1) my_corr += __shfl_xor_sync(0xffffffffu, my_corr, o);
+  if (lane_id() == 0 && my_corr) atomicAdd(&s_ncorr, my_corr);
+  __syncthreads();
+  if (threadIdx.x == 0 && s_ncorr) atomicAdd(&S->n_corr_acc, s_ncorr);
+  if (reduce_terms(A, partials, &S->ticket, s_sums) && threadIdx.x == 0) {
+    const int n_corr = atomicExch(&S->n_corr_acc, 0);
+    lm_start(*S, s_sums, n_corr);
+  }
+}
+
+// Evaluates cost, g and H at the pending candidate; the last CTA advances the trust-region loop.
+__global__ void __launch_bounds__(kEvalThreads) cand_eval_kernel(PoseState* __restrict__ S, const P4* __restrict__ ds_edge, const int* __restrict__ d_nde,
+                                                                  const P4* __restrict__ ds_surf, const int* __restrict__ d_nds, int qcap,
+                                                                  const double* __restrict__ corr, const unsigned char* __restrict__ corr_ok, int loss,
+                                                                  double* __restrict__ partials) {
+  if (S->skip_solve || S->lm_done) return;
+  __shared__ double s_sums[kLmTerms];
+  const int nde = *d_nde, nds = *d_nds;
+  double x[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) x[k] = S->x_cand[k];
+  Accum A;
+#pragma unroll
+  for (int k = 0; k < kLmTerms; ++k) A.v[k] = 0.0;
+  const size_t cs = (size_t)2 * qcap;
+  for (int slot = blockIdx.x * kEvalThreads + threadIdx.x; slot < nde + nds; slot += gridDim.x * kEvalThreads) {
+    const bool is_edge = slot < nde;
+    const int qi = is_edge ? slot : slot - nde;
+    const int out = is_edge ? qi : qcap + qi;
+    if (!corr_ok[out]) continue;
+    const float4 p = __ldg((is_edge ? ds_edge : ds_surf) + qi);
+    const m::V3 pc{(double)p.x, (double)p.y, (double)p.z};
+    double r, J[6], cost_term;
+    if (is_edge) {
+      const m::V3 a{corr[0 * cs + out], corr[1 * cs + out], corr[2 * cs + out]};
+      const m::V3 b{corr[3 * cs + out], corr[4 * cs + out], corr[5 * cs + out]};
+      eval_edge(x, pc, a, b, r, J);
+    } else {
+      const m::V3 n{corr[0 * cs + out], corr[1 * cs + out], corr[2 * cs + out]};
+      eval_surf(x, pc, n, corr[3 * cs + out], r, J);
+    }
+    loss_correct(loss, r, J, cost_term);
+    accumulate(A, r, J, cost_term);
+  }
+  if (reduce_terms(A, partials, &S->ticket, s_sums) && threadIdx.x == 0) lm_after_candidate(*S, s_sums);
+}
+
+// stand-alone 5-NN (floam_knn5): queries are used as given (no pose transform)
+__global__ void __launch_bounds__(kEvalThreads) knn5_kernel(const P4* __restrict__ queries, const int* __restrict__ d_nq, LocalMap map, int* __restrict__ ids,
+                                                             float* __restrict__ d2) {
+  const int nq = *d_nq;
+  const GridDims g = *map.dims;
+  for (int i = blockIdx.x * kEvalThreads + threadIdx.x; i < nq; i += gridDim.x * kEvalThreads) {
+    const float4 q = __ldg(queries + i);
+    Knn5 nn;
+    knn5_search(g, map.cell_start, map.cell_pts, q.x, q.y, q.z, nn);
+    const bool near = nn.d[4] < 1.0f;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) { ids[(size_t)i * 5 + j] = near ? nn.id[j] : -1; d2[(size_t)i * 5 + j] = near ? nn.d[j] : 0.f; }
+  }
+}
+
+// dmapping::CompensateVelocity (src/dataHandler.cpp:82-91) with GetVelocity() taken from the device state (Q14: no rotation)
+__global__ void __launch_bounds__(kThreads) compensate_velocity_kernel(PointIRT* __restrict__ pts, const int* __restrict__ d_n, const PoseState* __restrict__ S) {
+  const int n = *d_n;
+  const double vx = S->velocity[0], vy = S->velocity[1], vz = S->velocity[2];
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+    PointIRT* p = pts + i;
+    const double t = (double)p->time;
+    p->x = (float)((double)p->x + vx * t);
+    p->y = (float)((double)p->y + vy * t);
+    p->z = (float)((double)p->z + vz * t);
+  }
+}
+
+int* dims_ncells_ptr(GridDims* dims) { return reinterpret_cast<int*>(reinterpret_cast<char*>(dims) + offsetof(GridDims, ncells)); }
+
+void rebuild_grid(OdomDevice& od, LocalMap& map, const int* d_skip, cudaStream_t s) {
+  const int g = grid_for(map.cap);
+  grid_bbox_kernel<<<g, kThreads, 0, s>>>(map.pts, map.d_n, map.bbox, d_skip);
+  grid_dims_kernel<<<1, 32, 0, s>>>(map.bbox, map.d_n, map.dims, map.ncells_cap, od.state, d_skip);
+  grid_count_kernel<<<g, kThreads, 0, s>>>(map.pts, map.d_n, map.dims, map.cell_count, d_skip);
+  count_launch(3);
+  exclusive_scan_i32(map.cell_count, map.cell_start, dims_ncells_ptr(map.dims), 0, map.ncells_cap, od.vws->scan, d_skip, s);
+  grid_scatter_kernel<<<g, kThreads, 0, s>>>(map.pts, map.d_n, map.dims, map.cell_start, map.cell_count, map.cell_pts, d_skip);
+  count_launch(1);
+}
+
+}  // namespace
+
+int local_map_alloc(LocalMap& map, int cap, int ncells_cap, void* (*alloc)(void*, size_t), void* actx, cudaStream_t s) {
+  map.cap = cap;
+  map.ncells_cap = ncells_cap;
+  map.pts = (P4*)alloc(actx, (size_t)cap * sizeof(P4));
+  map.tmp = (P4*)alloc(actx, (size_t)cap * sizeof(P4));
+  map.cell_pts = (float4*)alloc(actx, (size_t)cap * sizeof(float4));
+  map.cell_start = (int*)alloc(actx, ((size_t)ncells_cap + 1) * 4);
+  map.cell_count = (int*)alloc(actx, (size_t)ncells_cap * 4);
+  map.dims = (GridDims*)alloc(actx, sizeof(GridDims));
+  map.bbox = (unsigned int*)alloc(actx, 32);
+  int* ints = (int*)alloc(actx, 4 * 4);
+  if (!map.pts || !map.tmp || !map.cell_pts || !map.cell_start || !map.cell_count || !map.dims || !map.bbox || !ints) return FLOAM_ERR_CUDA;
+  map.d_n = ints; map.d_ntmp = ints + 1; map.d_ncrop = ints + 2; map.d_ncells = ints + 3;
+  FLOAM_CUDA_OK(cudaMemsetAsync(map.cell_count, 0, (size_t)ncells_cap * 4, s));
+  FLOAM_CUDA_OK(cudaMemsetAsync(map.dims, 0, sizeof(GridDims), s));
+  FLOAM_CUDA_OK(cudaMemsetAsync(ints, 0, 16, s));
+  const unsigned int bb[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+  FLOAM_CUDA_OK(cudaMemcpyAsync(map.bbox, bb, sizeof(bb), cudaMemcpyHostToDevice, s));
+  FLOAM_CUDA_OK(cudaStreamSynchronize(s));
+  return FLOAM_OK;
+}
+
+int odom_device_init(OdomDevice& od, const floam_params& prm, VoxelWorkspace* vws, void* (*alloc)(void*, size_t), void* actx, cudaStream_t s) {
+  od.vws = vws;
+  od.leaf_edge = (float)prm.map_resolution;        // setLeafSize(float...) :13-14
+  od.leaf_surf = (float)(prm.map_resolution * 2);
+  od.scan_period = prm.scan_period;
+  od.loss = prm.loss;
+  od.optimization_count = 2;                       // :22
+  od.qcap = prm.max_scan_points;
+  const int ncells_cap = prm.max_grid_cells;
+  od.state = (PoseState*)alloc(actx, sizeof(PoseState));
+  if (!od.state) return FLOAM_ERR_CUDA;
+  int rc = local_map_alloc(od.edge_map, prm.max_map_points, ncells_cap, alloc, actx, s);
+  if (rc) return rc;
+  rc = local_map_alloc(od.surf_map, prm.max_map_points, ncells_cap, alloc, actx, s);
+  if (rc) return rc;
+  od.ds_edge = (P4*)alloc(actx, (size_t)od.qcap * sizeof(P4));
+  od.ds_surf = (P4*)alloc(actx, (size_t)od.qcap * sizeof(P4));
+  int* ints = (int*)alloc(actx, 16);
+  od.corr = (double*)alloc(actx, (size_t)6 * 2 * od.qcap * sizeof(double));
+  od.corr_ok = (unsigned char*)alloc(actx, (size_t)2 * od.qcap);
+  od.knn_ids = (int*)alloc(actx, (size_t)2 * od.qcap * 5 * 4);
+  od.knn_d2 = (float*)alloc(actx, (size_t)2 * od.qcap * 5 * 4);
+  od.partials = (double*)alloc(actx, (size_t)kAssocBlocks * kLmTerms * sizeof(double));
+  if (!od.ds_edge || !od.ds_surf || !ints || !od.corr || !od.corr_ok || !od.knn_ids || !od.knn_d2 || !od.partials) return FLOAM_ERR_CUDA;
+  od.d_nds_edge = ints; od.d_nds_surf = ints + 1;
+  FLOAM_CUDA_OK(cudaMemsetAsync(ints, 0, 16, s));
+  FLOAM_CUDA_OK(cudaMemsetAsync(od.corr_ok, 0, (size_t)2 * od.qcap, s));
+  state_init_kernel<<<1, 32, 0, s>>>(od.state);
+  FLOAM_CUDA_OK(cudaStreamSynchronize(s));
+  return FLOAM_OK;
+}
+
+void odom_reset_state(OdomDevice& od, cudaStream_t s) {
+  state_init_kernel<<<1, 32, 0, s>>>(od.state);
+  od.optimization_count = 2;
+}
+
+void odom_rebuild_grids(OdomDevice& od, cudaStream_t s) {
+  rebuild_grid(od, od.edge_map, nullptr, s);
+  rebuild_grid(od, od.surf_map, nullptr, s);
+}
+
+void local_map_load(OdomDevice& od, LocalMap& map, const void* d_pts, const int* d_n, int stride, int n_max, int replace, cudaStream_t s) {
+  map_append_raw_kernel<<<grid_for(n_max), kThreads, 0, s>>>((const char*)d_pts, stride, d_n, map.pts, map.d_n, map.cap, replace, &od.state->error_flags);
+  map_bump_kernel<<<1, 32, 0, s>>>(map.d_n, d_n, map.cap, replace, nullptr);
+  count_launch(2);
+  rebuild_grid(od, map, nullptr, s);
+}
+
+void odom_init_map_device(OdomDevice& od, const void* d_edge, const int* d_ne, const void* d_surf, const int* d_ns, int stride, int n_max, int replace,
+                          cudaStream_t s) {
+  local_map_load(od, od.edge_map, d_edge, d_ne, stride, n_max, replace, s);
+  local_map_load(od, od.surf_map, d_surf, d_ns, stride, n_max, replace, s);
+}
+
+void odom_update_device(OdomDevice& od, const void* d_edge, const int* d_ne, const void* d_surf, const int* d_ns, int stride, int n_max, int update_type,
+                        int tap, cudaStream_t s) {
+  // the caller has already applied `if (optimization_count > 2) optimization_count--` (:59-60, Q4)
+  PoseState* S = od.state;
+  predict_kernel<<<1, 32, 0, s>>>(S, od.edge_map.d_n, od.surf_map.d_n);
+  count_launch(1);
+  // downSamplingToMap :137-142
+  voxel_grid_device(d_edge, stride, d_ne, n_max, od.leaf_edge, od.ds_edge, od.d_nds_edge, *od.vws, nullptr, s);
+  voxel_grid_device(d_surf, stride, d_ns, n_max, od.leaf_surf, od.ds_surf, od.d_nds_surf, *od.vws, nullptr, s);
+  for (int it = 0; it < od.optimization_count; ++it) {
+    const int t = tap && (it == od.optimization_count - 1);
+    assoc_eval_kernel<<<kAssocBlocks, kEvalThreads, 0, s>>>(S, od.ds_edge, od.d_nds_edge, od.ds_surf, od.d_nds_surf, od.edge_map, od.surf_map, od.qcap,
+                                                            od.corr, od.corr_ok, od.knn_ids, od.knn_d2, od.loss, od.partials, t);
+    for (int k = 0; k < 4; ++k)
+      cand_eval_kernel<<<kCandBlocks, kEvalThreads, 0, s>>>(S, od.ds_edge, od.d_nds_edge, od.ds_surf, od.d_nds_surf, od.qcap, od.corr, od.corr_ok, od.loss,
+                                                            od.partials);
+    count_launch(5);
+  }
+  finish_kernel<<<1, 32, 0, s>>>(S, update_type, od.scan_period);
+  count_launch(1);
+  if (update_type == FLOAM_INITIAL_ITERATION) return;
+  // addPointsToMap :253-294, predicated on the device-side keyframe decision
+  const int* skip = &S->not_keyframe;
+  LocalMap* maps[2] = {&od.surf_map, &od.edge_map};
+  P4* dss[2] = {od.ds_surf, od.ds_edge};
+  int* nds[2] = {od.d_nds_surf, od.d_nds_edge};
+  const float leaf[2] = {od.leaf_surf, od.leaf_edge};
+  for (int k = 0; k < 2; ++k) {
+    LocalMap& mp = *maps[k];
+    map_append_kernel<<<grid_for(od.qcap), kThreads, 0, s>>>(dss[k], nds[k], mp.pts, mp.d_n, mp.cap, S, skip);
+    map_bump_kernel<<<1, 32, 0, s>>>(mp.d_n, nds[k], mp.cap, 0, skip);
+    count_launch(2);
+    crop_box_device(mp.pts, mp.d_n, mp.cap, S->crop_bounds, mp.tmp, mp.d_ncrop, *od.vws, skip, s);
+    voxel_grid_device(mp.tmp, 16, mp.d_ncrop, mp.cap, leaf[k], mp.pts, mp.d_n, *od.vws, skip, s);
+    rebuild_grid(od, mp, skip, s);
+  }
+}
+
+void compensate_velocity_device(OdomDevice& od, PointIRT* d_pts, const int* d_n, int n_max, cudaStream_t s) {
+  compensate_velocity_kernel<<<grid_for(n_max), kThreads, 0, s>>>(d_pts, d_n, od.state);
+  count_launch(1);
+}
+
+void knn5_device(OdomDevice& od, LocalMap& map, const P4* d_queries, const int* d_nq, int nq_max, int* d_ids, float* d_d2, cudaStream_t s) {
+  int g = (nq_max + kEvalThreads - 1) / kEvalThreads;
+  if (g > kNumSMs * 16) g = kNumSMs * 16;
+  if (g < 1) g = 1;
+  knn5_kernel<<<g, kEvalThreads, 0, s>>>(d_queries, d_nq, map, d_ids, d_d2);
+  count_launch(1);
+}
+
+}  // namespace floam

@@ -1,0 +1,95 @@
+// Subsystems (3) and (4): local maps with a uniform-grid exact 5-NN, fused line/plane fit, on-device Levenberg-Marquardt,
+// the pose/keyframe state machine and the keyframe map update. See odom.cu.
+#pragma once
+#include "common.cuh"
+#include "voxel.cuh"
+
+namespace floam {
+
+// Everything the per-frame state machine needs lives in one device struct so a frame needs no host decision.
+struct PoseState {
+  double odom[12];       // Isometry3d odom: R row-major (9) then t (3)   (include/odomEstimationClass.h:82)
+  double last_odom[12];  // :94
+  double x[7];           // parameters[7] = qx qy qz qw tx ty tz            (:90-92)
+  double kf_pose[12];    // keyframes_.back().pose
+  double velocity[3];    // GetVelocity() of the last update
+  float crop_bounds[6];  // CropBox min xyz / max xyz (cast to float like Eigen::Vector4f(x_min, ...))
+  int kf_first;          // Q10: first KeyFrameUpdate call returns true
+  int not_keyframe;      // device-side skip flag for the map-update kernels
+  int skip_solve;        // map too small ("not enough points in map to associate")
+  int keyframe;          // result of the last KeyFrameUpdate
+  // ---- Levenberg-Marquardt (Ceres trust-region loop) ----
+  int lm_done, lm_phase, iteration, accepted, termination, last_successful, reuse_diag;
+  double cost, H[21], g[6], scale[6], diag[6], radius, decrease_factor, x_norm, gmax, model_cost_change;
+  double x_cand[7];
+  double initial_cost, H0[21], g0[6];
+  int lm_iterations_last, lm_accepted_last, lm_termination_last;
+  double lm_final_cost_last;
+  unsigned int ticket;   // last-CTA-done counter for the reduction
+  int outer_iterations;
+  int error_flags;       // bit 0: map capacity exceeded, bit 1: grid capacity exceeded
+  int n_corr;            // accepted correspondences of the last association
+  int n_corr_acc;        // accumulator of the running association
+};
+
+struct GridDims {
+  int ix0, iy0, iz0;  // cell coordinate of the grid origin
+  int nx, ny, nz;
+  int ncells;
+};
+
+struct LocalMap {
+  P4* pts;          // the map cloud (reference order: ascending voxel index after every keyframe)
+  int* d_n;
+  P4* tmp;          // scratch (append -> crop -> voxel)
+  int *d_ntmp, *d_ncrop;
+  float4* cell_pts; // points bucketed by 1 m cell: xyz + map index (as int bits in w)
+  int* cell_start;  // [ncells_cap + 1]
+  int* cell_count;  // [ncells_cap]
+  GridDims* dims;
+  unsigned int* bbox;
+  int* d_ncells;
+  int cap, ncells_cap;
+};
+
+constexpr int kLmTerms = 28;  // 21 H (upper triangle) + 6 g + cost
+
+struct OdomDevice {
+  PoseState* state;
+  LocalMap edge_map, surf_map;
+  P4 *ds_edge, *ds_surf;       // downsampled current features (sensor frame)
+  int *d_nds_edge, *d_nds_surf;
+  int qcap;                    // capacity of each downsampled cloud
+  // correspondences, slot = query index (edge slots [0,qcap), surf slots [qcap, 2*qcap))
+  double* corr;                // [6][2*qcap]: edge a(3) b(3); surf n(3) d
+  unsigned char* corr_ok;      // [2*qcap]
+  int* knn_ids;                // [2*qcap*5] debug taps / floam_knn5
+  float* knn_d2;               // [2*qcap*5]
+  double* partials;            // [CTAs of the association kernel][kLmTerms]
+  VoxelWorkspace* vws;
+  float leaf_edge, leaf_surf;
+  double scan_period;
+  int loss;
+  int optimization_count;      // host mirror (deterministic schedule, Q4)
+};
+
+int local_map_alloc(LocalMap& map, int cap, int ncells_cap, void* (*alloc)(void*, size_t), void* alloc_ctx, cudaStream_t s);
+int odom_device_init(OdomDevice& od, const floam_params& prm, VoxelWorkspace* vws, void* (*alloc)(void*, size_t), void* alloc_ctx, cudaStream_t s);
+void odom_reset_state(OdomDevice& od, cudaStream_t s);
+
+// append (replace = 0) or overwrite (replace = 1) a map with a strided device cloud and rebuild its grid
+void local_map_load(OdomDevice& od, LocalMap& map, const void* d_pts, const int* d_n, int stride, int n_max, int replace, cudaStream_t s);
+// OdomEstimationClass::initMapWithPoints: append (stride-32 or stride-16 clouds), optimization_count = 12, rebuild grids
+void odom_init_map_device(OdomDevice& od, const void* d_edge, const int* d_ne, const void* d_surf, const int* d_ns, int stride, int n_max, int replace,
+                          cudaStream_t s);
+// OdomEstimationClass::updatePointsToMap on device-resident clouds (stride 32: PointXYZI / PointXYZIRT, stride 16: float4).
+// tap != 0: the last outer iteration also writes the kNN ids / distances for floam_debug_fetch.
+void odom_update_device(OdomDevice& od, const void* d_edge, const int* d_ne, const void* d_surf, const int* d_ns, int stride, int n_max, int update_type,
+                        int tap, cudaStream_t s);
+// dmapping::CompensateVelocity with GetVelocity() read from the device state
+void compensate_velocity_device(OdomDevice& od, PointIRT* d_pts, const int* d_n, int n_max, cudaStream_t s);
+void odom_rebuild_grids(OdomDevice& od, cudaStream_t s);
+// stand-alone exact 5-NN of raw queries against a map whose grid is built (floam_knn5)
+void knn5_device(OdomDevice& od, LocalMap& map, const P4* d_queries, const int* d_nq, int nq_max, int* d_ids, float* d_d2, cudaStream_t s);
+
+}  // namespace floam

@@ -1,0 +1,219 @@
+// Subsystem (2): pcl::VoxelGrid and pcl::CropBox on the device.
+// VoxelGrid (reference call sites src/odomEstimationClass.cpp:137-142,289-292, src/laserMappingClass.cpp:175-184; PCL 1.8.1
+// applyFilter restated in SURVEY.md Appendix A.1): bbox reduction -> voxel key per point (same float floor/int arithmetic)
+// -> stable radix sort of (key, index) -> segment heads -> exclusive scan -> one thread per voxel accumulates xyz and
+// intensity in float, in ascending point index, and divides by the count.  CropBox (src/odomEstimationClass.cpp:270-287,
+// Appendix A.2): predicate -> scan -> order-preserving scatter.
+#include "voxel.cuh"
+
+namespace floam {
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ float4 load_xyzi(const char* base, int stride, int i) {
+  const char* p = base + (size_t)i * stride;
+  if (stride == 16) return __ldg(reinterpret_cast<const float4*>(p));
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float in = __ldg(reinterpret_cast<const float*>(p + 16));
+  return make_float4(a.x, a.y, a.z, in);
+}
+
+__global__ void voxel_init_kernel(unsigned int* bbox, const int* d_skip) {
+  if (d_skip && *d_skip) return;
+  if (threadIdx.x < 3) bbox[threadIdx.x] = 0xffffffffu;
+  else if (threadIdx.x < 6) bbox[threadIdx.x] = 0u;
+}
+
+__global__ void __launch_bounds__(kThreads) voxel_bbox_kernel(const char* __restrict__ in, int stride, const int* __restrict__ d_n,
+                                                               unsigned int* __restrict__ bbox, const int* d_skip) {
+  if (d_skip && *d_skip) return;
+  const int n = *d_n;
+  float mn[3] = {3.402823466e38f, 3.402823466e38f, 3.402823466e38f}, mx[3] = {-3.402823466e38f, -3.402823466e38f, -3.402823466e38f};
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+    const float4 p = load_xyzi(in, stride, i);
+    mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
+    mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+      mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+    }
+  }
+  if (lane_id() == 0 && blockIdx.x * kThreads + (threadIdx.x & ~31) < n) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      atomicMin(&bbox[a], float_flip(mn[a]));
+      atomicMax(&bbox[3 + a], float_flip(mx[a]));
+    }
+  }
+}
+
+__device__ __forceinline__ int bits_for(long long cells) {  // number of key bits for indices in [0, cells)
+  int b = 0;
+  while (b < 32 && (1ll << b) < cells) ++b;
+  return b;
+}
+
+__global__ void __launch_bounds__(kThreads) voxel_keys_kernel(const char* __restrict__ in, int stride, const int* __restrict__ d_n, float leaf,
+                                                               const unsigned int* __restrict__ bbox, unsigned int* __restrict__ keys,
+                                                               int* __restrict__ vals, int* d_nbits, int* d_passthrough, const int* d_skip) {
+  if (d_skip && *d_skip) return;
+  const int n = *d_n;
+  // every thread derives the grid from the bbox exactly like VoxelGrid::applyFilter (float arithmetic, no contraction)
+  const float inv = __fdiv_rn(1.0f, leaf);
+  float mnp[3], mxp[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) { mnp[a] = float_unflip(bbox[a]); mxp[a] = float_unflip(bbox[3 + a]); }
+  const long long dx = (long long)fmul(fsub(mxp[0], mnp[0]), inv) + 1;
+  const long long dy = (long long)fmul(fsub(mxp[1], mnp[1]), inv) + 1;
+  const long long dz = (long long)fmul(fsub(mxp[2], mnp[2]), inv) + 1;
+  const bool pass = (dx * dy * dz) > 2147483647ll;  // "Leaf size is too small for the input dataset" -> output = input (Q13)
+  int min_b[3], div_b[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    min_b[a] = (int)floorf(fmul(mnp[a], inv));
+    const int max_b = (int)floorf(fmul(mxp[a], inv));
+    div_b[a] = max_b - min_b[a] + 1;
+  }
+  const int mul1 = div_b[0], mul2 = div_b[0] * div_b[1];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    *d_passthrough = pass ? 1 : 0;
+    *d_nbits = pass ? bits_for(n) : bits_for((long long)div_b[0] * div_b[1] * div_b[2]);
+  }
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+    unsigned int key;
+    if (pass) {
+      key = (unsigned int)i;  // every point its own voxel, order kept: the centroid of one point is the point
+    } else {
+      const float4 p = load_xyzi(in, stride, i);
+      const int ijk0 = (int)fsub(floorf(fmul(p.x, inv)), (float)min_b[0]);
+      const int ijk1 = (int)fsub(floorf(fmul(p.y, inv)), (float)min_b[1]);
+      const int ijk2 = (int)fsub(floorf(fmul(p.z, inv)), (float)min_b[2]);
+      key = (unsigned int)(ijk0 + ijk1 * mul1 + ijk2 * mul2);
+    }
+    keys[i] = key;
+    vals[i] = i;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) voxel_heads_kernel(const unsigned int* __restrict__ keys, const int* __restrict__ d_n, int* __restrict__ flags,
+                                                                const int* d_skip) {
+  if (d_skip && *d_skip) return;
+  const int n = *d_n;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(kThreads) voxel_reduce_kernel(const char* __restrict__ in, int stride, const unsigned int* __restrict__ keys,
+                                                                 const int* __restrict__ vals, const int* __restrict__ seg, const int* __restrict__ d_n,
+                                                                 P4* __restrict__ out, int* d_nout, const int* d_skip) {
+  if (d_skip && *d_skip) return;
+  const int n = *d_n;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *d_nout = (n > 0) ? seg[n] : 0;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+    const unsigned int k = keys[i];
+    if (i > 0 && keys[i - 1] == k) continue;  // not a segment head
+    float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+    int j = i;
+    do {  // CentroidPoint<PointXYZI>: float sums in run order, then / n
+      const float4 p = load_xyzi(in, stride, vals[j]);
+      sx = fadd(sx, p.x); sy = fadd(sy, p.y); sz = fadd(sz, p.z); si = fadd(si, p.w);
+      ++j;
+    } while (j < n && keys[j] == k);
+    const float cnt = (float)(j - i);
+    out[seg[i]] = make_float4(__fdiv_rn(sx, cnt), __fdiv_rn(sy, cnt), __fdiv_rn(sz, cnt), __fdiv_rn(si, cnt));
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) crop_flags_kernel(const P4* __restrict__ in, const int* __restrict__ d_n, const float* __restrict__ bounds,
+                                                               int* __restrict__ flags, const int* d_skip) {
+  if (d_skip && *d_skip) return;
+  const int n = *d_n;
+  const float mnx = bounds[0], mny = bounds[1], mnz = bounds[2], mxx = bounds[3], mxy = bounds[4], mxz = bounds[5];
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+    const float4 p = __ldg(in + i);
+    const bool outside = (p.x < mnx || p.y < mny || p.z < mnz) || (p.x > mxx || p.y > mxy || p.z > mxz);
+    flags[i] = outside ? 0 : 1;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) crop_scatter_kernel(const P4* __restrict__ in, const int* __restrict__ d_n, const float* __restrict__ bounds,
+                                                                 const int* __restrict__ pos, P4* __restrict__ out, int* d_nout, const int* d_skip) {
+  if (d_skip && *d_skip) return;
+  const int n = *d_n;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *d_nout = (n > 0) ? pos[n] : 0;
+  const float mnx = bounds[0], mny = bounds[1], mnz = bounds[2], mxx = bounds[3], mxy = bounds[4], mxz = bounds[5];
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+    const float4 p = __ldg(in + i);
+    const bool outside = (p.x < mnx || p.y < mny || p.z < mnz) || (p.x > mxx || p.y > mxy || p.z > mxz);
+    if (!outside) out[pos[i]] = p;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) repack_kernel(const char* __restrict__ in, const int* __restrict__ d_n, P4* __restrict__ out) {
+  const int n = *d_n;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) out[i] = load_xyzi(in, 32, i);
+}
+
+inline int grid_for(int n_max) {
+  int g = (n_max + kThreads - 1) / kThreads;
+  const int cap = kNumSMs * 8;
+  return g < 1 ? 1 : (g > cap ? cap : g);
+}
+
+}  // namespace
+
+size_t voxel_workspace_bytes(int n_max) {
+  return (size_t)n_max * 4 * 2 + ((size_t)n_max + 1) * 4 + 1024 + sort_workspace_bytes(n_max) + scan_workspace_bytes(n_max + 1) + 4096;
+}
+
+void voxel_workspace_bind(VoxelWorkspace& ws, void* mem, int n_max) {
+  char* p = (char*)mem;
+  auto take = [&](size_t bytes) { void* r = p; p += (bytes + 255) / 256 * 256; return r; };
+  ws.n_max = n_max;
+  ws.keys = (unsigned int*)take((size_t)n_max * 4);
+  ws.vals = (int*)take((size_t)n_max * 4);
+  ws.flags = (int*)take(((size_t)n_max + 1) * 4);
+  ws.bbox = (unsigned int*)take(32);
+  ws.d_nbits = (int*)take(4);
+  ws.d_passthrough = (int*)take(4);
+  sort_workspace_bind(ws.sort, take(sort_workspace_bytes(n_max)), n_max);
+  scan_workspace_bind(ws.scan, take(scan_workspace_bytes(n_max + 1)), n_max + 1);
+}
+
+void voxel_grid_device(const void* d_in, int stride_bytes, const int* d_n, int n_max, float leaf, P4* d_out, int* d_nout, VoxelWorkspace& ws,
+                       const int* d_skip, cudaStream_t s) {
+  if (n_max > ws.n_max) n_max = ws.n_max;
+  const char* in = (const char*)d_in;
+  const int g = grid_for(n_max);
+  voxel_init_kernel<<<1, 32, 0, s>>>(ws.bbox, d_skip);
+  voxel_bbox_kernel<<<g, kThreads, 0, s>>>(in, stride_bytes, d_n, ws.bbox, d_skip);
+  voxel_keys_kernel<<<g, kThreads, 0, s>>>(in, stride_bytes, d_n, leaf, ws.bbox, ws.keys, ws.vals, ws.d_nbits, ws.d_passthrough, d_skip);
+  count_launch(3);
+  radix_sort_pairs(ws.keys, ws.vals, d_n, ws.d_nbits, n_max, ws.sort, d_skip, s);
+  voxel_heads_kernel<<<g, kThreads, 0, s>>>(ws.keys, d_n, ws.flags, d_skip);
+  count_launch(1);
+  exclusive_scan_i32(ws.flags, ws.flags, d_n, 0, n_max, ws.scan, d_skip, s);
+  voxel_reduce_kernel<<<g, kThreads, 0, s>>>(in, stride_bytes, ws.keys, ws.vals, ws.flags, d_n, d_out, d_nout, d_skip);
+  count_launch(1);
+}
+
+void repack_xyzi_device(const void* d_in32, const int* d_n, int n_max, P4* d_out, cudaStream_t s) {
+  repack_kernel<<<grid_for(n_max), kThreads, 0, s>>>((const char*)d_in32, d_n, d_out);
+  count_launch(1);
+}
+
+void crop_box_device(const P4* d_in, const int* d_n, int n_max, const float* d_bounds, P4* d_out, int* d_nout, VoxelWorkspace& ws,
+                     const int* d_skip, cudaStream_t s) {
+  if (n_max > ws.n_max) n_max = ws.n_max;
+  const int g = grid_for(n_max);
+  crop_flags_kernel<<<g, kThreads, 0, s>>>(d_in, d_n, d_bounds, ws.flags, d_skip);
+  exclusive_scan_i32(ws.flags, ws.flags, d_n, 0, n_max, ws.scan, d_skip, s);
+  crop_scatter_kernel<<<g, kThreads, 0, s>>>(d_in, d_n, d_bounds, ws.flags, d_out, d_nout, d_skip);
+  count_launch(2);
+}
+
+}  // namespace floam

@@ -1,0 +1,36 @@
+// Subsystem (2): pcl::VoxelGrid / pcl::CropBox replacements — device entry points. See voxel.cu.
+#pragma once
+#include "common.cuh"
+
+namespace floam {
+
+struct VoxelWorkspace {
+  unsigned int* keys;   // [n_max]
+  int* vals;            // [n_max]
+  int* flags;           // [n_max + 1] segment-head flags -> exclusive scan (segment ids)
+  unsigned int* bbox;   // 6 order-preserving-encoded floats: min xyz, max xyz
+  int* d_nbits;         // key width of the current grid
+  int* d_passthrough;   // Q13: leaf too small for the extent -> output = input
+  SortWorkspace sort;
+  ScanWorkspace scan;
+  int n_max;
+};
+size_t voxel_workspace_bytes(int n_max);
+void voxel_workspace_bind(VoxelWorkspace& ws, void* mem, int n_max);
+
+// pcl::VoxelGrid<PointXYZI>::filter (PCL 1.8.1 semantics). Input points are read with a byte stride
+// (16 = float4 xyzi, 32 = PointXYZI / PointXYZIRT with intensity at +16). Output order = ascending voxel index; inside a
+// voxel the float accumulation runs in ascending input index (the stable stand-in for std::sort's unspecified order).
+// d_skip (optional): when *d_skip != 0 every kernel returns immediately (device-side "not a keyframe").
+void voxel_grid_device(const void* d_in, int stride_bytes, const int* d_n, int n_max, float leaf, P4* d_out, int* d_nout, VoxelWorkspace& ws,
+                       const int* d_skip, cudaStream_t s);
+
+// pcl::CropBox<PointXYZI>::filter, identity transform, negative=false, inclusive float bounds read from device memory
+// (d_bounds: min xyz, max xyz). Order-preserving compaction.
+void crop_box_device(const P4* d_in, const int* d_n, int n_max, const float* d_bounds, P4* d_out, int* d_nout, VoxelWorkspace& ws,
+                     const int* d_skip, cudaStream_t s);
+
+// stride-32 PointXYZI / PointXYZIRT cloud -> float4 (x, y, z, intensity)
+void repack_xyzi_device(const void* d_in32, const int* d_n, int n_max, P4* d_out, cudaStream_t s);
+
+}  // namespace floam

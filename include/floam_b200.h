@@ -1,0 +1,169 @@
+/* floam_b200 — C ABI of the B200-native FLOAM odometry hot path.
+ *
+ * The reference (dan11003/floam) has no FFI layer: its boundary is the C++ class API consumed by the three ROS nodes
+ * (SURVEY.md §8b).  This header is the plain-C surface those classes are re-implemented on; the header-only C++ shims in
+ * floam_b200/host/ give back the reference signatures (LaserProcessingClass, OdomEstimationClass, LaserMappingClass,
+ * dmapping::ImuHandler / Compensate) on top of it.  Every entry point cites the reference interface it replaces.
+ *
+ * Conventions: all pointers are HOST pointers unless the name says otherwise; the context owns every device buffer, one
+ * CUDA stream and one device; a context is not thread-safe (one context per sequence; contexts on different GPUs are
+ * independent — multi-GPU = replicas, no collective).  Every call returns a status (0 = OK) and never throws.
+ * There is no CPU fallback: without a CUDA device floam_create fails with FLOAM_ERR_NO_DEVICE.
+ */
+#ifndef FLOAM_B200_H_
+#define FLOAM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct floam_ctx floam_ctx;
+
+/* vel_point::PointXYZIRT, reference include/lidar.h:14-32 (32 bytes, 16-aligned) */
+typedef struct floam_point_xyzirt {
+  float x, y, z, _pad0;
+  float intensity;
+  uint16_t ring, _pad1;
+  float time;
+  float _pad2;
+} floam_point_xyzirt;
+
+/* pcl::PointXYZI (32 bytes, intensity at offset 16) */
+typedef struct floam_point_xyzi {
+  float x, y, z, _pad0;
+  float intensity;
+  float _pad1[3];
+} floam_point_xyzi;
+
+enum floam_status {
+  FLOAM_OK = 0,
+  FLOAM_ERR_NO_DEVICE = 1,   /* no CUDA device / wrong architecture: the product path refuses to run */
+  FLOAM_ERR_CUDA = 2,
+  FLOAM_ERR_CAPACITY = 3,    /* an input or intermediate exceeded the capacities given at create time */
+  FLOAM_ERR_ARG = 4,
+  FLOAM_NO_IMU = 5,          /* dmapping::Compensate returned false ("no imu data"), reference src/dataHandler.cpp:99-102 */
+  FLOAM_ERR_NONFINITE = 6    /* non-finite input coordinates (undefined in the reference, Q9) */
+};
+
+enum floam_loss {
+  FLOAM_LOSS_TRIVIAL = 0,    /* what the reference does for "cauchy" (loss_function stays nullptr, src/odomEstimationClass.cpp:88-91) */
+  FLOAM_LOSS_HUBER = 1,      /* ceres::HuberLoss(0.1), src/odomEstimationClass.cpp:86 */
+  FLOAM_LOSS_CAUCHY_TRUE = 2 /* opt-in: ceres::CauchyLoss(0.2) actually applied (not reachable in the reference) */
+};
+
+enum floam_update_type { FLOAM_VANILLA = 0, FLOAM_INITIAL_ITERATION = 1, FLOAM_REFINEMENT_AND_UPDATE = 2 }; /* include/odomEstimationClass.h:63 */
+
+/* lidar::Lidar (include/lidar.h:53-86) + OdomEstimationClass::init arguments + capacities */
+typedef struct floam_params {
+  int num_lines;            /* /scan_line, default 64 */
+  double scan_period;       /* /scan_period, default 0.1 */
+  double vertical_angle;    /* /vertical_angle, default 2.0 (unused by the algorithms) */
+  double max_distance;      /* /max_dis, default 60 */
+  double min_distance;      /* /min_dis, default 2 */
+  double map_resolution;    /* /map_resolution, default 0.4 */
+  int loss;                 /* floam_loss; floam_loss_from_string maps the reference's string */
+  int max_scan_points;      /* capacity of one scan (default 300000) */
+  int max_map_points;       /* capacity of each local map, edge and surf (default 4,000,000) */
+  int max_global_map_points;/* capacity of the LaserMappingClass map (default 8,000,000; 0 = mapping disabled) */
+  int max_grid_cells;       /* capacity of each local map's 1 m search grid, in cells (default 8,388,608) */
+} floam_params;
+
+void floam_params_default(floam_params* p);
+int floam_loss_from_string(const char* loss_function); /* lower-cases like src/odomEstimationClass.cpp:23; "huber" -> HUBER, else TRIVIAL */
+const char* floam_status_string(int status);
+const char* floam_version(void);
+
+/* LaserProcessingClass::init + OdomEstimationClass::init + LaserMappingClass::init
+ * (src/laserProcessingClass.cpp:6, src/odomEstimationClass.cpp:7-26, src/laserMappingClass.cpp:7-32) */
+int floam_create(const floam_params* params, int device, floam_ctx** out);
+void floam_destroy(floam_ctx* ctx);
+/* page-locked host buffers for scans handed to floam_process_submit (so the upload overlaps the previous frame's kernels) */
+void* floam_alloc_pinned(size_t bytes);
+void floam_free_pinned(void* p);
+/* per-frame launch sequences are replayed as CUDA graphs by default; 0 launches the kernels one by one (debugging / profiling) */
+int floam_set_graphs(floam_ctx* ctx, int enabled);
+
+/* Quaternions cross this ABI in Eigen coefficient order (x, y, z, w), like parameters[0..3] of the reference. */
+/* dmapping::ImuHandler::AddMsg (src/dataHandler.cpp:24-40): drops samples <= 10 us after the previous one. */
+int floam_imu_push(floam_ctx* ctx, double stamp, const double q_xyzw[4]);
+/* dmapping::ImuHandler::Get (src/dataHandler.cpp:51-75): zero-order hold; *valid = 0 and a zero quaternion when not covered. */
+int floam_imu_get(floam_ctx* ctx, double stamp, double q_xyzw[4], int* valid);
+int floam_imu_size(floam_ctx* ctx, int* n); /* ImuHandler::size() */
+
+/* CenterTime + dmapping::Compensate + IMU alignment, in place (src/laserProcessingNode.cpp:65-78,108-116; src/dataHandler.cpp:93-122).
+ * stamp_us is the pcl header stamp (microseconds) and is re-centred like the reference. Returns FLOAM_NO_IMU when
+ * Compensate would return false (points are then only time-centred). */
+int floam_deskew_align(floam_ctx* ctx, floam_point_xyzirt* pts, int n, uint64_t* stamp_us, const double extrinsics_xyzw[4]);
+
+/* LaserProcessingClass::featureExtraction (src/laserProcessingClass.cpp:72-231). Appending is the caller's job:
+ * edge/surf receive *ne / *ns points (capacities in points). */
+int floam_feature_extract(floam_ctx* ctx, const floam_point_xyzirt* pts, int n,
+                          floam_point_xyzirt* edge, int edge_cap, int* ne,
+                          floam_point_xyzirt* surf, int surf_cap, int* ns);
+
+/* OdomEstimationClass::initMapWithPoints (src/odomEstimationClass.cpp:28-32) */
+int floam_odom_init_map(floam_ctx* ctx, const floam_point_xyzi* edge, int ne, const floam_point_xyzi* surf, int ns);
+/* OdomEstimationClass::UpdatePointsToMapSelector (src/odomEstimationClass.cpp:34-50). In deskew mode edge/surf are
+ * velocity-compensated in place like the reference. pose_out = parameters[7] = (qx,qy,qz,qw,tx,ty,tz). */
+int floam_odom_update(floam_ctx* ctx, floam_point_xyzirt* edge, int ne, floam_point_xyzirt* surf, int ns, int deskew, double pose_out[7]);
+/* OdomEstimationClass::updatePointsToMap(PointXYZI overload, src/odomEstimationClass.cpp:57-124) */
+int floam_odom_update_xyzi(floam_ctx* ctx, const floam_point_xyzi* edge, int ne, const floam_point_xyzi* surf, int ns, int update_type, double pose_out[7]);
+/* public member `odom` (Isometry3d, row-major 4x4) and GetVelocity() (include/odomEstimationClass.h:78,82) */
+int floam_odom_get(floam_ctx* ctx, double odom_rowmajor[16], double velocity[3]);
+/* public members laserCloudCornerMap / laserCloudSurfMap; getMap (src/odomEstimationClass.cpp:296-300) concatenates surf+edge */
+int floam_odom_map_sizes(floam_ctx* ctx, int* n_edge, int* n_surf);
+int floam_odom_get_map(floam_ctx* ctx, floam_point_xyzi* edge, int edge_cap, floam_point_xyzi* surf, int surf_cap);
+/* test/stage-parity hooks: overwrite pose state / maps (no reference equivalent; the members are public or file-static there) */
+int floam_odom_set_state(floam_ctx* ctx, const double odom_rowmajor[16], const double last_odom_rowmajor[16], int optimization_count);
+int floam_odom_get_state(floam_ctx* ctx, double odom_rowmajor[16], double last_odom_rowmajor[16], int* optimization_count);
+int floam_odom_set_map(floam_ctx* ctx, const floam_point_xyzi* edge, int ne, const floam_point_xyzi* surf, int ns);
+
+/* Fused, device-resident frame: scan -> features -> (first frame: initMapWithPoints, else UpdatePointsToMapSelector),
+ * i.e. laser_processing() + odom_estimation() of src/laserProcessingNode.cpp:80-160 and src/odomEstimationNode.cpp:167-290
+ * without the TCPROS hops. Only the scan goes up and only the 7-double pose comes down. */
+int floam_process_scan(floam_ctx* ctx, const floam_point_xyzirt* pts, int n, int deskew, double pose_out[7]);
+/* Same, split so the upload of frame k+1 overlaps the kernels of frame k. pts must stay valid (ideally pinned) until
+ * the matching floam_process_wait returns. At most two submissions may be in flight. */
+int floam_process_submit(floam_ctx* ctx, const floam_point_xyzirt* pts, int n, int deskew);
+int floam_process_wait(floam_ctx* ctx, double pose_out[7]);
+/* Device-resident replay for kernel-only timing: the scans already sit in HBM (uploaded once with floam_stage_scans). */
+int floam_stage_scans(floam_ctx* ctx, const floam_point_xyzirt* pts, const int64_t* offsets, int n_frames);
+int floam_process_staged(floam_ctx* ctx, int frame, int deskew, double pose_out[7]);
+
+/* LaserMappingClass::updateCurrentPointsToMap / getMap (src/laserMappingClass.cpp:148-200) */
+int floam_mapping_update(floam_ctx* ctx, const floam_point_xyzi* pts, int n, const double pose_rowmajor[16]);
+int floam_mapping_get_map(floam_ctx* ctx, floam_point_xyzi* out, int cap, int* n);
+
+/* pcl::VoxelGrid<PointXYZI>::filter and pcl::CropBox<PointXYZI>::filter as used at src/odomEstimationClass.cpp:137-142,278-292
+ * (stage entry points; also what floam_b200/host/mini_pcl.h's filters call) */
+int floam_voxel_grid(floam_ctx* ctx, const floam_point_xyzi* pts, int n, float leaf, floam_point_xyzi* out, int cap, int* n_out);
+int floam_crop_box(floam_ctx* ctx, const floam_point_xyzi* pts, int n, const float min_xyz[3], const float max_xyz[3], floam_point_xyzi* out, int cap, int* n_out);
+/* pcl::KdTreeFLANN::setInputCloud + nearestKSearch(k=5) (src/odomEstimationClass.cpp:78-79,153,206): exact ids for every
+ * query whose 5th neighbour is closer than 1 m (the only ones the reference uses); others report ids = -1. */
+int floam_knn5(floam_ctx* ctx, const floam_point_xyzi* map, int m, const floam_point_xyzi* queries, int nq, int* ids, float* sqdist);
+
+/* Per-stage taps of the last odometry update (parity tests), see DESIGN.md for the record layouts. */
+enum floam_debug_what {
+  FLOAM_DBG_DS_EDGE = 0, FLOAM_DBG_DS_SURF = 1,       /* floam_point_xyzi[]  downsampled clouds */
+  FLOAM_DBG_EDGE_KNN = 2, FLOAM_DBG_SURF_KNN = 3,     /* int[5*n]  ids of the last outer iteration (-1 = not accepted by the 1 m gate) */
+  FLOAM_DBG_EDGE_D2 = 4, FLOAM_DBG_SURF_D2 = 5,       /* float[5*n] */
+  FLOAM_DBG_EDGE_OK = 6, FLOAM_DBG_SURF_OK = 7,       /* uint8[n] residual accepted */
+  FLOAM_DBG_RESIDUALS = 8,                            /* double[10*n] kind,curr(3),a(3),b(3) for accepted correspondences, edge then surf */
+  FLOAM_DBG_LM = 9,                                   /* double[47]: iterations, accepted, initial_cost, final_cost, termination, H0[36], g0[6] */
+  FLOAM_DBG_SCALARS = 10,                             /* int[6]: outer_iterations, keyframe, n_ds_edge, n_ds_surf, n_correspondences, solve_skipped */
+  FLOAM_DBG_FEATURE_SRC_EDGE = 11, FLOAM_DBG_FEATURE_SRC_SURF = 12 /* int[]: input indices of the last feature extraction's outputs */
+};
+int floam_debug_fetch(floam_ctx* ctx, int what, void* out, size_t cap_bytes, size_t* n_bytes);
+
+/* Launch accounting for bench.py ("gpu_launches"): kernels launched by this context since the last reset. */
+int floam_launch_count(floam_ctx* ctx, int64_t* launches, int reset);
+/* CUDA events around the device work of the last floam_process_* call, milliseconds. */
+int floam_last_frame_ms(floam_ctx* ctx, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLOAM_B200_H_ */
