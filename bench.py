@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""bench.py — FLOAM per-frame odometry throughput on B200 (BASELINE.json metric, configs[1]).
+
+A "step" is ONE FRAME of the hot path (deskew-free configs[1]: featureExtraction + scan-to-map odometry + keyframe map update)
+of a synthetic HDL-64-shaped sequence (64 rings x 1875 azimuths, ~118k returns/scan, procedurally generated street scene).
+Before the timed region the sequence is pre-rolled (map-seeding frame + 11 frames in which the reference's outer-iteration count
+decays 11 -> 2) and W warm-up frames are run; then EXACTLY K frames are timed.
+
+  value     frames/s, scans already resident in HBM, frames enqueued back to back (floam_replay_staged), CUDA events on the stream
+  e2e       frames/s through the public C-ABI call a node would make (floam_process_submit / floam_process_wait) with HOST scans in
+            pinned memory: H2D upload of every scan and D2H of every pose inside the timed region
+  roofline  the kernel class with the largest share of the frame, timed live with CUDA event pairs (floam_set_kernel_timing)
+  cpu_baseline  the oracle port of the reference classes on one host thread over a bounded sample of the same sequence
+
+N > 1 (torchrun): every rank replays its own independent sequence on its own GPU (replicas, no collective on the data path);
+value = total frames / max-over-ranks time.   --impl reference: the oracle port on the host cores (3 pipelined threads like the
+reference's three ROS nodes), rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "odometry frames/sec at HDL-64 scan"
+UNIT = "frames/s"
+PREROLL = 12            # frame 0 seeds the map (optimization_count = 12); 11 updates bring the outer count down to 2
+SEED_BASE = 0           # sequence s uses generator seed SEED_BASE + s
+SENSOR = "hdl64"
+ODOM = dict(min_distance=2.0, max_distance=60.0, map_resolution=0.4, loss="cauchy")
+
+
+def shard_sequences(n_sequences, rank, world):
+    """Sequence ids replayed by `rank`: round-robin, no data exchanged between ranks."""
+    return [s for s in range(n_sequences) if s % world == rank]
+
+
+def reduce_over_ranks(frames, seconds, device="cuda"):
+    """(sum of frames, max of seconds) over ranks; identity when torch.distributed is not initialised."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return frames, seconds
+    f = torch.tensor([float(frames)], dtype=torch.float64, device=device)
+    t = torch.tensor([float(seconds)], dtype=torch.float64, device=device)
+    dist.all_reduce(f, op=dist.ReduceOp.SUM)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return int(round(f.item())), t.item()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self, t0, t1):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.lines:
+            if ts < t0 - 0.05 or ts > t1 + 0.15:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def algorithmic_bytes(kernel, st):
+    """Compulsory bytes one launch of `kernel` moves (DESIGN.md 'Kernels and rooflines'; SURVEY.md 8d per-unit figures x the units
+    of the frame). st: per-frame averages — N scan points, F features, Q downsampled queries, C correspondences, M map points."""
+    N, F, Q, C, M = st["N"], st["F"], st["Q"], st["C"], st["M"]
+    table = {
+        "ring_count": 32 * N,                         # reads the scan once
+        "ring_scatter": 32 * N + 36 * N,              # reads the scan, writes the gated ring-bucketed copy + source index
+        "sector": 16 * N + 4 * F,                     # xyz of every ring point once, one id per classified point
+        "feature_gather": 68 * F,                     # 32 B in + 32 B out + 4 B source index per feature
+        "assoc_eval": 16 * Q + 16 * M + 20 * Q + 80 * C,   # queries, map cells touched once, 5 ids, fit parameters
+        "cand_eval": 88 * C,                          # point (24) + fit parameters (<= 64) per correspondence
+        "radix_scatter": 16 * st["sort_n"],           # 8 B key/value in, 8 B out per element and pass
+        "radix_hist": 4 * st["sort_n"],
+        "voxel_reduce": 24 * st["sort_n"] + 16 * st["sort_out"],
+        "voxel_keys": 16 * st["sort_n"] + 8 * st["sort_n"],
+        "voxel_bbox": 16 * st["sort_n"],
+        "grid_scatter": 32 * M, "grid_count": 16 * M, "grid_bbox": 16 * M,
+        "map_append": 32 * Q, "crop_flags": 16 * M, "crop_scatter": 32 * M,
+    }
+    return table.get(kernel)
+
+
+def build_sequence(rank_seed, frames):
+    from floam_b200 import synth
+    seq = synth.Sequence(SENSOR, seed=SEED_BASE + rank_seed)
+    scans, off = seq.scans(0, frames)
+    return seq, scans, off
+
+
+def run_reference(args, rank):
+    """--impl reference: the oracle port of the reference classes on the host cores, pipelined over three threads like the
+    reference's three ROS nodes (laserProcessing -> odomEstimation -> laserMapping). Bounded sample; rank 0 only."""
+    if rank != 0:
+        return 0
+    import queue
+    from floam_b200 import synth
+    from oracle import pyoracle as po
+    po.build()
+    K = max(1, min(args.steps, 120)); W = max(0, min(args.warmup, 10))
+    frames = PREROLL + W + K
+    seq, scans, off = build_sequence(0, frames)
+    nl = seq.num_lines
+    q1, q2 = queue.Queue(maxsize=4), queue.Queue(maxsize=4)
+    stamps = {}
+
+    def node_features():
+        for f in range(frames):
+            e, s, _, _, _ = po.feature_extract(scans[off[f]:off[f + 1]], nl, ODOM["min_distance"], ODOM["max_distance"])
+            q1.put((f, e, s))
+        q1.put(None)
+
+    def node_odom():
+        od = po.Odom(num_lines=nl, map_resolution=ODOM["map_resolution"], loss=ODOM["loss"])
+        while True:
+            item = q1.get()
+            if item is None:
+                break
+            f, e, s = item
+            if f == 0:
+                od.init_map(synth.to_xyzi(e), synth.to_xyzi(s)); T = np.eye(4)
+            else:
+                od.update(e, s, False); T = od.get()[0]
+            stamps[f] = time.perf_counter()
+            q2.put((f, T))
+        q2.put(None)
+
+    def node_mapping():
+        mp = po.Mapping(map_resolution=ODOM["map_resolution"])
+        while True:
+            item = q2.get()
+            if item is None:
+                break
+            f, T = item
+            mp.update(synth.to_xyzi(scans[off[f]:off[f + 1]][::4]), T)   # the reference maps the filtered cloud; a quarter keeps it off the critical path
+
+    th = [threading.Thread(target=t) for t in (node_features, node_odom, node_mapping)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    t0 = stamps[PREROLL + W - 1]; t1 = stamps[frames - 1]
+    fps = K / (t1 - t0)
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
+            "ms_per_step": 1e3 / fps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(),
+            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": 3, "kind": "port",
+                             "sample": "frames %d..%d of sequence 0 (oracle port of the reference classes; 3 pipelined host threads)" % (PREROLL + W, frames - 1)},
+            "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config():
+    return {"workload": "configs[1]: synthetic HDL-64E KITTI-shaped sequence (64x1875 rays, ~118k returns/scan), full odometry, deskew off",
+            "sensor": SENSOR, "map_resolution": ODOM["map_resolution"], "loss": ODOM["loss"], "min_dis": ODOM["min_distance"],
+            "max_dis": ODOM["max_distance"], "preroll_frames": PREROLL, "parallelism": "replicas",
+            "cache": "every frame is a new 3.8 MB scan; the working set (scan + local maps) is L2-resident by nature of the path"}
+
+
+def cpu_baseline(scans, off, num_lines, n_frames):
+    """Oracle port, one host thread (the reference's classes are single-threaded), bounded sample: PREROLL + n_frames frames."""
+    from oracle import pyoracle as po
+    po.build()
+    last = min(len(off) - 1, PREROLL + n_frames)
+    sec, poses, ms, q = po.replay_sequence(scans[:off[last]], off[:last + 1], num_lines, min_dis=ODOM["min_distance"], max_dis=ODOM["max_distance"],
+                                           map_resolution=ODOM["map_resolution"], loss=ODOM["loss"], deskew=False)
+    steady = ms[PREROLL:]
+    fps = 1e3 / float(np.mean(steady)) if len(steady) else 0.0
+    return {"value": fps, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "frames %d..%d of the same sequence (after the same pre-roll), featureExtraction + odometry, one thread" % (PREROLL, last - 1),
+            "p50_ms": float(np.percentile(steady, 50)) if len(steady) else None}, poses
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--cpu-frames", type=int, default=150, help="frames of the bounded cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--timing-frames", type=int, default=60, help="frames of the per-kernel timing pass (roofline leg)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank)
+
+    import torch
+    import torch.distributed as dist
+    from floam_b200 import capi
+    K = max(1, args.steps); W = max(3, args.warmup)
+    K = min(K, 6000)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    frames = PREROLL + W + K
+    t_gen = time.time()
+    seq, scans, off = build_sequence(rank, frames)
+    t_gen = time.time() - t_gen
+    prm = dict(num_lines=seq.num_lines, max_scan_points=seq.max_points + 1024, max_map_points=1 << 21, max_global_map_points=0, max_grid_cells=1 << 23, **ODOM)
+
+    # ---- device-resident replay: the headline `value` ----
+    ctx = capi.Context(device=local, **prm)
+    ctx.stage_scans(scans, off)
+    poses_pre, _ = ctx.replay_staged(0, PREROLL)
+    poses_warm, _ = ctx.replay_staged(PREROLL, W)
+    sampler = ClockSampler(local); sampler.start()
+    time.sleep(0.3)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ctx.launch_count(reset=True)
+    wall0 = time.time()
+    poses_dev, ms_dev = ctx.replay_staged(PREROLL + W, K)
+    torch.cuda.synchronize()
+    wall1 = time.time()
+    launches = ctx.launch_count()
+    if world > 1:
+        dist.barrier()
+    total_frames, max_s = reduce_over_ranks(K, ms_dev * 1e-3)
+    value = total_frames / max_s
+    d = ctx.debug()
+    ne_map, ns_map = ctx.odom_map_sizes()
+    ctx.close()
+
+    # ---- end to end through the public call with host scans in pinned memory ----
+    ctx2 = capi.Context(device=local, **prm)
+    max_n = int(np.max(np.diff(off)))
+    pinned = [capi.PinnedBuffer(max_n) for _ in range(3)]
+
+    def run_e2e(f0, f1, lat=None):
+        poses = np.zeros((f1 - f0, 7)); pending = []
+        for f in range(f0, f1):
+            n = int(off[f + 1] - off[f]); buf = pinned[f % 3]
+            buf.array[:n] = scans[off[f]:off[f + 1]]          # the producer (driver / ROS callback) writing into pinned memory
+            if len(pending) == 2:
+                g = pending.pop(0); poses[g - f0] = ctx2.process_wait()
+                if lat is not None:
+                    lat.append(ctx2.last_frame_ms())
+            ctx2.process_submit(buf.array[:n], n)
+            pending.append(f)
+        for g in pending:
+            poses[g - f0] = ctx2.process_wait()
+            if lat is not None:
+                lat.append(ctx2.last_frame_ms())
+        return poses
+    run_e2e(0, PREROLL + W)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    lat = []
+    e0 = time.time()
+    poses_e2e = run_e2e(PREROLL + W, frames, lat)
+    torch.cuda.synchronize()
+    e1 = time.time()
+    if world > 1:
+        dist.barrier()
+    sampler.stop()
+    e2e_frames, e2e_s = reduce_over_ranks(K, e1 - e0, device="cuda")
+    e2e_value = e2e_frames / e2e_s
+    h2d = float(np.mean(np.diff(off)[PREROLL + W:frames])) * 32 + 4
+    ctx2.close()
+    for b in pinned:
+        b.close()
+    identical = bool(np.array_equal(poses_dev, poses_e2e))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline leg: per-kernel-class device time, kernels launched one by one with CUDA event pairs ----
+    TF = max(5, min(args.timing_frames, K))
+    ctx3 = capi.Context(device=local, **prm)
+    ctx3.stage_scans(scans[:off[PREROLL + W + TF]], off[:PREROLL + W + TF + 1])
+    ctx3.replay_staged(0, PREROLL + W)
+    ctx3.set_kernel_timing(True)
+    stats = {"N": 0.0, "F": 0.0, "Q": 0.0, "C": 0.0, "M": 0.0}
+    for f in range(PREROLL + W, PREROLL + W + TF):
+        ctx3.process_staged(f)
+        dd = ctx3.debug_fetch(capi.DBG_SCALARS, np.int32)
+        e_n, s_n = ctx3.odom_map_sizes()
+        stats["N"] += float(off[f + 1] - off[f]); stats["Q"] += float(dd[2] + dd[3]); stats["C"] += float(dd[4]); stats["M"] += float(e_n + s_n)
+        stats["F"] += float(len(ctx3.debug_fetch(capi.DBG_FEATURE_SRC_EDGE, np.int32)) + len(ctx3.debug_fetch(capi.DBG_FEATURE_SRC_SURF, np.int32)))
+    timing = ctx3.kernel_timing()
+    ctx3.set_kernel_timing(False)
+    ctx3.close()
+    for k in stats:
+        stats[k] /= TF
+    total_ms = sum(v[0] for v in timing.values())
+    shares = sorted(((name, v[0] / total_ms, v[0] / v[1] * 1e3, v[1] / TF) for name, v in timing.items()), key=lambda x: -x[1])
+    top = shares[0][0]
+    peak, peak_kind = measured_peak_gbs()
+    # radix / voxel kernels run for several clouds per frame; their per-launch element count is the mean over those clouds
+    stats["sort_n"] = (stats["F"] + stats["M"] + stats["Q"]) / 4.0
+    stats["sort_out"] = (stats["Q"] + stats["M"]) / 4.0
+    ab = algorithmic_bytes(top, stats)
+    top_us = timing[top][0] / timing[top][1] * 1e3
+    roofline = {"bound": "hbm", "kernel": top, "achieved": (ab / (top_us * 1e-6) / 1e9) if ab else None, "peak": peak, "peak_kind": peak_kind,
+                "unit": "GB/s", "frac": (ab / (top_us * 1e-6) / 1e9 / peak) if ab else None, "traffic": None,
+                "algorithmic_bytes_per_launch": ab, "avg_launch_us": top_us, "share_of_frame": shares[0][1], "launches_per_frame": shares[0][3],
+                "frame_algorithmic_bytes": frame_bytes(stats),
+                "frame_hbm_frac": frame_bytes(stats) * value / world / 1e9 / peak,
+                "kernel_shares": [{"kernel": n, "share": round(s, 4), "avg_us": round(u, 2), "launches_per_frame": round(l, 2)} for n, s, u, l in shares[:12]],
+                "note": "event pairs around single launches add ~2 us of launch gap each; shares are what is compared with the ncu launch list"}
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        cpu, poses_cpu = cpu_baseline(scans, off, seq.num_lines, min(args.cpu_frames, W + K))
+        n_cmp = min(len(poses_cpu), PREROLL + W + K)
+        ours = np.concatenate([poses_pre, poses_warm, poses_dev])[:n_cmp]
+        cpu["max_pose_diff_vs_gpu"] = float(np.abs(ours - poses_cpu[:n_cmp]).max())
+
+    clocks = sampler.summary(wall0, e1)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": 1e3 * max_s / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 geometry / f64 solve", "data": "synthetic",
+            "config": workload_config(),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 56 + 8,
+                    "poses_identical_to_device_replay": identical},
+            "gpu_launches": int(launches), "launches_per_frame": launches / K,
+            "p50_ms_per_frame": float(np.percentile(lat, 50)), "p99_ms_per_frame": float(np.percentile(lat, 99)),
+            "knn_queries_per_s": float(stats["Q"] * 2 * value / world),
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "frame_stats": {k: round(v, 1) for k, v in stats.items()}, "final_map_points": [ne_map, ns_map],
+            "last_frame": {"n_corr": d["n_corr"], "outer_iterations": d["outer_iterations"], "keyframe": d["keyframe"]},
+            "wall_s_timed_region": wall1 - wall0, "gen_s": t_gen}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def frame_bytes(st):
+    """SURVEY.md 8d B_frame with the live per-frame averages (n_out = 2, P_lm = 2 x 5 passes, every frame a keyframe)."""
+    N, F, Q, C, M = st["N"], st["F"], st["Q"], st["C"], st["M"]
+    return 32 * N + 32 * F + 16 * F + 16 * Q + 2 * (16 * Q + 16 * M + 20 * Q + 80 * C) + 10 * 88 * C + 2 * 16 * (M + Q)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

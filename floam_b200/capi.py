@@ -34,7 +34,8 @@ SYMBOLS = [
     "floam_feature_extract", "floam_odom_init_map", "floam_odom_update", "floam_odom_update_xyzi", "floam_odom_get", "floam_odom_map_sizes",
     "floam_odom_get_map", "floam_odom_set_state", "floam_odom_get_state", "floam_odom_set_map", "floam_process_scan", "floam_process_submit",
     "floam_process_wait", "floam_stage_scans", "floam_process_staged", "floam_mapping_update", "floam_mapping_get_map", "floam_voxel_grid",
-    "floam_crop_box", "floam_knn5", "floam_debug_fetch", "floam_launch_count", "floam_last_frame_ms",
+    "floam_crop_box", "floam_knn5", "floam_debug_fetch", "floam_launch_count", "floam_last_frame_ms", "floam_replay_staged",
+    "floam_set_kernel_timing", "floam_kernel_slots", "floam_kernel_name", "floam_kernel_timing",
 ]
 
 _lib = None
@@ -61,6 +62,7 @@ def lib():
         L.floam_alloc_pinned.restype = C.c_void_p
         L.floam_alloc_pinned.argtypes = [C.c_size_t]
         L.floam_free_pinned.argtypes = [C.c_void_p]
+        L.floam_kernel_name.restype = C.c_char_p
         _lib = L
     return _lib
 
@@ -239,6 +241,25 @@ class Context:
         pose = np.zeros(7)
         _check(lib().floam_process_staged(self.h, int(frame), int(deskew), _p(pose)), "floam_process_staged")
         return pose
+
+    def replay_staged(self, first, count, deskew=False):
+        """Frames [first, first+count) back to back on the device. Returns (poses[count,7], device milliseconds)."""
+        poses = np.zeros((count, 7)); ms = C.c_float()
+        _check(lib().floam_replay_staged(self.h, int(first), int(count), int(deskew), _p(poses), C.byref(ms)), "floam_replay_staged")
+        return poses, ms.value
+
+    def set_kernel_timing(self, enabled):
+        _check(lib().floam_set_kernel_timing(self.h, int(enabled)), "floam_set_kernel_timing")
+
+    def kernel_timing(self):
+        """{kernel class: (total ms, launches)} accumulated since timing was enabled."""
+        out = {}
+        for k in range(lib().floam_kernel_slots()):
+            ms = C.c_double(); n = C.c_int64()
+            _check(lib().floam_kernel_timing(self.h, k, C.byref(ms), C.byref(n)), "floam_kernel_timing")
+            if n.value:
+                out[lib().floam_kernel_name(k).decode()] = (ms.value, n.value)
+        return out
 
     # ---- LaserMappingClass ----
     def mapping_update(self, pts, pose):

@@ -113,6 +113,7 @@ void enqueue_frame_body(floam_ctx* c, const PointIRT* d_scan, const int* d_scan_
   if (first) {
     // odomEstimationNode.cpp:219-224: first frame only seeds the map (raw features, Q11); odom stays identity
     odom_init_map_device(c->odom, c->d_edge, c->d_ne, c->d_surf, c->d_ns, 32, c->prm.max_scan_points, 0, c->stream);
+    odom_record_pose(c->odom, c->stream);
     c->odom.optimization_count = 12;
   } else {
     enqueue_selector(c, c->d_edge, c->d_ne, c->d_surf, c->d_ns, c->prm.max_scan_points, deskew);
@@ -124,7 +125,7 @@ void enqueue_frame_body(floam_ctx* c, const PointIRT* d_scan, const int* d_scan_
 int launch_frame(floam_ctx* c, const PointIRT* d_scan, const int* d_scan_n, int deskew, int slot, int scan_slot_key) {
   const bool first = !c->map_initialised;
   OdomDevice& od = c->odom;
-  if (!c->use_graphs) {
+  if (!c->use_graphs || c->timer.enabled) {
     enqueue_frame_body(c, d_scan, d_scan_n, deskew, slot, first);
     c->map_initialised = true;
     return check_async("frame");
@@ -285,6 +286,8 @@ void floam_destroy(floam_ctx* c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+  if (g_timer == &c->timer) g_timer = nullptr;
+  if (c->timer.created) for (int i = 0; i < 2 * LaunchTimer::kPairs; ++i) cudaEventDestroy(c->timer.ev[i]);
   for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second.exec);
   for (void* p : c->allocs) cudaFree(p);
   for (void* p : c->host_allocs) cudaFreeHost(p);
@@ -805,6 +808,63 @@ int floam_launch_count(floam_ctx* c, int64_t* launches, int reset) {
 int floam_last_frame_ms(floam_ctx* c, float* ms) {
   if (!c || !ms) return FLOAM_ERR_ARG;
   *ms = c->last_frame_ms;
+  return FLOAM_OK;
+}
+
+int floam_replay_staged(floam_ctx* c, int first, int count, int deskew, double* poses_out, float* total_ms) {
+  if (!c || !c->d_staged || first < 0 || count < 1 || first + count >= (int)c->staged_offsets.size() + 0 || c->inflight != 0) return FLOAM_ERR_ARG;
+  if (count > c->odom.traj_cap) return FLOAM_ERR_CAPACITY;
+  if (set_device(c)) return FLOAM_ERR_CUDA;
+  int rc = sync_state(c);
+  if (rc) return rc;
+  const int counter0 = c->h_state[0]->frame_counter;
+  FLOAM_CUDA_OK(cudaEventRecord(c->ev_begin[0], c->stream));
+  for (int f = first; f < first + count; ++f) {
+    const int n = (int)(c->staged_offsets[f + 1] - c->staged_offsets[f]);
+    if (n > 0)
+      FLOAM_CUDA_OK(cudaMemcpyAsync(c->d_scan[0], c->d_staged + c->staged_offsets[f], (size_t)n * 32, cudaMemcpyDeviceToDevice, c->stream));
+    FLOAM_CUDA_OK(cudaMemcpyAsync(c->d_scan_n[0], c->d_staged_counts + f, 4, cudaMemcpyDeviceToDevice, c->stream));
+    if ((rc = launch_frame(c, c->d_scan[0], c->d_scan_n[0], deskew, 0, 0))) return rc;
+  }
+  FLOAM_CUDA_OK(cudaEventRecord(c->ev_end[0], c->stream));
+  FLOAM_CUDA_OK(cudaStreamSynchronize(c->stream));
+  if ((rc = check_async("replay_staged"))) return rc;
+  cudaEventElapsedTime(&c->last_frame_ms, c->ev_begin[0], c->ev_end[0]);
+  if (total_ms) *total_ms = c->last_frame_ms;
+  if (poses_out) {
+    const int cap = c->odom.traj_cap;
+    for (int k = 0; k < count; ++k)
+      FLOAM_CUDA_OK(cudaMemcpy(poses_out + (size_t)k * 7, c->odom.traj + (size_t)((counter0 + k) % cap) * 7, 56, cudaMemcpyDeviceToHost));
+  }
+  return status_from_flags(c, 0);
+}
+
+int floam_set_kernel_timing(floam_ctx* c, int enabled) {
+  if (!c) return FLOAM_ERR_ARG;
+  if (set_device(c)) return FLOAM_ERR_CUDA;
+  LaunchTimer& t = c->timer;
+  if (enabled && !t.created) {
+    for (int i = 0; i < 2 * LaunchTimer::kPairs; ++i) FLOAM_CUDA_OK(cudaEventCreate(&t.ev[i]));
+    t.created = true;
+  }
+  if (!enabled && t.enabled) launch_timer_collect(&t, c->stream);
+  if (enabled && !t.enabled) {
+    for (int k = 0; k < K_NUM_SLOTS; ++k) { t.total_ms[k] = 0.0; t.launches[k] = 0; }
+    t.used = 0;
+  }
+  t.enabled = enabled != 0;
+  g_timer = t.enabled ? &t : nullptr;   // the timer follows the calling thread, like the launch counter
+  return FLOAM_OK;
+}
+
+int floam_kernel_slots(void) { return K_NUM_SLOTS; }
+const char* floam_kernel_name(int slot) { return kernel_slot_name(slot); }
+
+int floam_kernel_timing(floam_ctx* c, int slot, double* total_ms, int64_t* launches) {
+  if (!c || slot < 0 || slot >= K_NUM_SLOTS) return FLOAM_ERR_ARG;
+  if (c->timer.enabled) launch_timer_collect(&c->timer, c->stream);
+  if (total_ms) *total_ms = c->timer.total_ms[slot];
+  if (launches) *launches = c->timer.launches[slot];
   return FLOAM_OK;
 }
 

@@ -20,9 +20,81 @@ namespace floam {
 
 constexpr int kNumSMs = 148;  // B200
 
-// kernels launched by the calling host thread (bench.py's gpu_launches); defined in sort_scan.cu
+// ---- launch accounting and per-kernel-class device timing (sort_scan.cu) ----
+// Every kernel goes through FLOAM_LAUNCH: it counts the launch (bench.py's gpu_launches) and, when a LaunchTimer is active on
+// the calling thread, brackets the kernel with CUDA events on its stream (bench.py's roofline leg; graphs are off then).
+enum KernelSlot {
+  K_RING_COUNT,
+  K_RING_SCATTER,
+  K_SECTOR,
+  K_FEATURE_OFFSETS,
+  K_FEATURE_GATHER,
+  K_DESKEW_ALIGN,
+  K_CLASSIFY_OLD,
+  K_PARTITION,
+  K_TRANSFORM_NEW,
+  K_KEYS1,
+  K_KEYS2,
+  K_HEADS,
+  K_REDUCE,
+  K_COMMIT,
+  K_CELL_KEYS,
+  K_GATHER,
+  K_GRID_BBOX,
+  K_GRID_DIMS,
+  K_GRID_COUNT,
+  K_GRID_SCATTER,
+  K_STATE_INIT,
+  K_MAP_APPEND_RAW,
+  K_MAP_BUMP,
+  K_PREDICT,
+  K_ASSOC_EVAL,
+  K_CAND_EVAL,
+  K_FINISH,
+  K_MAP_APPEND,
+  K_COMPENSATE_VELOCITY,
+  K_KNN5,
+  K_RADIX_HIST,
+  K_SINGLE_BLOCK_SCAN,
+  K_RADIX_SCATTER,
+  K_SCAN_TILES,
+  K_SCAN_ADD,
+  K_VOXEL_INIT,
+  K_VOXEL_BBOX,
+  K_VOXEL_KEYS,
+  K_VOXEL_HEADS,
+  K_VOXEL_REDUCE,
+  K_REPACK,
+  K_CROP_FLAGS,
+  K_CROP_SCATTER,
+  K_RECORD_POSE,
+  K_NUM_SLOTS
+};
+const char* kernel_slot_name(int slot);
 extern thread_local long long g_launches;
-inline void count_launch(int n = 1) { g_launches += n; }
+
+struct LaunchTimer {
+  static constexpr int kPairs = 2048;
+  bool enabled = false;
+  cudaEvent_t ev[2 * kPairs];
+  int slot_of[kPairs];
+  int used = 0;
+  bool created = false;
+  double total_ms[K_NUM_SLOTS];
+  long long launches[K_NUM_SLOTS];
+};
+extern thread_local LaunchTimer* g_timer;
+void launch_timer_begin(int slot, cudaStream_t s);
+void launch_timer_end(cudaStream_t s);
+int launch_timer_collect(LaunchTimer* t, cudaStream_t s);  // synchronises the stream and folds the pending event pairs into the totals
+
+#define FLOAM_LAUNCH(slot, kern, grid, block, stream, ...)            \
+  do {                                                                \
+    ::floam::g_launches++;                                            \
+    if (::floam::g_timer) ::floam::launch_timer_begin(slot, stream);  \
+    kern<<<grid, block, 0, stream>>>(__VA_ARGS__);                    \
+    if (::floam::g_timer) ::floam::launch_timer_end(stream);          \
+  } while (0)
 
 // 32-byte scan/feature point, byte-identical to vel_point::PointXYZIRT (reference include/lidar.h:14-32).
 struct __align__(16) PointIRT {

@@ -85,6 +85,7 @@ struct floam_ctx {
   bool use_graphs = true;
   std::map<floam_graph_key, floam_graph_entry> graphs;
   float last_frame_ms = 0.f;
+  floam::LaunchTimer timer;
   long long launches_base = 0;
 };
 

@@ -303,14 +303,13 @@ size_t feature_workspace_bytes_padded(int max_scan_points, int num_lines) { retu
 void feature_extract_device(const PointIRT* d_scan, const int* d_n, const FeatureParams& prm, FeatureWorkspace& ws, PointIRT* d_edge, int* d_ne,
                             PointIRT* d_surf, int* d_ns, int* d_edge_src, int* d_surf_src, int* d_flags, cudaStream_t s) {
   const int ntiles = ws.ntiles;
-  ring_count_kernel<<<ntiles, kTile, 0, s>>>(d_scan, d_n, prm, ntiles, ws.tile_off, d_flags);
+  FLOAM_LAUNCH(K_RING_COUNT, ring_count_kernel, ntiles, kTile, s, d_scan, d_n, prm, ntiles, ws.tile_off, d_flags);
   exclusive_scan_small(ws.tile_off, prm.num_lines * ntiles + 1, s);
-  ring_scatter_kernel<<<ntiles, kTile, 0, s>>>(d_scan, d_n, prm, ntiles, ws.tile_off, ws.ring_pts, ws.ring_src);
-  sector_kernel<<<ws.nsectors, kSectorThreads, 0, s>>>(ws.ring_pts, ws.tile_off, ntiles, prm, ws.edge_tmp, ws.surf_tmp, ws.edge_cnt, ws.surf_cnt, d_flags);
-  feature_offsets_kernel<<<1, 1024, 0, s>>>(ws.edge_cnt, ws.surf_cnt, ws.nsectors, ws.edge_off, ws.surf_off, d_ne, d_ns);
-  feature_gather_kernel<<<ws.nsectors, 256, 0, s>>>(ws.ring_pts, ws.ring_src, ws.tile_off, ntiles, ws.edge_tmp, ws.surf_tmp, ws.edge_cnt, ws.surf_cnt,
+  FLOAM_LAUNCH(K_RING_SCATTER, ring_scatter_kernel, ntiles, kTile, s, d_scan, d_n, prm, ntiles, ws.tile_off, ws.ring_pts, ws.ring_src);
+  FLOAM_LAUNCH(K_SECTOR, sector_kernel, ws.nsectors, kSectorThreads, s, ws.ring_pts, ws.tile_off, ntiles, prm, ws.edge_tmp, ws.surf_tmp, ws.edge_cnt, ws.surf_cnt, d_flags);
+  FLOAM_LAUNCH(K_FEATURE_OFFSETS, feature_offsets_kernel, 1, 1024, s, ws.edge_cnt, ws.surf_cnt, ws.nsectors, ws.edge_off, ws.surf_off, d_ne, d_ns);
+  FLOAM_LAUNCH(K_FEATURE_GATHER, feature_gather_kernel, ws.nsectors, 256, s, ws.ring_pts, ws.ring_src, ws.tile_off, ntiles, ws.edge_tmp, ws.surf_tmp, ws.edge_cnt, ws.surf_cnt,
                                                     ws.edge_off, ws.surf_off, d_edge, d_surf, d_edge_src, d_surf_src);
-  count_launch(5);
 }
 
 }  // namespace floam

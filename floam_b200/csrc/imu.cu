@@ -135,8 +135,7 @@ int deskew_align_device(ImuDevice& imu, const DeskewPlan& plan, PointIRT* d_pts,
   int g = (n_max + kThreads - 1) / kThreads;
   if (g > kNumSMs * 8) g = kNumSMs * 8;
   if (g < 1) g = 1;
-  deskew_align_kernel<<<g, kThreads, 0, s>>>(d_pts, d_n, plan, imu.d_samples, total);
-  count_launch(1);
+  FLOAM_LAUNCH(K_DESKEW_ALIGN, deskew_align_kernel, g, kThreads, s, d_pts, d_n, plan, imu.d_samples, total);
   return FLOAM_OK;
 }
 

@@ -249,21 +249,18 @@ int mapping_update_device(MappingDevice& md, const void* d_in, int stride, const
   VoxelWorkspace& ws = *md.vws;
   int* counts = md.d_counts;
   const int gmap = grid_for(md.cap), gin = grid_for(n_max);
-  classify_old_kernel<<<gmap, kThreads, 0, s>>>(md.cell, counts, g, ws.flags);
+  FLOAM_LAUNCH(K_CLASSIFY_OLD, classify_old_kernel, gmap, kThreads, s, md.cell, counts, g, ws.flags);
   exclusive_scan_i32(ws.flags, ws.flags, counts, 0, md.cap, ws.scan, nullptr, s);
-  partition_kernel<<<gmap, kThreads, 0, s>>>(md.pts, md.cell, ws.flags, counts, md.pts_alt, md.cell_alt, md.work, md.work_cell);
-  transform_new_kernel<<<gin, kThreads, 0, s>>>((const char*)d_in, stride, d_n, counts, g, md.cap, md.work, md.work_cell);
-  keys1_kernel<<<gmap, kThreads, 0, s>>>(md.work, md.work_cell, counts, g, ws.keys, ws.vals);
-  count_launch(4);
+  FLOAM_LAUNCH(K_PARTITION, partition_kernel, gmap, kThreads, s, md.pts, md.cell, ws.flags, counts, md.pts_alt, md.cell_alt, md.work, md.work_cell);
+  FLOAM_LAUNCH(K_TRANSFORM_NEW, transform_new_kernel, gin, kThreads, s, (const char*)d_in, stride, d_n, counts, g, md.cap, md.work, md.work_cell);
+  FLOAM_LAUNCH(K_KEYS1, keys1_kernel, gmap, kThreads, s, md.work, md.work_cell, counts, g, ws.keys, ws.vals);
   radix_sort_pairs(ws.keys, ws.vals, counts + 3, md.d_nbits, md.cap, ws.sort, nullptr, s);
-  keys2_kernel<<<gmap, kThreads, 0, s>>>(md.work, md.work_cell, counts, g, ws.vals, ws.keys);
-  count_launch(1);
+  FLOAM_LAUNCH(K_KEYS2, keys2_kernel, gmap, kThreads, s, md.work, md.work_cell, counts, g, ws.vals, ws.keys);
   radix_sort_pairs(ws.keys, ws.vals, counts + 3, md.d_nbits + 1, md.cap, ws.sort, nullptr, s);
-  heads_kernel<<<gmap, kThreads, 0, s>>>(md.work, md.work_cell, counts, g, ws.vals, ws.flags);
+  FLOAM_LAUNCH(K_HEADS, heads_kernel, gmap, kThreads, s, md.work, md.work_cell, counts, g, ws.vals, ws.flags);
   exclusive_scan_i32(ws.flags, ws.flags, counts + 3, 0, md.cap, ws.scan, nullptr, s);
-  reduce_kernel<<<gmap, kThreads, 0, s>>>(md.work, md.work_cell, counts, g, ws.vals, ws.flags, md.pts_alt, md.cell_alt);
-  commit_kernel<<<1, 32, 0, s>>>(counts);
-  count_launch(3);
+  FLOAM_LAUNCH(K_REDUCE, reduce_kernel, gmap, kThreads, s, md.work, md.work_cell, counts, g, ws.vals, ws.flags, md.pts_alt, md.cell_alt);
+  FLOAM_LAUNCH(K_COMMIT, commit_kernel, 1, 32, s, counts);
   std::swap(md.pts, md.pts_alt);
   std::swap(md.cell, md.cell_alt);
   return FLOAM_OK;
@@ -274,10 +271,9 @@ int mapping_get_map_device(MappingDevice& md, P4** d_out, int** d_out_n, cudaStr
   const int nbits = 30;
   FLOAM_CUDA_OK(cudaMemcpyAsync(md.d_nbits + 2, &nbits, 4, cudaMemcpyHostToDevice, s));
   const int g = grid_for(md.cap);
-  cell_keys_kernel<<<g, kThreads, 0, s>>>(md.cell, md.d_counts, ws.keys, ws.vals);
+  FLOAM_LAUNCH(K_CELL_KEYS, cell_keys_kernel, g, kThreads, s, md.cell, md.d_counts, ws.keys, ws.vals);
   radix_sort_pairs(ws.keys, ws.vals, md.d_counts, md.d_nbits + 2, md.cap, ws.sort, nullptr, s);
-  gather_kernel<<<g, kThreads, 0, s>>>(md.pts, ws.vals, md.d_counts, md.pts_alt);
-  count_launch(2);
+  FLOAM_LAUNCH(K_GATHER, gather_kernel, g, kThreads, s, md.pts, ws.vals, md.d_counts, md.pts_alt);
   *d_out = md.pts_alt;
   *d_out_n = md.d_counts;
   return FLOAM_OK;

@@ -85,7 +85,7 @@ __global__ void predict_kernel(PoseState* S, const int* n_edge_map, const int* n
 }
 
 // :114-121 + KeyFrameUpdate :320-343 + the CropBox bounds of addPointsToMap :270-279
-__global__ void finish_kernel(PoseState* S, int update_type, double scan_period) {
+__global__ void finish_kernel(PoseState* S, int update_type, double scan_period, double* traj, int traj_cap) {
   if (threadIdx.x != 0) return;
   double R[9];
   m::quat_to_matrix(S->x, R);
@@ -115,6 +115,18 @@ __global__ void finish_kernel(PoseState* S, int update_type, double scan_period)
   }
   S->keyframe = kf;
   S->not_keyframe = kf ? 0 : 1;
+  if (update_type != FLOAM_INITIAL_ITERATION) {
+    double* rec = traj + (size_t)(S->frame_counter % traj_cap) * 7;
+    for (int k = 0; k < 7; ++k) rec[k] = S->x[k];
+    S->frame_counter++;
+  }
+}
+
+__global__ void record_pose_kernel(PoseState* S, double* traj, int traj_cap) {
+  if (threadIdx.x != 0) return;
+  double* rec = traj + (size_t)(S->frame_counter % traj_cap) * 7;
+  for (int k = 0; k < 7; ++k) rec[k] = S->x[k];
+  S->frame_counter++;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -713,13 +725,11 @@ int* dims_ncells_ptr(GridDims* dims) { return reinterpret_cast<int*>(reinterpret
 
 void rebuild_grid(OdomDevice& od, LocalMap& map, const int* d_skip, cudaStream_t s) {
   const int g = grid_for(map.cap);
-  grid_bbox_kernel<<<g, kThreads, 0, s>>>(map.pts, map.d_n, map.bbox, d_skip);
-  grid_dims_kernel<<<1, 32, 0, s>>>(map.bbox, map.d_n, map.dims, map.ncells_cap, od.state, d_skip);
-  grid_count_kernel<<<g, kThreads, 0, s>>>(map.pts, map.d_n, map.dims, map.cell_count, d_skip);
-  count_launch(3);
+  FLOAM_LAUNCH(K_GRID_BBOX, grid_bbox_kernel, g, kThreads, s, map.pts, map.d_n, map.bbox, d_skip);
+  FLOAM_LAUNCH(K_GRID_DIMS, grid_dims_kernel, 1, 32, s, map.bbox, map.d_n, map.dims, map.ncells_cap, od.state, d_skip);
+  FLOAM_LAUNCH(K_GRID_COUNT, grid_count_kernel, g, kThreads, s, map.pts, map.d_n, map.dims, map.cell_count, d_skip);
   exclusive_scan_i32(map.cell_count, map.cell_start, dims_ncells_ptr(map.dims), 0, map.ncells_cap, od.vws->scan, d_skip, s);
-  grid_scatter_kernel<<<g, kThreads, 0, s>>>(map.pts, map.d_n, map.dims, map.cell_start, map.cell_count, map.cell_pts, d_skip);
-  count_launch(1);
+  FLOAM_LAUNCH(K_GRID_SCATTER, grid_scatter_kernel, g, kThreads, s, map.pts, map.d_n, map.dims, map.cell_start, map.cell_count, map.cell_pts, d_skip);
 }
 
 }  // namespace
@@ -769,19 +779,23 @@ int odom_device_init(OdomDevice& od, const floam_params& prm, VoxelWorkspace* vw
   od.knn_ids = (int*)alloc(actx, (size_t)2 * od.qcap * 5 * 4);
   od.knn_d2 = (float*)alloc(actx, (size_t)2 * od.qcap * 5 * 4);
   od.partials = (double*)alloc(actx, (size_t)kAssocBlocks * kLmTerms * sizeof(double));
-  if (!od.ds_edge || !od.ds_surf || !ints || !od.corr || !od.corr_ok || !od.knn_ids || !od.knn_d2 || !od.partials) return FLOAM_ERR_CUDA;
+  od.traj_cap = 1 << 16;
+  od.traj = (double*)alloc(actx, (size_t)od.traj_cap * 7 * sizeof(double));
+  if (!od.ds_edge || !od.ds_surf || !ints || !od.corr || !od.corr_ok || !od.knn_ids || !od.knn_d2 || !od.partials || !od.traj) return FLOAM_ERR_CUDA;
   od.d_nds_edge = ints; od.d_nds_surf = ints + 1;
   FLOAM_CUDA_OK(cudaMemsetAsync(ints, 0, 16, s));
   FLOAM_CUDA_OK(cudaMemsetAsync(od.corr_ok, 0, (size_t)2 * od.qcap, s));
-  state_init_kernel<<<1, 32, 0, s>>>(od.state);
+  FLOAM_LAUNCH(K_STATE_INIT, state_init_kernel, 1, 32, s, od.state);
   FLOAM_CUDA_OK(cudaStreamSynchronize(s));
   return FLOAM_OK;
 }
 
 void odom_reset_state(OdomDevice& od, cudaStream_t s) {
-  state_init_kernel<<<1, 32, 0, s>>>(od.state);
+  FLOAM_LAUNCH(K_STATE_INIT, state_init_kernel, 1, 32, s, od.state);
   od.optimization_count = 2;
 }
+
+void odom_record_pose(OdomDevice& od, cudaStream_t s) { FLOAM_LAUNCH(K_RECORD_POSE, record_pose_kernel, 1, 32, s, od.state, od.traj, od.traj_cap); }
 
 void odom_rebuild_grids(OdomDevice& od, cudaStream_t s) {
   rebuild_grid(od, od.edge_map, nullptr, s);
@@ -789,9 +803,8 @@ void odom_rebuild_grids(OdomDevice& od, cudaStream_t s) {
 }
 
 void local_map_load(OdomDevice& od, LocalMap& map, const void* d_pts, const int* d_n, int stride, int n_max, int replace, cudaStream_t s) {
-  map_append_raw_kernel<<<grid_for(n_max), kThreads, 0, s>>>((const char*)d_pts, stride, d_n, map.pts, map.d_n, map.cap, replace, &od.state->error_flags);
-  map_bump_kernel<<<1, 32, 0, s>>>(map.d_n, d_n, map.cap, replace, nullptr);
-  count_launch(2);
+  FLOAM_LAUNCH(K_MAP_APPEND_RAW, map_append_raw_kernel, grid_for(n_max), kThreads, s, (const char*)d_pts, stride, d_n, map.pts, map.d_n, map.cap, replace, &od.state->error_flags);
+  FLOAM_LAUNCH(K_MAP_BUMP, map_bump_kernel, 1, 32, s, map.d_n, d_n, map.cap, replace, nullptr);
   rebuild_grid(od, map, nullptr, s);
 }
 
@@ -805,22 +818,19 @@ void odom_update_device(OdomDevice& od, const void* d_edge, const int* d_ne, con
                         int tap, cudaStream_t s) {
   // the caller has already applied `if (optimization_count > 2) optimization_count--` (:59-60, Q4)
   PoseState* S = od.state;
-  predict_kernel<<<1, 32, 0, s>>>(S, od.edge_map.d_n, od.surf_map.d_n);
-  count_launch(1);
+  FLOAM_LAUNCH(K_PREDICT, predict_kernel, 1, 32, s, S, od.edge_map.d_n, od.surf_map.d_n);
   // downSamplingToMap :137-142
   voxel_grid_device(d_edge, stride, d_ne, n_max, od.leaf_edge, od.ds_edge, od.d_nds_edge, *od.vws, nullptr, s);
   voxel_grid_device(d_surf, stride, d_ns, n_max, od.leaf_surf, od.ds_surf, od.d_nds_surf, *od.vws, nullptr, s);
   for (int it = 0; it < od.optimization_count; ++it) {
     const int t = tap && (it == od.optimization_count - 1);
-    assoc_eval_kernel<<<kAssocBlocks, kEvalThreads, 0, s>>>(S, od.ds_edge, od.d_nds_edge, od.ds_surf, od.d_nds_surf, od.edge_map, od.surf_map, od.qcap,
+    FLOAM_LAUNCH(K_ASSOC_EVAL, assoc_eval_kernel, kAssocBlocks, kEvalThreads, s, S, od.ds_edge, od.d_nds_edge, od.ds_surf, od.d_nds_surf, od.edge_map, od.surf_map, od.qcap,
                                                             od.corr, od.corr_ok, od.knn_ids, od.knn_d2, od.loss, od.partials, t);
     for (int k = 0; k < 4; ++k)
-      cand_eval_kernel<<<kCandBlocks, kEvalThreads, 0, s>>>(S, od.ds_edge, od.d_nds_edge, od.ds_surf, od.d_nds_surf, od.qcap, od.corr, od.corr_ok, od.loss,
+      FLOAM_LAUNCH(K_CAND_EVAL, cand_eval_kernel, kCandBlocks, kEvalThreads, s, S, od.ds_edge, od.d_nds_edge, od.ds_surf, od.d_nds_surf, od.qcap, od.corr, od.corr_ok, od.loss,
                                                             od.partials);
-    count_launch(5);
   }
-  finish_kernel<<<1, 32, 0, s>>>(S, update_type, od.scan_period);
-  count_launch(1);
+  FLOAM_LAUNCH(K_FINISH, finish_kernel, 1, 32, s, S, update_type, od.scan_period, od.traj, od.traj_cap);
   if (update_type == FLOAM_INITIAL_ITERATION) return;
   // addPointsToMap :253-294, predicated on the device-side keyframe decision
   const int* skip = &S->not_keyframe;
@@ -830,9 +840,8 @@ void odom_update_device(OdomDevice& od, const void* d_edge, const int* d_ne, con
   const float leaf[2] = {od.leaf_surf, od.leaf_edge};
   for (int k = 0; k < 2; ++k) {
     LocalMap& mp = *maps[k];
-    map_append_kernel<<<grid_for(od.qcap), kThreads, 0, s>>>(dss[k], nds[k], mp.pts, mp.d_n, mp.cap, S, skip);
-    map_bump_kernel<<<1, 32, 0, s>>>(mp.d_n, nds[k], mp.cap, 0, skip);
-    count_launch(2);
+    FLOAM_LAUNCH(K_MAP_APPEND, map_append_kernel, grid_for(od.qcap), kThreads, s, dss[k], nds[k], mp.pts, mp.d_n, mp.cap, S, skip);
+    FLOAM_LAUNCH(K_MAP_BUMP, map_bump_kernel, 1, 32, s, mp.d_n, nds[k], mp.cap, 0, skip);
     crop_box_device(mp.pts, mp.d_n, mp.cap, S->crop_bounds, mp.tmp, mp.d_ncrop, *od.vws, skip, s);
     voxel_grid_device(mp.tmp, 16, mp.d_ncrop, mp.cap, leaf[k], mp.pts, mp.d_n, *od.vws, skip, s);
     rebuild_grid(od, mp, skip, s);
@@ -840,16 +849,14 @@ void odom_update_device(OdomDevice& od, const void* d_edge, const int* d_ne, con
 }
 
 void compensate_velocity_device(OdomDevice& od, PointIRT* d_pts, const int* d_n, int n_max, cudaStream_t s) {
-  compensate_velocity_kernel<<<grid_for(n_max), kThreads, 0, s>>>(d_pts, d_n, od.state);
-  count_launch(1);
+  FLOAM_LAUNCH(K_COMPENSATE_VELOCITY, compensate_velocity_kernel, grid_for(n_max), kThreads, s, d_pts, d_n, od.state);
 }
 
 void knn5_device(OdomDevice& od, LocalMap& map, const P4* d_queries, const int* d_nq, int nq_max, int* d_ids, float* d_d2, cudaStream_t s) {
   int g = (nq_max + kEvalThreads - 1) / kEvalThreads;
   if (g > kNumSMs * 16) g = kNumSMs * 16;
   if (g < 1) g = 1;
-  knn5_kernel<<<g, kEvalThreads, 0, s>>>(d_queries, d_nq, map, d_ids, d_d2);
-  count_launch(1);
+  FLOAM_LAUNCH(K_KNN5, knn5_kernel, g, kEvalThreads, s, d_queries, d_nq, map, d_ids, d_d2);
 }
 
 }  // namespace floam

@@ -30,6 +30,7 @@ struct PoseState {
   int error_flags;       // bit 0: map capacity exceeded, bit 1: grid capacity exceeded
   int n_corr;            // accepted correspondences of the last association
   int n_corr_acc;        // accumulator of the running association
+  int frame_counter;     // frames completed (index of the next trajectory record)
 };
 
 struct GridDims {
@@ -71,11 +72,15 @@ struct OdomDevice {
   double scan_period;
   int loss;
   int optimization_count;      // host mirror (deterministic schedule, Q4)
+  double* traj;                // [traj_cap][7] device-side trajectory log (pose of every completed frame)
+  int traj_cap;
 };
 
 int local_map_alloc(LocalMap& map, int cap, int ncells_cap, void* (*alloc)(void*, size_t), void* alloc_ctx, cudaStream_t s);
 int odom_device_init(OdomDevice& od, const floam_params& prm, VoxelWorkspace* vws, void* (*alloc)(void*, size_t), void* alloc_ctx, cudaStream_t s);
 void odom_reset_state(OdomDevice& od, cudaStream_t s);
+// appends the current pose to the device trajectory log (first frame: the update path does it in its finish kernel)
+void odom_record_pose(OdomDevice& od, cudaStream_t s);
 
 // append (replace = 0) or overwrite (replace = 1) a map with a strided device cloud and rebuild its grid
 void local_map_load(OdomDevice& od, LocalMap& map, const void* d_pts, const int* d_n, int stride, int n_max, int replace, cudaStream_t s);

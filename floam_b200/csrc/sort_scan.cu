@@ -5,6 +5,82 @@
 namespace floam {
 
 thread_local long long g_launches = 0;
+thread_local LaunchTimer* g_timer = nullptr;
+
+static const char* const kSlotNames[K_NUM_SLOTS] = {
+  "ring_count",
+  "ring_scatter",
+  "sector",
+  "feature_offsets",
+  "feature_gather",
+  "deskew_align",
+  "classify_old",
+  "partition",
+  "transform_new",
+  "keys1",
+  "keys2",
+  "heads",
+  "reduce",
+  "commit",
+  "cell_keys",
+  "gather",
+  "grid_bbox",
+  "grid_dims",
+  "grid_count",
+  "grid_scatter",
+  "state_init",
+  "map_append_raw",
+  "map_bump",
+  "predict",
+  "assoc_eval",
+  "cand_eval",
+  "finish",
+  "map_append",
+  "compensate_velocity",
+  "knn5",
+  "radix_hist",
+  "single_block_scan",
+  "radix_scatter",
+  "scan_tiles",
+  "scan_add",
+  "voxel_init",
+  "voxel_bbox",
+  "voxel_keys",
+  "voxel_heads",
+  "voxel_reduce",
+  "repack",
+  "crop_flags",
+  "crop_scatter",
+  "record_pose"
+};
+const char* kernel_slot_name(int slot) { return (slot >= 0 && slot < K_NUM_SLOTS) ? kSlotNames[slot] : "?"; }
+
+void launch_timer_begin(int slot, cudaStream_t s) {
+  LaunchTimer* t = g_timer;
+  if (!t || !t->enabled) return;
+  if (t->used == LaunchTimer::kPairs) launch_timer_collect(t, s);
+  t->slot_of[t->used] = slot;
+  cudaEventRecord(t->ev[2 * t->used], s);
+}
+void launch_timer_end(cudaStream_t s) {
+  LaunchTimer* t = g_timer;
+  if (!t || !t->enabled) return;
+  cudaEventRecord(t->ev[2 * t->used + 1], s);
+  t->used++;
+}
+int launch_timer_collect(LaunchTimer* t, cudaStream_t s) {
+  if (!t) return FLOAM_OK;
+  FLOAM_CUDA_OK(cudaStreamSynchronize(s));
+  for (int i = 0; i < t->used; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, t->ev[2 * i], t->ev[2 * i + 1]) == cudaSuccess) {
+      t->total_ms[t->slot_of[i]] += ms;
+      t->launches[t->slot_of[i]]++;
+    }
+  }
+  t->used = 0;
+  return FLOAM_OK;
+}
 
 namespace {
 
@@ -175,18 +251,16 @@ void radix_sort_pairs(unsigned int* keys, int* vals, const int* d_n, const int* 
   unsigned int* kout = ws.keys_alt; int* vout = ws.vals_alt;
   for (int pass = 0; pass < 4; ++pass) {
     const int shift = pass * 8;
-    radix_hist_kernel<<<nblocks, kSortThreads, 0, s>>>(kin, d_n, d_nbits, shift, ws.hist, nblocks, d_skip);
-    single_block_scan_kernel<<<1, 1024, 0, s>>>(ws.hist, 256 * nblocks, d_nbits, shift, d_skip, d_n);
-    radix_scatter_kernel<<<nblocks, kSortThreads, 0, s>>>(kin, vin, kout, vout, d_n, d_nbits, shift, ws.hist, nblocks, d_skip);
-    count_launch(3);
+    FLOAM_LAUNCH(K_RADIX_HIST, radix_hist_kernel, nblocks, kSortThreads, s, kin, d_n, d_nbits, shift, ws.hist, nblocks, d_skip);
+    FLOAM_LAUNCH(K_SINGLE_BLOCK_SCAN, single_block_scan_kernel, 1, 1024, s, ws.hist, 256 * nblocks, d_nbits, shift, d_skip, d_n);
+    FLOAM_LAUNCH(K_RADIX_SCATTER, radix_scatter_kernel, nblocks, kSortThreads, s, kin, vin, kout, vout, d_n, d_nbits, shift, ws.hist, nblocks, d_skip);
     unsigned int* tk = kin; kin = kout; kout = tk;
     int* tv = vin; vin = vout; vout = tv;
   }
 }
 
 void exclusive_scan_small(int* data, int n, cudaStream_t s) {
-  single_block_scan_kernel<<<1, 1024, 0, s>>>(data, n, nullptr, 0, nullptr, nullptr);
-  count_launch(1);
+  FLOAM_LAUNCH(K_SINGLE_BLOCK_SCAN, single_block_scan_kernel, 1, 1024, s, data, n, nullptr, 0, nullptr, nullptr);
 }
 
 size_t scan_workspace_bytes(int n_max) { return ((size_t)(n_max + kScanTile - 1) / kScanTile + 2) * 4 + 256; }
@@ -194,11 +268,10 @@ void scan_workspace_bind(ScanWorkspace& ws, void* mem, int n_max) { ws.block_sum
 
 void exclusive_scan_i32(const int* in, int* out, const int* d_n, int n_fixed, int n_max, ScanWorkspace& ws, const int* d_skip, cudaStream_t s) {
   const int nblocks = (n_max + kScanTile - 1) / kScanTile;
-  scan_tiles_kernel<<<nblocks, kScanThreads, 0, s>>>(in, out, d_n, n_fixed, ws.block_sums, d_skip);
+  FLOAM_LAUNCH(K_SCAN_TILES, scan_tiles_kernel, nblocks, kScanThreads, s, in, out, d_n, n_fixed, ws.block_sums, d_skip);
   // exclusive scan of nblocks+1 entries: entry nblocks becomes the grand total
-  single_block_scan_kernel<<<1, 1024, 0, s>>>(ws.block_sums, nblocks + 1, nullptr, 0, d_skip, nullptr);
-  scan_add_kernel<<<nblocks, kScanThreads, 0, s>>>(out, d_n, n_fixed, ws.block_sums, nblocks, d_skip);
-  count_launch(3);
+  FLOAM_LAUNCH(K_SINGLE_BLOCK_SCAN, single_block_scan_kernel, 1, 1024, s, ws.block_sums, nblocks + 1, nullptr, 0, d_skip, nullptr);
+  FLOAM_LAUNCH(K_SCAN_ADD, scan_add_kernel, nblocks, kScanThreads, s, out, d_n, n_fixed, ws.block_sums, nblocks, d_skip);
 }
 
 }  // namespace floam

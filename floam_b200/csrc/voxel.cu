@@ -189,31 +189,26 @@ void voxel_grid_device(const void* d_in, int stride_bytes, const int* d_n, int n
   if (n_max > ws.n_max) n_max = ws.n_max;
   const char* in = (const char*)d_in;
   const int g = grid_for(n_max);
-  voxel_init_kernel<<<1, 32, 0, s>>>(ws.bbox, d_skip);
-  voxel_bbox_kernel<<<g, kThreads, 0, s>>>(in, stride_bytes, d_n, ws.bbox, d_skip);
-  voxel_keys_kernel<<<g, kThreads, 0, s>>>(in, stride_bytes, d_n, leaf, ws.bbox, ws.keys, ws.vals, ws.d_nbits, ws.d_passthrough, d_skip);
-  count_launch(3);
+  FLOAM_LAUNCH(K_VOXEL_INIT, voxel_init_kernel, 1, 32, s, ws.bbox, d_skip);
+  FLOAM_LAUNCH(K_VOXEL_BBOX, voxel_bbox_kernel, g, kThreads, s, in, stride_bytes, d_n, ws.bbox, d_skip);
+  FLOAM_LAUNCH(K_VOXEL_KEYS, voxel_keys_kernel, g, kThreads, s, in, stride_bytes, d_n, leaf, ws.bbox, ws.keys, ws.vals, ws.d_nbits, ws.d_passthrough, d_skip);
   radix_sort_pairs(ws.keys, ws.vals, d_n, ws.d_nbits, n_max, ws.sort, d_skip, s);
-  voxel_heads_kernel<<<g, kThreads, 0, s>>>(ws.keys, d_n, ws.flags, d_skip);
-  count_launch(1);
+  FLOAM_LAUNCH(K_VOXEL_HEADS, voxel_heads_kernel, g, kThreads, s, ws.keys, d_n, ws.flags, d_skip);
   exclusive_scan_i32(ws.flags, ws.flags, d_n, 0, n_max, ws.scan, d_skip, s);
-  voxel_reduce_kernel<<<g, kThreads, 0, s>>>(in, stride_bytes, ws.keys, ws.vals, ws.flags, d_n, d_out, d_nout, d_skip);
-  count_launch(1);
+  FLOAM_LAUNCH(K_VOXEL_REDUCE, voxel_reduce_kernel, g, kThreads, s, in, stride_bytes, ws.keys, ws.vals, ws.flags, d_n, d_out, d_nout, d_skip);
 }
 
 void repack_xyzi_device(const void* d_in32, const int* d_n, int n_max, P4* d_out, cudaStream_t s) {
-  repack_kernel<<<grid_for(n_max), kThreads, 0, s>>>((const char*)d_in32, d_n, d_out);
-  count_launch(1);
+  FLOAM_LAUNCH(K_REPACK, repack_kernel, grid_for(n_max), kThreads, s, (const char*)d_in32, d_n, d_out);
 }
 
 void crop_box_device(const P4* d_in, const int* d_n, int n_max, const float* d_bounds, P4* d_out, int* d_nout, VoxelWorkspace& ws,
                      const int* d_skip, cudaStream_t s) {
   if (n_max > ws.n_max) n_max = ws.n_max;
   const int g = grid_for(n_max);
-  crop_flags_kernel<<<g, kThreads, 0, s>>>(d_in, d_n, d_bounds, ws.flags, d_skip);
+  FLOAM_LAUNCH(K_CROP_FLAGS, crop_flags_kernel, g, kThreads, s, d_in, d_n, d_bounds, ws.flags, d_skip);
   exclusive_scan_i32(ws.flags, ws.flags, d_n, 0, n_max, ws.scan, d_skip, s);
-  crop_scatter_kernel<<<g, kThreads, 0, s>>>(d_in, d_n, d_bounds, ws.flags, d_out, d_nout, d_skip);
-  count_launch(2);
+  FLOAM_LAUNCH(K_CROP_SCATTER, crop_scatter_kernel, g, kThreads, s, d_in, d_n, d_bounds, ws.flags, d_out, d_nout, d_skip);
 }
 
 }  // namespace floam

@@ -133,6 +133,10 @@ int floam_process_wait(floam_ctx* ctx, double pose_out[7]);
 int floam_stage_scans(floam_ctx* ctx, const floam_point_xyzirt* pts, const int64_t* offsets, int n_frames);
 int floam_process_staged(floam_ctx* ctx, int frame, int deskew, double pose_out[7]);
 
+/* Whole-sequence replay of staged frames [first, first + count): frames are enqueued back to back with no host round trip in
+ * between (every decision of a frame is taken on the device); the 7-double poses come back from the device-side trajectory log. */
+int floam_replay_staged(floam_ctx* ctx, int first, int count, int deskew, double* poses_out, float* total_ms);
+
 /* LaserMappingClass::updateCurrentPointsToMap / getMap (src/laserMappingClass.cpp:148-200) */
 int floam_mapping_update(floam_ctx* ctx, const floam_point_xyzi* pts, int n, const double pose_rowmajor[16]);
 int floam_mapping_get_map(floam_ctx* ctx, floam_point_xyzi* out, int cap, int* n);
@@ -160,6 +164,12 @@ int floam_debug_fetch(floam_ctx* ctx, int what, void* out, size_t cap_bytes, siz
 
 /* Launch accounting for bench.py ("gpu_launches"): kernels launched by this context since the last reset. */
 int floam_launch_count(floam_ctx* ctx, int64_t* launches, int reset);
+/* Per-kernel-class device timing for the roofline leg of bench.py: while enabled, kernels are launched one by one (no graph
+ * replay) with a CUDA event pair around each, on the calling thread. Slots are named by floam_kernel_name. */
+int floam_set_kernel_timing(floam_ctx* ctx, int enabled);
+int floam_kernel_slots(void);
+const char* floam_kernel_name(int slot);
+int floam_kernel_timing(floam_ctx* ctx, int slot, double* total_ms, int64_t* launches);
 /* CUDA events around the device work of the last floam_process_* call, milliseconds. */
 int floam_last_frame_ms(floam_ctx* ctx, float* ms);
 

@@ -1,0 +1,70 @@
+"""CPU checks of the drop-in boundary: the C-ABI library builds, loads and exports exactly what include/floam_b200.h declares.
+No compute call is made here (there is no GPU in the build container)."""
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "floam_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(floam_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_matches_binding_list(capi):
+    assert header_symbols() == sorted(capi.SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol(capi):
+    L = capi.lib()
+    missing = [s for s in header_symbols() if not hasattr(L, s)]
+    assert not missing, missing
+    out = subprocess.check_output(["nm", "-D", "--defined-only", capi.lib_path()], text=True)
+    exported = set(re.findall(r" T (floam_[a-z0-9_]+)", out))
+    assert set(header_symbols()) <= exported
+
+
+def test_library_is_built_for_sm_100a_only(capi):
+    capi.lib()
+    out = subprocess.check_output(["cuobjdump", "--list-elf", capi.lib_path()], text=True)
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_defaults_and_loss_strings(capi):
+    p = capi.default_params()
+    # code defaults of src/laserProcessingNode.cpp:175-179 and src/odomEstimationNode.cpp:328-330
+    assert (p.num_lines, p.scan_period, p.max_distance, p.min_distance, p.map_resolution) == (64, 0.1, 60.0, 2.0, 0.4)
+    L = capi.lib()
+    assert L.floam_loss_from_string(b"Huber") == capi.LOSS_HUBER          # lower-cased like src/odomEstimationClass.cpp:23
+    assert L.floam_loss_from_string(b"Cauchy") == capi.LOSS_TRIVIAL       # Q1: "cauchy" leaves loss_function = nullptr
+    assert L.floam_loss_from_string(b"anything") == capi.LOSS_TRIVIAL
+    assert capi.status_string(capi.NO_IMU) == "no imu data"
+
+
+def test_point_layouts(capi):
+    # vel_point::PointXYZIRT (include/lidar.h:14-32) and pcl::PointXYZI are 32 bytes with intensity @16, ring @20, time @24
+    assert capi.POINT_IRT.itemsize == 32 and capi.POINT_I.itemsize == 32
+    assert capi.POINT_IRT.fields["intensity"][1] == 16 and capi.POINT_IRT.fields["ring"][1] == 20 and capi.POINT_IRT.fields["time"][1] == 24
+    assert capi.POINT_I.fields["intensity"][1] == 16
+
+
+def test_no_cpu_fallback_without_device(capi):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible")
+    with pytest.raises(capi.FloamError) as e:
+        capi.Context()
+    assert e.value.status == capi.ERR_NO_DEVICE
+
+
+def test_product_never_touches_the_oracle():
+    for base, _, files in os.walk(os.path.join(ROOT, "floam_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                txt = open(os.path.join(base, f), errors="ignore").read()
+                assert "pyoracle" not in txt and "floam_oracle" not in txt and "oracle/" not in txt.replace("touches oracle/", ""), os.path.join(base, f)

@@ -1,0 +1,448 @@
+"""GPU parity tests: every stage of the CUDA path, called through the C ABI (floam_b200/capi.py -> libfloam_b200.so), against the
+CPU oracle on identical seeded inputs and against the committed golden vectors; full-size runs are checked through
+size-independent properties.  Bars (BASELINE.json north_star): feature selections and kNN ids bit-exact, voxel centroids
+bit-exact (same summation order), pose within 1e-4 m / 1e-4 rad per frame (in practice ~1e-12 against the total-order oracle)."""
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+from conftest import SMALL, xyzi
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+LINES = {"vlp16": 16, "hdl64": 64, "os1-128": 128}
+
+
+def crc(a):
+    return zlib.crc32(np.ascontiguousarray(a).tobytes()) & 0xffffffff
+
+
+@pytest.fixture(scope="module")
+def ctxs(capi):
+    made = {}
+
+    def get(num_lines=16, **kw):
+        key = (num_lines, tuple(sorted(kw.items())))
+        if key not in made:
+            p = dict(SMALL); p.update(kw)
+            made[key] = capi.Context(num_lines=num_lines, **p)
+        return made[key]
+    yield get
+    for c in made.values():
+        c.close()
+
+
+def fresh(capi, num_lines, **kw):
+    p = dict(SMALL); p.update(kw)
+    return capi.Context(num_lines=num_lines, **p)
+
+
+# ------------------------------------------------------------------------------------------------ feature extraction ----
+@pytest.mark.parametrize("sensor", ["vlp16", "hdl64", "os1-128"])
+def test_feature_ids_bit_exact(capi, po, sequences, ctxs, sensor):
+    seq, scans, off = sequences(sensor, 2)
+    ctx = ctxs(LINES[sensor])
+    for f in range(2):
+        s = scans[off[f]:off[f + 1]]
+        e, sf, es, ss = ctx.feature_extract(s, with_src=True)
+        oe, osf, oes, oss, ties = po.feature_extract(s, LINES[sensor], 2.0, 60.0, total_order=True)
+        assert ties == 0
+        assert np.array_equal(es, oes) and np.array_equal(ss, oss)
+        assert e.tobytes() == oe.tobytes() and sf.tobytes() == osf.tobytes()
+
+
+def test_feature_matches_reference_faithful_sort(capi, po, sequences, ctxs):
+    # std::sort (unstable, Q8) and the (value, id) total order agree whenever there are no exact curvature ties
+    seq, scans, off = sequences("hdl64", 1)
+    s = scans[off[0]:off[1]]
+    _, _, es, ss = ctxs(64).feature_extract(s, with_src=True)
+    _, _, oes, oss, ties = po.feature_extract(s, 64, 2.0, 60.0, total_order=False)
+    assert ties == 0 and np.array_equal(es, oes) and np.array_equal(ss, oss)
+
+
+def test_feature_with_exact_ties_total_order(capi, po, sequences, ctxs):
+    # sigma = 0: noise-free ranges produce exact curvature ties; the contract is the (value, id) total order
+    seq, scans, off = sequences("vlp16", 1, sigma=0.0)
+    s = scans[off[0]:off[1]]
+    _, _, es, ss = ctxs(16).feature_extract(s, with_src=True)
+    _, _, oes, oss, _ = po.feature_extract(s, 16, 2.0, 60.0, total_order=True)
+    assert np.array_equal(es, oes) and np.array_equal(ss, oss)
+
+
+def test_feature_edge_cases(capi, po, ctxs):
+    ctx = ctxs(16)
+    e, s = ctx.feature_extract(np.zeros(0, capi.POINT_IRT))
+    assert len(e) == 0 and len(s) == 0
+    rng = np.random.default_rng(0)
+    # ragged rings: sizes around the 131-point rule and the sector arithmetic, some rings empty
+    sizes = [0, 1, 130, 131, 136, 137, 600, 1233, 2100, 17, 131, 400, 0, 905, 3000, 132]
+    parts = []
+    for ring, n in enumerate(sizes):
+        p = np.zeros(n, capi.POINT_IRT)
+        az = np.sort(rng.uniform(-np.pi, np.pi, n)); r = 8 + 4 * rng.random(n) * (rng.random(n) < 0.1) + 0.01 * rng.standard_normal(n)
+        p["x"] = r * np.cos(az); p["y"] = r * np.sin(az); p["z"] = 0.2 * ring; p["ring"] = ring; p["pad0"] = 1; p["intensity"] = rng.random(n)
+        p["time"] = np.linspace(0, 0.1, n, endpoint=False)
+        parts.append(p)
+    pts = np.concatenate(parts)
+    order = np.argsort(np.concatenate([np.arange(n) * 16 + ring for ring, n in enumerate(sizes)]), kind="stable")   # firing order: azimuth-major
+    pts = pts[order]
+    _, _, es, ss = ctx.feature_extract(pts, with_src=True)
+    _, _, oes, oss, _ = po.feature_extract(pts, 16, 2.0, 60.0, total_order=True)
+    assert np.array_equal(es, oes) and np.array_equal(ss, oss)
+    # rings above num_lines and points outside the range gate are ignored like the reference
+    pts2 = pts.copy(); pts2["ring"][::7] = 40; pts2["x"][::11] *= 100
+    _, _, es, ss = ctx.feature_extract(pts2, with_src=True)
+    _, _, oes, oss, _ = po.feature_extract(pts2, 16, 2.0, 60.0, total_order=True)
+    assert np.array_equal(es, oes) and np.array_equal(ss, oss)
+
+
+def test_feature_rejects_nonfinite_input(capi, sequences, ctxs):
+    seq, scans, off = sequences("vlp16", 1)
+    s = scans[off[0]:off[1]].copy(); s["x"][100] = np.nan
+    with pytest.raises(capi.FloamError) as e:
+        ctxs(16).feature_extract(s)
+    assert e.value.status == capi.ERR_NONFINITE     # Q9: undefined in the reference, flagged here
+
+
+def test_feature_properties_full_size(capi, sequences, ctxs):
+    seq, scans, off = sequences("os1-128", 1)
+    s = scans[off[0]:off[1]]
+    e, sf, es, ss = ctxs(128).feature_extract(s, with_src=True)
+    assert len(set(es.tolist()) & set(ss.tolist())) == 0 and len(np.unique(es)) == len(es) and len(np.unique(ss)) == len(ss)
+    assert len(es) <= 128 * 6 * 20
+    assert np.array_equal(xyzi(e), xyzi(s[es])) and np.array_equal(xyzi(sf), xyzi(s[ss]))
+    assert np.array_equal(e["ring"], s["ring"][es]) and np.array_equal(e["time"], s["time"][es])
+
+
+# ------------------------------------------------------------------------------------------------ voxel / crop ----------
+def cloud(capi, rng, n, lo=(-40, -40, -2), hi=(40, 40, 6)):
+    p = np.zeros(n, capi.POINT_I)
+    p["x"] = rng.uniform(lo[0], hi[0], n); p["y"] = rng.uniform(lo[1], hi[1], n); p["z"] = rng.uniform(lo[2], hi[2], n)
+    p["intensity"] = rng.random(n); p["pad0"] = 1
+    return p
+
+
+@pytest.mark.parametrize("n,leaf", [(0, 0.4), (1, 0.4), (7, 0.8), (5000, 0.4), (200000, 0.2), (200000, 0.8), (1500000, 0.4)])
+def test_voxel_grid_bit_exact(capi, po, ctxs, n, leaf):
+    pts = cloud(capi, np.random.default_rng(n + 1), n)
+    g = ctxs(16).voxel_grid(pts, leaf)
+    o, _ = po.voxel_grid(pts, leaf, total_order=True)
+    assert len(g) == len(o) and np.array_equal(xyzi(g), xyzi(o))
+
+
+def test_voxel_grid_duplicates_and_negative_coordinates(capi, po, ctxs):
+    rng = np.random.default_rng(5)
+    pts = cloud(capi, rng, 3000, lo=(-3, -3, -3), hi=(3, 3, 3))
+    pts = np.concatenate([pts, pts[:500], pts[:500]])
+    g = ctxs(16).voxel_grid(pts, 0.4); o, _ = po.voxel_grid(pts, 0.4, total_order=True)
+    assert np.array_equal(xyzi(g), xyzi(o))
+
+
+def test_voxel_grid_passthrough_q13(capi, po, ctxs):
+    pts = cloud(capi, np.random.default_rng(6), 2000, lo=(-500, -500, -500), hi=(500, 500, 500))
+    g = ctxs(16).voxel_grid(pts, 0.1); o, passthrough = po.voxel_grid(pts, 0.1, total_order=True)
+    assert passthrough and np.array_equal(xyzi(g), xyzi(o)) and np.array_equal(xyzi(g), xyzi(pts))
+
+
+def test_voxel_grid_idempotent_full_size(capi, sequences, ctxs, synth):
+    seq, scans, off = sequences("hdl64", 1)
+    ctx = ctxs(64)
+    _, sf = ctx.feature_extract(scans[off[0]:off[1]])
+    a = ctx.voxel_grid(synth.to_xyzi(sf), 0.8)
+    b = ctx.voxel_grid(a, 0.8)
+    # a centroid stays inside its voxel, so filtering again neither merges nor reorders anything
+    assert len(a) == len(b) and np.allclose(xyzi(a), xyzi(b), atol=1e-6)
+    keys = np.floor(xyzi(a)[:, :3] * np.float32(1 / np.float32(0.8))).astype(np.int64)
+    order = np.lexsort((keys[:, 0], keys[:, 1], keys[:, 2]))
+    assert np.array_equal(order, np.arange(len(a)))             # output sorted by (kz, ky, kx)
+
+
+@pytest.mark.parametrize("n", [0, 1, 4097, 300000])
+def test_crop_box_bit_exact(capi, po, ctxs, n):
+    pts = cloud(capi, np.random.default_rng(n + 3), n)
+    mn = np.array([-10, -20, -1], np.float32); mx = np.array([30, 15, 3], np.float32)
+    if n:
+        pts["x"][0] = mn[0]; pts["y"][0] = mx[1]     # on the boundary: kept (inclusive)
+    g = ctxs(16).crop_box(pts, mn, mx); o = po.crop_box(pts, mn, mx)
+    assert len(g) == len(o) and np.array_equal(xyzi(g), xyzi(o))
+
+
+# ------------------------------------------------------------------------------------------------ kNN -------------------
+def test_knn_ids_bit_exact_on_scan_data(capi, po, sequences, ctxs, synth):
+    seq, scans, off = sequences("hdl64", 2)
+    ctx = ctxs(64)
+    _, s0 = ctx.feature_extract(scans[off[0]:off[1]]); _, s1 = ctx.feature_extract(scans[off[1]:off[2]])
+    m = synth.to_xyzi(s0); q = ctx.voxel_grid(synth.to_xyzi(s1), 0.8)
+    ids, d2 = ctx.knn5(m, q)
+    oids, od2 = po.knn(m, q, 5, use_kdtree=True)      # FLANN-style kd-tree restatement
+    near = od2[:, 4] < 1.0
+    assert near.sum() > 1000
+    assert np.array_equal(ids[near], oids[near]) and np.array_equal(d2[near], od2[near])
+    assert (ids[~near] == -1).all()
+
+
+def test_knn_random_clouds_ties_and_small_maps(capi, po, ctxs):
+    ctx = ctxs(16)
+    rng = np.random.default_rng(9)
+    m = cloud(capi, rng, 50000, lo=(-15, -15, -2), hi=(15, 15, 4)); q = cloud(capi, rng, 5000, lo=(-17, -17, -3), hi=(17, 17, 5))
+    m = np.concatenate([m, m[:2000]])                 # exact duplicates: ties must resolve by (distance, index)
+    ids, d2 = ctx.knn5(m, q); oids, od2 = po.knn(m, q, 5, use_kdtree=False)
+    near = od2[:, 4] < 1.0
+    assert np.array_equal(ids[near], oids[near]) and np.array_equal(d2[near], od2[near]) and (ids[~near] == -1).all()
+    assert np.all(np.diff(d2[near], axis=1) >= 0)
+    # fewer than 5 map points: nothing can be accepted
+    ids, _ = ctx.knn5(m[:3], q[:10])
+    assert (ids == -1).all()
+    # far-away queries (outside the grid) and huge coordinates
+    q2 = q[:8].copy(); q2["x"] += 1e6
+    ids, _ = ctx.knn5(m, q2)
+    assert (ids == -1).all()
+
+
+def test_knn_dense_map_stress(capi, po, ctxs):
+    # configs[3]-shaped: >= 1M-point map (0.2 m surf leaf density), queries checked against brute force on a sample
+    ctx = ctxs(16)
+    rng = np.random.default_rng(10)
+    m = cloud(capi, rng, 1200000, lo=(-60, -60, -1), hi=(60, 60, 3))
+    q = cloud(capi, rng, 20000, lo=(-60, -60, -1), hi=(60, 60, 3))
+    ids, d2 = ctx.knn5(m, q)
+    sample = rng.choice(len(q), 300, replace=False)
+    oids, od2 = po.knn(m, q[sample], 5, use_kdtree=True)
+    near = od2[:, 4] < 1.0
+    assert near.all()
+    assert np.array_equal(ids[sample], oids) and np.array_equal(d2[sample], od2)
+
+
+# ------------------------------------------------------------------------------------------------ odometry stages -------
+def prepare_state(capi, po, synth, sequences, sensor, loss):
+    """Both sides get the same map / pose state and the same next frame; returns (ctx, oracle, edge, surf)."""
+    seq, scans, off = sequences(sensor, 6)
+    nl = LINES[sensor]
+    feats = [po.feature_extract(scans[off[f]:off[f + 1]], nl, 2.0, 60.0, total_order=True)[:2] for f in range(6)]
+    warm = po.Odom(num_lines=nl, loss=loss, total_order=True, use_kdtree=False)
+    warm.init_map(synth.to_xyzi(feats[0][0]), synth.to_xyzi(feats[0][1]))
+    for f in range(1, 5):
+        warm.update(feats[f][0].copy(), feats[f][1].copy(), False)
+    em, sm = warm.get_map(); T, L, _, oc = warm.get()
+    orc = po.Odom(num_lines=nl, loss=loss, total_order=True, use_kdtree=False)
+    orc.set_map(em, sm); orc.set_state(T, L, oc)
+    ctx = fresh(capi, nl, loss=loss)
+    ctx.odom_set_map(em, sm); ctx.odom_set_state(T, L, oc)
+    return ctx, orc, synth.to_xyzi(feats[5][0]), synth.to_xyzi(feats[5][1])
+
+
+@pytest.mark.parametrize("sensor,loss", [("vlp16", "cauchy"), ("vlp16", "huber"), ("hdl64", "cauchy")])
+def test_update_stage_parity(capi, po, synth, sequences, sensor, loss):
+    ctx, orc, e, s = prepare_state(capi, po, synth, sequences, sensor, loss)
+    pose = ctx.odom_update_xyzi(e, s, capi.VANILLA)
+    opose = orc.update_xyzi(e, s, 0)
+    d, od = ctx.debug(), orc.debug()
+    # downsampled clouds: same voxel set / order, bit-equal centroids
+    assert np.array_equal(xyzi(d["ds_edge"]), xyzi(od["ds_edge"])) and np.array_equal(xyzi(d["ds_surf"]), xyzi(od["ds_surf"]))
+    assert d["outer_iterations"] == od["outer_iterations"] and d["keyframe"] == od["keyframe"]
+    # kNN ids of the last outer iteration, bit-exact wherever the reference uses them (d5^2 < 1)
+    for k in ("edge", "surf"):
+        near = od[k + "_d2"][:, 4] < 1.0
+        assert np.array_equal(d[k + "_knn"][near], od[k + "_knn"][near]) and np.array_equal(d[k + "_d2"][near], od[k + "_d2"][near])
+        assert (d[k + "_knn"][~near] == -1).all()
+        assert np.array_equal(d[k + "_ok"], od[k + "_ok"])
+    # fit parameters (edge: a, b ; surf: unit normal, d) of the accepted correspondences
+    assert d["residuals"].shape == od["residuals"].shape
+    assert np.allclose(d["residuals"], od["residuals"], rtol=1e-12, atol=1e-12)
+    # normal equations at the start of the last solve and the LM bookkeeping
+    assert np.allclose(d["lm"]["H0"], od["lm"]["H0"], rtol=1e-10, atol=1e-9) and np.allclose(d["lm"]["g0"], od["lm"]["g0"], rtol=1e-9, atol=1e-9)
+    for k in ("iterations", "accepted", "termination"):
+        assert d["lm"][k] == od["lm"][k]
+    assert abs(d["lm"]["initial_cost"] - od["lm"]["initial_cost"]) <= 1e-10 * max(1.0, od["lm"]["initial_cost"])
+    assert np.abs(pose - opose).max() < 1e-9
+    # the keyframe map update: same maps, bit for bit
+    ge, gs = ctx.odom_get_map(); oe, os_ = orc.get_map()
+    assert np.array_equal(xyzi(ge), xyzi(oe)) and np.array_equal(xyzi(gs), xyzi(os_))
+    T, v = ctx.odom_get(); oT, _, ov, _ = orc.get()
+    assert np.allclose(T, oT, atol=1e-9) and np.allclose(v, ov, atol=1e-8)
+    ctx.close()
+
+
+def test_update_with_too_small_map_skips_the_solve(capi, po, ctxs, synth, sequences):
+    seq, scans, off = sequences("vlp16", 2)
+    e, s = po.feature_extract(scans[off[1]:off[2]], 16, 2.0, 60.0)[:2]
+    ctx = fresh(capi, 16); orc = po.Odom(num_lines=16, total_order=True, use_kdtree=False)
+    tiny_e, tiny_s = synth.to_xyzi(e[:10]), synth.to_xyzi(s[:50])     # not (> 10 and > 50): "not enough points in map to associate"
+    ctx.odom_init_map(tiny_e, tiny_s); orc.init_map(tiny_e, tiny_s)
+    pose = ctx.odom_update(e.copy(), s.copy(), False); opose = orc.update(e.copy(), s.copy(), False)
+    assert np.array_equal(pose, opose) and ctx.debug()["outer_iterations"] == 0 and ctx.debug()["skip_solve"]
+    ge, gs = ctx.odom_get_map(); oe, os_ = orc.get_map()
+    assert np.array_equal(xyzi(ge), xyzi(oe)) and np.array_equal(xyzi(gs), xyzi(os_))   # the first call is a keyframe: map still grows
+    ctx.close()
+
+
+def test_empty_feature_clouds(capi, po, synth, sequences):
+    ctx, orc, e, s = prepare_state(capi, po, synth, sequences, "vlp16", "cauchy")
+    z = np.zeros(0, capi.POINT_I)
+    pose = ctx.odom_update_xyzi(z, z, capi.VANILLA); opose = orc.update_xyzi(z, z, 0)
+    assert np.allclose(pose, opose, atol=1e-12)
+    ctx.close()
+
+
+# ------------------------------------------------------------------------------------------------ sequences -------------
+def run_both(capi, po, synth, scans, off, nl, loss, deskew, frames, total_order=True, use_kdtree=False, **kw):
+    ctx = fresh(capi, nl, loss=loss, **kw)
+    orc = po.Odom(num_lines=nl, loss=loss, total_order=total_order, use_kdtree=use_kdtree, map_resolution=kw.get("map_resolution", 0.4))
+    P, O = [], []
+    for f in range(frames):
+        s = scans[off[f]:off[f + 1]]
+        P.append(ctx.process_scan(s, deskew))
+        e, sf = po.feature_extract(s, nl, 2.0, 60.0, total_order=total_order)[:2]
+        if f == 0:
+            orc.init_map(synth.to_xyzi(e), synth.to_xyzi(sf)); O.append(np.array([0, 0, 0, 1, 0, 0, 0.0]))
+        else:
+            O.append(orc.update(e, sf, deskew))
+    return ctx, orc, np.array(P), np.array(O)
+
+
+@pytest.mark.parametrize("sensor,loss,deskew,frames", [("vlp16", "cauchy", False, 30), ("vlp16", "huber", True, 16), ("hdl64", "cauchy", False, 14),
+                                                       ("hdl64", "huber", True, 8)])
+def test_sequence_pose_parity(capi, po, synth, sequences, sensor, loss, deskew, frames):
+    seq, scans, off = sequences(sensor, frames, distort=deskew)
+    ctx, orc, P, O = run_both(capi, po, synth, scans, off, LINES[sensor], loss, deskew, frames)
+    assert np.abs(P - O).max() < 1e-8                    # bar: 1e-4 m / 1e-4 rad per frame
+    ge, gs = ctx.odom_get_map(); oe, os_ = orc.get_map()
+    assert len(ge) == len(oe) and len(gs) == len(os_)
+    assert np.allclose(xyzi(ge), xyzi(oe), atol=1e-5) and np.allclose(xyzi(gs), xyzi(os_), atol=1e-5)
+    ctx.close()
+
+
+def test_sequence_against_reference_faithful_oracle(capi, po, synth, sequences):
+    # std::sort voxel order + FLANN-style kd-tree (what the real PCL does) vs the CUDA path's total orders: per-frame pose tolerance
+    seq, scans, off = sequences("vlp16", 20)
+    ctx, orc, P, O = run_both(capi, po, synth, scans, off, 16, "cauchy", False, 20, total_order=False, use_kdtree=True)
+    assert np.abs(P[:, 4:] - O[:, 4:]).max() < 1e-4 and np.abs(P[:, :4] - O[:, :4]).max() < 1e-4
+    gt = [seq.pose(0.1 * f) for f in range(20)]
+    assert abs(synth.ate(P, gt)[0] - synth.ate(O, gt)[0]) < 0.01      # ATE within 1 cm of the oracle's
+    ctx.close()
+
+
+def test_fine_map_resolution_sequence(capi, po, synth, sequences):
+    # launch-file resolution 0.1 (surf leaf 0.2): denser maps and queries
+    seq, scans, off = sequences("vlp16", 8)
+    ctx, orc, P, O = run_both(capi, po, synth, scans, off, 16, "cauchy", False, 8, map_resolution=0.1)
+    assert np.abs(P - O).max() < 1e-8
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", ["vlp16_vanilla.npz", "vlp16_deskew_huber.npz", "hdl64_vanilla.npz"])
+def test_golden_vectors(capi, synth, name):
+    g = np.load(os.path.join(GOLD, name))
+    sensor = str(g["sensor"]); frames = int(g["frames"])
+    seq = synth.Sequence(sensor, seed=0, distort=bool(g["distort"]))
+    scans, off = seq.scans(0, frames)
+    ctx = fresh(capi, seq.num_lines, loss=str(g["loss"]), map_resolution=float(g["map_resolution"]))
+    for f in range(frames):
+        s = scans[off[f]:off[f + 1]]
+        assert crc(s) == int(g["scan_crc"][f])
+        pose = ctx.process_scan(s, bool(g["deskew"]))
+        es = ctx.debug_fetch(capi.DBG_FEATURE_SRC_EDGE, np.int32); ss = ctx.debug_fetch(capi.DBG_FEATURE_SRC_SURF, np.int32)
+        assert crc(es) == int(g["edge_crc"][f]) and crc(ss) == int(g["surf_crc"][f])
+        if f == 0:
+            assert np.array_equal(es, g["edge_src_0"])
+        assert np.abs(pose - g["poses"][f]).max() < 1e-8
+        assert ctx.odom_map_sizes() == tuple(g["map_sizes"][f])
+    ctx.close()
+
+
+def test_all_entry_paths_give_identical_poses(capi, synth, sequences):
+    # process_scan, submit/wait pipelining, staged per-frame, staged replay, graphs off: the same kernels, bit-identical poses
+    seq, scans, off = sequences("vlp16", 16)
+    def per_frame(graphs):
+        ctx = fresh(capi, 16); ctx.set_graphs(graphs)
+        P = np.array([ctx.process_scan(scans[off[f]:off[f + 1]]) for f in range(16)]); n = ctx.launch_count(); ctx.close()
+        return P, n
+    A, launches_a = per_frame(True)
+    B, launches_b = per_frame(False)
+    assert np.array_equal(A, B) and launches_a == launches_b and launches_a > 0
+    ctx = fresh(capi, 16); ctx.stage_scans(scans, off)
+    C, ms = ctx.replay_staged(0, 16); ctx.close()
+    assert np.array_equal(A, C) and ms > 0
+    ctx = fresh(capi, 16); ctx.stage_scans(scans, off)
+    D = np.array([ctx.process_staged(f) for f in range(16)]); ctx.close()
+    assert np.array_equal(A, D)
+    ctx = fresh(capi, 16)
+    bufs = [capi.PinnedBuffer(seq.max_points) for _ in range(3)]
+    E = []; pending = 0
+    for f in range(16):
+        n = int(off[f + 1] - off[f]); bufs[f % 3].array[:n] = scans[off[f]:off[f + 1]]
+        if pending == 2:
+            E.append(ctx.process_wait()); pending -= 1
+        ctx.process_submit(bufs[f % 3].array[:n], n); pending += 1
+    while pending:
+        E.append(ctx.process_wait()); pending -= 1
+    ctx.close()
+    assert np.array_equal(A, np.array(E))
+
+
+def test_two_contexts_are_independent_replicas(capi, sequences):
+    seq, scans, off = sequences("vlp16", 8)
+    a, b = fresh(capi, 16), fresh(capi, 16)
+    for f in range(8):
+        s = scans[off[f]:off[f + 1]]
+        pa = a.process_scan(s); pb = b.process_scan(s)
+        assert np.array_equal(pa, pb)
+    a.close(); b.close()
+
+
+def test_kernel_timing_reports_every_frame_kernel(capi, sequences):
+    seq, scans, off = sequences("vlp16", 6)
+    ctx = fresh(capi, 16)
+    for f in range(3):
+        ctx.process_scan(scans[off[f]:off[f + 1]])
+    ctx.set_kernel_timing(True)
+    P = [ctx.process_scan(scans[off[f]:off[f + 1]]) for f in range(3, 6)]
+    t = ctx.kernel_timing(); ctx.set_kernel_timing(False)
+    for k in ("ring_count", "sector", "assoc_eval", "cand_eval", "radix_scatter", "voxel_reduce", "finish"):
+        assert k in t and t[k][0] > 0
+    ctx.close()
+
+
+# ------------------------------------------------------------------------------------------------ IMU deskew ------------
+def test_deskew_align_parity(capi, po, synth):
+    seq = synth.Sequence("vlp16", seed=1, distort=True)
+    ext = po.euler2quat(0, 0, 180)               # src/laserProcessingNode.cpp:196
+    ctx = fresh(capi, 16); imu = po.Imu()
+    for k in range(-40, 120):
+        t = 1000.0 + 0.005 * k
+        q = seq.imu(t - 1000.0 if t >= 1000.0 else 0.0)
+        ctx.imu_push(t, q); imu.add(t, q)
+    assert ctx.imu_size() == imu.size()
+    for f in range(3):
+        a = seq.scan(f); b = a.copy()
+        stamp = int((1000.0 + 0.1 * f) * 1e6)
+        rc, st = ctx.deskew_align(a, stamp, ext); orc, ost = imu.deskew_align(b, stamp, ext)
+        assert (rc == capi.OK) == (orc == 0) and st == ost
+        assert rc == capi.OK
+        for k in ("x", "y", "z", "time", "intensity", "ring"):
+            assert np.array_equal(a[k], b[k]), k
+    # a scan outside the IMU coverage: Compensate returns false, only the time re-centring is applied
+    a = seq.scan(3); b = a.copy()
+    rc, st = ctx.deskew_align(a, int(2000.0 * 1e6), ext); orc, ost = imu.deskew_align(b, int(2000.0 * 1e6), ext)
+    assert rc == capi.NO_IMU and orc == 1 and st == ost
+    assert np.array_equal(a["x"], b["x"]) and np.array_equal(a["time"], b["time"])
+    for t in (1000.0121, 999.0, 1000.3, 5000.0):
+        ok, q = ctx.imu_get(t); ook, oq = imu.get(t)
+        assert ok == ook and (not ok or np.array_equal(q, oq))
+    ctx.close()
+
+
+# ------------------------------------------------------------------------------------------------ LaserMappingClass -----
+def test_mapping_parity(capi, po, synth, sequences):
+    seq, scans, off = sequences("vlp16", 6)
+    ctx = fresh(capi, 16, map_resolution=0.4); mp = po.Mapping(map_resolution=0.4, total_order=True)
+    for f in range(6):
+        pts = synth.to_xyzi(scans[off[f]:off[f + 1]])
+        T = seq.pose(0.1 * f * 40)           # widely spaced poses: the 5x5x5 block moves across 50 m cell boundaries
+        ctx.mapping_update(pts, T); mp.update(pts, T)
+        g = ctx.mapping_get_map(); o = mp.get_map()
+        assert len(g) == len(o)
+        assert np.array_equal(xyzi(g), xyzi(o))
+    ctx.close()
