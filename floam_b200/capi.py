@@ -35,7 +35,8 @@ SYMBOLS = [
     "floam_odom_get_map", "floam_odom_set_state", "floam_odom_get_state", "floam_odom_set_map", "floam_process_scan", "floam_process_submit",
     "floam_process_wait", "floam_stage_scans", "floam_process_staged", "floam_mapping_update", "floam_mapping_get_map", "floam_voxel_grid",
     "floam_crop_box", "floam_knn5", "floam_debug_fetch", "floam_launch_count", "floam_last_frame_ms", "floam_replay_staged",
-    "floam_set_kernel_timing", "floam_kernel_slots", "floam_kernel_name", "floam_kernel_timing",
+    "floam_set_kernel_timing", "floam_kernel_slots", "floam_kernel_name", "floam_kernel_timing", "floam_deskew_align_ex",
+    "floam_compensate_velocity",
 ]
 
 _lib = None
@@ -156,6 +157,17 @@ class Context:
         assert pts.dtype == POINT_IRT and pts.flags.c_contiguous
         st = C.c_uint64(int(stamp_us)); ex = np.ascontiguousarray(extr_xyzw, np.float64)
         rc = _check(lib().floam_deskew_align(self.h, _p(pts), len(pts), C.byref(st), _p(ex)), "floam_deskew_align", allow=(NO_IMU,))
+        return rc, st.value
+
+    def compensate_velocity(self, pts, v):
+        assert pts.dtype == POINT_IRT and pts.flags.c_contiguous
+        v = np.ascontiguousarray(v, np.float64)
+        _check(lib().floam_compensate_velocity(self.h, _p(pts), len(pts), _p(v)), "floam_compensate_velocity")
+
+    def deskew_align_ex(self, pts, stamp_us, extr_xyzw, flags):
+        assert pts.dtype == POINT_IRT and pts.flags.c_contiguous
+        st = C.c_uint64(int(stamp_us)); ex = np.ascontiguousarray(extr_xyzw, np.float64)
+        rc = _check(lib().floam_deskew_align_ex(self.h, _p(pts), len(pts), C.byref(st), _p(ex), int(flags)), "floam_deskew_align_ex", allow=(NO_IMU,))
         return rc, st.value
 
     # ---- feature extraction ----

@@ -277,6 +277,7 @@ int floam_create(const floam_params* params, int device, floam_ctx** out) {
     if (rc) return fail(rc);
   }
   if (cudaStreamSynchronize(c->stream) != cudaSuccess) return fail(FLOAM_ERR_CUDA);
+  c->launches_base = g_launches;
   *out = c;
   return FLOAM_OK;
 }
@@ -330,12 +331,29 @@ int floam_imu_size(floam_ctx* c, int* n) {
 }
 
 int floam_deskew_align(floam_ctx* c, floam_point_xyzirt* pts, int n, uint64_t* stamp_us, const double extr_xyzw[4]) {
+  return floam_deskew_align_ex(c, pts, n, stamp_us, extr_xyzw, FLOAM_DESKEW_CENTER_TIME | FLOAM_DESKEW_COMPENSATE | FLOAM_DESKEW_ALIGN);
+}
+
+int floam_compensate_velocity(floam_ctx* c, floam_point_xyzirt* pts, int n, const double velocity[3]) {
+  if (!c || (!pts && n > 0) || n < 0 || !velocity) return FLOAM_ERR_ARG;
+  if (n > c->prm.max_scan_points) return FLOAM_ERR_CAPACITY;
+  if (n == 0) return FLOAM_OK;
+  if (set_device(c)) return FLOAM_ERR_CUDA;
+  int rc = upload_cloud(c, pts, n, c->d_scan[0], c->d_scan_n[0], 0);
+  if (rc) return rc;
+  compensate_velocity_explicit_device(c->d_scan[0], c->d_scan_n[0], n, velocity, c->stream);
+  FLOAM_CUDA_OK(cudaMemcpyAsync(pts, c->d_scan[0], (size_t)n * 32, cudaMemcpyDeviceToHost, c->stream));
+  FLOAM_CUDA_OK(cudaStreamSynchronize(c->stream));
+  return check_async("compensate_velocity");
+}
+
+int floam_deskew_align_ex(floam_ctx* c, floam_point_xyzirt* pts, int n, uint64_t* stamp_us, const double extr_xyzw[4], int flags) {
   if (!c || !pts || !stamp_us || !extr_xyzw || n < 0) return FLOAM_ERR_ARG;
   if (n > c->prm.max_scan_points) return FLOAM_ERR_CAPACITY;
   if (n == 0) return FLOAM_NO_IMU;  // front()/back() on an empty cloud is undefined in the reference
   if (set_device(c)) return FLOAM_ERR_CUDA;
   DeskewPlan plan;
-  deskew_plan(c->imu, *stamp_us, pts[0].time, pts[n - 1].time, extr_xyzw, &plan);
+  deskew_plan(c->imu, *stamp_us, pts[0].time, pts[n - 1].time, extr_xyzw, flags, &plan);
   int rc = upload_cloud(c, pts, n, c->d_scan[0], c->d_scan_n[0], 0);
   if (rc) return rc;
   rc = deskew_align_device(c->imu, plan, c->d_scan[0], c->d_scan_n[0], n, c->stream);

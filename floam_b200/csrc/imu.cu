@@ -56,18 +56,22 @@ static uint64_t sec_to_stamp(double t) {         // ros::Time(double) + pcl_conv
   return nsec / 1000ull + sec * 1000000ull;
 }
 
-void deskew_plan(const ImuDevice& imu, uint64_t stamp_us, float time_front, float time_back, const double extr[4], DeskewPlan* p) {
+void deskew_plan(const ImuDevice& imu, uint64_t stamp_us, float time_front, float time_back, const double extr[4], int flags, DeskewPlan* p) {
+  p->do_center = (flags & FLOAM_DESKEW_CENTER_TIME) ? 1 : 0;
+  p->do_compensate = (flags & FLOAM_DESKEW_COMPENSATE) ? 1 : 0;
+  p->do_align = (flags & FLOAM_DESKEW_ALIGN) ? 1 : 0;
   const double tScan = stamp_to_sec(stamp_us);
   const double tEnd = tScan + time_back;
   const double tBegin = tScan + time_front;
   const double tCenter = tBegin + (tEnd - tBegin) / 2.0;
   p->t_scan_old = tScan;
   p->t_center = tCenter;
-  p->stamp_us_new = sec_to_stamp(tCenter);
+  p->stamp_us_new = p->do_center ? sec_to_stamp(tCenter) : stamp_us;
   p->t_scan_new = stamp_to_sec(p->stamp_us_new);
   for (int k = 0; k < 4; ++k) p->extr[k] = extr[k];
   // Compensate works on the re-centred times (float store of pnt.time + tScan - tCenter)
-  const float tf = (float)((double)time_front + tScan - tCenter), tb = (float)((double)time_back + tScan - tCenter);
+  const float tf = p->do_center ? (float)((double)time_front + tScan - tCenter) : time_front;
+  const float tb = p->do_center ? (float)((double)time_back + tScan - tCenter) : time_back;
   const double t0 = (double)tf + p->t_scan_new, t1 = (double)tb + p->t_scan_new;
   p->can_compensate = (imu_time_contained(imu, t0) && imu_time_contained(imu, t1)) ? 1 : 0;
   double qi[4] = {0, 0, 0, 0};  // default sensor_msgs::Imu orientation when Get fails (:71-75)
@@ -91,9 +95,9 @@ __global__ void __launch_bounds__(kThreads) deskew_align_kernel(PointIRT* __rest
     float4* raw = reinterpret_cast<float4*>(pts + i);
     float4 a = raw[0], b = raw[1];  // b = intensity, ring|pad, time, pad
     // CenterTime: pnt.time = pnt.time + tScan - tCenter (float + double - double, float store)
-    const float t_new = (float)(((double)b.z + plan.t_scan_old) - plan.t_center);
+    const float t_new = plan.do_center ? (float)(((double)b.z + plan.t_scan_old) - plan.t_center) : b.z;
     b.z = t_new;
-    if (plan.can_compensate) {
+    if (plan.can_compensate && plan.do_compensate) {
       const double t_cur = plan.t_scan_new + (double)t_new;
       // ImuHandler::Get: sample strictly before lower_bound(t_cur); invalid -> zero quaternion
       int lo = 0, hi = n_samples;
@@ -111,12 +115,15 @@ __global__ void __launch_bounds__(kThreads) deskew_align_kernel(PointIRT* __rest
       m::quat_mul(plan.q_init_inv, q_now, q_diff);
       const m::V3 pt = m::quat_rotate(q_diff, m::V3{(double)a.x, (double)a.y, (double)a.z});
       // compensated cloud is stored as float, then pcl::transformPointCloud(Affine3d): double R*p + 0, float store
-      const double x = (double)(float)pt.x, y = (double)(float)pt.y, z = (double)(float)pt.z;
+      a.x = (float)pt.x; a.y = (float)pt.y; a.z = (float)pt.z;
+      a.w = 1.0f;
+    }
+    if (plan.can_compensate && plan.do_align) {
+      const double x = (double)a.x, y = (double)a.y, z = (double)a.z;
       const double* R = plan.R_align;
       a.x = (float)(R[0] * x + R[1] * y + R[2] * z + 0.0);
       a.y = (float)(R[3] * x + R[4] * y + R[5] * z + 0.0);
       a.z = (float)(R[6] * x + R[7] * y + R[8] * z + 0.0);
-      a.w = 1.0f;
     }
     raw[0] = a; raw[1] = b;
   }

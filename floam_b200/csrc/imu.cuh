@@ -34,10 +34,11 @@ struct DeskewPlan {       // everything the per-point kernel needs, computed on 
   double extr[4];
   double R_align[9];      // rotation matrix of Imu(t_scan_new) * extrinsics (row-major)
   int can_compensate;     // dmapping::Compensate's return value
+  int do_center, do_compensate, do_align;   // which of CenterTime / Compensate / alignment run (floam_deskew_flags)
   uint64_t stamp_us_new;
 };
 // ros::Time / pcl stamp conversions + CenterTime + the host part of Compensate (TimeContained, qInit) and of the alignment
-void deskew_plan(const ImuDevice& imu, uint64_t stamp_us, float time_front, float time_back, const double extr_xyzw[4], DeskewPlan* plan);
+void deskew_plan(const ImuDevice& imu, uint64_t stamp_us, float time_front, float time_back, const double extr_xyzw[4], int flags, DeskewPlan* plan);
 // uploads new samples (if any) and runs the fused per-point kernel in place: time re-centring always; rotation-only deskew and
 // alignment only when plan.can_compensate
 int deskew_align_device(ImuDevice& imu, const DeskewPlan& plan, PointIRT* d_pts, const int* d_n, int n_max, cudaStream_t s);

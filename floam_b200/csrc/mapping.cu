@@ -9,11 +9,13 @@
 //      accumulating in arrival order exactly like the 125 separate filters (old centroid first, then the new points),
 //   4. writes rest ++ block back.
 // getMap() (:188-200) orders cells x-major, y, z like the reference's triple loop with one more stable sort by cell id.
-// Points that fall outside the allocated 5x5x5 block make the reference index unallocated cells (undefined behaviour); here they
-// are dropped and counted in d_counts[4].
+// Points that land in a cell allocated by an earlier block but outside the current one are appended unfiltered, like the
+// reference's push_back; points in cells that were never allocated make the reference dereference a null cloud (undefined
+// behaviour) — here they are dropped and counted in d_counts[4].
 #include "mapping.cuh"
 
 #include <cmath>
+#include <vector>
 
 namespace floam {
 namespace {
@@ -40,8 +42,10 @@ inline int grid_for(int n_max) {
 __host__ __device__ inline unsigned int pack_cell(int cx, int cy, int cz) {
   return ((unsigned int)(cx + 512) << 20) | ((unsigned int)(cy + 512) << 10) | (unsigned int)(cz + 512);
 }
+constexpr int kLcPass = 125;   // allocated cell outside the current block: kept as is, not filtered this frame
+constexpr int kLcDrop = 126;   // unallocated cell: the reference would index a null cloud here
 __device__ __forceinline__ int local_cell(unsigned int packed, const BlockGeom& g) {  // 0..124 inside the block, 125 otherwise
-  if (packed == kNoCell) return 125;
+  if (packed == kNoCell) return kLcDrop;
   const int dx = (int)(packed >> 20) - 512 - g.cx + kRange, dy = (int)((packed >> 10) & 1023u) - 512 - g.cy + kRange,
             dz = (int)(packed & 1023u) - 512 - g.cz + kRange;
   if (dx < 0 || dx > 2 * kRange || dy < 0 || dy > 2 * kRange || dz < 0 || dz > 2 * kRange) return 125;
@@ -52,7 +56,7 @@ __device__ __forceinline__ int cell_coord(float v) { return (int)floor((double)v
 __global__ void __launch_bounds__(kThreads) classify_old_kernel(const unsigned int* __restrict__ cell, const int* __restrict__ counts, BlockGeom g,
                                                                  int* __restrict__ flags) {
   const int n = counts[0];
-  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) flags[i] = local_cell(cell[i], g) < 125 ? 1 : 0;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) flags[i] = local_cell(cell[i], g) < kLcPass ? 1 : 0;
 }
 
 __global__ void __launch_bounds__(kThreads) partition_kernel(const P4* __restrict__ pts, const unsigned int* __restrict__ cell, const int* __restrict__ pos,
@@ -74,7 +78,8 @@ __global__ void __launch_bounds__(kThreads) partition_kernel(const P4* __restric
 
 // pcl::transformPointCloud(pose.cast<float>()) + intensity rewrite + cell id (:158-171)
 __global__ void __launch_bounds__(kThreads) transform_new_kernel(const char* __restrict__ in, int stride, const int* __restrict__ d_nin, int* __restrict__ counts,
-                                                                  BlockGeom g, int cap, P4* __restrict__ work, unsigned int* __restrict__ work_cell) {
+                                                                  BlockGeom g, int cap, P4* __restrict__ work, unsigned int* __restrict__ work_cell,
+                                                                  const unsigned int* __restrict__ allocated, int n_allocated) {
   const int nin = *d_nin, base = counts[2];
   const bool fits = counts[1] + base + nin <= cap;
   if (fits) {
@@ -86,8 +91,15 @@ __global__ void __launch_bounds__(kThreads) transform_new_kernel(const char* __r
       const float inten = (float)fmin(1.0, fmax((double)p.z + 2.0, 0.0) / 5);
       const int cx = cell_coord(x), cy = cell_coord(y), cz = cell_coord(z);
       unsigned int pc = kNoCell;
-      if (abs(cx - g.cx) <= kRange && abs(cy - g.cy) <= kRange && abs(cz - g.cz) <= kRange) pc = pack_cell(cx, cy, cz);
-      else atomicAdd(&counts[4], 1);
+      if (abs(cx - g.cx) <= kRange && abs(cy - g.cy) <= kRange && abs(cz - g.cz) <= kRange) {
+        pc = pack_cell(cx, cy, cz);
+      } else if (abs(cx) < 512 && abs(cy) < 512 && abs(cz) < 512) {
+        const unsigned int want = pack_cell(cx, cy, cz);
+        int lo = 0, hi = n_allocated;   // sorted list of every cell some earlier block allocated
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (allocated[mid] < want) lo = mid + 1; else hi = mid; }
+        if (lo < n_allocated && allocated[lo] == want) pc = want;
+      }
+      if (pc == kNoCell) atomicAdd(&counts[4], 1);
       work[base + i] = make_float4(x, y, z, inten);
       work_cell[base + i] = pc;
     }
@@ -110,7 +122,7 @@ __global__ void __launch_bounds__(kThreads) keys1_kernel(const P4* __restrict__ 
   const int n = counts[3];
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
     unsigned int key = 0;
-    if (work_cell[i] != kNoCell) {
+    if (local_cell(work_cell[i], g) < kLcPass) {
       int kx, ky, kz;
       voxel_of(work[i], g, kx, ky, kz);
       key = (unsigned int)(kx + ky * g.DX);
@@ -127,7 +139,7 @@ __global__ void __launch_bounds__(kThreads) keys2_kernel(const P4* __restrict__ 
     const int i = vals[j];
     const int lc = local_cell(work_cell[i], g);
     int kz = 0;
-    if (lc < 125) { int kx, ky; voxel_of(work[i], g, kx, ky, kz); }
+    if (lc < kLcPass) { int kx, ky; voxel_of(work[i], g, kx, ky, kz); }
     keys[j] = (unsigned int)(kz + lc * g.DZ);
   }
 }
@@ -141,7 +153,7 @@ __global__ void __launch_bounds__(kThreads) heads_kernel(const P4* __restrict__ 
     int head = 0;
     if (c != kNoCell) {
       head = 1;
-      if (j > 0) {
+      if (j > 0 && local_cell(c, g) < kLcPass) {   // pass-through points are never merged
         const int ip = vals[j - 1];
         if (work_cell[ip] == c) {
           int ax, ay, az, bx, by, bz;
@@ -216,9 +228,14 @@ int mapping_device_init(MappingDevice& md, int cap, double map_resolution, Voxel
   md.cell_alt = (unsigned int*)alloc(actx, (size_t)md.cap * 4);
   md.work_cell = (unsigned int*)alloc(actx, (size_t)md.cap * 4);
   md.d_counts = (int*)alloc(actx, 64);
+  md.alloc_cap = 1 << 16;
+  md.d_allocated = (unsigned int*)alloc(actx, (size_t)md.alloc_cap * 4);
   md.d_nbits = md.d_counts ? md.d_counts + 8 : nullptr;
-  if (!md.pts || !md.pts_alt || !md.work || !md.cell || !md.cell_alt || !md.work_cell || !md.d_counts) return FLOAM_ERR_CUDA;
+  if (!md.pts || !md.pts_alt || !md.work || !md.cell || !md.cell_alt || !md.work_cell || !md.d_counts || !md.d_allocated) return FLOAM_ERR_CUDA;
   FLOAM_CUDA_OK(cudaMemsetAsync(md.d_counts, 0, 64, s));
+  for (int dx = -kRange; dx <= kRange; ++dx)   // LaserMappingClass::init allocates the block around the origin (:12-29)
+    for (int dy = -kRange; dy <= kRange; ++dy)
+      for (int dz = -kRange; dz <= kRange; ++dz) md.allocated.insert(pack_cell(dx, dy, dz));
   md.enabled = true;
   return FLOAM_OK;
 }
@@ -240,19 +257,30 @@ int mapping_update_device(MappingDevice& md, const void* d_in, int stride, const
   g.ky0 = (int)std::floor(((g.cy - kRange - 0.5) * kCell - 1.0) * g.inv_leaf) - 1;
   g.kz0 = (int)std::floor(((g.cz - kRange - 0.5) * kCell - 1.0) * g.inv_leaf) - 1;
   const long long D = (long long)std::ceil(span * g.inv_leaf) + 4;
-  if (D * D >= (1ll << 32) || D * 126 >= (1ll << 32)) return FLOAM_ERR_ARG;  // leaf too small for 32-bit keys
+  if (D * D >= (1ll << 32) || D * 128 >= (1ll << 32)) return FLOAM_ERR_ARG;  // leaf too small for 32-bit keys
   g.DX = (int)D;
   g.DZ = (int)D;
-  const int nbits[2] = {bits_for(D * D), bits_for(D * 126)};
+  const int nbits[2] = {bits_for(D * D), bits_for(D * 128)};
   FLOAM_CUDA_OK(cudaMemcpyAsync(md.d_nbits, nbits, 8, cudaMemcpyHostToDevice, s));
 
+  // checkPoints (:106-145): the 5x5x5 block around the sensor is allocated; remember every cell that ever was
+  const size_t before = md.allocated.size();
+  for (int dx = -kRange; dx <= kRange; ++dx)
+    for (int dy = -kRange; dy <= kRange; ++dy)
+      for (int dz = -kRange; dz <= kRange; ++dz) md.allocated.insert(pack_cell(g.cx + dx, g.cy + dy, g.cz + dz));
+  if (md.allocated.size() != before) {
+    if ((int)md.allocated.size() > md.alloc_cap) return FLOAM_ERR_CAPACITY;
+    std::vector<unsigned int> sorted(md.allocated.begin(), md.allocated.end());
+    FLOAM_CUDA_OK(cudaMemcpyAsync(md.d_allocated, sorted.data(), sorted.size() * 4, cudaMemcpyHostToDevice, s));
+    FLOAM_CUDA_OK(cudaStreamSynchronize(s));
+  }
   VoxelWorkspace& ws = *md.vws;
   int* counts = md.d_counts;
   const int gmap = grid_for(md.cap), gin = grid_for(n_max);
   FLOAM_LAUNCH(K_CLASSIFY_OLD, classify_old_kernel, gmap, kThreads, s, md.cell, counts, g, ws.flags);
   exclusive_scan_i32(ws.flags, ws.flags, counts, 0, md.cap, ws.scan, nullptr, s);
   FLOAM_LAUNCH(K_PARTITION, partition_kernel, gmap, kThreads, s, md.pts, md.cell, ws.flags, counts, md.pts_alt, md.cell_alt, md.work, md.work_cell);
-  FLOAM_LAUNCH(K_TRANSFORM_NEW, transform_new_kernel, gin, kThreads, s, (const char*)d_in, stride, d_n, counts, g, md.cap, md.work, md.work_cell);
+  FLOAM_LAUNCH(K_TRANSFORM_NEW, transform_new_kernel, gin, kThreads, s, (const char*)d_in, stride, d_n, counts, g, md.cap, md.work, md.work_cell, md.d_allocated, (int)md.allocated.size());
   FLOAM_LAUNCH(K_KEYS1, keys1_kernel, gmap, kThreads, s, md.work, md.work_cell, counts, g, ws.keys, ws.vals);
   radix_sort_pairs(ws.keys, ws.vals, counts + 3, md.d_nbits, md.cap, ws.sort, nullptr, s);
   FLOAM_LAUNCH(K_KEYS2, keys2_kernel, gmap, kThreads, s, md.work, md.work_cell, counts, g, ws.vals, ws.keys);

@@ -2,6 +2,8 @@
 // point; a frame touches the 5x5x5 block of cells around the sensor exactly like the reference's 125 in-place VoxelGrid filters.
 // See mapping.cu.
 #pragma once
+#include <set>
+
 #include "common.cuh"
 #include "voxel.cuh"
 
@@ -20,6 +22,9 @@ struct MappingDevice {
   int* vals = nullptr;
   int* d_nbits = nullptr;     // [0] bits of the (kx,ky) key, [1] bits of the (kz,cell) key
   VoxelWorkspace* vws = nullptr;
+  std::set<unsigned int> allocated;   // cells some block has allocated so far (checkPoints), host mirror
+  unsigned int* d_allocated = nullptr; // the same, sorted, on the device
+  int alloc_cap = 0;
   int cap = 0;
   float leaf = 0.4f;
   bool enabled = false;

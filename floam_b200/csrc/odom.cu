@@ -721,6 +721,18 @@ __global__ void __launch_bounds__(kThreads) compensate_velocity_kernel(PointIRT*
   }
 }
 
+__global__ void __launch_bounds__(kThreads) compensate_velocity_explicit_kernel(PointIRT* __restrict__ pts, const int* __restrict__ d_n, double vx, double vy,
+                                                                                 double vz) {
+  const int n = *d_n;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+    PointIRT* p = pts + i;
+    const double t = (double)p->time;
+    p->x = (float)((double)p->x + vx * t);
+    p->y = (float)((double)p->y + vy * t);
+    p->z = (float)((double)p->z + vz * t);
+  }
+}
+
 int* dims_ncells_ptr(GridDims* dims) { return reinterpret_cast<int*>(reinterpret_cast<char*>(dims) + offsetof(GridDims, ncells)); }
 
 void rebuild_grid(OdomDevice& od, LocalMap& map, const int* d_skip, cudaStream_t s) {
@@ -850,6 +862,10 @@ void odom_update_device(OdomDevice& od, const void* d_edge, const int* d_ne, con
 
 void compensate_velocity_device(OdomDevice& od, PointIRT* d_pts, const int* d_n, int n_max, cudaStream_t s) {
   FLOAM_LAUNCH(K_COMPENSATE_VELOCITY, compensate_velocity_kernel, grid_for(n_max), kThreads, s, d_pts, d_n, od.state);
+}
+
+void compensate_velocity_explicit_device(PointIRT* d_pts, const int* d_n, int n_max, const double v[3], cudaStream_t s) {
+  FLOAM_LAUNCH(K_COMPENSATE_VELOCITY, compensate_velocity_explicit_kernel, grid_for(n_max), kThreads, s, d_pts, d_n, v[0], v[1], v[2]);
 }
 
 void knn5_device(OdomDevice& od, LocalMap& map, const P4* d_queries, const int* d_nq, int nq_max, int* d_ids, float* d_d2, cudaStream_t s) {

@@ -93,6 +93,7 @@ void odom_update_device(OdomDevice& od, const void* d_edge, const int* d_ne, con
                         int tap, cudaStream_t s);
 // dmapping::CompensateVelocity with GetVelocity() read from the device state
 void compensate_velocity_device(OdomDevice& od, PointIRT* d_pts, const int* d_n, int n_max, cudaStream_t s);
+void compensate_velocity_explicit_device(PointIRT* d_pts, const int* d_n, int n_max, const double v[3], cudaStream_t s);
 void odom_rebuild_grids(OdomDevice& od, cudaStream_t s);
 // stand-alone exact 5-NN of raw queries against a map whose grid is built (floam_knn5)
 void knn5_device(OdomDevice& od, LocalMap& map, const P4* d_queries, const int* d_nq, int nq_max, int* d_ids, float* d_d2, cudaStream_t s);

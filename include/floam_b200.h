@@ -97,6 +97,11 @@ int floam_imu_size(floam_ctx* ctx, int* n); /* ImuHandler::size() */
  * stamp_us is the pcl header stamp (microseconds) and is re-centred like the reference. Returns FLOAM_NO_IMU when
  * Compensate would return false (points are then only time-centred). */
 int floam_deskew_align(floam_ctx* ctx, floam_point_xyzirt* pts, int n, uint64_t* stamp_us, const double extrinsics_xyzw[4]);
+/* The same pass with the three steps selectable, so that dmapping::Compensate alone (src/dataHandler.cpp:93-122) can be served. */
+enum floam_deskew_flags { FLOAM_DESKEW_CENTER_TIME = 1, FLOAM_DESKEW_COMPENSATE = 2, FLOAM_DESKEW_ALIGN = 4 };
+int floam_deskew_align_ex(floam_ctx* ctx, floam_point_xyzirt* pts, int n, uint64_t* stamp_us, const double extrinsics_xyzw[4], int flags);
+/* dmapping::CompensateVelocity (src/dataHandler.cpp:82-91), in place: p += velocity * p.time (no rotation, Q14) */
+int floam_compensate_velocity(floam_ctx* ctx, floam_point_xyzirt* pts, int n, const double velocity[3]);
 
 /* LaserProcessingClass::featureExtraction (src/laserProcessingClass.cpp:72-231). Appending is the caller's job:
  * edge/surf receive *ne / *ns points (capacities in points). */
