@@ -256,6 +256,7 @@ int floam_create(const floam_params* params, int device, floam_ctx** out) {
   c->fprm.num_lines = params->num_lines;
   feature_workspace_bind(c->fws, fmem, ns, params->num_lines);
   voxel_workspace_bind(c->vws, vmem, c->stage_cap);
+  if (voxel_workspace_arm(c->vws, c->stream)) return fail(FLOAM_ERR_CUDA);
 
   c->h_ints = (int*)host_alloc(c, 64 * sizeof(int));
   c->h_doubles = (double*)host_alloc(c, 64 * sizeof(double));

@@ -59,7 +59,7 @@ enum KernelSlot {
   K_RADIX_SCATTER,
   K_SCAN_TILES,
   K_SCAN_ADD,
-  K_VOXEL_INIT,
+  K_VOXEL_RANK,
   K_VOXEL_BBOX,
   K_VOXEL_KEYS,
   K_VOXEL_HEADS,
@@ -165,6 +165,35 @@ __device__ __forceinline__ int block_excl_scan(int v, int* smem, int* total) {
   return r;
 }
 
+// block-wide sum of one int per thread (every thread gets the result). smem: 33 ints.
+__device__ __forceinline__ int block_sum(int v, int* smem) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = warp_id(), l = lane_id(), nw = blockDim.x >> 5;
+  __syncthreads();
+  if (l == 0) smem[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    int s = (l < nw) ? smem[l] : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (l == 0) smem[32] = s;
+  }
+  __syncthreads();
+  return smem[32];
+}
+
+// Two-kernel scans: kernel 1 leaves one total per tile in tile_sums; in kernel 2 every CTA adds up the totals of the tiles before
+// it by itself (a few thousand L2-resident ints at most) instead of waiting for a serial single-CTA scan in between.
+constexpr int kScanThreads = 1024;
+constexpr int kScanItems = 4;
+constexpr int kScanTile = kScanThreads * kScanItems;
+__device__ __forceinline__ int tile_offset(const int* __restrict__ tile_sums, int tile, int* smem) {
+  int s = 0;
+  for (int t = threadIdx.x; t < tile; t += blockDim.x) s += tile_sums[t];
+  return block_sum(s, smem);
+}
+
 // ---- device-wide primitives (sort_scan.cu). All sizes are read from device memory so a frame needs no host sync. ----
 struct SortWorkspace {
   unsigned int* keys_alt;   // capacity n_max
@@ -183,7 +212,7 @@ void radix_sort_pairs(unsigned int* keys, int* vals, const int* d_n, const int* 
 void exclusive_scan_small(int* data, int n, cudaStream_t s);
 
 struct ScanWorkspace {
-  int* block_sums;  // capacity ceil(n_max / 4096) + 1
+  int* block_sums;  // one total per 4096-element tile
   int n_max;
 };
 size_t scan_workspace_bytes(int n_max);

@@ -300,6 +300,55 @@ __device__ __forceinline__ void knn5_search(const GridDims& g, const int* __rest
   }
 }
 
+// The same search by a whole warp for ONE query: the nine x-contiguous cell runs are fetched up front (lanes 0..8 load the run
+// bounds), lanes stride over the candidates of each run keeping a private top-5, and five rounds of warp arg-min over the packed
+// (distance, index) heads merge the 32 lists. Every lane returns the final set.
+__device__ __forceinline__ void knn5_search_warp(const GridDims& g, const int* __restrict__ cell_start, const float4* __restrict__ cell_pts, float qx,
+                                                 float qy, float qz, Knn5& out) {
+  const int l = lane_id();
+  Knn5 k;
+#pragma unroll
+  for (int j = 0; j < 5; ++j) { k.d[j] = FLT_MAX; k.id[j] = 0x7fffffff; }
+  const int cx = (int)floorf(qx) - g.ix0, cy = (int)floorf(qy) - g.iy0, cz = (int)floorf(qz) - g.iz0;
+  const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
+  int rb = 0, re = 0;  // lane r < 9 owns run r = (dz+1)*3 + (dy+1)
+  if (l < 9 && g.ncells != 0 && x0 <= x1) {
+    const int y = cy + (l % 3) - 1, z = cz + (l / 3) - 1;
+    if (y >= 0 && y < g.ny && z >= 0 && z < g.nz) {
+      const int row = g.nx * (y + g.ny * z);
+      rb = __ldg(cell_start + row + x0);
+      re = __ldg(cell_start + row + x1 + 1);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 9; ++r) {
+    const int b = __shfl_sync(0xffffffffu, rb, r), e = __shfl_sync(0xffffffffu, re, r);
+    for (int i = b + l; i < e; i += 32) {
+      const float4 p = __ldg(cell_pts + i);
+      const float dx = fsub(qx, p.x), dy = fsub(qy, p.y), dz = fsub(qz, p.z);
+      const float dist = fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
+      knn5_insert(k, dist, __float_as_int(p.w));
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    // distances are >= 0, so their bit patterns order like the floats; ties fall to the smaller index
+    const unsigned long long mine = ((unsigned long long)__float_as_uint(k.d[0]) << 32) | (unsigned int)k.id[0];
+    unsigned long long best = mine;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+      best = other < best ? other : best;
+    }
+    out.d[j] = __uint_as_float((unsigned int)(best >> 32));
+    out.id[j] = (int)(unsigned int)(best & 0xffffffffu);
+    if (mine == best) {  // the winner pops its head
+      k.d[0] = k.d[1]; k.id[0] = k.id[1]; k.d[1] = k.d[2]; k.id[1] = k.id[2]; k.d[2] = k.d[3]; k.id[2] = k.id[3];
+      k.d[3] = k.d[4]; k.id[3] = k.id[4]; k.d[4] = FLT_MAX; k.id[4] = 0x7fffffff;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // residuals, Jacobians and the 28-term reduction (21 H upper triangle, 6 g, cost)
 // ------------------------------------------------------------------------------------------------------------------
@@ -567,7 +616,9 @@ __global__ void __launch_bounds__(kEvalThreads) assoc_eval_kernel(PoseState* __r
   for (int k = 0; k < kLmTerms; ++k) A.v[k] = 0.0;
   int my_corr = 0;
   const size_t cs = (size_t)2 * qcap;  // stride between the planes of corr
-  for (int slot = blockIdx.x * kEvalThreads + threadIdx.x; slot < nde + nds; slot += gridDim.x * kEvalThreads) {
+  // one warp per query: the 32 lanes share the candidate scan, lane 0 fits the line / plane and evaluates the residual
+  const int warps_total = gridDim.x * (kEvalThreads / 32);
+  for (int slot = blockIdx.x * (kEvalThreads / 32) + warp_id(); slot < nde + nds; slot += warps_total) {
     const bool is_edge = slot < nde;
     const int qi = is_edge ? slot : slot - nde;
     const int out = is_edge ? qi : qcap + qi;
@@ -578,7 +629,8 @@ __global__ void __launch_bounds__(kEvalThreads) assoc_eval_kernel(PoseState* __r
     const float qx = (float)pw.x, qy = (float)pw.y, qz = (float)pw.z;
     Knn5 nn;
     const LocalMap& map = is_edge ? emap : smap;
-    knn5_search(is_edge ? ge : gs, map.cell_start, map.cell_pts, qx, qy, qz, nn);
+    knn5_search_warp(is_edge ? ge : gs, map.cell_start, map.cell_pts, qx, qy, qz, nn);
+    if (lane_id() != 0) continue;
     const bool near = nn.d[4] < 1.0f;  // pointSearchSqDis[4] < 1.0
     if (tap) {
 #pragma unroll

@@ -19,12 +19,6 @@ __device__ __forceinline__ float4 load_xyzi(const char* base, int stride, int i)
   return make_float4(a.x, a.y, a.z, in);
 }
 
-__global__ void voxel_init_kernel(unsigned int* bbox, const int* d_skip) {
-  if (d_skip && *d_skip) return;
-  if (threadIdx.x < 3) bbox[threadIdx.x] = 0xffffffffu;
-  else if (threadIdx.x < 6) bbox[threadIdx.x] = 0u;
-}
-
 __global__ void __launch_bounds__(kThreads) voxel_bbox_kernel(const char* __restrict__ in, int stride, const int* __restrict__ d_n,
                                                                unsigned int* __restrict__ bbox, const int* d_skip) {
   if (d_skip && *d_skip) return;
@@ -100,57 +94,112 @@ __global__ void __launch_bounds__(kThreads) voxel_keys_kernel(const char* __rest
   }
 }
 
-__global__ void __launch_bounds__(kThreads) voxel_heads_kernel(const unsigned int* __restrict__ keys, const int* __restrict__ d_n, int* __restrict__ flags,
-                                                                const int* d_skip) {
+// ---- after the sort: voxel runs -> output ranks -> centroids, three kernels -------------------------------------------------
+// (1) per 4096-key tile: number of run heads; (2) every tile adds up the tiles before it, ranks its heads and records where
+// each run starts; (3) one thread per voxel walks its run [head_pos[v], head_pos[v+1]) — bounds known up front, so the loads of a
+// run are independent of the loop control and pipeline.
+__device__ __forceinline__ int is_head(const unsigned int* __restrict__ keys, int i) { return (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0; }
+
+__global__ void __launch_bounds__(kScanThreads) voxel_heads_kernel(const unsigned int* __restrict__ keys, const int* __restrict__ d_n,
+                                                                   int* __restrict__ tile_sums, unsigned int* bbox, const int* d_skip) {
   if (d_skip && *d_skip) return;
   const int n = *d_n;
-  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {  // every reader of the bounding box (voxel_keys_kernel) is done: re-arm it for the next filter
+    bbox[0] = bbox[1] = bbox[2] = 0xffffffffu;
+    bbox[3] = bbox[4] = bbox[5] = 0u;
+  }
+  if (blockIdx.x * kScanTile >= n) return;
+  __shared__ int smem[33];
+  const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+  int sum = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) sum += (base + k < n) ? is_head(keys, base + k) : 0;
+  const int total = block_sum(sum, smem);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
 }
 
-__global__ void __launch_bounds__(kThreads) voxel_reduce_kernel(const char* __restrict__ in, int stride, const unsigned int* __restrict__ keys,
-                                                                 const int* __restrict__ vals, const int* __restrict__ seg, const int* __restrict__ d_n,
-                                                                 P4* __restrict__ out, int* d_nout, const int* d_skip) {
+__global__ void __launch_bounds__(kScanThreads) voxel_rank_kernel(const unsigned int* __restrict__ keys, const int* __restrict__ d_n,
+                                                                  const int* __restrict__ tile_sums, int* __restrict__ head_pos, int* d_nout, const int* d_skip) {
   if (d_skip && *d_skip) return;
   const int n = *d_n;
-  if (blockIdx.x == 0 && threadIdx.x == 0) *d_nout = (n > 0) ? seg[n] : 0;
-  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
-    const unsigned int k = keys[i];
-    if (i > 0 && keys[i - 1] == k) continue;  // not a segment head
+  if (n == 0) { if (blockIdx.x == 0 && threadIdx.x == 0) { *d_nout = 0; head_pos[0] = 0; } return; }
+  if (blockIdx.x * kScanTile >= n) return;
+  __shared__ int smem[33];
+  const int offset = tile_offset(tile_sums, blockIdx.x, smem);
+  const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+  int h[kScanItems];
+  int sum = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) { h[k] = (base + k < n) ? is_head(keys, base + k) : 0; sum += h[k]; }
+  int total;
+  int rank = block_excl_scan(sum, smem, &total) + offset;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k)
+    if (h[k]) head_pos[rank++] = base + k;
+  if (blockIdx.x == (n - 1) / kScanTile && threadIdx.x == 0) { *d_nout = offset + total; head_pos[offset + total] = n; }
+}
+
+__global__ void __launch_bounds__(kThreads) voxel_reduce_kernel(const char* __restrict__ in, int stride, const int* __restrict__ vals,
+                                                                 const int* __restrict__ head_pos, const int* __restrict__ d_nout, P4* __restrict__ out,
+                                                                 const int* d_skip) {
+  if (d_skip && *d_skip) return;
+  const int nv = *d_nout;
+  for (int v = blockIdx.x * kThreads + threadIdx.x; v < nv; v += gridDim.x * kThreads) {
+    const int b = head_pos[v], e = head_pos[v + 1];
     float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
-    int j = i;
-    do {  // CentroidPoint<PointXYZI>: float sums in run order, then / n
-      const float4 p = load_xyzi(in, stride, vals[j]);
+    for (int j = b; j < e; ++j) {  // CentroidPoint<PointXYZI>: float sums in run order (ascending input index), then / n
+      const float4 p = load_xyzi(in, stride, __ldg(vals + j));
       sx = fadd(sx, p.x); sy = fadd(sy, p.y); sz = fadd(sz, p.z); si = fadd(si, p.w);
-      ++j;
-    } while (j < n && keys[j] == k);
-    const float cnt = (float)(j - i);
-    out[seg[i]] = make_float4(__fdiv_rn(sx, cnt), __fdiv_rn(sy, cnt), __fdiv_rn(sz, cnt), __fdiv_rn(si, cnt));
+    }
+    const float cnt = (float)(e - b);
+    out[v] = make_float4(__fdiv_rn(sx, cnt), __fdiv_rn(sy, cnt), __fdiv_rn(sz, cnt), __fdiv_rn(si, cnt));
   }
 }
 
-__global__ void __launch_bounds__(kThreads) crop_flags_kernel(const P4* __restrict__ in, const int* __restrict__ d_n, const float* __restrict__ bounds,
-                                                               int* __restrict__ flags, const int* d_skip) {
-  if (d_skip && *d_skip) return;
-  const int n = *d_n;
-  const float mnx = bounds[0], mny = bounds[1], mnz = bounds[2], mxx = bounds[3], mxy = bounds[4], mxz = bounds[5];
-  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
-    const float4 p = __ldg(in + i);
-    const bool outside = (p.x < mnx || p.y < mny || p.z < mnz) || (p.x > mxx || p.y > mxy || p.z > mxz);
-    flags[i] = outside ? 0 : 1;
-  }
+// ---- CropBox: count per tile, then rank + scatter with the predicate recomputed (two kernels) -----------------------------------
+__device__ __forceinline__ int crop_keep(const float4 p, const float* __restrict__ b) {
+  const bool outside = (p.x < b[0] || p.y < b[1] || p.z < b[2]) || (p.x > b[3] || p.y > b[4] || p.z > b[5]);
+  return outside ? 0 : 1;
 }
 
-__global__ void __launch_bounds__(kThreads) crop_scatter_kernel(const P4* __restrict__ in, const int* __restrict__ d_n, const float* __restrict__ bounds,
-                                                                 const int* __restrict__ pos, P4* __restrict__ out, int* d_nout, const int* d_skip) {
+__global__ void __launch_bounds__(kScanThreads) crop_flags_kernel(const P4* __restrict__ in, const int* __restrict__ d_n, const float* __restrict__ bounds,
+                                                                  int* __restrict__ tile_sums, const int* d_skip) {
   if (d_skip && *d_skip) return;
   const int n = *d_n;
-  if (blockIdx.x == 0 && threadIdx.x == 0) *d_nout = (n > 0) ? pos[n] : 0;
-  const float mnx = bounds[0], mny = bounds[1], mnz = bounds[2], mxx = bounds[3], mxy = bounds[4], mxz = bounds[5];
-  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
-    const float4 p = __ldg(in + i);
-    const bool outside = (p.x < mnx || p.y < mny || p.z < mnz) || (p.x > mxx || p.y > mxy || p.z > mxz);
-    if (!outside) out[pos[i]] = p;
+  if (blockIdx.x * kScanTile >= n) return;
+  __shared__ int smem[33];
+  const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+  int sum = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) sum += (base + k < n) ? crop_keep(__ldg(in + base + k), bounds) : 0;
+  const int total = block_sum(sum, smem);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kScanThreads) crop_scatter_kernel(const P4* __restrict__ in, const int* __restrict__ d_n, const float* __restrict__ bounds,
+                                                                    const int* __restrict__ tile_sums, P4* __restrict__ out, int* d_nout, const int* d_skip) {
+  if (d_skip && *d_skip) return;
+  const int n = *d_n;
+  if (n == 0) { if (blockIdx.x == 0 && threadIdx.x == 0) *d_nout = 0; return; }
+  if (blockIdx.x * kScanTile >= n) return;
+  __shared__ int smem[33];
+  const int offset = tile_offset(tile_sums, blockIdx.x, smem);
+  const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+  float4 p[kScanItems];
+  int keep[kScanItems];
+  int sum = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    keep[k] = 0;
+    if (base + k < n) { p[k] = __ldg(in + base + k); keep[k] = crop_keep(p[k], bounds); }
+    sum += keep[k];
   }
+  int total;
+  int pos = block_excl_scan(sum, smem, &total) + offset;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k)
+    if (keep[k]) out[pos++] = p[k];
+  if (blockIdx.x == (n - 1) / kScanTile && threadIdx.x == 0) *d_nout = offset + total;
 }
 
 __global__ void __launch_bounds__(kThreads) repack_kernel(const char* __restrict__ in, const int* __restrict__ d_n, P4* __restrict__ out) {
@@ -184,18 +233,25 @@ void voxel_workspace_bind(VoxelWorkspace& ws, void* mem, int n_max) {
   scan_workspace_bind(ws.scan, take(scan_workspace_bytes(n_max + 1)), n_max + 1);
 }
 
+int voxel_workspace_arm(VoxelWorkspace& ws, cudaStream_t s) {
+  const unsigned int bb[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+  FLOAM_CUDA_OK(cudaMemcpyAsync(ws.bbox, bb, sizeof(bb), cudaMemcpyHostToDevice, s));
+  FLOAM_CUDA_OK(cudaStreamSynchronize(s));
+  return FLOAM_OK;
+}
+
 void voxel_grid_device(const void* d_in, int stride_bytes, const int* d_n, int n_max, float leaf, P4* d_out, int* d_nout, VoxelWorkspace& ws,
                        const int* d_skip, cudaStream_t s) {
   if (n_max > ws.n_max) n_max = ws.n_max;
   const char* in = (const char*)d_in;
   const int g = grid_for(n_max);
-  FLOAM_LAUNCH(K_VOXEL_INIT, voxel_init_kernel, 1, 32, s, ws.bbox, d_skip);
+  const int gt = (n_max + kScanTile - 1) / kScanTile;
   FLOAM_LAUNCH(K_VOXEL_BBOX, voxel_bbox_kernel, g, kThreads, s, in, stride_bytes, d_n, ws.bbox, d_skip);
   FLOAM_LAUNCH(K_VOXEL_KEYS, voxel_keys_kernel, g, kThreads, s, in, stride_bytes, d_n, leaf, ws.bbox, ws.keys, ws.vals, ws.d_nbits, ws.d_passthrough, d_skip);
   radix_sort_pairs(ws.keys, ws.vals, d_n, ws.d_nbits, n_max, ws.sort, d_skip, s);
-  FLOAM_LAUNCH(K_VOXEL_HEADS, voxel_heads_kernel, g, kThreads, s, ws.keys, d_n, ws.flags, d_skip);
-  exclusive_scan_i32(ws.flags, ws.flags, d_n, 0, n_max, ws.scan, d_skip, s);
-  FLOAM_LAUNCH(K_VOXEL_REDUCE, voxel_reduce_kernel, g, kThreads, s, in, stride_bytes, ws.keys, ws.vals, ws.flags, d_n, d_out, d_nout, d_skip);
+  FLOAM_LAUNCH(K_VOXEL_HEADS, voxel_heads_kernel, gt, kScanThreads, s, ws.keys, d_n, ws.scan.block_sums, ws.bbox, d_skip);
+  FLOAM_LAUNCH(K_VOXEL_RANK, voxel_rank_kernel, gt, kScanThreads, s, ws.keys, d_n, ws.scan.block_sums, ws.flags, d_nout, d_skip);
+  FLOAM_LAUNCH(K_VOXEL_REDUCE, voxel_reduce_kernel, g, kThreads, s, in, stride_bytes, ws.vals, ws.flags, d_nout, d_out, d_skip);
 }
 
 void repack_xyzi_device(const void* d_in32, const int* d_n, int n_max, P4* d_out, cudaStream_t s) {
@@ -205,10 +261,9 @@ void repack_xyzi_device(const void* d_in32, const int* d_n, int n_max, P4* d_out
 void crop_box_device(const P4* d_in, const int* d_n, int n_max, const float* d_bounds, P4* d_out, int* d_nout, VoxelWorkspace& ws,
                      const int* d_skip, cudaStream_t s) {
   if (n_max > ws.n_max) n_max = ws.n_max;
-  const int g = grid_for(n_max);
-  FLOAM_LAUNCH(K_CROP_FLAGS, crop_flags_kernel, g, kThreads, s, d_in, d_n, d_bounds, ws.flags, d_skip);
-  exclusive_scan_i32(ws.flags, ws.flags, d_n, 0, n_max, ws.scan, d_skip, s);
-  FLOAM_LAUNCH(K_CROP_SCATTER, crop_scatter_kernel, g, kThreads, s, d_in, d_n, d_bounds, ws.flags, d_out, d_nout, d_skip);
+  const int gt = (n_max + kScanTile - 1) / kScanTile;
+  FLOAM_LAUNCH(K_CROP_FLAGS, crop_flags_kernel, gt, kScanThreads, s, d_in, d_n, d_bounds, ws.scan.block_sums, d_skip);
+  FLOAM_LAUNCH(K_CROP_SCATTER, crop_scatter_kernel, gt, kScanThreads, s, d_in, d_n, d_bounds, ws.scan.block_sums, d_out, d_nout, d_skip);
 }
 
 }  // namespace floam

@@ -17,6 +17,8 @@ struct VoxelWorkspace {
 };
 size_t voxel_workspace_bytes(int n_max);
 void voxel_workspace_bind(VoxelWorkspace& ws, void* mem, int n_max);
+// one-time initialisation of the bounding-box accumulators (every filter re-arms them for the next one)
+int voxel_workspace_arm(VoxelWorkspace& ws, cudaStream_t s);
 
 // pcl::VoxelGrid<PointXYZI>::filter (PCL 1.8.1 semantics). Input points are read with a byte stride
 // (16 = float4 xyzi, 32 = PointXYZI / PointXYZIRT with intensity at +16). Output order = ascending voxel index; inside a
