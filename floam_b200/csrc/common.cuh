@@ -48,6 +48,7 @@ enum KernelSlot {
   K_MAP_APPEND_RAW,
   K_MAP_BUMP,
   K_PREDICT,
+  K_ASSOC_KNN,
   K_ASSOC_EVAL,
   K_CAND_EVAL,
   K_FINISH,

@@ -29,8 +29,9 @@ namespace floam {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kAssocBlocks = kNumSMs * 4;   // 592 CTAs x 128 threads, grid-stride over the query slots
-constexpr int kCandBlocks = kNumSMs;        // candidate evaluations touch 88 B per correspondence: one CTA per SM is plenty
+constexpr int kAssocBlocks = kNumSMs * 2;   // 296 CTAs x 128 threads, grid-stride over the query slots
+constexpr int kKnnBlocks = kNumSMs * 4;     // 592 CTAs x 8 warps, one warp per query, grid-stride
+constexpr int kCandBlocks = kNumSMs / 2;    // candidate evaluations touch 88 B per correspondence: 74 CTAs keep the final reduction short
 static_assert(kAssocBlocks <= 1024, "partials rows");
 
 inline int grid_for(int n_max) {
@@ -417,6 +418,12 @@ __device__ __forceinline__ void accumulate(Accum& A, double r, const double* J, 
 
 // PoseSE3Parameterization gradient projection used for gradient_max_norm: |x - Plus(x, -g)|_inf
 __device__ double gradient_max_norm(const double* x, const double* g) {
+  // Only ever compared with gradient_tolerance = 1e-10. With max|g| >= 1e-3 the projected step moves x by far more than that
+  // (quaternion part by |g_w|/4 at least; if g_w is below 4e-10 the translation part moves by |g_v| - |g_w x t| > 1e-3 - 4e-5),
+  // so the exact value (a full se3 exponential) is only worth computing for tiny gradients.
+  double gm = 0.0;
+  for (int j = 0; j < 6; ++j) gm = fmax(gm, fabs(g[j]));
+  if (gm >= 1e-3 && isfinite(gm)) return 1.0;
   double ng[6], proj[7];
   for (int j = 0; j < 6; ++j) ng[j] = -g[j];
   m::se3_plus(x, ng, proj);
@@ -594,13 +601,47 @@ __device__ bool reduce_terms(const Accum& A, double* __restrict__ partials, unsi
   return true;
 }
 
-// One outer iteration's association (:144-251) fused with the iteration-0 evaluation of ceres::Solve.
-// Slots [0, nde) are edge queries against the edge map, [nde, nde+nds) surf queries against the surf map.
+// One outer iteration's association (:144-251), in two kernels.
+// (1) assoc_knn_kernel: pointAssociateToMap + nearestKSearch(5), one WARP per query (lanes share the candidate scan).
+//     Slots [0, nde) are edge queries against the edge map, [nde, nde+nds) surf queries against the surf map.
+constexpr int kKnnThreads = 256;
+__global__ void __launch_bounds__(kKnnThreads) assoc_knn_kernel(const PoseState* __restrict__ S, const P4* __restrict__ ds_edge, const int* __restrict__ d_nde,
+                                                                 const P4* __restrict__ ds_surf, const int* __restrict__ d_nds, LocalMap emap, LocalMap smap,
+                                                                 int qcap, int* __restrict__ knn_ids, float* __restrict__ knn_d2) {
+  if (S->skip_solve) return;
+  const int nde = *d_nde, nds = *d_nds;
+  double x[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) x[k] = S->x[k];
+  const GridDims ge = *emap.dims, gs = *smap.dims;
+  const int warps_total = gridDim.x * (kKnnThreads / 32);
+  for (int slot = blockIdx.x * (kKnnThreads / 32) + warp_id(); slot < nde + nds; slot += warps_total) {
+    const bool is_edge = slot < nde;
+    const int qi = is_edge ? slot : slot - nde;
+    const int out = is_edge ? qi : qcap + qi;
+    const float4 p = __ldg((is_edge ? ds_edge : ds_surf) + qi);
+    // pointAssociateToMap :126-135: double transform, float store
+    const m::V3 pw = m::add(m::quat_rotate(x, m::V3{(double)p.x, (double)p.y, (double)p.z}), m::V3{x[4], x[5], x[6]});
+    Knn5 nn;
+    const LocalMap& map = is_edge ? emap : smap;
+    knn5_search_warp(is_edge ? ge : gs, map.cell_start, map.cell_pts, (float)pw.x, (float)pw.y, (float)pw.z, nn);
+    const bool near = nn.d[4] < 1.0f;  // pointSearchSqDis[4] < 1.0 : the only queries the reference uses
+    if (lane_id() < 5) {
+      const int j = lane_id();
+      const int id = j == 0 ? nn.id[0] : j == 1 ? nn.id[1] : j == 2 ? nn.id[2] : j == 3 ? nn.id[3] : nn.id[4];
+      const float d = j == 0 ? nn.d[0] : j == 1 ? nn.d[1] : j == 2 ? nn.d[2] : j == 3 ? nn.d[3] : nn.d[4];
+      knn_ids[(size_t)out * 5 + j] = near ? id : -1;
+      knn_d2[(size_t)out * 5 + j] = near ? d : 0.f;
+    }
+  }
+}
+
+// (2) assoc_eval_kernel: one THREAD per query: PCA line fit / 5x3 QR plane fit of the five neighbours, acceptance gates, and the
+//     iteration-0 residual + Jacobian of ceres::Solve reduced into the normal equations; the last CTA starts the LM.
 __global__ void __launch_bounds__(kEvalThreads) assoc_eval_kernel(PoseState* __restrict__ S, const P4* __restrict__ ds_edge, const int* __restrict__ d_nde,
                                                                    const P4* __restrict__ ds_surf, const int* __restrict__ d_nds, LocalMap emap, LocalMap smap,
                                                                    int qcap, double* __restrict__ corr, unsigned char* __restrict__ corr_ok,
-                                                                   int* __restrict__ knn_ids, float* __restrict__ knn_d2, int loss,
-                                                                   double* __restrict__ partials, int tap) {
+                                                                   const int* __restrict__ knn_ids, int loss, double* __restrict__ partials) {
   if (S->skip_solve) return;
   __shared__ double s_sums[kLmTerms];
   __shared__ int s_ncorr;
@@ -610,42 +651,29 @@ __global__ void __launch_bounds__(kEvalThreads) assoc_eval_kernel(PoseState* __r
   double x[7];
 #pragma unroll
   for (int k = 0; k < 7; ++k) x[k] = S->x[k];
-  const GridDims ge = *emap.dims, gs = *smap.dims;
   Accum A;
 #pragma unroll
   for (int k = 0; k < kLmTerms; ++k) A.v[k] = 0.0;
   int my_corr = 0;
   const size_t cs = (size_t)2 * qcap;  // stride between the planes of corr
-  // one warp per query: the 32 lanes share the candidate scan, lane 0 fits the line / plane and evaluates the residual
-  const int warps_total = gridDim.x * (kEvalThreads / 32);
-  for (int slot = blockIdx.x * (kEvalThreads / 32) + warp_id(); slot < nde + nds; slot += warps_total) {
+  for (int slot = blockIdx.x * kEvalThreads + threadIdx.x; slot < nde + nds; slot += gridDim.x * kEvalThreads) {
     const bool is_edge = slot < nde;
     const int qi = is_edge ? slot : slot - nde;
     const int out = is_edge ? qi : qcap + qi;
-    const float4 p = __ldg((is_edge ? ds_edge : ds_surf) + qi);
-    const m::V3 pc{(double)p.x, (double)p.y, (double)p.z};
-    // pointAssociateToMap :126-135: double transform, float store
-    const m::V3 pw = m::add(m::quat_rotate(x, pc), m::V3{x[4], x[5], x[6]});
-    const float qx = (float)pw.x, qy = (float)pw.y, qz = (float)pw.z;
-    Knn5 nn;
-    const LocalMap& map = is_edge ? emap : smap;
-    knn5_search_warp(is_edge ? ge : gs, map.cell_start, map.cell_pts, qx, qy, qz, nn);
-    if (lane_id() != 0) continue;
-    const bool near = nn.d[4] < 1.0f;  // pointSearchSqDis[4] < 1.0
-    if (tap) {
+    int id[5];
 #pragma unroll
-      for (int j = 0; j < 5; ++j) {
-        knn_ids[(size_t)out * 5 + j] = near ? nn.id[j] : -1;
-        knn_d2[(size_t)out * 5 + j] = near ? nn.d[j] : 0.f;
-      }
-    }
+    for (int j = 0; j < 5; ++j) id[j] = __ldg(knn_ids + (size_t)out * 5 + j);
+    const bool near = id[0] >= 0;
     bool ok = false;
     double r = 0.0, J[6], cost_term = 0.0;
     if (near) {
+      const float4 p = __ldg((is_edge ? ds_edge : ds_surf) + qi);
+      const m::V3 pc{(double)p.x, (double)p.y, (double)p.z};
+      const P4* mpts = is_edge ? emap.pts : smap.pts;
       m::V3 q[5];
 #pragma unroll
       for (int j = 0; j < 5; ++j) {
-        const float4 mp = __ldg(map.pts + nn.id[j]);
+        const float4 mp = __ldg(mpts + id[j]);
         q[j] = m::V3{(double)mp.x, (double)mp.y, (double)mp.z};
       }
       if (is_edge) {
@@ -697,7 +725,7 @@ __global__ void __launch_bounds__(kEvalThreads) assoc_eval_kernel(PoseState* __r
       my_corr++;
     }
   }
-  // correspondences count (needed for the "no residual blocks" exit): warp sum -> shared -> global via the partials' spare slot
+  // correspondence count (needed for the "no residual blocks" exit)
   for (int o = 16; o > 0; o >>= 1) my_corr += __shfl_xor_sync(0xffffffffu, my_corr, o);
   if (lane_id() == 0 && my_corr) atomicAdd(&s_ncorr, my_corr);
   __syncthreads();
@@ -887,9 +915,10 @@ void odom_update_device(OdomDevice& od, const void* d_edge, const int* d_ne, con
   voxel_grid_device(d_edge, stride, d_ne, n_max, od.leaf_edge, od.ds_edge, od.d_nds_edge, *od.vws, nullptr, s);
   voxel_grid_device(d_surf, stride, d_ns, n_max, od.leaf_surf, od.ds_surf, od.d_nds_surf, *od.vws, nullptr, s);
   for (int it = 0; it < od.optimization_count; ++it) {
-    const int t = tap && (it == od.optimization_count - 1);
-    FLOAM_LAUNCH(K_ASSOC_EVAL, assoc_eval_kernel, kAssocBlocks, kEvalThreads, s, S, od.ds_edge, od.d_nds_edge, od.ds_surf, od.d_nds_surf, od.edge_map, od.surf_map, od.qcap,
-                                                            od.corr, od.corr_ok, od.knn_ids, od.knn_d2, od.loss, od.partials, t);
+    FLOAM_LAUNCH(K_ASSOC_KNN, assoc_knn_kernel, kKnnBlocks, kKnnThreads, s, S, od.ds_edge, od.d_nds_edge, od.ds_surf, od.d_nds_surf, od.edge_map, od.surf_map,
+                 od.qcap, od.knn_ids, od.knn_d2);
+    FLOAM_LAUNCH(K_ASSOC_EVAL, assoc_eval_kernel, kAssocBlocks, kEvalThreads, s, S, od.ds_edge, od.d_nds_edge, od.ds_surf, od.d_nds_surf, od.edge_map, od.surf_map,
+                 od.qcap, od.corr, od.corr_ok, od.knn_ids, od.loss, od.partials);
     for (int k = 0; k < 4; ++k)
       FLOAM_LAUNCH(K_CAND_EVAL, cand_eval_kernel, kCandBlocks, kEvalThreads, s, S, od.ds_edge, od.d_nds_edge, od.ds_surf, od.d_nds_surf, od.qcap, od.corr, od.corr_ok, od.loss,
                                                             od.partials);
@@ -905,8 +934,8 @@ void odom_update_device(OdomDevice& od, const void* d_edge, const int* d_ne, con
   for (int k = 0; k < 2; ++k) {
     LocalMap& mp = *maps[k];
     FLOAM_LAUNCH(K_MAP_APPEND, map_append_kernel, grid_for(od.qcap), kThreads, s, dss[k], nds[k], mp.pts, mp.d_n, mp.cap, S, skip);
-    FLOAM_LAUNCH(K_MAP_BUMP, map_bump_kernel, 1, 32, s, mp.d_n, nds[k], mp.cap, 0, skip);
-    crop_box_device(mp.pts, mp.d_n, mp.cap, S->crop_bounds, mp.tmp, mp.d_ncrop, *od.vws, skip, s);
+    // the appended points are counted in by the crop itself (no separate size bump); the voxel filter then rewrites *d_n
+    crop_box_device(mp.pts, mp.d_n, mp.cap, S->crop_bounds, mp.tmp, mp.d_ncrop, *od.vws, skip, s, nds[k], mp.cap);
     voxel_grid_device(mp.tmp, 16, mp.d_ncrop, mp.cap, leaf[k], mp.pts, mp.d_n, *od.vws, skip, s);
     rebuild_grid(od, mp, skip, s);
   }

@@ -35,6 +35,7 @@ static const char* const kSlotNames[K_NUM_SLOTS] = {
   "map_append_raw",
   "map_bump",
   "predict",
+  "assoc_knn",
   "assoc_eval",
   "cand_eval",
   "finish",

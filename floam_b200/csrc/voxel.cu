@@ -147,9 +147,19 @@ __global__ void __launch_bounds__(kThreads) voxel_reduce_kernel(const char* __re
   for (int v = blockIdx.x * kThreads + threadIdx.x; v < nv; v += gridDim.x * kThreads) {
     const int b = head_pos[v], e = head_pos[v + 1];
     float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
-    for (int j = b; j < e; ++j) {  // CentroidPoint<PointXYZI>: float sums in run order (ascending input index), then / n
-      const float4 p = load_xyzi(in, stride, __ldg(vals + j));
-      sx = fadd(sx, p.x); sy = fadd(sy, p.y); sz = fadd(sz, p.z); si = fadd(si, p.w);
+    // CentroidPoint<PointXYZI>: float sums in run order (ascending input index), then / n. Loads are issued eight at a time
+    // (index, then point) so that a run costs two L2 round trips per eight points instead of two per point.
+    for (int j = b; j < e; j += 8) {
+      int idx[8];
+      float4 p[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) idx[u] = (j + u < e) ? __ldg(vals + j + u) : -1;
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (idx[u] >= 0) p[u] = load_xyzi(in, stride, idx[u]);
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (idx[u] >= 0) { sx = fadd(sx, p[u].x); sy = fadd(sy, p[u].y); sz = fadd(sz, p[u].z); si = fadd(si, p[u].w); }
     }
     const float cnt = (float)(e - b);
     out[v] = make_float4(__fdiv_rn(sx, cnt), __fdiv_rn(sy, cnt), __fdiv_rn(sz, cnt), __fdiv_rn(si, cnt));
@@ -162,10 +172,17 @@ __device__ __forceinline__ int crop_keep(const float4 p, const float* __restrict
   return outside ? 0 : 1;
 }
 
-__global__ void __launch_bounds__(kScanThreads) crop_flags_kernel(const P4* __restrict__ in, const int* __restrict__ d_n, const float* __restrict__ bounds,
-                                                                  int* __restrict__ tile_sums, const int* d_skip) {
+// n = *d_n, plus *d_extra freshly appended points when they fitted into `cap` (addPointsToMap's push_backs)
+__device__ __forceinline__ int crop_count(const int* __restrict__ d_n, const int* __restrict__ d_extra, int cap) {
+  int n = *d_n;
+  if (d_extra && n + *d_extra <= cap) n += *d_extra;
+  return n;
+}
+
+__global__ void __launch_bounds__(kScanThreads) crop_flags_kernel(const P4* __restrict__ in, const int* __restrict__ d_n, const int* __restrict__ d_extra, int cap,
+                                                                  const float* __restrict__ bounds, int* __restrict__ tile_sums, const int* d_skip) {
   if (d_skip && *d_skip) return;
-  const int n = *d_n;
+  const int n = crop_count(d_n, d_extra, cap);
   if (blockIdx.x * kScanTile >= n) return;
   __shared__ int smem[33];
   const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
@@ -176,10 +193,11 @@ __global__ void __launch_bounds__(kScanThreads) crop_flags_kernel(const P4* __re
   if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
 }
 
-__global__ void __launch_bounds__(kScanThreads) crop_scatter_kernel(const P4* __restrict__ in, const int* __restrict__ d_n, const float* __restrict__ bounds,
-                                                                    const int* __restrict__ tile_sums, P4* __restrict__ out, int* d_nout, const int* d_skip) {
+__global__ void __launch_bounds__(kScanThreads) crop_scatter_kernel(const P4* __restrict__ in, const int* __restrict__ d_n, const int* __restrict__ d_extra, int cap,
+                                                                    const float* __restrict__ bounds, const int* __restrict__ tile_sums, P4* __restrict__ out,
+                                                                    int* d_nout, const int* d_skip) {
   if (d_skip && *d_skip) return;
-  const int n = *d_n;
+  const int n = crop_count(d_n, d_extra, cap);
   if (n == 0) { if (blockIdx.x == 0 && threadIdx.x == 0) *d_nout = 0; return; }
   if (blockIdx.x * kScanTile >= n) return;
   __shared__ int smem[33];
@@ -259,11 +277,11 @@ void repack_xyzi_device(const void* d_in32, const int* d_n, int n_max, P4* d_out
 }
 
 void crop_box_device(const P4* d_in, const int* d_n, int n_max, const float* d_bounds, P4* d_out, int* d_nout, VoxelWorkspace& ws,
-                     const int* d_skip, cudaStream_t s) {
+                     const int* d_skip, cudaStream_t s, const int* d_extra, int cap) {
   if (n_max > ws.n_max) n_max = ws.n_max;
   const int gt = (n_max + kScanTile - 1) / kScanTile;
-  FLOAM_LAUNCH(K_CROP_FLAGS, crop_flags_kernel, gt, kScanThreads, s, d_in, d_n, d_bounds, ws.scan.block_sums, d_skip);
-  FLOAM_LAUNCH(K_CROP_SCATTER, crop_scatter_kernel, gt, kScanThreads, s, d_in, d_n, d_bounds, ws.scan.block_sums, d_out, d_nout, d_skip);
+  FLOAM_LAUNCH(K_CROP_FLAGS, crop_flags_kernel, gt, kScanThreads, s, d_in, d_n, d_extra, cap, d_bounds, ws.scan.block_sums, d_skip);
+  FLOAM_LAUNCH(K_CROP_SCATTER, crop_scatter_kernel, gt, kScanThreads, s, d_in, d_n, d_extra, cap, d_bounds, ws.scan.block_sums, d_out, d_nout, d_skip);
 }
 
 }  // namespace floam

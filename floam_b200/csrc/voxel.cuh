@@ -29,8 +29,9 @@ void voxel_grid_device(const void* d_in, int stride_bytes, const int* d_n, int n
 
 // pcl::CropBox<PointXYZI>::filter, identity transform, negative=false, inclusive float bounds read from device memory
 // (d_bounds: min xyz, max xyz). Order-preserving compaction.
+// d_extra (optional): the input holds *d_n + *d_extra points when that sum fits into cap (points appended since *d_n was written).
 void crop_box_device(const P4* d_in, const int* d_n, int n_max, const float* d_bounds, P4* d_out, int* d_nout, VoxelWorkspace& ws,
-                     const int* d_skip, cudaStream_t s);
+                     const int* d_skip, cudaStream_t s, const int* d_extra = nullptr, int cap = 0);
 
 // stride-32 PointXYZI / PointXYZIRT cloud -> float4 (x, y, z, intensity)
 void repack_xyzi_device(const void* d_in32, const int* d_n, int n_max, P4* d_out, cudaStream_t s);
