@@ -36,7 +36,7 @@ SYMBOLS = [
     "floam_process_wait", "floam_stage_scans", "floam_process_staged", "floam_mapping_update", "floam_mapping_get_map", "floam_voxel_grid",
     "floam_crop_box", "floam_knn5", "floam_debug_fetch", "floam_launch_count", "floam_last_frame_ms", "floam_replay_staged",
     "floam_set_kernel_timing", "floam_kernel_slots", "floam_kernel_name", "floam_kernel_timing", "floam_deskew_align_ex",
-    "floam_compensate_velocity",
+    "floam_compensate_velocity", "floam_process_submit_imu", "floam_process_scan_imu",
 ]
 
 _lib = None
@@ -234,6 +234,13 @@ class Context:
         pose = np.zeros(7)
         _check(lib().floam_process_scan(self.h, _p(pts), len(pts), int(deskew), _p(pose)), "floam_process_scan")
         return pose
+
+    def process_scan_imu(self, pts, stamp_us, extr_xyzw, deskew=False):
+        """IMU deskew + alignment + features + odometry in one device pass. Returns (status, pose, new_stamp_us); status NO_IMU = scan skipped."""
+        pts = np.ascontiguousarray(pts, POINT_IRT)
+        pose = np.zeros(7); st = C.c_uint64(int(stamp_us)); ex = np.ascontiguousarray(extr_xyzw, np.float64)
+        rc = _check(lib().floam_process_scan_imu(self.h, _p(pts), len(pts), C.byref(st), _p(ex), int(deskew), _p(pose)), "floam_process_scan_imu", allow=(NO_IMU,))
+        return rc, pose, st.value
 
     def process_submit(self, pts, n=None, deskew=False):
         """pts must stay alive (ideally a PinnedBuffer.array slice) until the matching process_wait returns."""

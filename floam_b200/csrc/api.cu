@@ -108,7 +108,9 @@ void enqueue_selector(floam_ctx* c, PointIRT* d_edge, const int* d_ne, PointIRT*
 }
 
 // everything between "scan is in d_scan" and "pose is in the pinned mailbox" for one frame
-void enqueue_frame_body(floam_ctx* c, const PointIRT* d_scan, const int* d_scan_n, int deskew, int slot, bool first) {
+void enqueue_frame_body(floam_ctx* c, PointIRT* d_scan, const int* d_scan_n, int deskew, int slot, bool first, bool imu) {
+  // CenterTime + Compensate + IMU alignment folded into the frame (src/laserProcessingNode.cpp:100-116): in place on the uploaded scan
+  if (imu) deskew_launch(c->imu, c->d_plan[slot], d_scan, d_scan_n, c->prm.max_scan_points, c->stream);
   feature_extract_device(d_scan, d_scan_n, c->fprm, c->fws, c->d_edge, c->d_ne, c->d_surf, c->d_ns, c->d_edge_src, c->d_surf_src, c->d_flags, c->stream);
   if (first) {
     // odomEstimationNode.cpp:219-224: first frame only seeds the map (raw features, Q11); odom stays identity
@@ -122,22 +124,22 @@ void enqueue_frame_body(floam_ctx* c, const PointIRT* d_scan, const int* d_scan_
 }
 
 // Launch the frame body, through a CUDA graph when enabled. Graphs are keyed by everything that changes the launch sequence.
-int launch_frame(floam_ctx* c, const PointIRT* d_scan, const int* d_scan_n, int deskew, int slot, int scan_slot_key) {
+int launch_frame(floam_ctx* c, PointIRT* d_scan, const int* d_scan_n, int deskew, int slot, int scan_slot_key, bool imu = false) {
   const bool first = !c->map_initialised;
   OdomDevice& od = c->odom;
   if (!c->use_graphs || c->timer.enabled) {
-    enqueue_frame_body(c, d_scan, d_scan_n, deskew, slot, first);
+    enqueue_frame_body(c, d_scan, d_scan_n, deskew, slot, first, imu);
     c->map_initialised = true;
     return check_async("frame");
   }
-  floam_graph_key key{first ? 0 : 1, first ? 0 : next_outer(od.optimization_count), first ? 0 : (deskew ? 1 : 0), scan_slot_key * 2 + slot};
+  floam_graph_key key{(first ? 0 : 1) + (imu ? 2 : 0), first ? 0 : next_outer(od.optimization_count), first ? 0 : (deskew ? 1 : 0), scan_slot_key * 2 + slot};
   auto it = c->graphs.find(key);
   if (it == c->graphs.end()) {
     const long long before = g_launches;
     const int saved_count = od.optimization_count;
     cudaGraph_t graph = nullptr;
     FLOAM_CUDA_OK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-    enqueue_frame_body(c, d_scan, d_scan_n, deskew, slot, first);
+    enqueue_frame_body(c, d_scan, d_scan_n, deskew, slot, first, imu);
     FLOAM_CUDA_OK(cudaStreamEndCapture(c->stream, &graph));
     floam_graph_entry e;
     FLOAM_CUDA_OK(cudaGraphInstantiate(&e.exec, graph, 0));
@@ -220,6 +222,7 @@ int floam_create(const floam_params* params, int device, floam_ctx** out) {
   auto fail = [&](int rc) { floam_destroy(c); return rc; };
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(FLOAM_ERR_CUDA);
   if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(FLOAM_ERR_CUDA);
+  if (cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(FLOAM_ERR_CUDA);
   for (int k = 0; k < 2; ++k) {
     if (cudaEventCreate(&c->ev_begin[k]) != cudaSuccess || cudaEventCreate(&c->ev_end[k]) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_upload[k], cudaEventDisableTiming) != cudaSuccess ||
@@ -246,8 +249,12 @@ int floam_create(const floam_params* params, int device, floam_ctx** out) {
   c->d_stage_bounds = (float*)A(32);
   void* fmem = A(feature_workspace_bytes_padded(ns, params->num_lines));
   void* vmem = A(voxel_workspace_bytes(c->stage_cap));
+  const int aux_cap = std::max(ns, nm);
+  void* vmem_aux = A(voxel_workspace_bytes(aux_cap));
   c->imu.dev_cap = 1 << 20;
   c->imu.d_samples = (ImuSample*)A((size_t)c->imu.dev_cap * sizeof(ImuSample));
+  c->imu.d_plan = (DeskewPlan*)A(sizeof(DeskewPlan));
+  for (int k = 0; k < 2; ++k) c->d_plan[k] = (DeskewPlan*)A(sizeof(DeskewPlan));
   if (!ok) return fail(FLOAM_ERR_CUDA);
   c->d_ne = ints; c->d_ns = ints + 1; c->d_flags = ints + 2; c->d_stage_n = ints + 4; c->d_staged_n = ints + 8;
   if (cudaMemsetAsync(ints, 0, 64, c->stream) != cudaSuccess) return fail(FLOAM_ERR_CUDA);
@@ -257,6 +264,8 @@ int floam_create(const floam_params* params, int device, floam_ctx** out) {
   feature_workspace_bind(c->fws, fmem, ns, params->num_lines);
   voxel_workspace_bind(c->vws, vmem, c->stage_cap);
   if (voxel_workspace_arm(c->vws, c->stream)) return fail(FLOAM_ERR_CUDA);
+  voxel_workspace_bind(c->vws_aux, vmem_aux, aux_cap);
+  if (voxel_workspace_arm(c->vws_aux, c->stream)) return fail(FLOAM_ERR_CUDA);
 
   c->h_ints = (int*)host_alloc(c, 64 * sizeof(int));
   c->h_doubles = (double*)host_alloc(c, 64 * sizeof(double));
@@ -271,7 +280,7 @@ int floam_create(const floam_params* params, int device, floam_ctx** out) {
   }
   if (!c->h_ints || !c->h_doubles) return fail(FLOAM_ERR_CUDA);
 
-  int rc = odom_device_init(c->odom, c->prm, &c->vws, ctx_alloc, c, c->stream);
+  int rc = odom_device_init(c->odom, c->prm, &c->vws, &c->vws_aux, c->aux_stream, ctx_alloc, c, c->stream);
   if (rc) return fail(rc);
   if (params->max_global_map_points > 0) {
     rc = mapping_device_init(c->mapping, params->max_global_map_points, params->map_resolution, &c->vws, ctx_alloc, c, c->stream);
@@ -288,6 +297,7 @@ void floam_destroy(floam_ctx* c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+  if (c->aux_stream) cudaStreamSynchronize(c->aux_stream);
   if (g_timer == &c->timer) g_timer = nullptr;
   if (c->timer.created) for (int i = 0; i < 2 * LaunchTimer::kPairs; ++i) cudaEventDestroy(c->timer.ev[i]);
   for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second.exec);
@@ -301,6 +311,9 @@ void floam_destroy(floam_ctx* c) {
   }
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+  if (c->odom.ev_fork) cudaEventDestroy(c->odom.ev_fork);
+  if (c->odom.ev_join) cudaEventDestroy(c->odom.ev_join);
   cudaGetLastError();
   delete c;
 }
@@ -542,7 +555,7 @@ int floam_odom_get_map(floam_ctx* c, floam_point_xyzi* edge, int edge_cap, floam
 }
 
 // ---- fused frame path ---------------------------------------------------------------------------------------------
-int floam_process_submit(floam_ctx* c, const floam_point_xyzirt* pts, int n, int deskew) {
+static int submit_common(floam_ctx* c, const floam_point_xyzirt* pts, int n, int deskew, DeskewPlan* plan) {
   if (!c || (!pts && n > 0) || n < 0) return FLOAM_ERR_ARG;
   if (n > c->prm.max_scan_points) return FLOAM_ERR_CAPACITY;
   if (c->inflight >= 2) return FLOAM_ERR_ARG;
@@ -553,11 +566,15 @@ int floam_process_submit(floam_ctx* c, const floam_point_xyzirt* pts, int n, int
   if (n > 0) FLOAM_CUDA_OK(cudaMemcpyAsync(c->d_scan[slot], pts, (size_t)n * 32, cudaMemcpyHostToDevice, c->copy_stream));
   c->h_ints[32 + slot] = n;
   FLOAM_CUDA_OK(cudaMemcpyAsync(c->d_scan_n[slot], &c->h_ints[32 + slot], 4, cudaMemcpyHostToDevice, c->copy_stream));
+  if (plan) {
+    const int rc = deskew_upload(c->imu, *plan, c->d_plan[slot], c->copy_stream);
+    if (rc) return rc;
+  }
   FLOAM_CUDA_OK(cudaEventRecord(c->ev_upload[slot], c->copy_stream));
   FLOAM_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_upload[slot], 0));
   FLOAM_CUDA_OK(cudaEventRecord(c->ev_begin[slot], c->stream));
   c->frame_was_init[slot] = !c->map_initialised;
-  int rc = launch_frame(c, c->d_scan[slot], c->d_scan_n[slot], deskew, slot, 0);
+  int rc = launch_frame(c, c->d_scan[slot], c->d_scan_n[slot], deskew, slot, 0, plan != nullptr);
   if (rc) return rc;
   FLOAM_CUDA_OK(cudaEventRecord(c->ev_end[slot], c->stream));
   FLOAM_CUDA_OK(cudaEventRecord(c->ev_consumed[slot], c->stream));
@@ -565,6 +582,24 @@ int floam_process_submit(floam_ctx* c, const floam_point_xyzirt* pts, int n, int
   c->submit_slot ^= 1;
   c->inflight++;
   return FLOAM_OK;
+}
+
+int floam_process_submit(floam_ctx* c, const floam_point_xyzirt* pts, int n, int deskew) { return submit_common(c, pts, n, deskew, nullptr); }
+
+int floam_process_submit_imu(floam_ctx* c, const floam_point_xyzirt* pts, int n, uint64_t* stamp_us, const double extr_xyzw[4], int deskew) {
+  if (!c || !pts || n < 1 || !stamp_us || !extr_xyzw) return FLOAM_ERR_ARG;
+  DeskewPlan plan;
+  deskew_plan(c->imu, *stamp_us, pts[0].time, pts[n - 1].time, extr_xyzw, FLOAM_DESKEW_CENTER_TIME | FLOAM_DESKEW_COMPENSATE | FLOAM_DESKEW_ALIGN, &plan);
+  *stamp_us = plan.stamp_us_new;
+  if (!plan.can_compensate) return FLOAM_NO_IMU;  // "cannot compensate - no IMU data": the node drops the scan (src/laserProcessingNode.cpp:108-112)
+  return submit_common(c, pts, n, deskew, &plan);
+}
+
+int floam_process_scan_imu(floam_ctx* c, const floam_point_xyzirt* pts, int n, uint64_t* stamp_us, const double extr_xyzw[4], int deskew, double pose_out[7]) {
+  if (!c || c->inflight != 0) return FLOAM_ERR_ARG;
+  const int rc = floam_process_submit_imu(c, pts, n, stamp_us, extr_xyzw, deskew);
+  if (rc) return rc;
+  return floam_process_wait(c, pose_out);
 }
 
 int floam_process_wait(floam_ctx* c, double pose_out[7]) {

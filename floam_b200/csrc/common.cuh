@@ -50,6 +50,7 @@ enum KernelSlot {
   K_PREDICT,
   K_ASSOC_KNN,
   K_ASSOC_EVAL,
+  K_LM_CLUSTER,
   K_CAND_EVAL,
   K_FINISH,
   K_MAP_APPEND,

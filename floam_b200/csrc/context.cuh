@@ -48,6 +48,8 @@ struct floam_ctx {
   floam::FeatureParams fprm;
   floam::FeatureWorkspace fws;
   floam::VoxelWorkspace vws;
+  floam::VoxelWorkspace vws_aux;        // edge-side branch (sized for scans and local maps)
+  cudaStream_t aux_stream = nullptr;
 
   // staging for the stage entry points (voxel/crop/knn/set_map on host clouds)
   char* d_stage_in = nullptr;            // stage_cap x 32 B
@@ -63,6 +65,7 @@ struct floam_ctx {
 
   floam::OdomDevice odom;      // odometry state, maps, grids, LM (odom.cuh)
   floam::ImuDevice imu;        // dmapping::ImuHandler mirror + device samples (imu.cuh)
+  floam::DeskewPlan* d_plan[2] = {nullptr, nullptr};   // per scan slot, for the fused IMU path
   floam::MappingDevice mapping;
 
   // pinned host mailboxes

@@ -88,9 +88,11 @@ namespace {
 
 constexpr int kThreads = 256;
 
-__global__ void __launch_bounds__(kThreads) deskew_align_kernel(PointIRT* __restrict__ pts, const int* __restrict__ d_n, DeskewPlan plan,
-                                                                 const ImuSample* __restrict__ samples, int n_samples) {
+__global__ void __launch_bounds__(kThreads) deskew_align_kernel(PointIRT* __restrict__ pts, const int* __restrict__ d_n, const DeskewPlan* __restrict__ d_plan,
+                                                                 const ImuSample* __restrict__ samples) {
   const int n = *d_n;
+  const DeskewPlan plan = *d_plan;
+  const int n_samples = plan.n_samples;
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
     float4* raw = reinterpret_cast<float4*>(pts + i);
     float4 a = raw[0], b = raw[1];  // b = intensity, ring|pad, time, pad
@@ -131,18 +133,31 @@ __global__ void __launch_bounds__(kThreads) deskew_align_kernel(PointIRT* __rest
 
 }  // namespace
 
-int deskew_align_device(ImuDevice& imu, const DeskewPlan& plan, PointIRT* d_pts, const int* d_n, int n_max, cudaStream_t s) {
+int deskew_upload(ImuDevice& imu, DeskewPlan& plan, DeskewPlan* d_plan, cudaStream_t copy) {
   const int total = (int)imu.host.size();
   if (total > imu.dev_cap) return FLOAM_ERR_CAPACITY;
   if (total > imu.dev_count) {
     FLOAM_CUDA_OK(cudaMemcpyAsync(imu.d_samples + imu.dev_count, imu.host.data() + imu.dev_count, (size_t)(total - imu.dev_count) * sizeof(ImuSample),
-                                  cudaMemcpyHostToDevice, s));
+                                  cudaMemcpyHostToDevice, copy));
     imu.dev_count = total;
   }
+  plan.n_samples = total;
+  FLOAM_CUDA_OK(cudaMemcpyAsync(d_plan, &plan, sizeof(DeskewPlan), cudaMemcpyHostToDevice, copy));  // pageable source: staged before the call returns
+  return FLOAM_OK;
+}
+
+void deskew_launch(ImuDevice& imu, const DeskewPlan* d_plan, PointIRT* d_pts, const int* d_n, int n_max, cudaStream_t s) {
   int g = (n_max + kThreads - 1) / kThreads;
   if (g > kNumSMs * 8) g = kNumSMs * 8;
   if (g < 1) g = 1;
-  FLOAM_LAUNCH(K_DESKEW_ALIGN, deskew_align_kernel, g, kThreads, s, d_pts, d_n, plan, imu.d_samples, total);
+  FLOAM_LAUNCH(K_DESKEW_ALIGN, deskew_align_kernel, g, kThreads, s, d_pts, d_n, d_plan, imu.d_samples);
+}
+
+int deskew_align_device(ImuDevice& imu, const DeskewPlan& plan_in, PointIRT* d_pts, const int* d_n, int n_max, cudaStream_t s) {
+  DeskewPlan plan = plan_in;
+  const int rc = deskew_upload(imu, plan, imu.d_plan, s);
+  if (rc) return rc;
+  deskew_launch(imu, imu.d_plan, d_pts, d_n, n_max, s);
   return FLOAM_OK;
 }
 

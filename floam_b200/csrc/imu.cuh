@@ -13,11 +13,13 @@ struct ImuSample {   // device record
   double q[4];       // x, y, z, w (Eigen coefficient order)
 };
 
+struct DeskewPlan;
 struct ImuDevice {
   std::vector<ImuSample> host;   // time-sorted, same admission rule as ImuHandler::AddMsg (:24-40)
   ImuSample* d_samples = nullptr;
   int dev_count = 0;             // samples already uploaded
   int dev_cap = 0;
+  struct DeskewPlan* d_plan = nullptr;   // plan of the stand-alone entry point
 };
 
 // ImuHandler::AddMsg: keeps the sample iff it is the first or more than 10 us after the previous one
@@ -36,11 +38,16 @@ struct DeskewPlan {       // everything the per-point kernel needs, computed on 
   int can_compensate;     // dmapping::Compensate's return value
   int do_center, do_compensate, do_align;   // which of CenterTime / Compensate / alignment run (floam_deskew_flags)
   uint64_t stamp_us_new;
+  int n_samples;          // IMU samples resident on the device when the kernel runs
 };
 // ros::Time / pcl stamp conversions + CenterTime + the host part of Compensate (TimeContained, qInit) and of the alignment
 void deskew_plan(const ImuDevice& imu, uint64_t stamp_us, float time_front, float time_back, const double extr_xyzw[4], int flags, DeskewPlan* plan);
 // uploads new samples (if any) and runs the fused per-point kernel in place: time re-centring always; rotation-only deskew and
 // alignment only when plan.can_compensate
 int deskew_align_device(ImuDevice& imu, const DeskewPlan& plan, PointIRT* d_pts, const int* d_n, int n_max, cudaStream_t s);
+// graph-friendly split of the same thing: (1) uploads new IMU samples and the plan into d_plan on `copy`, (2) launches the kernel,
+// which reads the plan from device memory, on `s` (fixed arguments -> capturable)
+int deskew_upload(ImuDevice& imu, DeskewPlan& plan, DeskewPlan* d_plan, cudaStream_t copy);
+void deskew_launch(ImuDevice& imu, const DeskewPlan* d_plan, PointIRT* d_pts, const int* d_n, int n_max, cudaStream_t s);
 
 }  // namespace floam

@@ -23,6 +23,8 @@
 #include <cfloat>
 #include <cstddef>
 
+#include <cooperative_groups.h>
+
 #include "odom_math.cuh"
 
 namespace floam {
@@ -588,13 +590,23 @@ __device__ bool reduce_terms(const Accum& A, double* __restrict__ partials, unsi
   __syncthreads();
   if (!s_last) return false;
   __threadfence();
-  // warp w sums terms w, w+4, ...; lane l takes rows l, l+32, ... then a shuffle tree
-  for (int k = w; k < kLmTerms; k += kEvalThreads / 32) {
+  // thread (g, k): term k of the rows g, g+4, ... (a row's 28 terms are contiguous: coalesced); the loads of a thread are independent
+  // of one another, the additions run in a fixed order -> deterministic totals
+  {
+    const int k = l, g = w;
     double v = 0.0;
-    for (int r = l; r < (int)gridDim.x; r += 32) v += __ldcg(partials + (size_t)r * kLmTerms + k);
+    if (k < kLmTerms) {
+#pragma unroll 4
+      for (int r = g; r < (int)gridDim.x; r += kEvalThreads / 32) v += __ldcg(partials + (size_t)r * kLmTerms + k);
+      s_part[g][k] = v;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < kLmTerms) {
+    double v = 0.0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (l == 0) s_sums[k] = v;
+    for (int ww = 0; ww < kEvalThreads / 32; ++ww) v += s_part[ww][threadIdx.x];
+    s_sums[threadIdx.x] = v;
   }
   __syncthreads();
   if (threadIdx.x == 0) *ticket = 0;
@@ -773,6 +785,104 @@ __global__ void __launch_bounds__(kEvalThreads) cand_eval_kernel(PoseState* __re
   if (reduce_terms(A, partials, &S->ticket, s_sums) && threadIdx.x == 0) lm_after_candidate(*S, s_sums);
 }
 
+// The whole ceres::Solve step loop (<= 4 attempts) of one outer iteration in ONE thread-block cluster (8 CTAs on 8 SMs), for the
+// usual problem sizes: every CTA evaluates its share of the correspondences at the pending candidate and reduces the 28 terms in
+// its own shared memory; after a cluster barrier CTA 0 adds the eight partial rows through distributed shared memory (fixed order)
+// and its thread 0 advances the trust-region state; a second barrier publishes the next candidate to the other CTAs, again through
+// DSMEM. No partials in global memory, no ticket, no kernel boundary between attempts. Problems with more than kClusterMaxSlots
+// query slots are left to the multi-CTA cand_eval_kernel launches that follow (which otherwise are not even enqueued).
+constexpr int kClusterCtas = 8;
+constexpr int kClusterThreads = 256;
+constexpr int kClusterMaxSlots = 65536;
+struct ClusterShared {
+  double part[kClusterThreads / 32][kLmTerms];
+  double row[kLmTerms];   // this CTA's 28 totals
+  double x[7];            // candidate pose (valid in CTA 0, read remotely)
+  int done;
+};
+__global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClusterThreads)
+    lm_cluster_kernel(PoseState* S, const P4* __restrict__ ds_edge, const int* __restrict__ d_nde, const P4* __restrict__ ds_surf,
+                      const int* __restrict__ d_nds, int qcap, const double* __restrict__ corr, const unsigned char* __restrict__ corr_ok, int loss) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  // uniform across the cluster: decided from values the previous kernel wrote
+  if (S->skip_solve || S->lm_done) return;
+  const int nde = *d_nde, nds = *d_nds;
+  if (nde + nds > kClusterMaxSlots) return;
+  __shared__ ClusterShared sh;
+  const unsigned int rank = cluster.block_rank();
+  ClusterShared* sh0 = cluster.map_shared_rank(&sh, 0);
+  double x[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) x[k] = S->x_cand[k];
+  const size_t cs = (size_t)2 * qcap;
+  const int w = warp_id(), l = lane_id();
+  const int tid = rank * kClusterThreads + threadIdx.x, nthreads = kClusterCtas * kClusterThreads;
+  for (int attempt = 0; attempt < 4; ++attempt) {
+    Accum A;
+#pragma unroll
+    for (int k = 0; k < kLmTerms; ++k) A.v[k] = 0.0;
+    for (int slot = tid; slot < nde + nds; slot += nthreads) {
+      const bool is_edge = slot < nde;
+      const int qi = is_edge ? slot : slot - nde;
+      const int out = is_edge ? qi : qcap + qi;
+      if (!corr_ok[out]) continue;
+      const float4 p = __ldg((is_edge ? ds_edge : ds_surf) + qi);
+      const m::V3 pc{(double)p.x, (double)p.y, (double)p.z};
+      double r, J[6], cost_term;
+      if (is_edge) {
+        const m::V3 a{corr[0 * cs + out], corr[1 * cs + out], corr[2 * cs + out]};
+        const m::V3 b{corr[3 * cs + out], corr[4 * cs + out], corr[5 * cs + out]};
+        eval_edge(x, pc, a, b, r, J);
+      } else {
+        const m::V3 n{corr[0 * cs + out], corr[1 * cs + out], corr[2 * cs + out]};
+        eval_surf(x, pc, n, corr[3 * cs + out], r, J);
+      }
+      loss_correct(loss, r, J, cost_term);
+      accumulate(A, r, J, cost_term);
+    }
+#pragma unroll
+    for (int k = 0; k < kLmTerms; ++k) {
+      double v = A.v[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (l == 0) sh.part[w][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < kLmTerms) {
+      double v = 0.0;
+#pragma unroll
+      for (int ww = 0; ww < kClusterThreads / 32; ++ww) v += sh.part[ww][threadIdx.x];
+      sh.row[threadIdx.x] = v;
+    }
+    cluster.sync();   // every CTA's row is in place
+    if (rank == 0) {
+      __shared__ double s_sums[kLmTerms];
+      if (threadIdx.x < kLmTerms) {
+        double v = 0.0;
+#pragma unroll
+        for (int c = 0; c < kClusterCtas; ++c) v += cluster.map_shared_rank(&sh, c)->row[threadIdx.x];
+        s_sums[threadIdx.x] = v;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        lm_after_candidate(*S, s_sums);
+        sh.done = S->lm_done;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) sh.x[k] = S->x_cand[k];
+      }
+    }
+    cluster.sync();   // CTA 0 has published the verdict and the next candidate
+    const int done = sh0->done;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) x[k] = sh0->x[k];
+    if (done) break;
+    // no third barrier: row[] is rewritten only after this barrier pair, and CTA 0 rewrites x/done only after the next round's first
+    // barrier, which every CTA reaches after it has read this round's values
+  }
+  cluster.sync();     // CTA 0's shared memory must outlive the last remote read
+}
+
 // stand-alone 5-NN (floam_knn5): queries are used as given (no pose transform)
 __global__ void __launch_bounds__(kEvalThreads) knn5_kernel(const P4* __restrict__ queries, const int* __restrict__ d_nq, LocalMap map, int* __restrict__ ids,
                                                              float* __restrict__ d2) {
@@ -815,12 +925,13 @@ __global__ void __launch_bounds__(kThreads) compensate_velocity_explicit_kernel(
 
 int* dims_ncells_ptr(GridDims* dims) { return reinterpret_cast<int*>(reinterpret_cast<char*>(dims) + offsetof(GridDims, ncells)); }
 
-void rebuild_grid(OdomDevice& od, LocalMap& map, const int* d_skip, cudaStream_t s) {
+void rebuild_grid(OdomDevice& od, LocalMap& map, const int* d_skip, cudaStream_t s, VoxelWorkspace* ws = nullptr) {
+  if (!ws) ws = od.vws;
   const int g = grid_for(map.cap);
   FLOAM_LAUNCH(K_GRID_BBOX, grid_bbox_kernel, g, kThreads, s, map.pts, map.d_n, map.bbox, d_skip);
   FLOAM_LAUNCH(K_GRID_DIMS, grid_dims_kernel, 1, 32, s, map.bbox, map.d_n, map.dims, map.ncells_cap, od.state, d_skip);
   FLOAM_LAUNCH(K_GRID_COUNT, grid_count_kernel, g, kThreads, s, map.pts, map.d_n, map.dims, map.cell_count, d_skip);
-  exclusive_scan_i32(map.cell_count, map.cell_start, dims_ncells_ptr(map.dims), 0, map.ncells_cap, od.vws->scan, d_skip, s);
+  exclusive_scan_i32(map.cell_count, map.cell_start, dims_ncells_ptr(map.dims), 0, map.ncells_cap, ws->scan, d_skip, s);
   FLOAM_LAUNCH(K_GRID_SCATTER, grid_scatter_kernel, g, kThreads, s, map.pts, map.d_n, map.dims, map.cell_start, map.cell_count, map.cell_pts, d_skip);
 }
 
@@ -848,8 +959,13 @@ int local_map_alloc(LocalMap& map, int cap, int ncells_cap, void* (*alloc)(void*
   return FLOAM_OK;
 }
 
-int odom_device_init(OdomDevice& od, const floam_params& prm, VoxelWorkspace* vws, void* (*alloc)(void*, size_t), void* actx, cudaStream_t s) {
+int odom_device_init(OdomDevice& od, const floam_params& prm, VoxelWorkspace* vws, VoxelWorkspace* vws_aux, cudaStream_t aux, void* (*alloc)(void*, size_t),
+                     void* actx, cudaStream_t s) {
   od.vws = vws;
+  od.vws_aux = vws_aux;
+  od.aux_stream = aux;
+  FLOAM_CUDA_OK(cudaEventCreateWithFlags(&od.ev_fork, cudaEventDisableTiming));
+  FLOAM_CUDA_OK(cudaEventCreateWithFlags(&od.ev_join, cudaEventDisableTiming));
   od.leaf_edge = (float)prm.map_resolution;        // setLeafSize(float...) :13-14
   od.leaf_surf = (float)(prm.map_resolution * 2);
   od.scan_period = prm.scan_period;
@@ -912,14 +1028,23 @@ void odom_update_device(OdomDevice& od, const void* d_edge, const int* d_ne, con
   PoseState* S = od.state;
   FLOAM_LAUNCH(K_PREDICT, predict_kernel, 1, 32, s, S, od.edge_map.d_n, od.surf_map.d_n);
   // downSamplingToMap :137-142
-  voxel_grid_device(d_edge, stride, d_ne, n_max, od.leaf_edge, od.ds_edge, od.d_nds_edge, *od.vws, nullptr, s);
+  // the edge and surf clouds are independent until the association: the edge side runs on the aux stream (a parallel branch of the
+  // frame graph) with its own workspace
+  cudaStream_t a = od.aux_stream;
+  cudaEventRecord(od.ev_fork, s);
+  cudaStreamWaitEvent(a, od.ev_fork, 0);
+  voxel_grid_device(d_edge, stride, d_ne, n_max, od.leaf_edge, od.ds_edge, od.d_nds_edge, *od.vws_aux, nullptr, a);
   voxel_grid_device(d_surf, stride, d_ns, n_max, od.leaf_surf, od.ds_surf, od.d_nds_surf, *od.vws, nullptr, s);
+  cudaEventRecord(od.ev_join, a);
+  cudaStreamWaitEvent(s, od.ev_join, 0);
   for (int it = 0; it < od.optimization_count; ++it) {
     FLOAM_LAUNCH(K_ASSOC_KNN, assoc_knn_kernel, kKnnBlocks, kKnnThreads, s, S, od.ds_edge, od.d_nds_edge, od.ds_surf, od.d_nds_surf, od.edge_map, od.surf_map,
                  od.qcap, od.knn_ids, od.knn_d2);
     FLOAM_LAUNCH(K_ASSOC_EVAL, assoc_eval_kernel, kAssocBlocks, kEvalThreads, s, S, od.ds_edge, od.d_nds_edge, od.ds_surf, od.d_nds_surf, od.edge_map, od.surf_map,
                  od.qcap, od.corr, od.corr_ok, od.knn_ids, od.loss, od.partials);
-    for (int k = 0; k < 4; ++k)
+    FLOAM_LAUNCH(K_LM_CLUSTER, lm_cluster_kernel, kClusterCtas, kClusterThreads, s, S, od.ds_edge, od.d_nds_edge, od.ds_surf, od.d_nds_surf, od.qcap, od.corr, od.corr_ok,
+                 od.loss);
+    for (int k = 0; k < 4 && od.qcap * 2 > kClusterMaxSlots; ++k)   // fallback for problems too large for one cluster; exits at once otherwise
       FLOAM_LAUNCH(K_CAND_EVAL, cand_eval_kernel, kCandBlocks, kEvalThreads, s, S, od.ds_edge, od.d_nds_edge, od.ds_surf, od.d_nds_surf, od.qcap, od.corr, od.corr_ok, od.loss,
                                                             od.partials);
   }
@@ -931,14 +1056,20 @@ void odom_update_device(OdomDevice& od, const void* d_edge, const int* d_ne, con
   P4* dss[2] = {od.ds_surf, od.ds_edge};
   int* nds[2] = {od.d_nds_surf, od.d_nds_edge};
   const float leaf[2] = {od.leaf_surf, od.leaf_edge};
-  for (int k = 0; k < 2; ++k) {
+  cudaEventRecord(od.ev_fork, s);
+  cudaStreamWaitEvent(a, od.ev_fork, 0);
+  for (int k = 0; k < 2; ++k) {   // k = 0: surf map on the main branch; k = 1: edge map on the aux branch
     LocalMap& mp = *maps[k];
-    FLOAM_LAUNCH(K_MAP_APPEND, map_append_kernel, grid_for(od.qcap), kThreads, s, dss[k], nds[k], mp.pts, mp.d_n, mp.cap, S, skip);
+    cudaStream_t st = k == 0 ? s : a;
+    VoxelWorkspace& ws = k == 0 ? *od.vws : *od.vws_aux;
+    FLOAM_LAUNCH(K_MAP_APPEND, map_append_kernel, grid_for(od.qcap), kThreads, st, dss[k], nds[k], mp.pts, mp.d_n, mp.cap, S, skip);
     // the appended points are counted in by the crop itself (no separate size bump); the voxel filter then rewrites *d_n
-    crop_box_device(mp.pts, mp.d_n, mp.cap, S->crop_bounds, mp.tmp, mp.d_ncrop, *od.vws, skip, s, nds[k], mp.cap);
-    voxel_grid_device(mp.tmp, 16, mp.d_ncrop, mp.cap, leaf[k], mp.pts, mp.d_n, *od.vws, skip, s);
-    rebuild_grid(od, mp, skip, s);
+    crop_box_device(mp.pts, mp.d_n, mp.cap, S->crop_bounds, mp.tmp, mp.d_ncrop, ws, skip, st, nds[k], mp.cap);
+    voxel_grid_device(mp.tmp, 16, mp.d_ncrop, mp.cap, leaf[k], mp.pts, mp.d_n, ws, skip, st);
+    rebuild_grid(od, mp, skip, st, &ws);
   }
+  cudaEventRecord(od.ev_join, a);
+  cudaStreamWaitEvent(s, od.ev_join, 0);
 }
 
 void compensate_velocity_device(OdomDevice& od, PointIRT* d_pts, const int* d_n, int n_max, cudaStream_t s) {

@@ -67,7 +67,10 @@ struct OdomDevice {
   int* knn_ids;                // [2*qcap*5] debug taps / floam_knn5
   float* knn_d2;               // [2*qcap*5]
   double* partials;            // [CTAs of the association kernel][kLmTerms]
-  VoxelWorkspace* vws;
+  VoxelWorkspace* vws;         // main-branch workspace (surf side)
+  VoxelWorkspace* vws_aux;     // second workspace: the edge side runs as a parallel branch of the frame graph
+  cudaStream_t aux_stream;     // fork/join partner of the context stream
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   float leaf_edge, leaf_surf;
   double scan_period;
   int loss;
@@ -77,7 +80,8 @@ struct OdomDevice {
 };
 
 int local_map_alloc(LocalMap& map, int cap, int ncells_cap, void* (*alloc)(void*, size_t), void* alloc_ctx, cudaStream_t s);
-int odom_device_init(OdomDevice& od, const floam_params& prm, VoxelWorkspace* vws, void* (*alloc)(void*, size_t), void* alloc_ctx, cudaStream_t s);
+int odom_device_init(OdomDevice& od, const floam_params& prm, VoxelWorkspace* vws, VoxelWorkspace* vws_aux, cudaStream_t aux, void* (*alloc)(void*, size_t),
+                     void* alloc_ctx, cudaStream_t s);
 void odom_reset_state(OdomDevice& od, cudaStream_t s);
 // appends the current pose to the device trajectory log (first frame: the update path does it in its finish kernel)
 void odom_record_pose(OdomDevice& od, cudaStream_t s);

@@ -294,28 +294,32 @@ FM_HD void colpiv_qr_solve_5x3(double* a, const double* b, double* x_out) {
 
 // Solve the symmetric positive definite 6x6 system A y = b (A full row-major 36). Cholesky; returns false when not SPD / non-finite.
 FM_HD bool cholesky6_solve(const double* A, const double* b, double* y) {
-  double L[36];
-  for (int i = 0; i < 6; ++i)
-    for (int j = 0; j <= i; ++j) {
-      double s = A[i * 6 + j];
-      for (int k = 0; k < j; ++k) s -= L[i * 6 + k] * L[j * 6 + k];
-      if (i == j) {
-        if (!(s > 0.0)) return false;
-        L[i * 6 + i] = sqrt(s);
-      } else {
-        L[i * 6 + j] = s / L[j * 6 + j];
-      }
+  // L L^T = A with one reciprocal per column and fused multiply-adds (this solve replaces Ceres' Householder QR of the stacked
+  // Jacobian; it is not part of the bit-exact arithmetic, only of the 1e-4 pose tolerance)
+  double L[36], inv[6];
+  for (int j = 0; j < 6; ++j) {
+    double s = A[j * 6 + j];
+    for (int k = 0; k < j; ++k) s = fma(-L[j * 6 + k], L[j * 6 + k], s);
+    if (!(s > 0.0)) return false;
+    const double d = sqrt(s);
+    L[j * 6 + j] = d;
+    inv[j] = 1.0 / d;
+    for (int i = j + 1; i < 6; ++i) {
+      double t = A[i * 6 + j];
+      for (int k = 0; k < j; ++k) t = fma(-L[i * 6 + k], L[j * 6 + k], t);
+      L[i * 6 + j] = t * inv[j];
     }
+  }
   double z[6];
   for (int i = 0; i < 6; ++i) {
     double s = b[i];
-    for (int k = 0; k < i; ++k) s -= L[i * 6 + k] * z[k];
-    z[i] = s / L[i * 6 + i];
+    for (int k = 0; k < i; ++k) s = fma(-L[i * 6 + k], z[k], s);
+    z[i] = s * inv[i];
   }
   for (int i = 5; i >= 0; --i) {
     double s = z[i];
-    for (int k = i + 1; k < 6; ++k) s -= L[k * 6 + i] * y[k];
-    y[i] = s / L[i * 6 + i];
+    for (int k = i + 1; k < 6; ++k) s = fma(-L[k * 6 + i], y[k], s);
+    y[i] = s * inv[i];
   }
   for (int i = 0; i < 6; ++i) if (!isfinite(y[i])) return false;
   return true;

@@ -37,6 +37,7 @@ static const char* const kSlotNames[K_NUM_SLOTS] = {
   "predict",
   "assoc_knn",
   "assoc_eval",
+  "lm_cluster",
   "cand_eval",
   "finish",
   "map_append",
@@ -77,6 +78,7 @@ int launch_timer_collect(LaunchTimer* t, cudaStream_t s) {
   FLOAM_CUDA_OK(cudaStreamSynchronize(s));
   for (int i = 0; i < t->used; ++i) {
     float ms = 0.f;
+    cudaEventSynchronize(t->ev[2 * i + 1]);  // pairs recorded on the aux branch are not covered by the stream synchronise
     if (cudaEventElapsedTime(&ms, t->ev[2 * i], t->ev[2 * i + 1]) == cudaSuccess) {
       t->total_ms[t->slot_of[i]] += ms;
       t->launches[t->slot_of[i]]++;

@@ -134,6 +134,12 @@ int floam_process_scan(floam_ctx* ctx, const floam_point_xyzirt* pts, int n, int
  * the matching floam_process_wait returns. At most two submissions may be in flight. */
 int floam_process_submit(floam_ctx* ctx, const floam_point_xyzirt* pts, int n, int deskew);
 int floam_process_wait(floam_ctx* ctx, double pose_out[7]);
+/* The same with the IMU steps of laser_processing() folded in: CenterTime + dmapping::Compensate + IMU alignment run on the
+ * uploaded scan before feature extraction (src/laserProcessingNode.cpp:100-116). *stamp_us is re-centred like the reference.
+ * Returns FLOAM_NO_IMU — and processes nothing — when Compensate would return false (the node skips such scans, :108-112). */
+int floam_process_submit_imu(floam_ctx* ctx, const floam_point_xyzirt* pts, int n, uint64_t* stamp_us, const double extrinsics_xyzw[4], int deskew);
+int floam_process_scan_imu(floam_ctx* ctx, const floam_point_xyzirt* pts, int n, uint64_t* stamp_us, const double extrinsics_xyzw[4], int deskew,
+                           double pose_out[7]);
 /* Device-resident replay for kernel-only timing: the scans already sit in HBM (uploaded once with floam_stage_scans). */
 int floam_stage_scans(floam_ctx* ctx, const floam_point_xyzirt* pts, const int64_t* offsets, int n_frames);
 int floam_process_staged(floam_ctx* ctx, int frame, int deskew, double pose_out[7]);

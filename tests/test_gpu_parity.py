@@ -474,3 +474,36 @@ def test_long_sequence_trajectory_error(capi, po, synth, sequences):
     assert rmse_faithful < 0.01, rmse_faithful
     gt = [seq.pose(0.1 * f) for f in range(frames)]
     assert abs(synth.ate(P, gt)[0] - synth.ate(O_total, gt)[0]) < 0.01
+
+
+@pytest.mark.parametrize("sensor,deskew", [("vlp16", True), ("hdl64", False)])
+def test_fused_imu_frame_path(capi, po, synth, sensor, deskew):
+    # configs[2]: CenterTime + Compensate + IMU alignment + features + (two-pass deskew) odometry as one device pass per frame
+    frames = 6
+    seq = synth.Sequence(sensor, seed=2, distort=True)
+    nl = LINES[sensor]
+    ext = po.euler2quat(0, 0, 180)
+    ctx = fresh(capi, nl, loss="huber"); imu = po.Imu()
+    orc = po.Odom(num_lines=nl, loss="huber", total_order=True, use_kdtree=False)
+    for k in range(-40, 40 + 20 * frames):
+        t = 500.0 + 0.005 * k
+        q = seq.imu(max(t - 500.0, 0.0))
+        ctx.imu_push(t, q); imu.add(t, q)
+    for f in range(frames):
+        s = seq.scan(f); ref = s.copy()
+        stamp = int((500.0 + 0.1 * f) * 1e6)
+        rc, pose, st = ctx.process_scan_imu(s, stamp, ext, deskew)
+        orc_rc, ost = imu.deskew_align(ref, stamp, ext)
+        assert rc == capi.OK and orc_rc == 0 and st == ost
+        e, sf, es, ss, _ = po.feature_extract(ref, nl, 2.0, 60.0, total_order=True)
+        assert np.array_equal(ctx.debug_fetch(capi.DBG_FEATURE_SRC_EDGE, np.int32), es)
+        assert np.array_equal(ctx.debug_fetch(capi.DBG_FEATURE_SRC_SURF, np.int32), ss)
+        if f == 0:
+            orc.init_map(synth.to_xyzi(e), synth.to_xyzi(sf)); opose = np.array([0, 0, 0, 1, 0, 0, 0.0])
+        else:
+            opose = orc.update(e, sf, deskew)
+        assert np.abs(pose - opose).max() < 1e-8
+    # a scan the IMU buffer does not cover is skipped, like the node's `continue`
+    rc, _, _ = ctx.process_scan_imu(seq.scan(frames), int(9000.0 * 1e6), ext, deskew)
+    assert rc == capi.NO_IMU
+    ctx.close()
