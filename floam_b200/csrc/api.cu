@@ -846,6 +846,13 @@ int floam_debug_fetch(floam_ctx* c, int what, void* out, size_t cap_bytes, size_
       std::memcpy(out, sc, sizeof(sc));
       return FLOAM_OK;
     }
+    case FLOAM_DBG_CLOCKS: {
+      *n_bytes = sizeof(S->dbg_clk);
+      if (!out) return FLOAM_OK;
+      if (*n_bytes > cap_bytes) return FLOAM_ERR_CAPACITY;
+      std::memcpy(out, S->dbg_clk, sizeof(S->dbg_clk));
+      return FLOAM_OK;
+    }
     case FLOAM_DBG_FEATURE_SRC_EDGE: return copy_dev(c->d_edge_src, (size_t)ne * 4);
     case FLOAM_DBG_FEATURE_SRC_SURF: return copy_dev(c->d_surf_src, (size_t)ns * 4);
     default: return FLOAM_ERR_ARG;

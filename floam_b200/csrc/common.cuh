@@ -51,7 +51,6 @@ enum KernelSlot {
   K_ASSOC_KNN,
   K_ASSOC_EVAL,
   K_LM_CLUSTER,
-  K_CAND_EVAL,
   K_FINISH,
   K_MAP_APPEND,
   K_COMPENSATE_VELOCITY,

@@ -9,9 +9,9 @@
 //   addEdgeCostFactor/addSurfCostFactor :144-251         assoc_eval_kernel: pointAssociateToMap, exact 5-NN over the 27
 //                                                         neighbouring cells with (distance, index) order, PCA line fit /
 //                                                         5x3 QR plane fit, and the iteration-0 residual+Jacobian reduction
-//   ceres::Solve :100-108 (LM, <= 4 step attempts)       cand_eval_kernel x4: evaluates the candidate pose; the last CTA
-//                                                         to finish runs the trust-region bookkeeping (accept / reject,
-//                                                         radius law, tolerances, next step) on the device
+//   ceres::Solve :100-108 (LM, <= 4 step attempts)       lm_cluster_kernel: one 8-CTA cluster evaluates each candidate pose and
+//                                                         CTA 0 runs the trust-region bookkeeping (accept / reject, radius law,
+//                                                         tolerances, next step) between two cluster barriers, on the device
 //   odom write-back, KeyFrameUpdate :114-118,320-343     finish_kernel (1 thread)
 //   addPointsToMap :253-294                              append_kernel -> crop_box_device -> voxel_grid_device -> grid rebuild,
 //                                                         all predicated on the device-side keyframe flag (no host sync)
@@ -33,7 +33,6 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kAssocBlocks = kNumSMs * 2;   // 296 CTAs x 128 threads, grid-stride over the query slots
 constexpr int kKnnBlocks = kNumSMs * 4;     // 592 CTAs x 8 warps, one warp per query, grid-stride
-constexpr int kCandBlocks = kNumSMs / 2;    // candidate evaluations touch 88 B per correspondence: 74 CTAs keep the final reduction short
 static_assert(kAssocBlocks <= 1024, "partials rows");
 
 inline int grid_for(int n_max) {
@@ -462,22 +461,23 @@ __device__ void lm_next_candidate(PoseState& S) {
     S.iteration++;
     S.last_successful = 0;
     if (!S.reuse_diag) {
+#pragma unroll
       for (int j = 0; j < 6; ++j) {
         const double d = S.scale[j] * S.scale[j] * S.H[tri(j, j)];
         S.diag[j] = fmin(fmax(d, 1e-6), 1e32);
       }
     }
-    double A[36], gs[6], y[6];
+    // lower triangle of H_s = S H S (Jacobi-scaled normal matrix); the damped system adds D^2 on the diagonal
+    double A[36], gs[6], y[6], hs_diag[6];
+#pragma unroll
     for (int a = 0; a < 6; ++a) {
       gs[a] = S.scale[a] * S.g[a];
-      for (int b = 0; b < 6; ++b) {
-        const int lo = a < b ? a : b, hi = a < b ? b : a;
-        A[a * 6 + b] = S.scale[a] * S.scale[b] * S.H[tri(lo, hi)];
-      }
+#pragma unroll
+      for (int b = 0; b <= a; ++b) A[a * 6 + b] = S.scale[a] * S.scale[b] * S.H[tri(b, a)];
     }
-    double Hs[36];
-    for (int i = 0; i < 36; ++i) Hs[i] = A[i];
+#pragma unroll
     for (int j = 0; j < 6; ++j) {
+      hs_diag[j] = A[j * 6 + j];
       const double lm_diagonal = sqrt(S.diag[j] / S.radius);
       A[j * 6 + j] += lm_diagonal * lm_diagonal;
     }
@@ -485,12 +485,15 @@ __device__ void lm_next_candidate(PoseState& S) {
     S.reuse_diag = 1;
     double step[6], mcc = 0.0;
     if (ok) {
+#pragma unroll
       for (int j = 0; j < 6; ++j) step[j] = -y[j];
       double lin = 0.0, quad = 0.0;
+#pragma unroll
       for (int a = 0; a < 6; ++a) {
         lin += step[a] * gs[a];
         double t = 0.0;
-        for (int b = 0; b < 6; ++b) t += Hs[a * 6 + b] * step[b];
+#pragma unroll
+        for (int b = 0; b < 6; ++b) t += (a == b ? hs_diag[a] : (b < a ? A[a * 6 + b] : A[b * 6 + a])) * step[b];
         quad += step[a] * t;
       }
       mcc = -(lin + 0.5 * quad);
@@ -501,6 +504,7 @@ __device__ void lm_next_candidate(PoseState& S) {
     }
     S.model_cost_change = mcc;
     double delta[6];
+#pragma unroll
     for (int j = 0; j < 6; ++j) delta[j] = step[j] * S.scale[j];
     m::se3_plus(S.x, delta, S.x_cand);
     return;  // candidate pending
@@ -560,6 +564,20 @@ __device__ void lm_after_candidate(PoseState& S, const double* sums) {
 }
 
 constexpr int kEvalThreads = 128;
+
+// The trust-region bookkeeping runs on one thread; it works on a shared-memory copy of the state (tens of dependent reads and
+// writes per step: ~30-cycle shared accesses instead of L2 round trips) that the whole CTA copies in and out.
+static_assert(sizeof(PoseState) % 4 == 0, "PoseState is copied as 32-bit words");
+__device__ __forceinline__ void state_load(PoseState* shared_dst, const PoseState* global_src) {
+  const unsigned int* s = reinterpret_cast<const unsigned int*>(global_src);
+  unsigned int* d = reinterpret_cast<unsigned int*>(shared_dst);
+  for (int i = threadIdx.x; i < (int)(sizeof(PoseState) / 4); i += blockDim.x) d[i] = __ldcg(s + i);  // L2: where the atomics of this kernel landed
+}
+__device__ __forceinline__ void state_store(PoseState* global_dst, const PoseState* shared_src) {
+  const unsigned int* s = reinterpret_cast<const unsigned int*>(shared_src);
+  unsigned int* d = reinterpret_cast<unsigned int*>(global_dst);
+  for (int i = threadIdx.x; i < (int)(sizeof(PoseState) / 4); i += blockDim.x) d[i] = s[i];
+}
 
 // Block reduction of the 28 accumulators into partials[blockIdx.x][*]; returns true in every thread of the last CTA to finish,
 // after which sums[] (shared) holds the grid totals, reduced in a fixed order (deterministic).
@@ -742,58 +760,31 @@ __global__ void __launch_bounds__(kEvalThreads) assoc_eval_kernel(PoseState* __r
   if (lane_id() == 0 && my_corr) atomicAdd(&s_ncorr, my_corr);
   __syncthreads();
   if (threadIdx.x == 0 && s_ncorr) atomicAdd(&S->n_corr_acc, s_ncorr);
-  if (reduce_terms(A, partials, &S->ticket, s_sums) && threadIdx.x == 0) {
-    const int n_corr = atomicExch(&S->n_corr_acc, 0);
-    lm_start(*S, s_sums, n_corr);
-  }
-}
-
-// Evaluates cost, g and H at the pending candidate; the last CTA advances the trust-region loop.
-__global__ void __launch_bounds__(kEvalThreads) cand_eval_kernel(PoseState* __restrict__ S, const P4* __restrict__ ds_edge, const int* __restrict__ d_nde,
-                                                                  const P4* __restrict__ ds_surf, const int* __restrict__ d_nds, int qcap,
-                                                                  const double* __restrict__ corr, const unsigned char* __restrict__ corr_ok, int loss,
-                                                                  double* __restrict__ partials) {
-  if (S->skip_solve || S->lm_done) return;
-  __shared__ double s_sums[kLmTerms];
-  const int nde = *d_nde, nds = *d_nds;
-  double x[7];
-#pragma unroll
-  for (int k = 0; k < 7; ++k) x[k] = S->x_cand[k];
-  Accum A;
-#pragma unroll
-  for (int k = 0; k < kLmTerms; ++k) A.v[k] = 0.0;
-  const size_t cs = (size_t)2 * qcap;
-  for (int slot = blockIdx.x * kEvalThreads + threadIdx.x; slot < nde + nds; slot += gridDim.x * kEvalThreads) {
-    const bool is_edge = slot < nde;
-    const int qi = is_edge ? slot : slot - nde;
-    const int out = is_edge ? qi : qcap + qi;
-    if (!corr_ok[out]) continue;
-    const float4 p = __ldg((is_edge ? ds_edge : ds_surf) + qi);
-    const m::V3 pc{(double)p.x, (double)p.y, (double)p.z};
-    double r, J[6], cost_term;
-    if (is_edge) {
-      const m::V3 a{corr[0 * cs + out], corr[1 * cs + out], corr[2 * cs + out]};
-      const m::V3 b{corr[3 * cs + out], corr[4 * cs + out], corr[5 * cs + out]};
-      eval_edge(x, pc, a, b, r, J);
-    } else {
-      const m::V3 n{corr[0 * cs + out], corr[1 * cs + out], corr[2 * cs + out]};
-      eval_surf(x, pc, n, corr[3 * cs + out], r, J);
+  if (reduce_terms(A, partials, &S->ticket, s_sums)) {   // true in every thread of the last CTA
+    __shared__ PoseState st;
+    __shared__ int s_total_corr;
+    if (threadIdx.x == 0) s_total_corr = atomicExch(&S->n_corr_acc, 0);
+    __syncthreads();
+    state_load(&st, S);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      st.ticket = 0;        // reduce_terms re-armed it in global memory; keep the copy consistent whatever the copy-in saw
+      st.n_corr_acc = 0;
+      lm_start(st, s_sums, s_total_corr);
     }
-    loss_correct(loss, r, J, cost_term);
-    accumulate(A, r, J, cost_term);
+    __syncthreads();
+    state_store(S, &st);
   }
-  if (reduce_terms(A, partials, &S->ticket, s_sums) && threadIdx.x == 0) lm_after_candidate(*S, s_sums);
 }
 
 // The whole ceres::Solve step loop (<= 4 attempts) of one outer iteration in ONE thread-block cluster (8 CTAs on 8 SMs), for the
 // usual problem sizes: every CTA evaluates its share of the correspondences at the pending candidate and reduces the 28 terms in
 // its own shared memory; after a cluster barrier CTA 0 adds the eight partial rows through distributed shared memory (fixed order)
 // and its thread 0 advances the trust-region state; a second barrier publishes the next candidate to the other CTAs, again through
-// DSMEM. No partials in global memory, no ticket, no kernel boundary between attempts. Problems with more than kClusterMaxSlots
-// query slots are left to the multi-CTA cand_eval_kernel launches that follow (which otherwise are not even enqueued).
+// DSMEM. No partials in global memory, no ticket, no kernel boundary between attempts. (2048 threads stride over the slots, so a
+// 100k-query problem costs ~50 evaluations per thread and attempt: still tens of microseconds.)
 constexpr int kClusterCtas = 8;
 constexpr int kClusterThreads = 256;
-constexpr int kClusterMaxSlots = 65536;
 struct ClusterShared {
   double part[kClusterThreads / 32][kLmTerms];
   double row[kLmTerms];   // this CTA's 28 totals
@@ -808,9 +799,10 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClusterT
   // uniform across the cluster: decided from values the previous kernel wrote
   if (S->skip_solve || S->lm_done) return;
   const int nde = *d_nde, nds = *d_nds;
-  if (nde + nds > kClusterMaxSlots) return;
   __shared__ ClusterShared sh;
+  __shared__ PoseState st;   // CTA 0's working copy of the state
   const unsigned int rank = cluster.block_rank();
+  if (rank == 0) state_load(&st, S);
   ClusterShared* sh0 = cluster.map_shared_rank(&sh, 0);
   double x[7];
 #pragma unroll
@@ -818,7 +810,9 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClusterT
   const size_t cs = (size_t)2 * qcap;
   const int w = warp_id(), l = lane_id();
   const int tid = rank * kClusterThreads + threadIdx.x, nthreads = kClusterCtas * kClusterThreads;
+  long long clk[6] = {0, 0, 0, 0, 0, 0};
   for (int attempt = 0; attempt < 4; ++attempt) {
+    clk[0] = clock64();
     Accum A;
 #pragma unroll
     for (int k = 0; k < kLmTerms; ++k) A.v[k] = 0.0;
@@ -841,6 +835,7 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClusterT
       loss_correct(loss, r, J, cost_term);
       accumulate(A, r, J, cost_term);
     }
+    clk[1] = clock64();
 #pragma unroll
     for (int k = 0; k < kLmTerms; ++k) {
       double v = A.v[k];
@@ -855,7 +850,9 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClusterT
       for (int ww = 0; ww < kClusterThreads / 32; ++ww) v += sh.part[ww][threadIdx.x];
       sh.row[threadIdx.x] = v;
     }
+    clk[2] = clock64();
     cluster.sync();   // every CTA's row is in place
+    clk[3] = clock64();
     if (rank == 0) {
       __shared__ double s_sums[kLmTerms];
       if (threadIdx.x < kLmTerms) {
@@ -866,13 +863,17 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClusterT
       }
       __syncthreads();
       if (threadIdx.x == 0) {
-        lm_after_candidate(*S, s_sums);
-        sh.done = S->lm_done;
+        lm_after_candidate(st, s_sums);
+        sh.done = st.lm_done;
 #pragma unroll
-        for (int k = 0; k < 7; ++k) sh.x[k] = S->x_cand[k];
+        for (int k = 0; k < 7; ++k) sh.x[k] = st.x_cand[k];
+        clk[4] = clock64();
       }
     }
     cluster.sync();   // CTA 0 has published the verdict and the next candidate
+    clk[5] = clock64();
+    if (rank == 0 && threadIdx.x == 0)
+      for (int k = 0; k < 6; ++k) st.dbg_clk[k] = clk[k];
     const int done = sh0->done;
 #pragma unroll
     for (int k = 0; k < 7; ++k) x[k] = sh0->x[k];
@@ -880,6 +881,7 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClusterT
     // no third barrier: row[] is rewritten only after this barrier pair, and CTA 0 rewrites x/done only after the next round's first
     // barrier, which every CTA reaches after it has read this round's values
   }
+  if (rank == 0) state_store(S, &st);   // ordered after thread 0's last update by the barrier pair above
   cluster.sync();     // CTA 0's shared memory must outlive the last remote read
 }
 
@@ -1044,9 +1046,6 @@ void odom_update_device(OdomDevice& od, const void* d_edge, const int* d_ne, con
                  od.qcap, od.corr, od.corr_ok, od.knn_ids, od.loss, od.partials);
     FLOAM_LAUNCH(K_LM_CLUSTER, lm_cluster_kernel, kClusterCtas, kClusterThreads, s, S, od.ds_edge, od.d_nds_edge, od.ds_surf, od.d_nds_surf, od.qcap, od.corr, od.corr_ok,
                  od.loss);
-    for (int k = 0; k < 4 && od.qcap * 2 > kClusterMaxSlots; ++k)   // fallback for problems too large for one cluster; exits at once otherwise
-      FLOAM_LAUNCH(K_CAND_EVAL, cand_eval_kernel, kCandBlocks, kEvalThreads, s, S, od.ds_edge, od.d_nds_edge, od.ds_surf, od.d_nds_surf, od.qcap, od.corr, od.corr_ok, od.loss,
-                                                            od.partials);
   }
   FLOAM_LAUNCH(K_FINISH, finish_kernel, 1, 32, s, S, update_type, od.scan_period, od.traj, od.traj_cap);
   if (update_type == FLOAM_INITIAL_ITERATION) return;

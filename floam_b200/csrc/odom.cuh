@@ -31,6 +31,7 @@ struct PoseState {
   int n_corr;            // accepted correspondences of the last association
   int n_corr_acc;        // accumulator of the running association
   int frame_counter;     // frames completed (index of the next trajectory record)
+  long long dbg_clk[8];  // clock64 stamps of the last lm_cluster_kernel attempt (development aid, FLOAM_DBG_CLOCKS)
 };
 
 struct GridDims {

@@ -128,42 +128,45 @@ FM_HD void givens(double p, double q, double& c, double& s) {
   else if (fabs(p) > fabs(q)) { const double t = q / p; double u = sqrt(1.0 + t * t); if (p < 0.0) u = -u; c = 1.0 / u; s = -t * c; }
   else { const double t = p / q; double u = sqrt(1.0 + t * t); if (q < 0.0) u = -u; s = -1.0 / u; c = -t * s; }
 }
+// Written with scalars and fully unrolled, statically indexed steps so that everything stays in registers on the device (the 3x3
+// QL loop only ever rotates at k = 0 and/or k = 1); the arithmetic and its order are those of the general algorithm.
 FM_HD bool eigen3_sym(double m00, double m10, double m11, double m20, double m21, double m22, double* vals, double* vmax) {
   double scale_ = fmax(fmax(fmax(fabs(m00), fabs(m10)), fmax(fabs(m11), fabs(m20))), fmax(fabs(m21), fabs(m22)));
   if (scale_ == 0.0) scale_ = 1.0;
   m00 /= scale_; m10 /= scale_; m11 /= scale_; m20 /= scale_; m21 /= scale_; m22 /= scale_;
-  double diag[3], sub[2], Q[9];
+  double d0, d1, d2, s0, s1;
+  double q00 = 1, q01 = 0, q02 = 0, q10 = 0, q11 = 1, q12 = 0, q20 = 0, q21 = 0, q22 = 1;
   const double tiny = 2.2250738585072014e-308;
-  diag[0] = m00;
+  d0 = m00;
   const double v1norm2 = m20 * m20;
   if (v1norm2 <= tiny) {
-    diag[1] = m11; diag[2] = m22; sub[0] = m10; sub[1] = m21;
-    Q[0] = 1; Q[1] = 0; Q[2] = 0; Q[3] = 0; Q[4] = 1; Q[5] = 0; Q[6] = 0; Q[7] = 0; Q[8] = 1;
+    d1 = m11; d2 = m22; s0 = m10; s1 = m21;
   } else {
     const double beta = sqrt(m10 * m10 + v1norm2);
     const double invBeta = 1.0 / beta;
     const double m01 = m10 * invBeta, m02 = m20 * invBeta;
     const double q = 2.0 * m01 * m21 + m02 * (m22 - m11);
-    diag[1] = m11 + m02 * q;
-    diag[2] = m22 - m02 * q;
-    sub[0] = beta;
-    sub[1] = m21 - m01 * q;
-    Q[0] = 1; Q[1] = 0; Q[2] = 0; Q[3] = 0; Q[4] = m01; Q[5] = m02; Q[6] = 0; Q[7] = m02; Q[8] = -m01;
+    d1 = m11 + m02 * q;
+    d2 = m22 - m02 * q;
+    s0 = beta;
+    s1 = m21 - m01 * q;
+    q11 = m01; q12 = m02; q21 = m02; q22 = -m01;
   }
   int end = 2, start = 0, iter = 0;
   const double precision = 2.0 * 2.220446049250313e-16;
   while (end > 0) {
-    for (int i = start; i < end; ++i)
-      if (fabs(sub[i]) <= (fabs(diag[i]) + fabs(diag[i + 1])) * precision || fabs(sub[i]) <= tiny) sub[i] = 0.0;
-    while (end > 0 && sub[end - 1] == 0.0) end--;
+    if (start <= 0 && 0 < end && (fabs(s0) <= (fabs(d0) + fabs(d1)) * precision || fabs(s0) <= tiny)) s0 = 0.0;
+    if (start <= 1 && 1 < end && (fabs(s1) <= (fabs(d1) + fabs(d2)) * precision || fabs(s1) <= tiny)) s1 = 0.0;
+    if (end == 2 && s1 == 0.0) end = 1;
+    if (end == 1 && s0 == 0.0) end = 0;
     if (end <= 0) break;
     iter++;
     if (iter > 90) break;
     start = end - 1;
-    while (start > 0 && sub[start - 1] != 0.0) start--;
-    const double td = (diag[end - 1] - diag[end]) * 0.5;
-    const double e = sub[end - 1];
-    double mu = diag[end];
+    if (start == 1 && s0 != 0.0) start = 0;
+    const double td = (end == 2 ? (d1 - d2) : (d0 - d1)) * 0.5;
+    const double e = end == 2 ? s1 : s0;
+    double mu = end == 2 ? d2 : d1;
     if (td == 0.0) {
       mu -= fabs(e);
     } else {
@@ -172,71 +175,138 @@ FM_HD bool eigen3_sym(double m00, double m10, double m11, double m20, double m21
       if (e2 == 0.0) mu -= (e / (td + (td > 0.0 ? 1.0 : -1.0))) * (e / h);
       else mu -= e2 / (td + (td > 0.0 ? h : -h));
     }
-    double x = diag[start] - mu;
-    double z = sub[start];
-    for (int k = start; k < end; ++k) {
+    double x = (start == 0 ? d0 : d1) - mu;
+    double z = start == 0 ? s0 : s1;
+    if (start == 0) {  // k = 0
       double c, s;
       givens(x, z, c, s);
-      const double sdk = s * diag[k] + c * sub[k];
-      const double dkp1 = s * sub[k] + c * diag[k + 1];
-      diag[k] = c * (c * diag[k] - s * sub[k]) - s * (c * sub[k] - s * diag[k + 1]);
-      diag[k + 1] = s * sdk + c * dkp1;
-      sub[k] = c * sdk - s * dkp1;
-      if (k > start) sub[k - 1] = c * sub[k - 1] - s * z;
-      x = sub[k];
-      if (k < end - 1) { z = -s * sub[k + 1]; sub[k + 1] = c * sub[k + 1]; }
-      for (int i = 0; i < 3; ++i) {
-        const double xi = Q[i * 3 + k], yi = Q[i * 3 + k + 1];
-        Q[i * 3 + k] = c * xi - s * yi;
-        Q[i * 3 + k + 1] = s * xi + c * yi;
-      }
+      const double sdk = s * d0 + c * s0;
+      const double dkp1 = s * s0 + c * d1;
+      d0 = c * (c * d0 - s * s0) - s * (c * s0 - s * d1);
+      d1 = s * sdk + c * dkp1;
+      s0 = c * sdk - s * dkp1;
+      x = s0;
+      if (end == 2) { z = -s * s1; s1 = c * s1; }
+      double xi, yi;
+      xi = q00; yi = q01; q00 = c * xi - s * yi; q01 = s * xi + c * yi;
+      xi = q10; yi = q11; q10 = c * xi - s * yi; q11 = s * xi + c * yi;
+      xi = q20; yi = q21; q20 = c * xi - s * yi; q21 = s * xi + c * yi;
+    }
+    if (end == 2) {    // k = 1
+      double c, s;
+      givens(x, z, c, s);
+      const double sdk = s * d1 + c * s1;
+      const double dkp1 = s * s1 + c * d2;
+      d1 = c * (c * d1 - s * s1) - s * (c * s1 - s * d2);
+      d2 = s * sdk + c * dkp1;
+      s1 = c * sdk - s * dkp1;
+      if (start == 0) s0 = c * s0 - s * z;
+      double xi, yi;
+      xi = q01; yi = q02; q01 = c * xi - s * yi; q02 = s * xi + c * yi;
+      xi = q11; yi = q12; q11 = c * xi - s * yi; q12 = s * xi + c * yi;
+      xi = q21; yi = q22; q21 = c * xi - s * yi; q22 = s * xi + c * yi;
     }
   }
   // ascending selection sort with matching eigenvector columns
-  for (int i = 0; i < 2; ++i) {
-    int k = i;
-    for (int j = i + 1; j < 3; ++j) if (diag[j] < diag[k]) k = j;
-    if (k != i) {
-      const double t = diag[i]; diag[i] = diag[k]; diag[k] = t;
-      for (int r = 0; r < 3; ++r) { const double u = Q[r * 3 + i]; Q[r * 3 + i] = Q[r * 3 + k]; Q[r * 3 + k] = u; }
-    }
+#define FM_SWAPD(a, b) { const double t_ = a; a = b; b = t_; }
+  {
+    int k = 0;
+    if (d1 < d0) k = 1;
+    if (d2 < (k == 1 ? d1 : d0)) k = 2;
+    if (k == 1) { FM_SWAPD(d0, d1); FM_SWAPD(q00, q01); FM_SWAPD(q10, q11); FM_SWAPD(q20, q21); }
+    else if (k == 2) { FM_SWAPD(d0, d2); FM_SWAPD(q00, q02); FM_SWAPD(q10, q12); FM_SWAPD(q20, q22); }
+    if (d2 < d1) { FM_SWAPD(d1, d2); FM_SWAPD(q01, q02); FM_SWAPD(q11, q12); FM_SWAPD(q21, q22); }
   }
-  vals[0] = diag[0] * scale_; vals[1] = diag[1] * scale_; vals[2] = diag[2] * scale_;
-  vmax[0] = Q[2]; vmax[1] = Q[5]; vmax[2] = Q[8];
+#undef FM_SWAPD
+  vals[0] = d0 * scale_; vals[1] = d1 * scale_; vals[2] = d2 * scale_;
+  vmax[0] = q02; vmax[1] = q12; vmax[2] = q22;
   return iter <= 90;
 }
 
 // Matrix<double,5,3>::colPivHouseholderQr().solve(b): A column-major a[c*5+r], overwritten. (Eigen 3.3 ColPivHouseholderQR)
-FM_HD void householder_make(double* v, int n, double& tau, double& beta) {
+// Template sizes + full unrolling keep every array index static (registers on the device); pivot swaps are predicated.
+template <int N>
+FM_HD void householder_make(double* v, double& tau, double& beta) {
   double tail = 0.0;
-  for (int i = 1; i < n; ++i) tail += v[i] * v[i];
+#pragma unroll
+  for (int i = 1; i < N; ++i) tail += v[i] * v[i];
   const double c0 = v[0];
-  if (n == 1 || tail <= 2.2250738585072014e-308) {
+  if (N == 1 || tail <= 2.2250738585072014e-308) {
     tau = 0.0; beta = c0;
-    for (int i = 1; i < n; ++i) v[i] = 0.0;
+#pragma unroll
+    for (int i = 1; i < N; ++i) v[i] = 0.0;
   } else {
     beta = sqrt(c0 * c0 + tail);
     if (c0 >= 0.0) beta = -beta;
-    for (int i = 1; i < n; ++i) v[i] = v[i] / (c0 - beta);
+#pragma unroll
+    for (int i = 1; i < N; ++i) v[i] = v[i] / (c0 - beta);
     tau = (beta - c0) / beta;
   }
 }
-FM_HD void householder_apply(double* x, int n, const double* ess, double tau) {
-  if (n == 1) { x[0] *= (1.0 - tau); return; }
+template <int N>
+FM_HD void householder_apply(double* x, const double* ess, double tau) {
+  if (N == 1) { x[0] *= (1.0 - tau); return; }
   if (tau == 0.0) return;
   double tmp = 0.0;
-  for (int i = 1; i < n; ++i) tmp += ess[i - 1] * x[i];
+#pragma unroll
+  for (int i = 1; i < N; ++i) tmp += ess[i - 1] * x[i];
   tmp += x[0];
   x[0] -= tau * tmp;
-  for (int i = 1; i < n; ++i) x[i] -= tau * ess[i - 1] * tmp;
+#pragma unroll
+  for (int i = 1; i < N; ++i) x[i] -= tau * ess[i - 1] * tmp;
+}
+template <int K>
+FM_HD void colpiv_step(double* a, double* h, double* nu, double* nd, int* transp, int& nonzero, double threshold_helper, double downdate) {
+  constexpr int rows = 5, cols = 3;
+  int big = K;
+  double bn = nu[K];
+#pragma unroll
+  for (int j = K + 1; j < cols; ++j) if (nu[j] > bn) { bn = nu[j]; big = j; }
+  if (nonzero == cols && bn * bn < threshold_helper * (double)(rows - K)) nonzero = K;
+  transp[K] = big;
+#pragma unroll
+  for (int j = K + 1; j < cols; ++j) {
+    if (big == j) {
+#pragma unroll
+      for (int r = 0; r < rows; ++r) { const double t = a[K * 5 + r]; a[K * 5 + r] = a[j * 5 + r]; a[j * 5 + r] = t; }
+      double t = nu[K]; nu[K] = nu[j]; nu[j] = t;
+      t = nd[K]; nd[K] = nd[j]; nd[j] = t;
+    }
+  }
+  double beta;
+  householder_make<rows - K>(&a[K * 5 + K], h[K], beta);
+  a[K * 5 + K] = beta;
+#pragma unroll
+  for (int j = K + 1; j < cols; ++j) householder_apply<rows - K>(&a[j * 5 + K], &a[K * 5 + K + 1], h[K]);
+#pragma unroll
+  for (int j = K + 1; j < cols; ++j) {
+    if (nu[j] != 0.0) {
+      double temp = fabs(a[j * 5 + K]) / nu[j];
+      temp = (1.0 + temp) * (1.0 - temp);
+      temp = temp < 0.0 ? 0.0 : temp;
+      const double ratio = nu[j] / nd[j];
+      const double temp2 = temp * ratio * ratio;
+      if (temp2 <= downdate) {
+        double s = 0;
+#pragma unroll
+        for (int r = K + 1; r < rows; ++r) s += a[j * 5 + r] * a[j * 5 + r];
+        nd[j] = sqrt(s);
+        nu[j] = nd[j];
+      } else {
+        nu[j] *= sqrt(temp);
+      }
+    }
+  }
 }
 FM_HD void colpiv_qr_solve_5x3(double* a, const double* b, double* x_out) {
-  const int rows = 5, cols = 3;
+  constexpr int rows = 5, cols = 3;
   double h[3], nu[3], nd[3];
   int transp[3];
   const double eps = 2.220446049250313e-16;
+#pragma unroll
   for (int k = 0; k < cols; ++k) {
     double s = 0;
+#pragma unroll
     for (int r = 0; r < rows; ++r) s += a[k * 5 + r] * a[k * 5 + r];
     nd[k] = nu[k] = sqrt(s);
   }
@@ -244,52 +314,38 @@ FM_HD void colpiv_qr_solve_5x3(double* a, const double* b, double* x_out) {
   const double threshold_helper = (maxn * eps) * (maxn * eps) / (double)rows;
   const double downdate = sqrt(eps);
   int nonzero = cols;
-  for (int k = 0; k < cols; ++k) {
-    int big = k;
-    double bn = nu[k];
-    for (int j = k + 1; j < cols; ++j) if (nu[j] > bn) { bn = nu[j]; big = j; }
-    if (nonzero == cols && bn * bn < threshold_helper * (double)(rows - k)) nonzero = k;
-    transp[k] = big;
-    if (k != big) {
-      for (int r = 0; r < rows; ++r) { const double t = a[k * 5 + r]; a[k * 5 + r] = a[big * 5 + r]; a[big * 5 + r] = t; }
-      double t = nu[k]; nu[k] = nu[big]; nu[big] = t;
-      t = nd[k]; nd[k] = nd[big]; nd[big] = t;
-    }
-    double beta;
-    householder_make(&a[k * 5 + k], rows - k, h[k], beta);
-    a[k * 5 + k] = beta;
-    for (int j = k + 1; j < cols; ++j) householder_apply(&a[j * 5 + k], rows - k, &a[k * 5 + k + 1], h[k]);
-    for (int j = k + 1; j < cols; ++j) {
-      if (nu[j] != 0.0) {
-        double temp = fabs(a[j * 5 + k]) / nu[j];
-        temp = (1.0 + temp) * (1.0 - temp);
-        temp = temp < 0.0 ? 0.0 : temp;
-        const double ratio = nu[j] / nd[j];
-        const double temp2 = temp * ratio * ratio;
-        if (temp2 <= downdate) {
-          double s = 0;
-          for (int r = k + 1; r < rows; ++r) s += a[j * 5 + r] * a[j * 5 + r];
-          nd[j] = sqrt(s);
-          nu[j] = nd[j];
-        } else {
-          nu[j] *= sqrt(temp);
-        }
-      }
-    }
-  }
-  int perm[3] = {0, 1, 2};
-  for (int k = 0; k < cols; ++k) { const int t = perm[k]; perm[k] = perm[transp[k]]; perm[transp[k]] = t; }
+  colpiv_step<0>(a, h, nu, nd, transp, nonzero, threshold_helper, downdate);
+  colpiv_step<1>(a, h, nu, nd, transp, nonzero, threshold_helper, downdate);
+  colpiv_step<2>(a, h, nu, nd, transp, nonzero, threshold_helper, downdate);
+  // column permutation: perm = identity with the recorded transpositions applied in order
+  int p0 = 0, p1 = 1, p2 = 2;
+  if (transp[0] == 1) { const int t = p0; p0 = p1; p1 = t; } else if (transp[0] == 2) { const int t = p0; p0 = p2; p2 = t; }
+  if (transp[1] == 2) { const int t = p1; p1 = p2; p2 = t; }
   x_out[0] = x_out[1] = x_out[2] = 0.0;
   if (nonzero == 0) return;
   double c[5];
+#pragma unroll
   for (int r = 0; r < rows; ++r) c[r] = b[r];
-  for (int k = 0; k < nonzero; ++k) householder_apply(&c[k], rows - k, &a[k * 5 + k + 1], h[k]);
-  for (int i = nonzero - 1; i >= 0; --i) {
-    double s = c[i];
-    for (int j = i + 1; j < nonzero; ++j) s -= a[j * 5 + i] * c[j];
-    c[i] = s / a[i * 5 + i];
+  if (0 < nonzero) householder_apply<5>(&c[0], &a[0 * 5 + 1], h[0]);
+  if (1 < nonzero) householder_apply<4>(&c[1], &a[1 * 5 + 2], h[1]);
+  if (2 < nonzero) householder_apply<3>(&c[2], &a[2 * 5 + 3], h[2]);
+  // back substitution on the leading nonzero x nonzero block
+  if (nonzero == 3) {
+    c[2] = c[2] / a[2 * 5 + 2];
+    c[1] = (c[1] - a[2 * 5 + 1] * c[2]) / a[1 * 5 + 1];
+    c[0] = ((c[0] - a[1 * 5 + 0] * c[1]) - a[2 * 5 + 0] * c[2]) / a[0 * 5 + 0];
+  } else if (nonzero == 2) {
+    c[1] = c[1] / a[1 * 5 + 1];
+    c[0] = (c[0] - a[1 * 5 + 0] * c[1]) / a[0 * 5 + 0];
+  } else {
+    c[0] = c[0] / a[0 * 5 + 0];
   }
-  for (int i = 0; i < nonzero; ++i) x_out[perm[i]] = c[i];
+  const int pk[3] = {p0, p1, p2};
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    if (i < nonzero) {
+      if (pk[i] == 0) x_out[0] = c[i]; else if (pk[i] == 1) x_out[1] = c[i]; else x_out[2] = c[i];
+    }
 }
 
 // Solve the symmetric positive definite 6x6 system A y = b (A full row-major 36). Cholesky; returns false when not SPD / non-finite.
@@ -297,27 +353,35 @@ FM_HD bool cholesky6_solve(const double* A, const double* b, double* y) {
   // L L^T = A with one reciprocal per column and fused multiply-adds (this solve replaces Ceres' Householder QR of the stacked
   // Jacobian; it is not part of the bit-exact arithmetic, only of the 1e-4 pose tolerance)
   double L[36], inv[6];
+#pragma unroll
   for (int j = 0; j < 6; ++j) {
     double s = A[j * 6 + j];
+#pragma unroll
     for (int k = 0; k < j; ++k) s = fma(-L[j * 6 + k], L[j * 6 + k], s);
     if (!(s > 0.0)) return false;
     const double d = sqrt(s);
     L[j * 6 + j] = d;
     inv[j] = 1.0 / d;
+#pragma unroll
     for (int i = j + 1; i < 6; ++i) {
       double t = A[i * 6 + j];
+#pragma unroll
       for (int k = 0; k < j; ++k) t = fma(-L[i * 6 + k], L[j * 6 + k], t);
       L[i * 6 + j] = t * inv[j];
     }
   }
   double z[6];
+#pragma unroll
   for (int i = 0; i < 6; ++i) {
     double s = b[i];
+#pragma unroll
     for (int k = 0; k < i; ++k) s = fma(-L[i * 6 + k], z[k], s);
     z[i] = s * inv[i];
   }
+#pragma unroll
   for (int i = 5; i >= 0; --i) {
     double s = z[i];
+#pragma unroll
     for (int k = i + 1; k < 6; ++k) s = fma(-L[k * 6 + i], y[k], s);
     y[i] = s * inv[i];
   }

@@ -38,7 +38,6 @@ static const char* const kSlotNames[K_NUM_SLOTS] = {
   "assoc_knn",
   "assoc_eval",
   "lm_cluster",
-  "cand_eval",
   "finish",
   "map_append",
   "compensate_velocity",
