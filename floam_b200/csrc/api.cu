@@ -127,21 +127,24 @@ void enqueue_frame_body(floam_ctx* c, PointIRT* d_scan, const int* d_scan_n, int
 int launch_frame(floam_ctx* c, PointIRT* d_scan, const int* d_scan_n, int deskew, int slot, int scan_slot_key, bool imu = false) {
   const bool first = !c->map_initialised;
   OdomDevice& od = c->odom;
-  if (!c->use_graphs || c->timer.enabled) {
+  if (!c->use_graphs) {
     enqueue_frame_body(c, d_scan, d_scan_n, deskew, slot, first, imu);
     c->map_initialised = true;
     return check_async("frame");
   }
-  floam_graph_key key{(first ? 0 : 1) + (imu ? 2 : 0), first ? 0 : next_outer(od.optimization_count), first ? 0 : (deskew ? 1 : 0), scan_slot_key * 2 + slot};
+  const bool timing = c->timer.enabled;
+  floam_graph_key key{(first ? 0 : 1) + (imu ? 2 : 0) + (timing ? 4 : 0), first ? 0 : next_outer(od.optimization_count), first ? 0 : (deskew ? 1 : 0), scan_slot_key * 2 + slot};
   auto it = c->graphs.find(key);
   if (it == c->graphs.end()) {
     const long long before = g_launches;
     const int saved_count = od.optimization_count;
     cudaGraph_t graph = nullptr;
+    floam_graph_entry e;
+    if (timing) { launch_timer_collect(&c->timer, c->stream); e.pair_first = c->timer.used; }
     FLOAM_CUDA_OK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
     enqueue_frame_body(c, d_scan, d_scan_n, deskew, slot, first, imu);
     FLOAM_CUDA_OK(cudaStreamEndCapture(c->stream, &graph));
-    floam_graph_entry e;
+    if (timing) { e.pair_last = c->timer.used; c->timer.persist = c->timer.used; }
     FLOAM_CUDA_OK(cudaGraphInstantiate(&e.exec, graph, 0));
     cudaGraphDestroy(graph);
     e.launches = (int)(g_launches - before);
@@ -158,6 +161,10 @@ int launch_frame(floam_ctx* c, PointIRT* d_scan, const int* d_scan_n, int deskew
   c->map_initialised = true;
   g_launches += it->second.launches;
   FLOAM_CUDA_OK(cudaGraphLaunch(it->second.exec, c->stream));
+  if (timing) {  // per-kernel event pairs live inside the graph: read them back after this replay
+    FLOAM_CUDA_OK(cudaStreamSynchronize(c->stream));
+    launch_timer_fold(&c->timer, it->second.pair_first, it->second.pair_last);
+  }
   return FLOAM_OK;
 }
 
@@ -911,7 +918,7 @@ int floam_set_kernel_timing(floam_ctx* c, int enabled) {
   if (!enabled && t.enabled) launch_timer_collect(&t, c->stream);
   if (enabled && !t.enabled) {
     for (int k = 0; k < K_NUM_SLOTS; ++k) { t.total_ms[k] = 0.0; t.launches[k] = 0; }
-    t.used = 0;
+    t.used = t.persist;
   }
   t.enabled = enabled != 0;
   g_timer = t.enabled ? &t : nullptr;   // the timer follows the calling thread, like the launch counter

@@ -79,7 +79,8 @@ struct LaunchTimer {
   bool enabled = false;
   cudaEvent_t ev[2 * kPairs];
   int slot_of[kPairs];
-  int used = 0;
+  int used = 0;      // pairs handed out so far
+  int persist = 0;   // pairs [0, persist) belong to captured frame graphs (event-record nodes) and are re-read after every replay
   bool created = false;
   double total_ms[K_NUM_SLOTS];
   long long launches[K_NUM_SLOTS];
@@ -87,7 +88,8 @@ struct LaunchTimer {
 extern thread_local LaunchTimer* g_timer;
 void launch_timer_begin(int slot, cudaStream_t s);
 void launch_timer_end(cudaStream_t s);
-int launch_timer_collect(LaunchTimer* t, cudaStream_t s);  // synchronises the stream and folds the pending event pairs into the totals
+int launch_timer_collect(LaunchTimer* t, cudaStream_t s);  // synchronises the stream and folds the pending (non-graph) event pairs into the totals
+void launch_timer_fold(LaunchTimer* t, int first, int last);  // folds the pairs [first, last) of a replayed graph (after a synchronise)
 
 #define FLOAM_LAUNCH(slot, kern, grid, block, stream, ...)            \
   do {                                                                \

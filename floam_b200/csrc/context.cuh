@@ -26,6 +26,7 @@ struct floam_graph_key {
 struct floam_graph_entry {
   cudaGraphExec_t exec = nullptr;
   int launches = 0;   // kernels inside the graph (bench.py's gpu_launches)
+  int pair_first = 0, pair_last = 0;   // event pairs recorded inside the graph (kernel-timing mode)
 };
 
 struct floam_ctx {

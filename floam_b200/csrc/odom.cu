@@ -385,24 +385,36 @@ __device__ __forceinline__ void loss_correct(int loss, double& r, double* J, dou
   for (int j = 0; j < 6; ++j) J[j] *= sr;
 }
 
+// The residual / Jacobian evaluation is not part of the bit-exact arithmetic (only the 1e-4 pose bar applies), and it is what the
+// FP64 pipe spends its time on: explicit fused multiply-adds (the library is built with -fmad=false) and one reciprocal per norm.
+__device__ __forceinline__ m::V3 fcross(m::V3 a, m::V3 b) {
+  return {fma(a.y, b.z, -(a.z * b.y)), fma(a.z, b.x, -(a.x * b.z)), fma(a.x, b.y, -(a.y * b.x))};
+}
+__device__ __forceinline__ double fdot(m::V3 a, m::V3 b) { return fma(a.z, b.z, fma(a.y, b.y, a.x * b.x)); }
+__device__ __forceinline__ m::V3 frotate_translate(const double* x, m::V3 v) {  // q * v + t, Eigen's _transformVector form
+  const m::V3 qv{x[0], x[1], x[2]};
+  m::V3 uv = fcross(qv, v);
+  uv = {uv.x + uv.x, uv.y + uv.y, uv.z + uv.z};
+  const m::V3 c = fcross(qv, uv);
+  return {fma(x[3], uv.x, v.x) + c.x + x[4], fma(x[3], uv.y, v.y) + c.y + x[5], fma(x[3], uv.z, v.z) + c.z + x[6]};
+}
 // EdgeAnalyticCostFunction::Evaluate (src/lidarOptimization.cpp:12-43)
 __device__ __forceinline__ void eval_edge(const double* x, m::V3 p, m::V3 a, m::V3 b, double& r, double* J) {
-  const m::V3 lp = m::add(m::quat_rotate(x, p), m::V3{x[4], x[5], x[6]});
-  const m::V3 nu = m::cross(m::sub(lp, a), m::sub(lp, b));
+  const m::V3 lp = frotate_translate(x, p);
+  const m::V3 nu = fcross(m::sub(lp, a), m::sub(lp, b));
   const m::V3 de = m::sub(a, b);
-  const double de_norm = m::norm(de), nun = m::norm(nu);
-  r = nun / de_norm;
-  const m::V3 w{-nu.x / nun, -nu.y / nun, -nu.z / nun};
-  const m::V3 ws = m::cross(w, de);      // w^T * skew(de)
-  const m::V3 jr = m::cross(lp, ws);     // (w^T skew(de)) * (-skew(lp))
-  J[0] = jr.x / de_norm; J[1] = jr.y / de_norm; J[2] = jr.z / de_norm;
-  J[3] = ws.x / de_norm; J[4] = ws.y / de_norm; J[5] = ws.z / de_norm;
+  const double inv_de = rsqrt(fdot(de, de)), nun = sqrt(fdot(nu, nu));
+  r = nun * inv_de;
+  const double k = -inv_de / nun;          // w / |de|, w = -nu / |nu|
+  const m::V3 ws = fcross(m::V3{nu.x * k, nu.y * k, nu.z * k}, de);   // (w^T skew(de)) / |de|
+  const m::V3 jr = fcross(lp, ws);                                    // ... * (-skew(lp))
+  J[0] = jr.x; J[1] = jr.y; J[2] = jr.z; J[3] = ws.x; J[4] = ws.y; J[5] = ws.z;
 }
 // SurfNormAnalyticCostFunction::Evaluate (:51-74)
 __device__ __forceinline__ void eval_surf(const double* x, m::V3 p, m::V3 n, double d, double& r, double* J) {
-  const m::V3 pw = m::add(m::quat_rotate(x, p), m::V3{x[4], x[5], x[6]});
-  r = m::dot(n, pw) + d;
-  const m::V3 jr = m::cross(pw, n);      // n^T * (-skew(pw))
+  const m::V3 pw = frotate_translate(x, p);
+  r = fdot(n, pw) + d;
+  const m::V3 jr = fcross(pw, n);      // n^T * (-skew(pw))
   J[0] = jr.x; J[1] = jr.y; J[2] = jr.z; J[3] = n.x; J[4] = n.y; J[5] = n.z;
 }
 
@@ -411,10 +423,31 @@ __device__ __forceinline__ void accumulate(Accum& A, double r, const double* J, 
 #pragma unroll
   for (int a = 0; a < 6; ++a)
 #pragma unroll
-    for (int b = a; b < 6; ++b) A.v[k++] += J[a] * J[b];
+    for (int b = a; b < 6; ++b) { A.v[k] = fma(J[a], J[b], A.v[k]); ++k; }
 #pragma unroll
-  for (int a = 0; a < 6; ++a) A.v[21 + a] += J[a] * r;
+  for (int a = 0; a < 6; ++a) A.v[21 + a] = fma(J[a], r, A.v[21 + a]);
   A.v[27] += cost_term;
+}
+
+// Sum of each of the 28 accumulators over the 32 lanes of a warp with a transposing butterfly: at every level a lane hands half of
+// its (padded to 32) values to its partner and keeps the other half, so 16+8+4+2+1 = 31 shuffles replace 28 x 5; lane t ends up
+// holding the warp total of term t. The summation order is fixed.
+__device__ __forceinline__ double warp_reduce_terms(const Accum& A) {
+  const int l = lane_id();
+  double v[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) v[k] = k < kLmTerms ? A.v[k] : 0.0;
+#pragma unroll
+  for (int h = 16; h >= 1; h >>= 1) {
+    const bool upper = (l & h) != 0;   // this lane keeps terms [h, 2h) of its current 2h, its partner keeps [0, h)
+#pragma unroll
+    for (int i = 0; i < h; ++i) {
+      const double send = upper ? v[i] : v[i + h];
+      const double keep = upper ? v[i + h] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+    }
+  }
+  return v[0];
 }
 
 // PoseSE3Parameterization gradient projection used for gradient_max_norm: |x - Plus(x, -g)|_inf
@@ -585,12 +618,9 @@ __device__ bool reduce_terms(const Accum& A, double* __restrict__ partials, unsi
   __shared__ double s_part[kEvalThreads / 32][kLmTerms];
   __shared__ int s_last;
   const int w = warp_id(), l = lane_id();
-#pragma unroll
-  for (int k = 0; k < kLmTerms; ++k) {
-    double v = A.v[k];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (l == 0) s_part[w][k] = v;
+  {
+    const double v = warp_reduce_terms(A);
+    if (l < kLmTerms) s_part[w][l] = v;
   }
   __syncthreads();
   if (threadIdx.x < kLmTerms) {
@@ -836,12 +866,9 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClusterT
       accumulate(A, r, J, cost_term);
     }
     clk[1] = clock64();
-#pragma unroll
-    for (int k = 0; k < kLmTerms; ++k) {
-      double v = A.v[k];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (l == 0) sh.part[w][k] = v;
+    {
+      const double v = warp_reduce_terms(A);
+      if (l < kLmTerms) sh.part[w][l] = v;
     }
     __syncthreads();
     if (threadIdx.x < kLmTerms) {

@@ -59,31 +59,41 @@ static const char* const kSlotNames[K_NUM_SLOTS] = {
 };
 const char* kernel_slot_name(int slot) { return (slot >= 0 && slot < K_NUM_SLOTS) ? kSlotNames[slot] : "?"; }
 
+static void timer_record(cudaEvent_t ev, cudaStream_t s) {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(s, &st);
+  // inside a capture the record becomes an event-record node of the graph; "external" lets the host read it after the replay
+  if (st == cudaStreamCaptureStatusActive) cudaEventRecordWithFlags(ev, s, cudaEventRecordExternal);
+  else cudaEventRecord(ev, s);
+}
 void launch_timer_begin(int slot, cudaStream_t s) {
   LaunchTimer* t = g_timer;
-  if (!t || !t->enabled) return;
-  if (t->used == LaunchTimer::kPairs) launch_timer_collect(t, s);
+  if (!t || !t->enabled || t->used >= LaunchTimer::kPairs) return;
   t->slot_of[t->used] = slot;
-  cudaEventRecord(t->ev[2 * t->used], s);
+  timer_record(t->ev[2 * t->used], s);
 }
 void launch_timer_end(cudaStream_t s) {
   LaunchTimer* t = g_timer;
-  if (!t || !t->enabled) return;
-  cudaEventRecord(t->ev[2 * t->used + 1], s);
+  if (!t || !t->enabled || t->used >= LaunchTimer::kPairs) return;
+  timer_record(t->ev[2 * t->used + 1], s);
   t->used++;
 }
-int launch_timer_collect(LaunchTimer* t, cudaStream_t s) {
-  if (!t) return FLOAM_OK;
-  FLOAM_CUDA_OK(cudaStreamSynchronize(s));
-  for (int i = 0; i < t->used; ++i) {
+void launch_timer_fold(LaunchTimer* t, int first, int last) {
+  for (int i = first; i < last; ++i) {
     float ms = 0.f;
-    cudaEventSynchronize(t->ev[2 * i + 1]);  // pairs recorded on the aux branch are not covered by the stream synchronise
+    cudaEventSynchronize(t->ev[2 * i + 1]);
     if (cudaEventElapsedTime(&ms, t->ev[2 * i], t->ev[2 * i + 1]) == cudaSuccess) {
       t->total_ms[t->slot_of[i]] += ms;
       t->launches[t->slot_of[i]]++;
     }
   }
-  t->used = 0;
+  cudaGetLastError();
+}
+int launch_timer_collect(LaunchTimer* t, cudaStream_t s) {
+  if (!t) return FLOAM_OK;
+  FLOAM_CUDA_OK(cudaStreamSynchronize(s));
+  launch_timer_fold(t, t->persist, t->used);
+  t->used = t->persist;
   return FLOAM_OK;
 }
 

@@ -176,8 +176,9 @@ int floam_debug_fetch(floam_ctx* ctx, int what, void* out, size_t cap_bytes, siz
 
 /* Launch accounting for bench.py ("gpu_launches"): kernels launched by this context since the last reset. */
 int floam_launch_count(floam_ctx* ctx, int64_t* launches, int reset);
-/* Per-kernel-class device timing for the roofline leg of bench.py: while enabled, kernels are launched one by one (no graph
- * replay) with a CUDA event pair around each, on the calling thread. Slots are named by floam_kernel_name. */
+/* Per-kernel-class device timing for the roofline leg of bench.py: while enabled, every kernel is bracketed by a CUDA event pair
+ * on its stream; frame graphs are re-captured with the pairs as event-record nodes, so the measured durations contain no host
+ * launch gaps. Slots are named by floam_kernel_name. */
 int floam_set_kernel_timing(floam_ctx* ctx, int enabled);
 int floam_kernel_slots(void);
 const char* floam_kernel_name(int slot);
