@@ -120,6 +120,7 @@ void enqueue_frame_body(floam_ctx* c, PointIRT* d_scan, const int* d_scan_n, int
   } else {
     enqueue_selector(c, c->d_edge, c->d_ne, c->d_surf, c->d_ns, c->prm.max_scan_points, deskew);
   }
+  if (c->timer.enabled) launch_noop(c->stream);   // calibration of the event-pair overhead (kernel-timing mode only)
   fetch_state(c, slot);
 }
 

@@ -69,6 +69,7 @@ enum KernelSlot {
   K_CROP_FLAGS,
   K_CROP_SCATTER,
   K_RECORD_POSE,
+  K_NOOP,
   K_NUM_SLOTS
 };
 const char* kernel_slot_name(int slot);
@@ -89,6 +90,8 @@ extern thread_local LaunchTimer* g_timer;
 void launch_timer_begin(int slot, cudaStream_t s);
 void launch_timer_end(cudaStream_t s);
 int launch_timer_collect(LaunchTimer* t, cudaStream_t s);  // synchronises the stream and folds the pending (non-graph) event pairs into the totals
+// empty kernel launched once per frame in timing mode: its measured duration is the cost of the event-pair bracketing itself
+void launch_noop(cudaStream_t s);
 void launch_timer_fold(LaunchTimer* t, int first, int last);  // folds the pairs [first, last) of a replayed graph (after a synchronise)
 
 #define FLOAM_LAUNCH(slot, kern, grid, block, stream, ...)            \

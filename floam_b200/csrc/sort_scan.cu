@@ -55,9 +55,13 @@ static const char* const kSlotNames[K_NUM_SLOTS] = {
   "repack",
   "crop_flags",
   "crop_scatter",
-  "record_pose"
+  "record_pose",
+  "noop"
 };
 const char* kernel_slot_name(int slot) { return (slot >= 0 && slot < K_NUM_SLOTS) ? kSlotNames[slot] : "?"; }
+
+__global__ void noop_kernel() {}
+void launch_noop(cudaStream_t s) { FLOAM_LAUNCH(K_NOOP, noop_kernel, 1, 32, s); }
 
 static void timer_record(cudaEvent_t ev, cudaStream_t s) {
   cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;

@@ -139,16 +139,23 @@ __global__ void __launch_bounds__(kScanThreads) voxel_rank_kernel(const unsigned
   if (blockIdx.x == (n - 1) / kScanTile && threadIdx.x == 0) { *d_nout = offset + total; head_pos[offset + total] = n; }
 }
 
-// pcl::CentroidPoint<PointXYZI>: float sums in run order (ascending input index), then / n. One thread per voxel; the run bounds are
-// known up front, so the loads are issued eight at a time (index, then point): two L2 round trips per eight points instead of two
-// per point. (A warp-cooperative variant for long runs measured 6x slower under ncu — 50 us vs 8 us — and was dropped.)
+// pcl::CentroidPoint<PointXYZI>: float sums in run order (ascending input index), then / n. The ORDER of the additions is fixed, so
+// a run is a serial chain of float adds — but its loads are not. Runs are mostly ~10 points and reach a thousand (ground rings next
+// to the sensor; one such run took 160 us when a single thread also did its loads):
+//   phase 1: one thread per voxel for runs <= 32 points, loads issued eight at a time (index, then point);
+//   phase 2: one WARP per long run: the lanes gather 256 points per step into shared memory (coalesced index reads, parallel
+//            point loads), lane 0 adds them up in order from shared memory.
+constexpr int kShortRun = 32;
+constexpr int kStage = 256;
 __global__ void __launch_bounds__(kThreads) voxel_reduce_kernel(const char* __restrict__ in, int stride, const int* __restrict__ vals,
                                                                  const int* __restrict__ head_pos, const int* __restrict__ d_nout, P4* __restrict__ out,
                                                                  const int* d_skip) {
   if (d_skip && *d_skip) return;
+  __shared__ float4 s_stage[kThreads / 32][kStage];
   const int nv = *d_nout;
   for (int v = blockIdx.x * kThreads + threadIdx.x; v < nv; v += gridDim.x * kThreads) {
     const int b = __ldg(head_pos + v), e = __ldg(head_pos + v + 1);
+    if (e - b > kShortRun) continue;
     float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
     for (int j = b; j < e; j += 8) {
       int idx[8];
@@ -164,6 +171,35 @@ __global__ void __launch_bounds__(kThreads) voxel_reduce_kernel(const char* __re
     }
     const float cnt = (float)(e - b);
     out[v] = make_float4(__fdiv_rn(sx, cnt), __fdiv_rn(sy, cnt), __fdiv_rn(sz, cnt), __fdiv_rn(si, cnt));
+  }
+  const int w = warp_id(), l = lane_id();
+  const int warps_total = gridDim.x * (kThreads / 32);
+  for (int v = blockIdx.x * (kThreads / 32) + w; v < nv; v += warps_total) {
+    const int b = __ldg(head_pos + v), e = __ldg(head_pos + v + 1);
+    if (e - b <= kShortRun) continue;
+    float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+    for (int c = b; c < e; c += kStage) {
+      int idx[kStage / 32];
+#pragma unroll
+      for (int u = 0; u < kStage / 32; ++u) { const int j = c + u * 32 + l; idx[u] = j < e ? __ldg(vals + j) : -1; }
+#pragma unroll
+      for (int u = 0; u < kStage / 32; ++u)
+        if (idx[u] >= 0) s_stage[w][u * 32 + l] = load_xyzi(in, stride, idx[u]);
+      __syncwarp();
+      if (l == 0) {
+        const int m = min(kStage, e - c);
+#pragma unroll 8
+        for (int i = 0; i < m; ++i) {
+          const float4 p = s_stage[w][i];
+          sx = fadd(sx, p.x); sy = fadd(sy, p.y); sz = fadd(sz, p.z); si = fadd(si, p.w);
+        }
+      }
+      __syncwarp();
+    }
+    if (l == 0) {
+      const float cnt = (float)(e - b);
+      out[v] = make_float4(__fdiv_rn(sx, cnt), __fdiv_rn(sy, cnt), __fdiv_rn(sz, cnt), __fdiv_rn(si, cnt));
+    }
   }
 }
 
