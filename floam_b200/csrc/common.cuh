@@ -94,12 +94,37 @@ int launch_timer_collect(LaunchTimer* t, cudaStream_t s);  // synchronises the s
 void launch_noop(cudaStream_t s);
 void launch_timer_fold(LaunchTimer* t, int first, int last);  // folds the pairs [first, last) of a replayed graph (after a synchronise)
 
-#define FLOAM_LAUNCH(slot, kern, grid, block, stream, ...)            \
-  do {                                                                \
-    ::floam::g_launches++;                                            \
-    if (::floam::g_timer) ::floam::launch_timer_begin(slot, stream);  \
-    kern<<<grid, block, 0, stream>>>(__VA_ARGS__);                    \
-    if (::floam::g_timer) ::floam::launch_timer_end(stream);          \
+// Programmatic dependent launch: every kernel starts with pdl_prologue() — it lets the NEXT kernel of the stream be scheduled
+// right away (griddepcontrol.launch_dependents) and then waits until the PREVIOUS kernel has completed and flushed
+// (griddepcontrol.wait) before touching memory. With the launch attribute below, the launch latency of kernel k+1 overlaps the
+// execution of kernel k; without it both instructions are no-ops. The frame is a chain of ~60 dependent, microsecond-sized
+// kernels, so this is where the time goes.
+extern bool g_use_pdl;
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+inline void launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t s, Args&&... args) {
+  if (!g_use_pdl) {
+    kern<<<grid, block, 0, s>>>(KArgs(args)...);
+    return;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
+#define FLOAM_LAUNCH(slot, kern, grid, block, stream, ...)                 \
+  do {                                                                     \
+    ::floam::g_launches++;                                                 \
+    if (::floam::g_timer) ::floam::launch_timer_begin(slot, stream);       \
+    ::floam::launch_kernel(kern, dim3(grid), dim3(block), stream, __VA_ARGS__); \
+    if (::floam::g_timer) ::floam::launch_timer_end(stream);               \
   } while (0)
 
 // 32-byte scan/feature point, byte-identical to vel_point::PointXYZIRT (reference include/lidar.h:14-32).
@@ -204,15 +229,21 @@ __device__ __forceinline__ int tile_offset(const int* __restrict__ tile_sums, in
 struct SortWorkspace {
   unsigned int* keys_alt;   // capacity n_max
   int* vals_alt;            // capacity n_max
-  int* hist;                // 256 * max_blocks
+  int* hist;                // 2048 * max_blocks digit counts
+  unsigned int* ticket;     // last-CTA-done counter of the count kernel
   int max_blocks;
   int n_max;
 };
 size_t sort_workspace_bytes(int n_max);
 void sort_workspace_bind(SortWorkspace& ws, void* mem, int n_max);
-// Stable LSD radix sort of (key,value) pairs, 8 bits per pass; passes beyond *d_nbits (device) degrade to copies so that
-// the sorted result always lands back in keys/vals. n is read from *d_n; launch geometry is sized for n_max.
-void radix_sort_pairs(unsigned int* keys, int* vals, const int* d_n, const int* d_nbits, int n_max, SortWorkspace& ws, const int* d_skip, cudaStream_t s);
+int sort_workspace_arm(SortWorkspace& ws, cudaStream_t s);
+// Stable LSD radix sort of (key,value) pairs in three passes of ceil(*d_nbits / 3) bits each (decided on the device). n is read from
+// *d_n; launch geometry is sized for n_max. The sorted arrays are returned through sorted_keys / sorted_vals (workspace buffers).
+void radix_sort_pairs(unsigned int* keys, int* vals, const int* d_n, const int* d_nbits, int n_max, SortWorkspace& ws, const int* d_skip, cudaStream_t s,
+                      unsigned int** sorted_keys, int** sorted_vals);
+// same, with the ping-pong partner buffers given explicitly (the result lands in keys_alt / vals_alt)
+void radix_sort_pairs_from(unsigned int* keys, int* vals, unsigned int* keys_alt, int* vals_alt, const int* d_n, const int* d_nbits, int n_max,
+                           SortWorkspace& ws, const int* d_skip, cudaStream_t s, unsigned int** sorted_keys, int** sorted_vals);
 
 // in-place exclusive scan of a small device array (n known on the host) by a single CTA
 void exclusive_scan_small(int* data, int n, cudaStream_t s);

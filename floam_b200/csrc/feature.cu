@@ -42,6 +42,7 @@ __device__ __forceinline__ void store_point(PointIRT* pts, int i, const PointIRT
 // tile_cnt[ring * ntiles + tile] = number of gated points of that ring in the tile
 __global__ void __launch_bounds__(kTile) ring_count_kernel(const PointIRT* __restrict__ pts, const int* __restrict__ d_n, FeatureParams prm,
                                                             int ntiles, int* __restrict__ tile_cnt, int* __restrict__ d_flags) {
+  pdl_prologue();
   __shared__ int s_cnt[kMaxRings];
   const int n = *d_n;
   if (threadIdx.x < kMaxRings) s_cnt[threadIdx.x] = 0;
@@ -63,6 +64,7 @@ __global__ void __launch_bounds__(kTile) ring_count_kernel(const PointIRT* __res
 __global__ void __launch_bounds__(kTile) ring_scatter_kernel(const PointIRT* __restrict__ pts, const int* __restrict__ d_n, FeatureParams prm,
                                                               int ntiles, const int* __restrict__ tile_off, PointIRT* __restrict__ ring_pts,
                                                               int* __restrict__ ring_src) {
+  pdl_prologue();
   __shared__ int s_cnt[32][kMaxRings];  // per-warp counts -> exclusive prefix over warps
   const int n = *d_n;
   if (blockIdx.x * kTile >= n) return;
@@ -103,6 +105,7 @@ __device__ __forceinline__ bool key_less(double va, int ia, double vb, int ib) {
 __global__ void __launch_bounds__(kSectorThreads) sector_kernel(const PointIRT* __restrict__ ring_pts, const int* __restrict__ tile_off, int ntiles,
                                                                 FeatureParams prm, int* __restrict__ edge_tmp, int* __restrict__ surf_tmp,
                                                                 int* __restrict__ edge_cnt, int* __restrict__ surf_cnt, int* __restrict__ d_flags) {
+  pdl_prologue();
   __shared__ float sx[kSectorCap + kHalo], sy[kSectorCap + kHalo], sz[kSectorCap + kHalo];
   __shared__ double sval[kSectorCap];
   __shared__ short sid[kSectorCap];
@@ -229,6 +232,7 @@ __global__ void __launch_bounds__(kSectorThreads) sector_kernel(const PointIRT* 
 // exclusive offsets over <= 1024 sectors; totals to d_ne / d_ns
 __global__ void __launch_bounds__(1024) feature_offsets_kernel(const int* __restrict__ edge_cnt, const int* __restrict__ surf_cnt, int nsectors,
                                                                 int* __restrict__ edge_off, int* __restrict__ surf_off, int* d_ne, int* d_ns) {
+  pdl_prologue();
   __shared__ int smem[33];
   const int t = threadIdx.x;
   int e = t < nsectors ? edge_cnt[t] : 0, s = t < nsectors ? surf_cnt[t] : 0;
@@ -246,6 +250,7 @@ __global__ void __launch_bounds__(256) feature_gather_kernel(const PointIRT* __r
                                                               const int* __restrict__ surf_cnt, const int* __restrict__ edge_off,
                                                               const int* __restrict__ surf_off, PointIRT* __restrict__ edge_out,
                                                               PointIRT* __restrict__ surf_out, int* __restrict__ edge_src, int* __restrict__ surf_src) {
+  pdl_prologue();
   const int sector = blockIdx.x;
   const int ne = edge_cnt[sector], ns = surf_cnt[sector];
   if (ne == 0 && ns == 0) return;

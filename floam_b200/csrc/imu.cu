@@ -90,6 +90,7 @@ constexpr int kThreads = 256;
 
 __global__ void __launch_bounds__(kThreads) deskew_align_kernel(PointIRT* __restrict__ pts, const int* __restrict__ d_n, const DeskewPlan* __restrict__ d_plan,
                                                                  const ImuSample* __restrict__ samples) {
+  pdl_prologue();
   const int n = *d_n;
   const DeskewPlan plan = *d_plan;
   const int n_samples = plan.n_samples;

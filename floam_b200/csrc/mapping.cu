@@ -55,6 +55,7 @@ __device__ __forceinline__ int cell_coord(float v) { return (int)floor((double)v
 
 __global__ void __launch_bounds__(kThreads) classify_old_kernel(const unsigned int* __restrict__ cell, const int* __restrict__ counts, BlockGeom g,
                                                                  int* __restrict__ flags) {
+  pdl_prologue();
   const int n = counts[0];
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) flags[i] = local_cell(cell[i], g) < kLcPass ? 1 : 0;
 }
@@ -62,6 +63,7 @@ __global__ void __launch_bounds__(kThreads) classify_old_kernel(const unsigned i
 __global__ void __launch_bounds__(kThreads) partition_kernel(const P4* __restrict__ pts, const unsigned int* __restrict__ cell, const int* __restrict__ pos,
                                                               int* __restrict__ counts, P4* __restrict__ rest, unsigned int* __restrict__ rest_cell,
                                                               P4* __restrict__ work, unsigned int* __restrict__ work_cell) {
+  pdl_prologue();
   const int n = counts[0];
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
     const int p = pos[i];
@@ -80,6 +82,7 @@ __global__ void __launch_bounds__(kThreads) partition_kernel(const P4* __restric
 __global__ void __launch_bounds__(kThreads) transform_new_kernel(const char* __restrict__ in, int stride, const int* __restrict__ d_nin, int* __restrict__ counts,
                                                                   BlockGeom g, int cap, P4* __restrict__ work, unsigned int* __restrict__ work_cell,
                                                                   const unsigned int* __restrict__ allocated, int n_allocated) {
+  pdl_prologue();
   const int nin = *d_nin, base = counts[2];
   const bool fits = counts[1] + base + nin <= cap;
   if (fits) {
@@ -119,6 +122,7 @@ __device__ __forceinline__ void voxel_of(const float4 p, const BlockGeom& g, int
 
 __global__ void __launch_bounds__(kThreads) keys1_kernel(const P4* __restrict__ work, const unsigned int* __restrict__ work_cell, const int* __restrict__ counts,
                                                           BlockGeom g, unsigned int* __restrict__ keys, int* __restrict__ vals) {
+  pdl_prologue();
   const int n = counts[3];
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
     unsigned int key = 0;
@@ -134,6 +138,7 @@ __global__ void __launch_bounds__(kThreads) keys1_kernel(const P4* __restrict__ 
 
 __global__ void __launch_bounds__(kThreads) keys2_kernel(const P4* __restrict__ work, const unsigned int* __restrict__ work_cell, const int* __restrict__ counts,
                                                           BlockGeom g, const int* __restrict__ vals, unsigned int* __restrict__ keys) {
+  pdl_prologue();
   const int n = counts[3];
   for (int j = blockIdx.x * kThreads + threadIdx.x; j < n; j += gridDim.x * kThreads) {
     const int i = vals[j];
@@ -146,6 +151,7 @@ __global__ void __launch_bounds__(kThreads) keys2_kernel(const P4* __restrict__ 
 
 __global__ void __launch_bounds__(kThreads) heads_kernel(const P4* __restrict__ work, const unsigned int* __restrict__ work_cell, const int* __restrict__ counts,
                                                           BlockGeom g, const int* __restrict__ vals, int* __restrict__ flags) {
+  pdl_prologue();
   const int n = counts[3];
   for (int j = blockIdx.x * kThreads + threadIdx.x; j < n; j += gridDim.x * kThreads) {
     const int i = vals[j];
@@ -170,6 +176,7 @@ __global__ void __launch_bounds__(kThreads) heads_kernel(const P4* __restrict__ 
 __global__ void __launch_bounds__(kThreads) reduce_kernel(const P4* __restrict__ work, const unsigned int* __restrict__ work_cell, int* __restrict__ counts,
                                                            BlockGeom g, const int* __restrict__ vals, const int* __restrict__ seg, P4* __restrict__ out,
                                                            unsigned int* __restrict__ out_cell) {
+  pdl_prologue();
   const int n = counts[3], base = counts[1];
   for (int j = blockIdx.x * kThreads + threadIdx.x; j < n; j += gridDim.x * kThreads) {
     if (seg[j + 1] == seg[j]) continue;  // not a voxel head (or a dropped point)
@@ -194,16 +201,19 @@ __global__ void __launch_bounds__(kThreads) reduce_kernel(const P4* __restrict__
 }
 
 __global__ void commit_kernel(int* counts) {
+  pdl_prologue();
   if (threadIdx.x == 0) counts[0] = counts[6];
 }
 
 __global__ void __launch_bounds__(kThreads) cell_keys_kernel(const unsigned int* __restrict__ cell, const int* __restrict__ counts, unsigned int* __restrict__ keys,
                                                               int* __restrict__ vals) {
+  pdl_prologue();
   const int n = counts[0];
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) { keys[i] = cell[i]; vals[i] = i; }
 }
 __global__ void __launch_bounds__(kThreads) gather_kernel(const P4* __restrict__ pts, const int* __restrict__ vals, const int* __restrict__ counts,
                                                            P4* __restrict__ out) {
+  pdl_prologue();
   const int n = counts[0];
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) out[i] = pts[vals[i]];
 }
@@ -282,12 +292,16 @@ int mapping_update_device(MappingDevice& md, const void* d_in, int stride, const
   FLOAM_LAUNCH(K_PARTITION, partition_kernel, gmap, kThreads, s, md.pts, md.cell, ws.flags, counts, md.pts_alt, md.cell_alt, md.work, md.work_cell);
   FLOAM_LAUNCH(K_TRANSFORM_NEW, transform_new_kernel, gin, kThreads, s, (const char*)d_in, stride, d_n, counts, g, md.cap, md.work, md.work_cell, md.d_allocated, (int)md.allocated.size());
   FLOAM_LAUNCH(K_KEYS1, keys1_kernel, gmap, kThreads, s, md.work, md.work_cell, counts, g, ws.keys, ws.vals);
-  radix_sort_pairs(ws.keys, ws.vals, counts + 3, md.d_nbits, md.cap, ws.sort, nullptr, s);
-  FLOAM_LAUNCH(K_KEYS2, keys2_kernel, gmap, kThreads, s, md.work, md.work_cell, counts, g, ws.vals, ws.keys);
-  radix_sort_pairs(ws.keys, ws.vals, counts + 3, md.d_nbits + 1, md.cap, ws.sort, nullptr, s);
-  FLOAM_LAUNCH(K_HEADS, heads_kernel, gmap, kThreads, s, md.work, md.work_cell, counts, g, ws.vals, ws.flags);
+  unsigned int* k1 = nullptr; int* v1 = nullptr;
+  radix_sort_pairs(ws.keys, ws.vals, counts + 3, md.d_nbits, md.cap, ws.sort, nullptr, s, &k1, &v1);
+  // second-level keys are written next to the first-level order (k1/v1 live in the workspace's alternate buffers; the sort below
+  // ping-pongs between them and the primary buffers again)
+  FLOAM_LAUNCH(K_KEYS2, keys2_kernel, gmap, kThreads, s, md.work, md.work_cell, counts, g, v1, k1);
+  unsigned int* k2 = nullptr; int* v2 = nullptr;
+  radix_sort_pairs_from(k1, v1, ws.keys, ws.vals, counts + 3, md.d_nbits + 1, md.cap, ws.sort, nullptr, s, &k2, &v2);
+  FLOAM_LAUNCH(K_HEADS, heads_kernel, gmap, kThreads, s, md.work, md.work_cell, counts, g, v2, ws.flags);
   exclusive_scan_i32(ws.flags, ws.flags, counts + 3, 0, md.cap, ws.scan, nullptr, s);
-  FLOAM_LAUNCH(K_REDUCE, reduce_kernel, gmap, kThreads, s, md.work, md.work_cell, counts, g, ws.vals, ws.flags, md.pts_alt, md.cell_alt);
+  FLOAM_LAUNCH(K_REDUCE, reduce_kernel, gmap, kThreads, s, md.work, md.work_cell, counts, g, v2, ws.flags, md.pts_alt, md.cell_alt);
   FLOAM_LAUNCH(K_COMMIT, commit_kernel, 1, 32, s, counts);
   std::swap(md.pts, md.pts_alt);
   std::swap(md.cell, md.cell_alt);
@@ -300,8 +314,9 @@ int mapping_get_map_device(MappingDevice& md, P4** d_out, int** d_out_n, cudaStr
   FLOAM_CUDA_OK(cudaMemcpyAsync(md.d_nbits + 2, &nbits, 4, cudaMemcpyHostToDevice, s));
   const int g = grid_for(md.cap);
   FLOAM_LAUNCH(K_CELL_KEYS, cell_keys_kernel, g, kThreads, s, md.cell, md.d_counts, ws.keys, ws.vals);
-  radix_sort_pairs(ws.keys, ws.vals, md.d_counts, md.d_nbits + 2, md.cap, ws.sort, nullptr, s);
-  FLOAM_LAUNCH(K_GATHER, gather_kernel, g, kThreads, s, md.pts, ws.vals, md.d_counts, md.pts_alt);
+  unsigned int* sk = nullptr; int* sv = nullptr;
+  radix_sort_pairs(ws.keys, ws.vals, md.d_counts, md.d_nbits + 2, md.cap, ws.sort, nullptr, s, &sk, &sv);
+  FLOAM_LAUNCH(K_GATHER, gather_kernel, g, kThreads, s, md.pts, sv, md.d_counts, md.pts_alt);
   *d_out = md.pts_alt;
   *d_out_n = md.d_counts;
   return FLOAM_OK;

@@ -52,6 +52,7 @@ __device__ __forceinline__ float4 load_xyzi(const char* base, int stride, int i)
 // state machine: prediction and write-back
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void state_init_kernel(PoseState* S) {
+  pdl_prologue();
   if (threadIdx.x != 0) return;
   PoseState z;
   memset(&z, 0, sizeof(z));
@@ -66,6 +67,7 @@ __global__ void state_init_kernel(PoseState* S) {
 
 // updatePointsToMap :62-71. The motion prediction is unconditional (Q2).
 __global__ void predict_kernel(PoseState* S, const int* n_edge_map, const int* n_surf_map) {
+  pdl_prologue();
   if (threadIdx.x != 0) return;
   double inv[12], rel[12], pred[12];
   m::iso_inverse(S->last_odom, inv);
@@ -88,6 +90,7 @@ __global__ void predict_kernel(PoseState* S, const int* n_edge_map, const int* n
 
 // :114-121 + KeyFrameUpdate :320-343 + the CropBox bounds of addPointsToMap :270-279
 __global__ void finish_kernel(PoseState* S, int update_type, double scan_period, double* traj, int traj_cap) {
+  pdl_prologue();
   if (threadIdx.x != 0) return;
   double R[9];
   m::quat_to_matrix(S->x, R);
@@ -125,6 +128,7 @@ __global__ void finish_kernel(PoseState* S, int update_type, double scan_period,
 }
 
 __global__ void record_pose_kernel(PoseState* S, double* traj, int traj_cap) {
+  pdl_prologue();
   if (threadIdx.x != 0) return;
   double* rec = traj + (size_t)(S->frame_counter % traj_cap) * 7;
   for (int k = 0; k < 7; ++k) rec[k] = S->x[k];
@@ -137,6 +141,7 @@ __global__ void record_pose_kernel(PoseState* S, double* traj, int traj_cap) {
 // initMapWithPoints :28-32 / set_map: raw append of a strided cloud (no transform)
 __global__ void __launch_bounds__(kThreads) map_append_raw_kernel(const char* __restrict__ in, int stride, const int* __restrict__ d_nin, P4* __restrict__ map,
                                                                    int* d_nmap, int cap, int replace, int* d_err) {
+  pdl_prologue();
   const int nin = *d_nin;
   const int base = replace ? 0 : *d_nmap;
   const bool fits = base + nin <= cap;
@@ -145,6 +150,7 @@ __global__ void __launch_bounds__(kThreads) map_append_raw_kernel(const char* __
   if (blockIdx.x == 0 && threadIdx.x == 0 && !fits) atomicOr(d_err, 1);
 }
 __global__ void map_bump_kernel(int* d_nmap, const int* d_nin, int cap, int replace, const int* d_skip) {
+  pdl_prologue();
   if (d_skip && *d_skip) return;
   if (threadIdx.x != 0) return;
   const int base = replace ? 0 : *d_nmap;
@@ -154,6 +160,7 @@ __global__ void map_bump_kernel(int* d_nmap, const int* d_nin, int cap, int repl
 // addPointsToMap :256-268: pointAssociateToMap (double transform, float store) and push_back
 __global__ void __launch_bounds__(kThreads) map_append_kernel(const P4* __restrict__ ds, const int* __restrict__ d_nds, P4* __restrict__ map,
                                                                const int* __restrict__ d_nmap, int cap, PoseState* S, const int* d_skip) {
+  pdl_prologue();
   if (*d_skip) return;
   const int nds = *d_nds, base = *d_nmap;
   if (base + nds > cap) {
@@ -172,6 +179,7 @@ __global__ void __launch_bounds__(kThreads) map_append_kernel(const P4* __restri
 
 __global__ void __launch_bounds__(kThreads) grid_bbox_kernel(const P4* __restrict__ pts, const int* __restrict__ d_n, unsigned int* __restrict__ bbox,
                                                               const int* d_skip) {
+  pdl_prologue();
   if (d_skip && *d_skip) return;
   const int n = *d_n;
   float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
@@ -202,6 +210,7 @@ __global__ void __launch_bounds__(kThreads) grid_bbox_kernel(const P4* __restric
 
 // one thread: grid extent from the bounding box; re-arms the bbox accumulators for the next build
 __global__ void grid_dims_kernel(unsigned int* bbox, const int* d_n, GridDims* dims, int ncells_cap, PoseState* S, const int* d_skip) {
+  pdl_prologue();
   if (d_skip && *d_skip) return;
   if (threadIdx.x != 0) return;
   GridDims g;
@@ -229,6 +238,7 @@ __device__ __forceinline__ int cell_of(const GridDims& g, float x, float y, floa
 
 __global__ void __launch_bounds__(kThreads) grid_count_kernel(const P4* __restrict__ pts, const int* __restrict__ d_n, const GridDims* __restrict__ dims,
                                                                int* __restrict__ cell_count, const int* d_skip) {
+  pdl_prologue();
   if (d_skip && *d_skip) return;
   const GridDims g = *dims;
   if (g.ncells == 0) return;
@@ -244,6 +254,7 @@ __global__ void __launch_bounds__(kThreads) grid_count_kernel(const P4* __restri
 __global__ void __launch_bounds__(kThreads) grid_scatter_kernel(const P4* __restrict__ pts, const int* __restrict__ d_n, const GridDims* __restrict__ dims,
                                                                  const int* __restrict__ cell_start, int* __restrict__ cell_count,
                                                                  float4* __restrict__ cell_pts, const int* d_skip) {
+  pdl_prologue();
   if (d_skip && *d_skip) return;
   const GridDims g = *dims;
   if (g.ncells == 0) return;
@@ -668,6 +679,7 @@ constexpr int kKnnThreads = 256;
 __global__ void __launch_bounds__(kKnnThreads) assoc_knn_kernel(const PoseState* __restrict__ S, const P4* __restrict__ ds_edge, const int* __restrict__ d_nde,
                                                                  const P4* __restrict__ ds_surf, const int* __restrict__ d_nds, LocalMap emap, LocalMap smap,
                                                                  int qcap, int* __restrict__ knn_ids, float* __restrict__ knn_d2) {
+  pdl_prologue();
   if (S->skip_solve) return;
   const int nde = *d_nde, nds = *d_nds;
   double x[7];
@@ -702,6 +714,7 @@ __global__ void __launch_bounds__(kEvalThreads) assoc_eval_kernel(PoseState* __r
                                                                    const P4* __restrict__ ds_surf, const int* __restrict__ d_nds, LocalMap emap, LocalMap smap,
                                                                    int qcap, double* __restrict__ corr, unsigned char* __restrict__ corr_ok,
                                                                    const int* __restrict__ knn_ids, int loss, double* __restrict__ partials) {
+  pdl_prologue();
   if (S->skip_solve) return;
   __shared__ double s_sums[kLmTerms];
   __shared__ int s_ncorr;
@@ -824,6 +837,7 @@ struct ClusterShared {
 __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClusterThreads)
     lm_cluster_kernel(PoseState* S, const P4* __restrict__ ds_edge, const int* __restrict__ d_nde, const P4* __restrict__ ds_surf,
                       const int* __restrict__ d_nds, int qcap, const double* __restrict__ corr, const unsigned char* __restrict__ corr_ok, int loss) {
+  pdl_prologue();
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   // uniform across the cluster: decided from values the previous kernel wrote
@@ -915,6 +929,7 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClusterT
 // stand-alone 5-NN (floam_knn5): queries are used as given (no pose transform)
 __global__ void __launch_bounds__(kEvalThreads) knn5_kernel(const P4* __restrict__ queries, const int* __restrict__ d_nq, LocalMap map, int* __restrict__ ids,
                                                              float* __restrict__ d2) {
+  pdl_prologue();
   const int nq = *d_nq;
   const GridDims g = *map.dims;
   for (int i = blockIdx.x * kEvalThreads + threadIdx.x; i < nq; i += gridDim.x * kEvalThreads) {
@@ -929,6 +944,7 @@ __global__ void __launch_bounds__(kEvalThreads) knn5_kernel(const P4* __restrict
 
 // dmapping::CompensateVelocity (src/dataHandler.cpp:82-91) with GetVelocity() taken from the device state (Q14: no rotation)
 __global__ void __launch_bounds__(kThreads) compensate_velocity_kernel(PointIRT* __restrict__ pts, const int* __restrict__ d_n, const PoseState* __restrict__ S) {
+  pdl_prologue();
   const int n = *d_n;
   const double vx = S->velocity[0], vy = S->velocity[1], vz = S->velocity[2];
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
@@ -942,6 +958,7 @@ __global__ void __launch_bounds__(kThreads) compensate_velocity_kernel(PointIRT*
 
 __global__ void __launch_bounds__(kThreads) compensate_velocity_explicit_kernel(PointIRT* __restrict__ pts, const int* __restrict__ d_n, double vx, double vy,
                                                                                  double vz) {
+  pdl_prologue();
   const int n = *d_n;
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
     PointIRT* p = pts + i;

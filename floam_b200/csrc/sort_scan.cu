@@ -9,6 +9,7 @@ namespace floam {
 
 thread_local long long g_launches = 0;
 thread_local LaunchTimer* g_timer = nullptr;
+bool g_use_pdl = false;
 
 static const char* const kSlotNames[K_NUM_SLOTS] = {
   "ring_count",
@@ -61,7 +62,7 @@ static const char* const kSlotNames[K_NUM_SLOTS] = {
 const char* kernel_slot_name(int slot) { return (slot >= 0 && slot < K_NUM_SLOTS) ? kSlotNames[slot] : "?"; }
 
 __global__ void noop_kernel() {}
-void launch_noop(cudaStream_t s) { FLOAM_LAUNCH(K_NOOP, noop_kernel, 1, 32, s); }
+void launch_noop(cudaStream_t s) { g_launches++; if (g_timer) launch_timer_begin(K_NOOP, s); noop_kernel<<<1, 32, 0, s>>>(); if (g_timer) launch_timer_end(s); }
 
 static void timer_record(cudaEvent_t ev, cudaStream_t s) {
   cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
@@ -103,55 +104,85 @@ int launch_timer_collect(LaunchTimer* t, cudaStream_t s) {
 
 namespace {
 
+// Stable LSD radix sort in exactly THREE passes whatever the key width: the digit width is ceil(nbits / 3) bits, decided on the
+// device (nbits <= 24 -> the usual 8-bit digits or narrower; up to 11 bits = 2048 bins for 31-bit keys, on a slower but correct
+// path). A pass is two kernels: per-tile digit counts (+ the scan of the count table by the last CTA to finish, only needed above
+// 262,144 keys) and the ranking scatter.
 constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
 constexpr int kSortRounds = 4;                                 // keys per lane
 constexpr int kSortItemsPerWarp = 32 * kSortRounds;            // 128: a warp owns a contiguous chunk (stability)
 constexpr int kSortTile = kSortWarps * kSortItemsPerWarp;      // 1024 keys per CTA
 constexpr int kDirectTiles = 256;                              // <= 262,144 keys: scatter CTAs scan the count table themselves
+constexpr int kMaxBins = 2048;                                 // 11-bit digits at most (3 x 11 >= 31 key bits)
 
 __device__ __forceinline__ int sort_tiles(int n) { return (n + kSortTile - 1) / kSortTile; }
+__device__ __forceinline__ int digit_bits(int nbits) {
+  const int b = (nbits + 2) / 3;
+  return b < 1 ? 1 : b;
+}
 
-// counts of this tile's digits -> hist. Layout [tile][digit] (direct mode) or [digit][tile] (scanned by single_block_scan_kernel).
+// counts of this tile's digits -> hist. Layout [tile][digit] (direct mode) or [digit][tile], which the last CTA then scans in place.
 __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const unsigned int* __restrict__ keys, const int* __restrict__ d_n,
-                                                                  const int* __restrict__ d_nbits, int shift, int* __restrict__ hist, const int* d_skip) {
+                                                                  const int* __restrict__ d_nbits, int pass, int* __restrict__ hist, unsigned int* ticket,
+                                                                  const int* d_skip) {
+  pdl_prologue();
   if (d_skip && *d_skip) return;
-  if (shift >= *d_nbits) return;
   const int n = *d_n;
   const int tile0 = blockIdx.x * kSortTile;
   if (tile0 >= n) return;
+  const int bits = digit_bits(*d_nbits), shift = pass * bits, nbins = 1 << bits;
+  const unsigned int dmask = (unsigned int)nbins - 1u;
   const int nb = sort_tiles(n);
-  __shared__ int s_hist[256];
+  __shared__ int s_hist[kMaxBins];
+  __shared__ int s_scan[33];
+  __shared__ int s_last;
   unsigned int k[kSortRounds];
 #pragma unroll
   for (int r = 0; r < kSortRounds; ++r) {
     const int i = tile0 + r * kSortThreads + threadIdx.x;
     k[r] = (i < n) ? keys[i] : 0xffffffffu;
   }
-  s_hist[threadIdx.x] = 0;
+  for (int d = threadIdx.x; d < nbins; d += kSortThreads) s_hist[d] = 0;
   __syncthreads();
 #pragma unroll
   for (int r = 0; r < kSortRounds; ++r) {
     const int i = tile0 + r * kSortThreads + threadIdx.x;
-    if (i < n) atomicAdd(&s_hist[(k[r] >> shift) & 0xffu], 1);
+    if (i < n) atomicAdd(&s_hist[(k[r] >> shift) & dmask], 1);
   }
   __syncthreads();
-  const int d = threadIdx.x;
-  if (nb <= kDirectTiles) hist[blockIdx.x * 256 + d] = s_hist[d];
-  else hist[d * nb + blockIdx.x] = s_hist[d];
+  if (nb <= kDirectTiles) {
+    for (int d = threadIdx.x; d < nbins; d += kSortThreads) hist[blockIdx.x * nbins + d] = s_hist[d];
+    return;
+  }
+  for (int d = threadIdx.x; d < nbins; d += kSortThreads) hist[d * nb + blockIdx.x] = s_hist[d];
+  // large inputs: the last CTA to finish turns the [digit][tile] counts into exclusive offsets (no separate scan launch)
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == (unsigned int)nb - 1u) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int total_entries = nbins * nb;
+  int carry = 0;
+  for (int base = 0; base < total_entries; base += kSortThreads * 4) {
+    const int i = base + threadIdx.x * 4;
+    int v[4], sum = 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { v[u] = (i + u < total_entries) ? __ldcg(hist + i + u) : 0; sum += v[u]; }
+    int total;
+    int ex = block_excl_scan(sum, s_scan, &total) + carry;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { if (i + u < total_entries) hist[i + u] = ex; ex += v[u]; }
+    carry += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *ticket = 0;
 }
 
 // in-place exclusive scan of a small array by one block
-// d_sort_n (optional): the array is the [digit][tile] radix count table of *d_sort_n keys; nothing to do in direct mode
-__global__ void __launch_bounds__(1024) single_block_scan_kernel(int* __restrict__ data, int n, const int* __restrict__ d_nbits, int shift, const int* d_skip,
-                                                                 const int* __restrict__ d_sort_n) {
-  if (d_skip && *d_skip) return;
-  if (d_nbits && shift >= *d_nbits) return;
-  if (d_sort_n) {
-    const int nb = sort_tiles(*d_sort_n);
-    if (nb <= kDirectTiles) return;
-    n = 256 * nb;
-  }
+__global__ void __launch_bounds__(1024) single_block_scan_kernel(int* __restrict__ data, int n) {
+  pdl_prologue();
   __shared__ int smem[33];
   int carry = 0;
   for (int base = 0; base < n; base += 1024) {
@@ -167,8 +198,9 @@ __global__ void __launch_bounds__(1024) single_block_scan_kernel(int* __restrict
 
 __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const unsigned int* __restrict__ keys_in, const int* __restrict__ vals_in,
                                                                      unsigned int* __restrict__ keys_out, int* __restrict__ vals_out,
-                                                                     const int* __restrict__ d_n, const int* __restrict__ d_nbits, int shift,
+                                                                     const int* __restrict__ d_n, const int* __restrict__ d_nbits, int pass,
                                                                      const int* __restrict__ hist, const int* d_skip) {
+  pdl_prologue();
   if (d_skip && *d_skip) return;
   const int n = *d_n;
   const int tile0 = blockIdx.x * kSortTile;
@@ -184,65 +216,97 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const unsig
     k[r] = 0; v[r] = 0;
     if (i < n) { k[r] = keys_in[i]; v[r] = vals_in[i]; }
   }
-  if (shift >= *d_nbits) {  // pass not needed for this key width: keep ping-pong parity with a straight copy
-#pragma unroll
-    for (int r = 0; r < kSortRounds; ++r) {
-      const int i = begin + r * 32 + l;
-      if (i < n) { keys_out[i] = k[r]; vals_out[i] = v[r]; }
-    }
-    return;
-  }
+  const int bits = digit_bits(*d_nbits), shift = pass * bits, nbins = 1 << bits;
+  const unsigned int dmask = (unsigned int)nbins - 1u;
   const int nb = sort_tiles(n);
-  __shared__ int s_cnt[kSortWarps][256];
+  __shared__ int s_cnt[kSortWarps][256];   // narrow digits: per-warp counters / running offsets
+  __shared__ int s_base[kMaxBins];         // wide digits: one running offset per bin, warps take turns
   __shared__ int s_scan[33];
-  for (int i = threadIdx.x; i < kSortWarps * 256; i += kSortThreads) (&s_cnt[0][0])[i] = 0;
-  __syncthreads();
+  const bool narrow = nbins <= 256;
   unsigned int mask[kSortRounds];
   int* cnt = s_cnt[w];
+  if (narrow) {
+    for (int i = threadIdx.x; i < kSortWarps * 256; i += kSortThreads) (&s_cnt[0][0])[i] = 0;
+    __syncthreads();
 #pragma unroll
-  for (int r = 0; r < kSortRounds; ++r) {
-    const bool valid = begin + r * 32 + l < n;
-    const unsigned int d = valid ? ((k[r] >> shift) & 0xffu) : 0xffffffffu;
-    mask[r] = __match_any_sync(0xffffffffu, d);
-    if (valid && (__ffs(mask[r]) - 1) == l) cnt[d] += __popc(mask[r]);
-    __syncwarp();
+    for (int r = 0; r < kSortRounds; ++r) {
+      const bool valid = begin + r * 32 + l < n;
+      const unsigned int d = valid ? ((k[r] >> shift) & dmask) : 0xffffffffu;
+      mask[r] = __match_any_sync(0xffffffffu, d);
+      if (valid && (__ffs(mask[r]) - 1) == l) cnt[d] += __popc(mask[r]);
+      __syncwarp();
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  {  // digit d = threadIdx.x: global base of (digit, tile), then the exclusive prefix over this tile's warps
-    const int d = threadIdx.x;
-    int base;
+  // global base of (digit, this tile): everything with a smaller digit, plus the same digit in earlier tiles
+  int carry = 0;
+  for (int d0 = 0; d0 < nbins; d0 += kSortThreads) {
+    const int d = d0 + threadIdx.x;
+    int base = 0, total = 0;
     if (nb <= kDirectTiles) {
-      int total = 0, before = 0;
-      const int b = blockIdx.x;
+      if (d < nbins) {
+        int before = 0;
+        const int b = blockIdx.x;
 #pragma unroll 4
-      for (int t = 0; t < nb; ++t) {
-        const int c = hist[t * 256 + d];
-        total += c;
-        before += (t < b) ? c : 0;
+        for (int t = 0; t < nb; ++t) {
+          const int c = hist[t * nbins + d];
+          total += c;
+          before += (t < b) ? c : 0;
+        }
+        base = before;
       }
       int grand;
-      base = block_excl_scan(total, s_scan, &grand) + before;
-    } else {
+      base += block_excl_scan(total, s_scan, &grand) + carry;
+      carry += grand;
+      __syncthreads();
+    } else if (d < nbins) {
       base = hist[d * nb + blockIdx.x];
     }
+    if (d < nbins) {
+      if (narrow) {
 #pragma unroll
-    for (int ww = 0; ww < kSortWarps; ++ww) {
-      const int c = s_cnt[ww][d];
-      s_cnt[ww][d] = base;
-      base += c;
+        for (int ww = 0; ww < kSortWarps; ++ww) {
+          const int c = s_cnt[ww][d];
+          s_cnt[ww][d] = base;
+          base += c;
+        }
+      } else {
+        s_base[d] = base;
+      }
     }
   }
   __syncthreads();
+  if (narrow) {
 #pragma unroll
-  for (int r = 0; r < kSortRounds; ++r) {
-    const bool valid = begin + r * 32 + l < n;
-    const unsigned int d = (k[r] >> shift) & 0xffu;
-    int pos = 0;
-    if (valid) pos = cnt[d] + __popc(mask[r] & ((1u << l) - 1u));
-    __syncwarp();
-    if (valid && (__ffs(mask[r]) - 1) == l) cnt[d] += __popc(mask[r]);
-    __syncwarp();
-    if (valid) { keys_out[pos] = k[r]; vals_out[pos] = v[r]; }
+    for (int r = 0; r < kSortRounds; ++r) {
+      const bool valid = begin + r * 32 + l < n;
+      const unsigned int d = (k[r] >> shift) & dmask;
+      int pos = 0;
+      if (valid) pos = cnt[d] + __popc(mask[r] & ((1u << l) - 1u));
+      __syncwarp();
+      if (valid && (__ffs(mask[r]) - 1) == l) cnt[d] += __popc(mask[r]);
+      __syncwarp();
+      if (valid) { keys_out[pos] = k[r]; vals_out[pos] = v[r]; }
+    }
+  } else {
+    // wide digits (keys above 24 bits): the warps of the tile rank one after the other against the shared running offsets
+    for (int ww = 0; ww < kSortWarps; ++ww) {
+      if (w == ww) {
+#pragma unroll
+        for (int r = 0; r < kSortRounds; ++r) {
+          const bool valid = begin + r * 32 + l < n;
+          const unsigned int d = valid ? ((k[r] >> shift) & dmask) : 0xffffffffu;
+          const unsigned int m = __match_any_sync(0xffffffffu, d);
+          int pos = 0;
+          if (valid) pos = s_base[d] + __popc(m & ((1u << l) - 1u));
+          __syncwarp();
+          if (valid && (__ffs(m) - 1) == l) s_base[d] += __popc(m);
+          __syncwarp();
+          if (valid) { keys_out[pos] = k[r]; vals_out[pos] = v[r]; }
+        }
+      }
+      __syncthreads();
+    }
   }
 }
 
@@ -250,7 +314,7 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const unsig
 
 size_t sort_workspace_bytes(int n_max) {
   const int nblocks = (n_max + kSortTile - 1) / kSortTile;
-  return (size_t)n_max * 8 + (size_t)256 * nblocks * 4 + 256;
+  return (size_t)n_max * 8 + (size_t)kMaxBins * nblocks * 4 + 512;
 }
 void sort_workspace_bind(SortWorkspace& ws, void* mem, int n_max) {
   char* p = (char*)mem;
@@ -258,27 +322,37 @@ void sort_workspace_bind(SortWorkspace& ws, void* mem, int n_max) {
   ws.max_blocks = (n_max + kSortTile - 1) / kSortTile;
   ws.keys_alt = (unsigned int*)p; p += (size_t)n_max * 4;
   ws.vals_alt = (int*)p; p += (size_t)n_max * 4;
+  ws.ticket = (unsigned int*)p; p += 256;
   ws.hist = (int*)p;
 }
+int sort_workspace_arm(SortWorkspace& ws, cudaStream_t s) {
+  FLOAM_CUDA_OK(cudaMemsetAsync(ws.ticket, 0, 256, s));
+  return FLOAM_OK;
+}
 
-void radix_sort_pairs(unsigned int* keys, int* vals, const int* d_n, const int* d_nbits, int n_max, SortWorkspace& ws, const int* d_skip, cudaStream_t s) {
+void radix_sort_pairs_from(unsigned int* keys, int* vals, unsigned int* keys_alt, int* vals_alt, const int* d_n, const int* d_nbits, int n_max,
+                           SortWorkspace& ws, const int* d_skip, cudaStream_t s, unsigned int** sorted_keys, int** sorted_vals) {
   if (n_max > ws.n_max) n_max = ws.n_max;
   const int nblocks = (n_max + kSortTile - 1) / kSortTile;
   unsigned int* kin = keys; int* vin = vals;
-  unsigned int* kout = ws.keys_alt; int* vout = ws.vals_alt;
-  for (int pass = 0; pass < 4; ++pass) {
-    const int shift = pass * 8;
-    FLOAM_LAUNCH(K_RADIX_HIST, radix_hist_kernel, nblocks, kSortThreads, s, kin, d_n, d_nbits, shift, ws.hist, d_skip);
-    if (nblocks > kDirectTiles)  // only inputs that can exceed 262,144 keys need the separate scan of the count table
-      FLOAM_LAUNCH(K_SINGLE_BLOCK_SCAN, single_block_scan_kernel, 1, 1024, s, ws.hist, 256 * nblocks, d_nbits, shift, d_skip, d_n);
-    FLOAM_LAUNCH(K_RADIX_SCATTER, radix_scatter_kernel, nblocks, kSortThreads, s, kin, vin, kout, vout, d_n, d_nbits, shift, ws.hist, d_skip);
+  unsigned int* kout = keys_alt; int* vout = vals_alt;
+  for (int pass = 0; pass < 3; ++pass) {
+    FLOAM_LAUNCH(K_RADIX_HIST, radix_hist_kernel, nblocks, kSortThreads, s, kin, d_n, d_nbits, pass, ws.hist, ws.ticket, d_skip);
+    FLOAM_LAUNCH(K_RADIX_SCATTER, radix_scatter_kernel, nblocks, kSortThreads, s, kin, vin, kout, vout, d_n, d_nbits, pass, ws.hist, d_skip);
     unsigned int* tk = kin; kin = kout; kout = tk;
     int* tv = vin; vin = vout; vout = tv;
   }
+  *sorted_keys = kin;   // three passes: the result sits in the alternate buffers
+  *sorted_vals = vin;
+}
+
+void radix_sort_pairs(unsigned int* keys, int* vals, const int* d_n, const int* d_nbits, int n_max, SortWorkspace& ws, const int* d_skip, cudaStream_t s,
+                      unsigned int** sorted_keys, int** sorted_vals) {
+  radix_sort_pairs_from(keys, vals, ws.keys_alt, ws.vals_alt, d_n, d_nbits, n_max, ws, d_skip, s, sorted_keys, sorted_vals);
 }
 
 void exclusive_scan_small(int* data, int n, cudaStream_t s) {
-  FLOAM_LAUNCH(K_SINGLE_BLOCK_SCAN, single_block_scan_kernel, 1, 1024, s, data, n, nullptr, 0, nullptr, nullptr);
+  FLOAM_LAUNCH(K_SINGLE_BLOCK_SCAN, single_block_scan_kernel, 1, 1024, s, data, n);
 }
 
 // ---- generic exclusive scan: two kernels, no serial single-CTA step -------------------------------------------------------------
@@ -286,6 +360,7 @@ namespace {
 
 __global__ void __launch_bounds__(kScanThreads) scan_tiles_kernel(const int* __restrict__ in, const int* __restrict__ d_n, int n_fixed,
                                                                   int* __restrict__ block_sums, const int* d_skip) {
+  pdl_prologue();
   if (d_skip && *d_skip) return;
   const int n = d_n ? *d_n : n_fixed;
   if (blockIdx.x * kScanTile >= n) return;
@@ -305,6 +380,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_tiles_kernel(const int* __r
 
 __global__ void __launch_bounds__(kScanThreads) scan_add_kernel(const int* __restrict__ in, int* __restrict__ out, const int* __restrict__ d_n, int n_fixed,
                                                                 const int* __restrict__ block_sums, const int* d_skip) {
+  pdl_prologue();
   if (d_skip && *d_skip) return;
   const int n = d_n ? *d_n : n_fixed;
   if (n == 0) { if (blockIdx.x == 0 && threadIdx.x == 0) out[0] = 0; return; }

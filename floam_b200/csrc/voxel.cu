@@ -21,6 +21,7 @@ __device__ __forceinline__ float4 load_xyzi(const char* base, int stride, int i)
 
 __global__ void __launch_bounds__(kThreads) voxel_bbox_kernel(const char* __restrict__ in, int stride, const int* __restrict__ d_n,
                                                                unsigned int* __restrict__ bbox, const int* d_skip) {
+  pdl_prologue();
   if (d_skip && *d_skip) return;
   const int n = *d_n;
   float mn[3] = {3.402823466e38f, 3.402823466e38f, 3.402823466e38f}, mx[3] = {-3.402823466e38f, -3.402823466e38f, -3.402823466e38f};
@@ -55,6 +56,7 @@ __device__ __forceinline__ int bits_for(long long cells) {  // number of key bit
 __global__ void __launch_bounds__(kThreads) voxel_keys_kernel(const char* __restrict__ in, int stride, const int* __restrict__ d_n, float leaf,
                                                                const unsigned int* __restrict__ bbox, unsigned int* __restrict__ keys,
                                                                int* __restrict__ vals, int* d_nbits, int* d_passthrough, const int* d_skip) {
+  pdl_prologue();
   if (d_skip && *d_skip) return;
   const int n = *d_n;
   // every thread derives the grid from the bbox exactly like VoxelGrid::applyFilter (float arithmetic, no contraction)
@@ -102,6 +104,7 @@ __device__ __forceinline__ int is_head(const unsigned int* __restrict__ keys, in
 
 __global__ void __launch_bounds__(kScanThreads) voxel_heads_kernel(const unsigned int* __restrict__ keys, const int* __restrict__ d_n,
                                                                    int* __restrict__ tile_sums, unsigned int* bbox, const int* d_skip) {
+  pdl_prologue();
   if (d_skip && *d_skip) return;
   const int n = *d_n;
   if (blockIdx.x == 0 && threadIdx.x == 0) {  // every reader of the bounding box (voxel_keys_kernel) is done: re-arm it for the next filter
@@ -120,6 +123,7 @@ __global__ void __launch_bounds__(kScanThreads) voxel_heads_kernel(const unsigne
 
 __global__ void __launch_bounds__(kScanThreads) voxel_rank_kernel(const unsigned int* __restrict__ keys, const int* __restrict__ d_n,
                                                                   const int* __restrict__ tile_sums, int* __restrict__ head_pos, int* d_nout, const int* d_skip) {
+  pdl_prologue();
   if (d_skip && *d_skip) return;
   const int n = *d_n;
   if (n == 0) { if (blockIdx.x == 0 && threadIdx.x == 0) { *d_nout = 0; head_pos[0] = 0; } return; }
@@ -150,6 +154,7 @@ constexpr int kStage = 256;
 __global__ void __launch_bounds__(kThreads) voxel_reduce_kernel(const char* __restrict__ in, int stride, const int* __restrict__ vals,
                                                                  const int* __restrict__ head_pos, const int* __restrict__ d_nout, P4* __restrict__ out,
                                                                  const int* d_skip) {
+  pdl_prologue();
   if (d_skip && *d_skip) return;
   __shared__ float4 s_stage[kThreads / 32][kStage];
   const int nv = *d_nout;
@@ -218,6 +223,7 @@ __device__ __forceinline__ int crop_count(const int* __restrict__ d_n, const int
 
 __global__ void __launch_bounds__(kScanThreads) crop_flags_kernel(const P4* __restrict__ in, const int* __restrict__ d_n, const int* __restrict__ d_extra, int cap,
                                                                   const float* __restrict__ bounds, int* __restrict__ tile_sums, const int* d_skip) {
+  pdl_prologue();
   if (d_skip && *d_skip) return;
   const int n = crop_count(d_n, d_extra, cap);
   if (blockIdx.x * kScanTile >= n) return;
@@ -233,6 +239,7 @@ __global__ void __launch_bounds__(kScanThreads) crop_flags_kernel(const P4* __re
 __global__ void __launch_bounds__(kScanThreads) crop_scatter_kernel(const P4* __restrict__ in, const int* __restrict__ d_n, const int* __restrict__ d_extra, int cap,
                                                                     const float* __restrict__ bounds, const int* __restrict__ tile_sums, P4* __restrict__ out,
                                                                     int* d_nout, const int* d_skip) {
+  pdl_prologue();
   if (d_skip && *d_skip) return;
   const int n = crop_count(d_n, d_extra, cap);
   if (n == 0) { if (blockIdx.x == 0 && threadIdx.x == 0) *d_nout = 0; return; }
@@ -258,6 +265,7 @@ __global__ void __launch_bounds__(kScanThreads) crop_scatter_kernel(const P4* __
 }
 
 __global__ void __launch_bounds__(kThreads) repack_kernel(const char* __restrict__ in, const int* __restrict__ d_n, P4* __restrict__ out) {
+  pdl_prologue();
   const int n = *d_n;
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) out[i] = load_xyzi(in, 32, i);
 }
@@ -291,6 +299,7 @@ void voxel_workspace_bind(VoxelWorkspace& ws, void* mem, int n_max) {
 int voxel_workspace_arm(VoxelWorkspace& ws, cudaStream_t s) {
   const unsigned int bb[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
   FLOAM_CUDA_OK(cudaMemcpyAsync(ws.bbox, bb, sizeof(bb), cudaMemcpyHostToDevice, s));
+  if (sort_workspace_arm(ws.sort, s)) return FLOAM_ERR_CUDA;
   FLOAM_CUDA_OK(cudaStreamSynchronize(s));
   return FLOAM_OK;
 }
@@ -303,10 +312,12 @@ void voxel_grid_device(const void* d_in, int stride_bytes, const int* d_n, int n
   const int gt = (n_max + kScanTile - 1) / kScanTile;
   FLOAM_LAUNCH(K_VOXEL_BBOX, voxel_bbox_kernel, g, kThreads, s, in, stride_bytes, d_n, ws.bbox, d_skip);
   FLOAM_LAUNCH(K_VOXEL_KEYS, voxel_keys_kernel, g, kThreads, s, in, stride_bytes, d_n, leaf, ws.bbox, ws.keys, ws.vals, ws.d_nbits, ws.d_passthrough, d_skip);
-  radix_sort_pairs(ws.keys, ws.vals, d_n, ws.d_nbits, n_max, ws.sort, d_skip, s);
-  FLOAM_LAUNCH(K_VOXEL_HEADS, voxel_heads_kernel, gt, kScanThreads, s, ws.keys, d_n, ws.scan.block_sums, ws.bbox, d_skip);
-  FLOAM_LAUNCH(K_VOXEL_RANK, voxel_rank_kernel, gt, kScanThreads, s, ws.keys, d_n, ws.scan.block_sums, ws.flags, d_nout, d_skip);
-  FLOAM_LAUNCH(K_VOXEL_REDUCE, voxel_reduce_kernel, g, kThreads, s, in, stride_bytes, ws.vals, ws.flags, d_nout, d_out, d_skip);
+  unsigned int* skeys = nullptr;
+  int* svals = nullptr;
+  radix_sort_pairs(ws.keys, ws.vals, d_n, ws.d_nbits, n_max, ws.sort, d_skip, s, &skeys, &svals);
+  FLOAM_LAUNCH(K_VOXEL_HEADS, voxel_heads_kernel, gt, kScanThreads, s, skeys, d_n, ws.scan.block_sums, ws.bbox, d_skip);
+  FLOAM_LAUNCH(K_VOXEL_RANK, voxel_rank_kernel, gt, kScanThreads, s, skeys, d_n, ws.scan.block_sums, ws.flags, d_nout, d_skip);
+  FLOAM_LAUNCH(K_VOXEL_REDUCE, voxel_reduce_kernel, g, kThreads, s, in, stride_bytes, svals, ws.flags, d_nout, d_out, d_skip);
 }
 
 void repack_xyzi_device(const void* d_in32, const int* d_n, int n_max, P4* d_out, cudaStream_t s) {

@@ -132,6 +132,15 @@ def test_voxel_grid_bit_exact(capi, po, ctxs, n, leaf):
     assert len(g) == len(o) and np.array_equal(xyzi(g), xyzi(o))
 
 
+@pytest.mark.parametrize("n", [3000, 400000])
+def test_voxel_grid_wide_keys(capi, po, ctxs, n):
+    # 600 x 600 x 60 m at leaf 0.4: 1500 x 1500 x 150 voxels = 29 key bits -> the sort's 10-bit digit path (and, for 400k points, the
+    # in-kernel scan of the count table)
+    pts = cloud(capi, np.random.default_rng(n), n, lo=(-300, -300, -30), hi=(300, 300, 30))
+    g = ctxs(16).voxel_grid(pts, 0.4); o, passthrough = po.voxel_grid(pts, 0.4, total_order=True)
+    assert not passthrough and len(g) == len(o) and np.array_equal(xyzi(g), xyzi(o))
+
+
 def test_voxel_grid_duplicates_and_negative_coordinates(capi, po, ctxs):
     rng = np.random.default_rng(5)
     pts = cloud(capi, rng, 3000, lo=(-3, -3, -3), hi=(3, 3, 3))
