@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(kSectorThreads) sector_kernel(const PointIRT* 
                                                                 int* __restrict__ edge_cnt, int* __restrict__ surf_cnt, int* __restrict__ d_flags) {
   pdl_prologue();
   __shared__ float sx[kSectorCap + kHalo], sy[kSectorCap + kHalo], sz[kSectorCap + kHalo];
-  __shared__ double sval[kSectorCap];
+  __shared__ double sval[kSectorCap], sval_sorted[kSectorCap];
   __shared__ short sid[kSectorCap];
   __shared__ unsigned char spicked[kSectorCap + kHalo], sgap[kSectorCap + kHalo];
   __shared__ int s_scan[33];
@@ -169,48 +169,78 @@ __global__ void __launch_bounds__(kSectorThreads) sector_kernel(const PointIRT* 
     sgap[q] = dadd(dadd(dmul(ax, ax), dmul(ay, ay)), dmul(az, az)) > 0.05 ? 1 : 0;
   }
   __syncthreads();
-  // bitonic sort ascending by (value, id): the total order that stands in for std::sort's tie behaviour (Q8)
-  for (int k = 2; k <= mpad; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = tid; i < mpad; i += kSectorThreads) {
-        const int ixj = i ^ j;
-        if (ixj > i) {
-          const double va = sval[i], vb = sval[ixj];
-          const short ia = sid[i], ib = sid[ixj];
-          const bool up = ((i & k) == 0);
-          const bool a_gt_b = key_less(vb, ib, va, ia);
-          if (a_gt_b == up) { sval[i] = vb; sval[ixj] = va; sid[i] = ib; sid[ixj] = ia; }
-        }
-      }
-      __syncthreads();
+  // sort ascending by (value, id) — the total order that stands in for std::sort's tie behaviour (Q8) — by RANK: every entry counts
+  // the entries ordered before it (broadcast shared-memory reads, no barriers inside the loop), then drops itself at that position.
+  // ~m^2 / 256 = 400 compares per thread at m = 320 instead of 45 barrier-separated bitonic stages.
+  {
+    double mv[(kSectorCap + kSectorThreads - 1) / kSectorThreads];
+    int mr[(kSectorCap + kSectorThreads - 1) / kSectorThreads];
+#pragma unroll
+    for (int u = 0; u < (kSectorCap + kSectorThreads - 1) / kSectorThreads; ++u) {
+      const int c = tid + u * kSectorThreads;
+      mv[u] = c < m ? sval[c] : 0.0;
+      mr[u] = 0;
     }
+    for (int j = 0; j < m; ++j) {
+      const double vj = sval[j];
+#pragma unroll
+      for (int u = 0; u < (kSectorCap + kSectorThreads - 1) / kSectorThreads; ++u) {
+        const int c = tid + u * kSectorThreads;
+        mr[u] += (vj < mv[u] || (vj == mv[u] && j < c)) ? 1 : 0;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < (kSectorCap + kSectorThreads - 1) / kSectorThreads; ++u) {
+      const int c = tid + u * kSectorThreads;
+      if (c < m) { sval_sorted[mr[u]] = mv[u]; sid[mr[u]] = (short)c; }
+    }
+    __syncthreads();
   }
-  // greedy pick from the largest curvature down (:132-170); local point index of entry c is c + 5
-  if (tid == 0) {
+  // greedy pick from the largest curvature down (:132-170); local point index of entry c is c + 5. One warp walks the sorted list 32
+  // candidates at a time: a ballot finds the next un-suppressed candidate, lanes 0..9 apply the +-5 neighbour suppression (which
+  // stops at the first gap > 0.05 m^2 on either side), and the batch is re-examined because the suppression may have hit it.
+  if (tid < 32) {
+    const int l = tid;
     int largestPickedNum = 0, nedge = 0;
-    for (int i = m - 1; i >= 0; --i) {
-      const int c = sid[i];
-      const int q = c + 5;
-      if (spicked[q]) continue;
-      if (sval[i] <= 0.1) break;
-      largestPickedNum++;
-      spicked[q] = 1;
-      if (largestPickedNum <= 20) {
-        edge_tmp[blockIdx.x * 20 + nedge] = ring_start + sector_start + q;
-        nedge++;
-      } else {
-        break;  // the 21st candidate stays picked: neither edge nor surf (Q6)
-      }
-      for (int k = 1; k <= 5; ++k) {
-        if (sgap[q + k - 1]) break;
-        spicked[q + k] = 1;
-      }
-      for (int k = -1; k >= -5; --k) {
-        if (sgap[q + k]) break;
-        spicked[q + k] = 1;
+    bool stop = false;
+    for (int top = m - 1; top >= 0 && !stop; top -= 32) {
+      const int i = top - l;                       // this lane's sorted position (descending curvature)
+      const int q = i >= 0 ? sid[i] + 5 : 0;
+      const bool above = i >= 0 && sval_sorted[i] > 0.1;
+      unsigned int done_mask = 0;                  // lanes of this batch already handled
+      for (;;) {
+        const bool cand = i >= 0 && !((done_mask >> l) & 1u) && !spicked[q];
+        const unsigned int cm = __ballot_sync(0xffffffffu, cand);
+        if (cm == 0) break;
+        const int src = __ffs(cm) - 1;             // largest remaining curvature of the batch
+        if (!__shfl_sync(0xffffffffu, (int)above, src)) { stop = true; break; }   // sorted: nothing below qualifies either
+        const int qs = __shfl_sync(0xffffffffu, q, src);
+        largestPickedNum++;
+        if (l == 0) spicked[qs] = 1;
+        if (largestPickedNum <= 20) {
+          if (l == 0) edge_tmp[blockIdx.x * 20 + nedge] = ring_start + sector_start + qs;
+          nedge++;
+        } else {
+          stop = true;                             // the 21st candidate stays picked: neither edge nor surf (Q6)
+          break;
+        }
+        // lanes 0..4: forward neighbours k = 1..5 (gap between qs+k-1 and qs+k); lanes 5..9: backward k = -1..-5 (gap at qs+k)
+        const bool fwd = l < 5, bwd = l >= 5 && l < 10;
+        const int k = fwd ? l + 1 : l - 4;
+        bool gap = false;
+        if (fwd) gap = sgap[qs + k - 1] != 0;
+        if (bwd) gap = sgap[qs - k] != 0;
+        const unsigned int gm = __ballot_sync(0xffffffffu, gap);
+        const int first_f = (gm & 0x1fu) ? __ffs(gm & 0x1fu) - 1 : 5;          // suppression stops before the first gap
+        const int first_b = ((gm >> 5) & 0x1fu) ? __ffs((gm >> 5) & 0x1fu) - 1 : 5;
+        if (fwd && l < first_f) spicked[qs + k] = 1;
+        if (bwd && (l - 5) < first_b) spicked[qs - k] = 1;
+        __syncwarp();
+        done_mask |= (src == 31) ? 0xffffffffu : ((2u << src) - 1u);           // everything up to and including src is settled
       }
     }
-    s_nedge = nedge;
+    if (l == 0) s_nedge = nedge;
   }
   __syncthreads();
   // surf = every non-picked entry in ascending curvature order (:220-227): stable compaction of the sorted list
