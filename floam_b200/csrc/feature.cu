@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(kSectorThreads) sector_kernel(const PointIRT* 
                                                                 int* __restrict__ edge_cnt, int* __restrict__ surf_cnt, int* __restrict__ d_flags) {
   pdl_prologue();
   __shared__ float sx[kSectorCap + kHalo], sy[kSectorCap + kHalo], sz[kSectorCap + kHalo];
-  __shared__ double sval[kSectorCap], sval_sorted[kSectorCap];
+  __shared__ double sval[kSectorCap];
   __shared__ short sid[kSectorCap];
   __shared__ unsigned char spicked[kSectorCap + kHalo], sgap[kSectorCap + kHalo];
   __shared__ int s_scan[33];
@@ -169,33 +169,22 @@ __global__ void __launch_bounds__(kSectorThreads) sector_kernel(const PointIRT* 
     sgap[q] = dadd(dadd(dmul(ax, ax), dmul(ay, ay)), dmul(az, az)) > 0.05 ? 1 : 0;
   }
   __syncthreads();
-  // sort ascending by (value, id) — the total order that stands in for std::sort's tie behaviour (Q8) — by RANK: every entry counts
-  // the entries ordered before it (broadcast shared-memory reads, no barriers inside the loop), then drops itself at that position.
-  // ~m^2 / 256 = 400 compares per thread at m = 320 instead of 45 barrier-separated bitonic stages.
-  {
-    double mv[(kSectorCap + kSectorThreads - 1) / kSectorThreads];
-    int mr[(kSectorCap + kSectorThreads - 1) / kSectorThreads];
-#pragma unroll
-    for (int u = 0; u < (kSectorCap + kSectorThreads - 1) / kSectorThreads; ++u) {
-      const int c = tid + u * kSectorThreads;
-      mv[u] = c < m ? sval[c] : 0.0;
-      mr[u] = 0;
-    }
-    for (int j = 0; j < m; ++j) {
-      const double vj = sval[j];
-#pragma unroll
-      for (int u = 0; u < (kSectorCap + kSectorThreads - 1) / kSectorThreads; ++u) {
-        const int c = tid + u * kSectorThreads;
-        mr[u] += (vj < mv[u] || (vj == mv[u] && j < c)) ? 1 : 0;
+  // bitonic sort ascending by (value, id): the total order that stands in for std::sort's tie behaviour (Q8).
+  // (A barrier-free rank sort — every entry counting its predecessors — was measured slower: m^2 64-bit compares per sector.)
+  for (int k = 2; k <= mpad; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < mpad; i += kSectorThreads) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const double va = sval[i], vb = sval[ixj];
+          const short ia = sid[i], ib = sid[ixj];
+          const bool up = ((i & k) == 0);
+          const bool a_gt_b = key_less(vb, ib, va, ia);
+          if (a_gt_b == up) { sval[i] = vb; sval[ixj] = va; sid[i] = ib; sid[ixj] = ia; }
+        }
       }
+      __syncthreads();
     }
-    __syncthreads();
-#pragma unroll
-    for (int u = 0; u < (kSectorCap + kSectorThreads - 1) / kSectorThreads; ++u) {
-      const int c = tid + u * kSectorThreads;
-      if (c < m) { sval_sorted[mr[u]] = mv[u]; sid[mr[u]] = (short)c; }
-    }
-    __syncthreads();
   }
   // greedy pick from the largest curvature down (:132-170); local point index of entry c is c + 5. One warp walks the sorted list 32
   // candidates at a time: a ballot finds the next un-suppressed candidate, lanes 0..9 apply the +-5 neighbour suppression (which
@@ -207,7 +196,7 @@ __global__ void __launch_bounds__(kSectorThreads) sector_kernel(const PointIRT* 
     for (int top = m - 1; top >= 0 && !stop; top -= 32) {
       const int i = top - l;                       // this lane's sorted position (descending curvature)
       const int q = i >= 0 ? sid[i] + 5 : 0;
-      const bool above = i >= 0 && sval_sorted[i] > 0.1;
+      const bool above = i >= 0 && sval[i] > 0.1;
       unsigned int done_mask = 0;                  // lanes of this batch already handled
       for (;;) {
         const bool cand = i >= 0 && !((done_mask >> l) & 1u) && !spicked[q];
