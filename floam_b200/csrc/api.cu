@@ -72,6 +72,14 @@ int upload_cloud(floam_ctx* c, const void* host, int n, void* d_buf, int* d_n, i
   return FLOAM_OK;
 }
 
+// point the unsuffixed buffer names at the set of frame parity p (host-side aliases read at enqueue time)
+void select_parity(floam_ctx* c, int p) {
+  c->d_edge = c->d_edge_b[p]; c->d_surf = c->d_surf_b[p];
+  c->d_ne = c->d_ne_b[p]; c->d_ns = c->d_ns_b[p];
+  c->d_edge_src = c->d_edge_src_b[p]; c->d_surf_src = c->d_surf_src_b[p];
+  odom_select_buffers(c->odom, p);
+}
+
 int fetch_state(floam_ctx* c, int slot) {
   FLOAM_CUDA_OK(cudaMemcpyAsync(c->h_state[slot], c->odom.state, sizeof(PoseState), cudaMemcpyDeviceToHost, c->stream));
   FLOAM_CUDA_OK(cudaMemcpyAsync(c->h_flags[slot], c->d_flags, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -92,67 +100,102 @@ void pose_out_from_state(const PoseState* S, double pose[7]) {
 int next_outer(int count) { return count > 2 ? count - 1 : count; }
 
 // OdomEstimationClass::UpdatePointsToMapSelector (src/odomEstimationClass.cpp:34-50) on device-resident feature clouds
-void enqueue_selector(floam_ctx* c, PointIRT* d_edge, const int* d_ne, PointIRT* d_surf, const int* d_ns, int n_max, int deskew) {
+void enqueue_selector(floam_ctx* c, PointIRT* d_edge, const int* d_ne, PointIRT* d_surf, const int* d_ns, int n_max, int deskew, bool ds_ready = false) {
   OdomDevice& od = c->odom;
   if (!deskew) {
     od.optimization_count = next_outer(od.optimization_count);
-    odom_update_device(od, d_edge, d_ne, d_surf, d_ns, 32, n_max, FLOAM_VANILLA, 1, c->stream);
+    odom_update_device(od, d_edge, d_ne, d_surf, d_ns, 32, n_max, FLOAM_VANILLA, ds_ready ? 1 : 0, c->stream);
   } else {
     od.optimization_count = next_outer(od.optimization_count);
     odom_update_device(od, d_edge, d_ne, d_edge, d_ne, 32, n_max, FLOAM_INITIAL_ITERATION, 0, c->stream);  // Q3: edge as both clouds
     compensate_velocity_device(od, d_edge, d_ne, n_max, c->stream);
     compensate_velocity_device(od, d_surf, d_ns, n_max, c->stream);
     od.optimization_count = next_outer(od.optimization_count);
-    odom_update_device(od, d_edge, d_ne, d_surf, d_ns, 32, n_max, FLOAM_REFINEMENT_AND_UPDATE, 1, c->stream);
+    odom_update_device(od, d_edge, d_ne, d_surf, d_ns, 32, n_max, FLOAM_REFINEMENT_AND_UPDATE, 0, c->stream);
   }
 }
 
-// everything between "scan is in d_scan" and "pose is in the pinned mailbox" for one frame
-void enqueue_frame_body(floam_ctx* c, PointIRT* d_scan, const int* d_scan_n, int deskew, int slot, bool first, bool imu) {
+// A frame is enqueued as two halves on two stream pairs (context.cuh): FRONT = [IMU deskew] + feature extraction + (no-deskew mode)
+// downSamplingToMap — everything that depends on neither the pose nor the map; BACK = prediction, association + solve, write-back,
+// keyframe map update. FRONT(k+1) overlaps BACK(k); the buffers the two halves exchange exist twice (frame parity).
+void enqueue_front(floam_ctx* c, PointIRT* d_scan, const int* d_scan_n, int deskew, int slot, bool first, bool imu) {
+  cudaStream_t s = c->front_stream;
   // CenterTime + Compensate + IMU alignment folded into the frame (src/laserProcessingNode.cpp:100-116): in place on the uploaded scan
-  if (imu) deskew_launch(c->imu, c->d_plan[slot], d_scan, d_scan_n, c->prm.max_scan_points, c->stream);
-  feature_extract_device(d_scan, d_scan_n, c->fprm, c->fws, c->d_edge, c->d_ne, c->d_surf, c->d_ns, c->d_edge_src, c->d_surf_src, c->d_flags, c->stream);
+  if (imu) deskew_launch(c->imu, c->d_plan[slot], d_scan, d_scan_n, c->prm.max_scan_points, s);
+  feature_extract_device(d_scan, d_scan_n, c->fprm, c->fws, c->d_edge, c->d_ne, c->d_surf, c->d_ns, c->d_edge_src, c->d_surf_src, c->d_flags, s);
+  if (!first && !deskew)   // the two-pass deskew mode downsamples different clouds in each pass (Q3): it stays inside the BACK
+    odom_downsample_device(c->odom, c->d_edge, c->d_ne, c->d_surf, c->d_ns, 32, c->prm.max_scan_points, c->vws_front, c->vws_front_aux, s, c->front_aux,
+                           c->ev_ffork, c->ev_fjoin);
+}
+
+void enqueue_back(floam_ctx* c, int deskew, int slot, bool first) {
   if (first) {
     // odomEstimationNode.cpp:219-224: first frame only seeds the map (raw features, Q11); odom stays identity
     odom_init_map_device(c->odom, c->d_edge, c->d_ne, c->d_surf, c->d_ns, 32, c->prm.max_scan_points, 0, c->stream);
     odom_record_pose(c->odom, c->stream);
     c->odom.optimization_count = 12;
   } else {
-    enqueue_selector(c, c->d_edge, c->d_ne, c->d_surf, c->d_ns, c->prm.max_scan_points, deskew);
+    enqueue_selector(c, c->d_edge, c->d_ne, c->d_surf, c->d_ns, c->prm.max_scan_points, deskew, !deskew);
   }
   if (c->timer.enabled) launch_noop(c->stream);   // calibration of the event-pair overhead (kernel-timing mode only)
   fetch_state(c, slot);
 }
 
-// Launch the frame body, through a CUDA graph when enabled. Graphs are keyed by everything that changes the launch sequence.
-int launch_frame(floam_ctx* c, PointIRT* d_scan, const int* d_scan_n, int deskew, int slot, int scan_slot_key, bool imu = false) {
-  const bool first = !c->map_initialised;
-  OdomDevice& od = c->odom;
+// Capture-or-replay of one half. Graphs are keyed by everything that changes the launch sequence or the buffers it touches.
+template <class Body>
+int launch_half(floam_ctx* c, const floam_graph_key& key, cudaStream_t s, Body body) {
   if (!c->use_graphs) {
-    enqueue_frame_body(c, d_scan, d_scan_n, deskew, slot, first, imu);
-    c->map_initialised = true;
+    body();
     return check_async("frame");
   }
   const bool timing = c->timer.enabled;
-  floam_graph_key key{(first ? 0 : 1) + (imu ? 2 : 0) + (timing ? 4 : 0), first ? 0 : next_outer(od.optimization_count), first ? 0 : (deskew ? 1 : 0), scan_slot_key * 2 + slot};
   auto it = c->graphs.find(key);
   if (it == c->graphs.end()) {
     const long long before = g_launches;
-    const int saved_count = od.optimization_count;
     cudaGraph_t graph = nullptr;
     floam_graph_entry e;
     if (timing) { launch_timer_collect(&c->timer, c->stream); e.pair_first = c->timer.used; }
-    FLOAM_CUDA_OK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-    enqueue_frame_body(c, d_scan, d_scan_n, deskew, slot, first, imu);
-    FLOAM_CUDA_OK(cudaStreamEndCapture(c->stream, &graph));
+    FLOAM_CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    body();
+    FLOAM_CUDA_OK(cudaStreamEndCapture(s, &graph));
     if (timing) { e.pair_last = c->timer.used; c->timer.persist = c->timer.used; }
     FLOAM_CUDA_OK(cudaGraphInstantiate(&e.exec, graph, 0));
     cudaGraphDestroy(graph);
     e.launches = (int)(g_launches - before);
     g_launches = before;                  // the capture launched nothing; replays are counted below
-    od.optimization_count = saved_count;  // host-side transitions are applied below, like for any cached graph
     it = c->graphs.emplace(key, e).first;
   }
+  g_launches += it->second.launches;
+  FLOAM_CUDA_OK(cudaGraphLaunch(it->second.exec, s));
+  if (timing) {  // per-kernel event pairs live inside the graph: read them back after this replay
+    FLOAM_CUDA_OK(cudaStreamSynchronize(s));
+    launch_timer_fold(&c->timer, it->second.pair_first, it->second.pair_last);
+  }
+  return FLOAM_OK;
+}
+
+// Both halves of the frame whose scan sits in d_scan[slot] (slot = frame parity). The caller has made front_stream wait for the scan.
+int launch_frame(floam_ctx* c, int deskew, int slot, bool imu) {
+  const bool first = !c->map_initialised;
+  OdomDevice& od = c->odom;
+  const bool timing = c->timer.enabled;
+  select_parity(c, slot);
+  const int outer = first ? 0 : next_outer(od.optimization_count);
+  const int flags = (first ? 0 : 1) + (imu ? 2 : 0) + (timing ? 4 : 0);
+  // FRONT(k) may not overwrite the parity's buffers before BACK(k-2) has finished with them
+  if (c->back_valid[slot]) FLOAM_CUDA_OK(cudaStreamWaitEvent(c->front_stream, c->ev_back_done[slot], 0));
+  int rc = launch_half(c, floam_graph_key{flags + 8, 0, first ? 0 : (deskew ? 1 : 0), slot}, c->front_stream,
+                       [&]() { enqueue_front(c, c->d_scan[slot], c->d_scan_n[slot], deskew, slot, first, imu); });
+  if (rc) return rc;
+  FLOAM_CUDA_OK(cudaEventRecord(c->ev_front_done[slot], c->front_stream));
+  FLOAM_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_front_done[slot], 0));
+  const int saved_count = od.optimization_count;
+  rc = launch_half(c, floam_graph_key{flags, outer, first ? 0 : (deskew ? 1 : 0), slot}, c->stream, [&]() { enqueue_back(c, deskew, slot, first); });
+  if (rc) return rc;
+  FLOAM_CUDA_OK(cudaEventRecord(c->ev_back_done[slot], c->stream));
+  c->back_valid[slot] = true;
+  // host-side transitions of the deterministic outer-iteration schedule (the enqueue applies them only when it is actually run)
+  od.optimization_count = saved_count;
   if (first) {
     od.optimization_count = 12;  // initMapWithPoints, src/odomEstimationClass.cpp:31
   } else {
@@ -160,12 +203,6 @@ int launch_frame(floam_ctx* c, PointIRT* d_scan, const int* d_scan_n, int deskew
     if (deskew) od.optimization_count = next_outer(od.optimization_count);  // second pass (Q4)
   }
   c->map_initialised = true;
-  g_launches += it->second.launches;
-  FLOAM_CUDA_OK(cudaGraphLaunch(it->second.exec, c->stream));
-  if (timing) {  // per-kernel event pairs live inside the graph: read them back after this replay
-    FLOAM_CUDA_OK(cudaStreamSynchronize(c->stream));
-    launch_timer_fold(&c->timer, it->second.pair_first, it->second.pair_last);
-  }
   return FLOAM_OK;
 }
 
@@ -232,12 +269,19 @@ int floam_create(const floam_params* params, int device, floam_ctx** out) {
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(FLOAM_ERR_CUDA);
   if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(FLOAM_ERR_CUDA);
   if (cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(FLOAM_ERR_CUDA);
+  if (cudaStreamCreateWithFlags(&c->front_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(FLOAM_ERR_CUDA);
+  if (cudaStreamCreateWithFlags(&c->front_aux, cudaStreamNonBlocking) != cudaSuccess) return fail(FLOAM_ERR_CUDA);
+  if (cudaEventCreateWithFlags(&c->ev_ffork, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_fjoin, cudaEventDisableTiming) != cudaSuccess)
+    return fail(FLOAM_ERR_CUDA);
   for (int k = 0; k < 2; ++k) {
     if (cudaEventCreate(&c->ev_begin[k]) != cudaSuccess || cudaEventCreate(&c->ev_end[k]) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_upload[k], cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c->ev_consumed[k], cudaEventDisableTiming) != cudaSuccess)
+        cudaEventCreateWithFlags(&c->ev_consumed[k], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_front_done[k], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_back_done[k], cudaEventDisableTiming) != cudaSuccess)
       return fail(FLOAM_ERR_CUDA);
   }
+  if (cudaEventCreate(&c->ev_replay_begin) != cudaSuccess || cudaEventCreate(&c->ev_replay_end) != cudaSuccess) return fail(FLOAM_ERR_CUDA);
   const int ns = params->max_scan_points;
   const int nm = params->max_map_points;
   c->stage_cap = std::max(std::max(ns, nm), params->max_global_map_points);
@@ -247,11 +291,13 @@ int floam_create(const floam_params* params, int device, floam_ctx** out) {
     c->d_scan[k] = (PointIRT*)A((size_t)ns * 32);
     c->d_scan_n[k] = (int*)A(4);
   }
-  c->d_edge = (PointIRT*)A((size_t)ns * 32);
-  c->d_surf = (PointIRT*)A((size_t)ns * 32);
-  c->d_edge_src = (int*)A((size_t)ns * 4);
-  c->d_surf_src = (int*)A((size_t)ns * 4);
-  int* ints = (int*)A(64);
+  for (int k = 0; k < 2; ++k) {
+    c->d_edge_b[k] = (PointIRT*)A((size_t)ns * 32);
+    c->d_surf_b[k] = (PointIRT*)A((size_t)ns * 32);
+    c->d_edge_src_b[k] = (int*)A((size_t)ns * 4);
+    c->d_surf_src_b[k] = (int*)A((size_t)ns * 4);
+  }
+  int* ints = (int*)A(128);
   c->d_stage_in = (char*)A((size_t)c->stage_cap * 32);
   c->d_stage_p4 = (P4*)A((size_t)c->stage_cap * 16);
   c->d_stage_out = (P4*)A((size_t)c->stage_cap * 16);
@@ -260,13 +306,17 @@ int floam_create(const floam_params* params, int device, floam_ctx** out) {
   void* vmem = A(voxel_workspace_bytes(c->stage_cap));
   const int aux_cap = std::max(ns, nm);
   void* vmem_aux = A(voxel_workspace_bytes(aux_cap));
+  void* vmem_front = A(voxel_workspace_bytes(ns));
+  void* vmem_front_aux = A(voxel_workspace_bytes(ns));
   c->imu.dev_cap = 1 << 20;
   c->imu.d_samples = (ImuSample*)A((size_t)c->imu.dev_cap * sizeof(ImuSample));
   c->imu.d_plan = (DeskewPlan*)A(sizeof(DeskewPlan));
   for (int k = 0; k < 2; ++k) c->d_plan[k] = (DeskewPlan*)A(sizeof(DeskewPlan));
   if (!ok) return fail(FLOAM_ERR_CUDA);
-  c->d_ne = ints; c->d_ns = ints + 1; c->d_flags = ints + 2; c->d_stage_n = ints + 4; c->d_staged_n = ints + 8;
-  if (cudaMemsetAsync(ints, 0, 64, c->stream) != cudaSuccess) return fail(FLOAM_ERR_CUDA);
+  c->d_ne_b[0] = ints; c->d_ns_b[0] = ints + 1; c->d_flags = ints + 2; c->d_stage_n = ints + 4; c->d_staged_n = ints + 8;
+  c->d_ne_b[1] = ints + 16; c->d_ns_b[1] = ints + 17;
+  if (cudaMemsetAsync(ints, 0, 128, c->stream) != cudaSuccess) return fail(FLOAM_ERR_CUDA);
+  select_parity(c, 0);
   c->fprm.min_distance = params->min_distance;
   c->fprm.max_distance = params->max_distance;
   c->fprm.num_lines = params->num_lines;
@@ -275,6 +325,9 @@ int floam_create(const floam_params* params, int device, floam_ctx** out) {
   if (voxel_workspace_arm(c->vws, c->stream)) return fail(FLOAM_ERR_CUDA);
   voxel_workspace_bind(c->vws_aux, vmem_aux, aux_cap);
   if (voxel_workspace_arm(c->vws_aux, c->stream)) return fail(FLOAM_ERR_CUDA);
+  voxel_workspace_bind(c->vws_front, vmem_front, ns);
+  voxel_workspace_bind(c->vws_front_aux, vmem_front_aux, ns);
+  if (voxel_workspace_arm(c->vws_front, c->stream) || voxel_workspace_arm(c->vws_front_aux, c->stream)) return fail(FLOAM_ERR_CUDA);
 
   c->h_ints = (int*)host_alloc(c, 64 * sizeof(int));
   c->h_doubles = (double*)host_alloc(c, 64 * sizeof(double));
@@ -307,6 +360,8 @@ void floam_destroy(floam_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
   if (c->aux_stream) cudaStreamSynchronize(c->aux_stream);
+  if (c->front_stream) cudaStreamSynchronize(c->front_stream);
+  if (c->front_aux) cudaStreamSynchronize(c->front_aux);
   if (g_timer == &c->timer) g_timer = nullptr;
   if (c->timer.created) for (int i = 0; i < 2 * LaunchTimer::kPairs; ++i) cudaEventDestroy(c->timer.ev[i]);
   for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second.exec);
@@ -317,10 +372,18 @@ void floam_destroy(floam_ctx* c) {
     if (c->ev_end[k]) cudaEventDestroy(c->ev_end[k]);
     if (c->ev_upload[k]) cudaEventDestroy(c->ev_upload[k]);
     if (c->ev_consumed[k]) cudaEventDestroy(c->ev_consumed[k]);
+    if (c->ev_front_done[k]) cudaEventDestroy(c->ev_front_done[k]);
+    if (c->ev_back_done[k]) cudaEventDestroy(c->ev_back_done[k]);
   }
+  if (c->ev_replay_begin) cudaEventDestroy(c->ev_replay_begin);
+  if (c->ev_replay_end) cudaEventDestroy(c->ev_replay_end);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+  if (c->front_stream) cudaStreamDestroy(c->front_stream);
+  if (c->front_aux) cudaStreamDestroy(c->front_aux);
+  if (c->ev_ffork) cudaEventDestroy(c->ev_ffork);
+  if (c->ev_fjoin) cudaEventDestroy(c->ev_fjoin);
   if (c->odom.ev_fork) cudaEventDestroy(c->odom.ev_fork);
   if (c->odom.ev_join) cudaEventDestroy(c->odom.ev_join);
   cudaGetLastError();
@@ -476,7 +539,7 @@ int floam_odom_update_xyzi(floam_ctx* c, const floam_point_xyzi* edge, int ne, c
   if (rc) return rc;
   if ((rc = upload_cloud(c, surf, ns, c->d_surf, c->d_ns, 1))) return rc;
   c->odom.optimization_count = next_outer(c->odom.optimization_count);
-  odom_update_device(c->odom, c->d_edge, c->d_ne, c->d_surf, c->d_ns, 32, std::max(std::max(ne, ns), 1), update_type, 1, c->stream);
+  odom_update_device(c->odom, c->d_edge, c->d_ne, c->d_surf, c->d_ns, 32, std::max(std::max(ne, ns), 1), update_type, 0, c->stream);
   return finish_update(c, pose_out);
 }
 
@@ -570,8 +633,8 @@ static int submit_common(floam_ctx* c, const floam_point_xyzirt* pts, int n, int
   if (c->inflight >= 2) return FLOAM_ERR_ARG;
   if (set_device(c)) return FLOAM_ERR_CUDA;
   const int slot = c->submit_slot;
-  // upload on the copy stream once the kernels that read this buffer two frames ago are done
-  if (c->consumed_valid[slot]) FLOAM_CUDA_OK(cudaStreamWaitEvent(c->copy_stream, c->ev_consumed[slot], 0));
+  // upload on the copy stream once the FRONT that read this scan buffer two frames ago is done
+  if (c->consumed_valid[slot]) FLOAM_CUDA_OK(cudaStreamWaitEvent(c->copy_stream, c->ev_front_done[slot], 0));
   if (n > 0) FLOAM_CUDA_OK(cudaMemcpyAsync(c->d_scan[slot], pts, (size_t)n * 32, cudaMemcpyHostToDevice, c->copy_stream));
   c->h_ints[32 + slot] = n;
   FLOAM_CUDA_OK(cudaMemcpyAsync(c->d_scan_n[slot], &c->h_ints[32 + slot], 4, cudaMemcpyHostToDevice, c->copy_stream));
@@ -580,16 +643,32 @@ static int submit_common(floam_ctx* c, const floam_point_xyzirt* pts, int n, int
     if (rc) return rc;
   }
   FLOAM_CUDA_OK(cudaEventRecord(c->ev_upload[slot], c->copy_stream));
-  FLOAM_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_upload[slot], 0));
-  FLOAM_CUDA_OK(cudaEventRecord(c->ev_begin[slot], c->stream));
+  FLOAM_CUDA_OK(cudaStreamWaitEvent(c->front_stream, c->ev_upload[slot], 0));
+  FLOAM_CUDA_OK(cudaEventRecord(c->ev_begin[slot], c->front_stream));
   c->frame_was_init[slot] = !c->map_initialised;
-  int rc = launch_frame(c, c->d_scan[slot], c->d_scan_n[slot], deskew, slot, 0, plan != nullptr);
+  int rc = launch_frame(c, deskew, slot, plan != nullptr);
   if (rc) return rc;
   FLOAM_CUDA_OK(cudaEventRecord(c->ev_end[slot], c->stream));
-  FLOAM_CUDA_OK(cudaEventRecord(c->ev_consumed[slot], c->stream));
   c->consumed_valid[slot] = true;
   c->submit_slot ^= 1;
   c->inflight++;
+  return FLOAM_OK;
+}
+
+// same for a scan that already sits in device memory (staged replay): the copy into the frame's scan buffer rides on the front stream
+static int enqueue_staged_frame(floam_ctx* c, int frame, int deskew) {
+  const int slot = c->submit_slot;
+  const int n = (int)(c->staged_offsets[frame + 1] - c->staged_offsets[frame]);
+  FLOAM_CUDA_OK(cudaEventRecord(c->ev_begin[slot], c->front_stream));
+  if (n > 0)
+    FLOAM_CUDA_OK(cudaMemcpyAsync(c->d_scan[slot], c->d_staged + c->staged_offsets[frame], (size_t)n * 32, cudaMemcpyDeviceToDevice, c->front_stream));
+  FLOAM_CUDA_OK(cudaMemcpyAsync(c->d_scan_n[slot], c->d_staged_counts + frame, 4, cudaMemcpyDeviceToDevice, c->front_stream));
+  const int rc = launch_frame(c, deskew, slot, false);
+  if (rc) return rc;
+  FLOAM_CUDA_OK(cudaEventRecord(c->ev_end[slot], c->stream));
+  c->consumed_valid[slot] = true;
+  c->submit_slot ^= 1;
+  c->wait_slot = c->submit_slot;   // nothing stays in flight across these calls: keep the submit / wait slots aligned
   return FLOAM_OK;
 }
 
@@ -653,20 +732,14 @@ int floam_stage_scans(floam_ctx* c, const floam_point_xyzirt* pts, const int64_t
 int floam_process_staged(floam_ctx* c, int frame, int deskew, double pose_out[7]) {
   if (!c || !c->d_staged || frame < 0 || frame + 1 >= (int)c->staged_offsets.size() || c->inflight != 0) return FLOAM_ERR_ARG;
   if (set_device(c)) return FLOAM_ERR_CUDA;
-  // the frame is copied device-to-device into scan slot 0 so that the cached graphs (which read fixed buffers) can be replayed
-  const int n = (int)(c->staged_offsets[frame + 1] - c->staged_offsets[frame]);
-  FLOAM_CUDA_OK(cudaEventRecord(c->ev_begin[0], c->stream));
-  if (n > 0)
-    FLOAM_CUDA_OK(cudaMemcpyAsync(c->d_scan[0], c->d_staged + c->staged_offsets[frame], (size_t)n * 32, cudaMemcpyDeviceToDevice, c->stream));
-  FLOAM_CUDA_OK(cudaMemcpyAsync(c->d_scan_n[0], c->d_staged_counts + frame, 4, cudaMemcpyDeviceToDevice, c->stream));
-  int rc = launch_frame(c, c->d_scan[0], c->d_scan_n[0], deskew, 0, 0);
+  const int slot = c->submit_slot;
+  int rc = enqueue_staged_frame(c, frame, deskew);
   if (rc) return rc;
-  FLOAM_CUDA_OK(cudaEventRecord(c->ev_end[0], c->stream));
   FLOAM_CUDA_OK(cudaStreamSynchronize(c->stream));
   if ((rc = check_async("process_staged"))) return rc;
-  cudaEventElapsedTime(&c->last_frame_ms, c->ev_begin[0], c->ev_end[0]);
-  if (pose_out) pose_out_from_state(c->h_state[0], pose_out);
-  return status_from_flags(c, 0);
+  cudaEventElapsedTime(&c->last_frame_ms, c->ev_begin[slot], c->ev_end[slot]);
+  if (pose_out) pose_out_from_state(c->h_state[slot], pose_out);
+  return status_from_flags(c, slot);
 }
 
 // ---- stage entry points: pcl::VoxelGrid, pcl::CropBox, pcl::KdTreeFLANN ------------------------------------------------
@@ -888,25 +961,25 @@ int floam_replay_staged(floam_ctx* c, int first, int count, int deskew, double* 
   int rc = sync_state(c);
   if (rc) return rc;
   const int counter0 = c->h_state[0]->frame_counter;
-  FLOAM_CUDA_OK(cudaEventRecord(c->ev_begin[0], c->stream));
+  FLOAM_CUDA_OK(cudaEventRecord(c->ev_replay_begin, c->front_stream));
+  int last_slot = 0;
   for (int f = first; f < first + count; ++f) {
-    const int n = (int)(c->staged_offsets[f + 1] - c->staged_offsets[f]);
-    if (n > 0)
-      FLOAM_CUDA_OK(cudaMemcpyAsync(c->d_scan[0], c->d_staged + c->staged_offsets[f], (size_t)n * 32, cudaMemcpyDeviceToDevice, c->stream));
-    FLOAM_CUDA_OK(cudaMemcpyAsync(c->d_scan_n[0], c->d_staged_counts + f, 4, cudaMemcpyDeviceToDevice, c->stream));
-    if ((rc = launch_frame(c, c->d_scan[0], c->d_scan_n[0], deskew, 0, 0))) return rc;
+    last_slot = c->submit_slot;
+    if ((rc = enqueue_staged_frame(c, f, deskew))) return rc;
   }
-  FLOAM_CUDA_OK(cudaEventRecord(c->ev_end[0], c->stream));
+  FLOAM_CUDA_OK(cudaEventRecord(c->ev_replay_end, c->stream));
   FLOAM_CUDA_OK(cudaStreamSynchronize(c->stream));
   if ((rc = check_async("replay_staged"))) return rc;
-  cudaEventElapsedTime(&c->last_frame_ms, c->ev_begin[0], c->ev_end[0]);
+  cudaEventElapsedTime(&c->last_frame_ms, c->ev_replay_begin, c->ev_replay_end);
   if (total_ms) *total_ms = c->last_frame_ms;
   if (poses_out) {
     const int cap = c->odom.traj_cap;
     for (int k = 0; k < count; ++k)
       FLOAM_CUDA_OK(cudaMemcpy(poses_out + (size_t)k * 7, c->odom.traj + (size_t)((counter0 + k) % cap) * 7, 56, cudaMemcpyDeviceToHost));
   }
-  return status_from_flags(c, 0);
+  // status of the last frame's mailbox; earlier frames' sticky error flags are part of the same state
+  if (c->h_state[last_slot]->error_flags == 0 && c->h_state[last_slot ^ 1]->error_flags != 0 && count > 1) return FLOAM_ERR_CAPACITY;
+  return status_from_flags(c, last_slot);
 }
 
 int floam_set_kernel_timing(floam_ctx* c, int enabled) {

@@ -36,6 +36,7 @@ struct floam_ctx {
   cudaStream_t copy_stream = nullptr;  // uploads of the next scan
   cudaEvent_t ev_begin[2] = {nullptr, nullptr}, ev_end[2] = {nullptr, nullptr};
   cudaEvent_t ev_upload[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+  cudaEvent_t ev_replay_begin = nullptr, ev_replay_end = nullptr;
   bool consumed_valid[2] = {false, false};
   std::vector<void*> allocs;           // everything cudaMalloc'ed
   std::vector<void*> host_allocs;      // everything cudaMallocHost'ed
@@ -43,14 +44,24 @@ struct floam_ctx {
   // scan + features (device)
   floam::PointIRT* d_scan[2] = {nullptr, nullptr};  // double-buffered upload target
   int* d_scan_n[2] = {nullptr, nullptr};
+  // feature clouds: two buffer sets (frame parity); the unsuffixed names alias the set of the frame being enqueued / last completed
   floam::PointIRT *d_edge = nullptr, *d_surf = nullptr;
   int *d_ne = nullptr, *d_ns = nullptr, *d_edge_src = nullptr, *d_surf_src = nullptr;
+  floam::PointIRT *d_edge_b[2] = {nullptr, nullptr}, *d_surf_b[2] = {nullptr, nullptr};
+  int *d_ne_b[2] = {nullptr, nullptr}, *d_ns_b[2] = {nullptr, nullptr}, *d_edge_src_b[2] = {nullptr, nullptr}, *d_surf_src_b[2] = {nullptr, nullptr};
   int* d_flags = nullptr;
   floam::FeatureParams fprm;
   floam::FeatureWorkspace fws;
   floam::VoxelWorkspace vws;
   floam::VoxelWorkspace vws_aux;        // edge-side branch (sized for scans and local maps)
   cudaStream_t aux_stream = nullptr;
+  // frame pipeline: the FRONT of frame k+1 (features + downsampling, independent of pose and map) runs on its own stream pair while
+  // the BACK of frame k (prediction, association + solve, keyframe map update) is still running on stream / aux_stream
+  floam::VoxelWorkspace vws_front, vws_front_aux;
+  cudaStream_t front_stream = nullptr, front_aux = nullptr;
+  cudaEvent_t ev_ffork = nullptr, ev_fjoin = nullptr;
+  cudaEvent_t ev_front_done[2] = {nullptr, nullptr}, ev_back_done[2] = {nullptr, nullptr};
+  bool back_valid[2] = {false, false};
 
   // staging for the stage entry points (voxel/crop/knn/set_map on host clouds)
   char* d_stage_in = nullptr;            // stage_cap x 32 B

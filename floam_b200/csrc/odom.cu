@@ -1025,8 +1025,11 @@ int odom_device_init(OdomDevice& od, const floam_params& prm, VoxelWorkspace* vw
   if (rc) return rc;
   rc = local_map_alloc(od.surf_map, prm.max_map_points, ncells_cap, alloc, actx, s);
   if (rc) return rc;
-  od.ds_edge = (P4*)alloc(actx, (size_t)od.qcap * sizeof(P4));
-  od.ds_surf = (P4*)alloc(actx, (size_t)od.qcap * sizeof(P4));
+  for (int k = 0; k < 2; ++k) {
+    od.ds_edge_b[k] = (P4*)alloc(actx, (size_t)od.qcap * sizeof(P4));
+    od.ds_surf_b[k] = (P4*)alloc(actx, (size_t)od.qcap * sizeof(P4));
+    if (!od.ds_edge_b[k] || !od.ds_surf_b[k]) return FLOAM_ERR_CUDA;
+  }
   int* ints = (int*)alloc(actx, 16);
   od.corr = (double*)alloc(actx, (size_t)6 * 2 * od.qcap * sizeof(double));
   od.corr_ok = (unsigned char*)alloc(actx, (size_t)2 * od.qcap);
@@ -1035,8 +1038,9 @@ int odom_device_init(OdomDevice& od, const floam_params& prm, VoxelWorkspace* vw
   od.partials = (double*)alloc(actx, (size_t)kAssocBlocks * kLmTerms * sizeof(double));
   od.traj_cap = 1 << 16;
   od.traj = (double*)alloc(actx, (size_t)od.traj_cap * 7 * sizeof(double));
-  if (!od.ds_edge || !od.ds_surf || !ints || !od.corr || !od.corr_ok || !od.knn_ids || !od.knn_d2 || !od.partials || !od.traj) return FLOAM_ERR_CUDA;
-  od.d_nds_edge = ints; od.d_nds_surf = ints + 1;
+  if (!ints || !od.corr || !od.corr_ok || !od.knn_ids || !od.knn_d2 || !od.partials || !od.traj) return FLOAM_ERR_CUDA;
+  od.d_nds_edge_b[0] = ints; od.d_nds_surf_b[0] = ints + 1; od.d_nds_edge_b[1] = ints + 2; od.d_nds_surf_b[1] = ints + 3;
+  odom_select_buffers(od, 0);
   FLOAM_CUDA_OK(cudaMemsetAsync(ints, 0, 16, s));
   FLOAM_CUDA_OK(cudaMemsetAsync(od.corr_ok, 0, (size_t)2 * od.qcap, s));
   FLOAM_LAUNCH(K_STATE_INIT, state_init_kernel, 1, 32, s, od.state);
@@ -1069,20 +1073,13 @@ void odom_init_map_device(OdomDevice& od, const void* d_edge, const int* d_ne, c
 }
 
 void odom_update_device(OdomDevice& od, const void* d_edge, const int* d_ne, const void* d_surf, const int* d_ns, int stride, int n_max, int update_type,
-                        int tap, cudaStream_t s) {
+                        int ds_ready, cudaStream_t s) {
   // the caller has already applied `if (optimization_count > 2) optimization_count--` (:59-60, Q4)
   PoseState* S = od.state;
   FLOAM_LAUNCH(K_PREDICT, predict_kernel, 1, 32, s, S, od.edge_map.d_n, od.surf_map.d_n);
-  // downSamplingToMap :137-142
-  // the edge and surf clouds are independent until the association: the edge side runs on the aux stream (a parallel branch of the
-  // frame graph) with its own workspace
   cudaStream_t a = od.aux_stream;
-  cudaEventRecord(od.ev_fork, s);
-  cudaStreamWaitEvent(a, od.ev_fork, 0);
-  voxel_grid_device(d_edge, stride, d_ne, n_max, od.leaf_edge, od.ds_edge, od.d_nds_edge, *od.vws_aux, nullptr, a);
-  voxel_grid_device(d_surf, stride, d_ns, n_max, od.leaf_surf, od.ds_surf, od.d_nds_surf, *od.vws, nullptr, s);
-  cudaEventRecord(od.ev_join, a);
-  cudaStreamWaitEvent(s, od.ev_join, 0);
+  // downSamplingToMap :137-142, unless the frame pipeline already did it ahead of time
+  if (!ds_ready) odom_downsample_device(od, d_edge, d_ne, d_surf, d_ns, stride, n_max, *od.vws, *od.vws_aux, s, a, od.ev_fork, od.ev_join);
   for (int it = 0; it < od.optimization_count; ++it) {
     FLOAM_LAUNCH(K_ASSOC_KNN, assoc_knn_kernel, kKnnBlocks, kKnnThreads, s, S, od.ds_edge, od.d_nds_edge, od.ds_surf, od.d_nds_surf, od.edge_map, od.surf_map,
                  od.qcap, od.knn_ids, od.knn_d2);
@@ -1113,6 +1110,23 @@ void odom_update_device(OdomDevice& od, const void* d_edge, const int* d_ne, con
   }
   cudaEventRecord(od.ev_join, a);
   cudaStreamWaitEvent(s, od.ev_join, 0);
+}
+
+void odom_downsample_device(OdomDevice& od, const void* d_edge, const int* d_ne, const void* d_surf, const int* d_ns, int stride, int n_max,
+                            VoxelWorkspace& ws_surf, VoxelWorkspace& ws_edge, cudaStream_t s, cudaStream_t aux, cudaEvent_t ev_fork, cudaEvent_t ev_join) {
+  // the edge and surf clouds are independent until the association: the edge side runs on the aux stream (a parallel branch of the
+  // graph) with its own workspace
+  cudaEventRecord(ev_fork, s);
+  cudaStreamWaitEvent(aux, ev_fork, 0);
+  voxel_grid_device(d_edge, stride, d_ne, n_max, od.leaf_edge, od.ds_edge, od.d_nds_edge, ws_edge, nullptr, aux);
+  voxel_grid_device(d_surf, stride, d_ns, n_max, od.leaf_surf, od.ds_surf, od.d_nds_surf, ws_surf, nullptr, s);
+  cudaEventRecord(ev_join, aux);
+  cudaStreamWaitEvent(s, ev_join, 0);
+}
+
+void odom_select_buffers(OdomDevice& od, int parity) {
+  od.ds_edge = od.ds_edge_b[parity]; od.ds_surf = od.ds_surf_b[parity];
+  od.d_nds_edge = od.d_nds_edge_b[parity]; od.d_nds_surf = od.d_nds_surf_b[parity];
 }
 
 void compensate_velocity_device(OdomDevice& od, PointIRT* d_pts, const int* d_n, int n_max, cudaStream_t s) {

@@ -59,8 +59,10 @@ constexpr int kLmTerms = 28;  // 21 H (upper triangle) + 6 g + cost
 struct OdomDevice {
   PoseState* state;
   LocalMap edge_map, surf_map;
-  P4 *ds_edge, *ds_surf;       // downsampled current features (sensor frame)
+  P4 *ds_edge, *ds_surf;       // downsampled current features (sensor frame): aliases of the buffer set of the frame being enqueued
   int *d_nds_edge, *d_nds_surf;
+  P4 *ds_edge_b[2], *ds_surf_b[2];     // two sets: frame k+1 is downsampled while frame k is still being solved / merged into the map
+  int *d_nds_edge_b[2], *d_nds_surf_b[2];
   int qcap;                    // capacity of each downsampled cloud
   // correspondences, slot = query index (edge slots [0,qcap), surf slots [qcap, 2*qcap))
   double* corr;                // [6][2*qcap]: edge a(3) b(3); surf n(3) d
@@ -95,7 +97,12 @@ void odom_init_map_device(OdomDevice& od, const void* d_edge, const int* d_ne, c
 // OdomEstimationClass::updatePointsToMap on device-resident clouds (stride 32: PointXYZI / PointXYZIRT, stride 16: float4).
 // tap != 0: the last outer iteration also writes the kNN ids / distances for floam_debug_fetch.
 void odom_update_device(OdomDevice& od, const void* d_edge, const int* d_ne, const void* d_surf, const int* d_ns, int stride, int n_max, int update_type,
-                        int tap, cudaStream_t s);
+                        int ds_ready, cudaStream_t s);
+// downSamplingToMap (:137-142) on its own: edge cloud on `aux` with ws_edge, surf cloud on `s` with ws_surf (fork / join through the
+// two events). Used by the frame pipeline to downsample frame k+1 while frame k is still in its solve / map update.
+void odom_downsample_device(OdomDevice& od, const void* d_edge, const int* d_ne, const void* d_surf, const int* d_ns, int stride, int n_max,
+                            VoxelWorkspace& ws_surf, VoxelWorkspace& ws_edge, cudaStream_t s, cudaStream_t aux, cudaEvent_t ev_fork, cudaEvent_t ev_join);
+void odom_select_buffers(OdomDevice& od, int parity);
 // dmapping::CompensateVelocity with GetVelocity() read from the device state
 void compensate_velocity_device(OdomDevice& od, PointIRT* d_pts, const int* d_n, int n_max, cudaStream_t s);
 void compensate_velocity_explicit_device(PointIRT* d_pts, const int* d_n, int n_max, const double v[3], cudaStream_t s);
