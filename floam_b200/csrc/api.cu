@@ -929,10 +929,11 @@ int floam_debug_fetch(floam_ctx* c, int what, void* out, size_t cap_bytes, size_
       return FLOAM_OK;
     }
     case FLOAM_DBG_CLOCKS: {
-      *n_bytes = sizeof(S->dbg_clk);
+      *n_bytes = sizeof(S->dbg_clk) + sizeof(S->dbg_clk2);
       if (!out) return FLOAM_OK;
       if (*n_bytes > cap_bytes) return FLOAM_ERR_CAPACITY;
       std::memcpy(out, S->dbg_clk, sizeof(S->dbg_clk));
+      std::memcpy((char*)out + sizeof(S->dbg_clk), S->dbg_clk2, sizeof(S->dbg_clk2));
       return FLOAM_OK;
     }
     case FLOAM_DBG_FEATURE_SRC_EDGE: return copy_dev(c->d_edge_src, (size_t)ne * 4);

@@ -31,7 +31,7 @@ namespace floam {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kAssocBlocks = kNumSMs * 2;   // 296 CTAs x 128 threads, grid-stride over the query slots
+constexpr int kAssocBlocks = kNumSMs / 2;   // 74 CTAs x 128 threads, grid-stride over the query slots: one partial row per CTA
 constexpr int kKnnBlocks = kNumSMs * 4;     // 592 CTAs x 8 warps, one warp per query, grid-stride
 static_assert(kAssocBlocks <= 1024, "partials rows");
 
@@ -438,6 +438,7 @@ __device__ __forceinline__ void accumulate(Accum& A, double r, const double* J, 
 #pragma unroll
   for (int a = 0; a < 6; ++a) A.v[21 + a] = fma(J[a], r, A.v[21 + a]);
   A.v[27] += cost_term;
+  A.v[28] += 1.0;   // correspondence count (exact in double)
 }
 
 // Sum of each of the 28 accumulators over the 32 lanes of a warp with a transposing butterfly: at every level a lane hands half of
@@ -623,11 +624,10 @@ __device__ __forceinline__ void state_store(PoseState* global_dst, const PoseSta
   for (int i = threadIdx.x; i < (int)(sizeof(PoseState) / 4); i += blockDim.x) d[i] = s[i];
 }
 
-// Block reduction of the 28 accumulators into partials[blockIdx.x][*]; returns true in every thread of the last CTA to finish,
-// after which sums[] (shared) holds the grid totals, reduced in a fixed order (deterministic).
-__device__ bool reduce_terms(const Accum& A, double* __restrict__ partials, unsigned int* ticket, double* s_sums /*[kLmTerms]*/) {
+// Block reduction of the accumulators into partials[blockIdx.x][*] (fixed order -> deterministic). The rows are added up by CTA 0 of
+// the cluster kernel that follows.
+__device__ void write_partials(const Accum& A, double* __restrict__ partials) {
   __shared__ double s_part[kEvalThreads / 32][kLmTerms];
-  __shared__ int s_last;
   const int w = warp_id(), l = lane_id();
   {
     const double v = warp_reduce_terms(A);
@@ -640,36 +640,6 @@ __device__ bool reduce_terms(const Accum& A, double* __restrict__ partials, unsi
     for (int ww = 0; ww < kEvalThreads / 32; ++ww) v += s_part[ww][threadIdx.x];
     partials[(size_t)blockIdx.x * kLmTerms + threadIdx.x] = v;
   }
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned int t = atomicAdd(ticket, 1u);
-    s_last = (t == gridDim.x - 1) ? 1 : 0;
-  }
-  __syncthreads();
-  if (!s_last) return false;
-  __threadfence();
-  // thread (g, k): term k of the rows g, g+4, ... (a row's 28 terms are contiguous: coalesced); the loads of a thread are independent
-  // of one another, the additions run in a fixed order -> deterministic totals
-  {
-    const int k = l, g = w;
-    double v = 0.0;
-    if (k < kLmTerms) {
-#pragma unroll 4
-      for (int r = g; r < (int)gridDim.x; r += kEvalThreads / 32) v += __ldcg(partials + (size_t)r * kLmTerms + k);
-      s_part[g][k] = v;
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x < kLmTerms) {
-    double v = 0.0;
-#pragma unroll
-    for (int ww = 0; ww < kEvalThreads / 32; ++ww) v += s_part[ww][threadIdx.x];
-    s_sums[threadIdx.x] = v;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) *ticket = 0;
-  return true;
 }
 
 // One outer iteration's association (:144-251), in two kernels.
@@ -716,10 +686,6 @@ __global__ void __launch_bounds__(kEvalThreads) assoc_eval_kernel(PoseState* __r
                                                                    const int* __restrict__ knn_ids, int loss, double* __restrict__ partials) {
   pdl_prologue();
   if (S->skip_solve) return;
-  __shared__ double s_sums[kLmTerms];
-  __shared__ int s_ncorr;
-  if (threadIdx.x == 0) s_ncorr = 0;
-  __syncthreads();
   const int nde = *d_nde, nds = *d_nds;
   double x[7];
 #pragma unroll
@@ -727,7 +693,6 @@ __global__ void __launch_bounds__(kEvalThreads) assoc_eval_kernel(PoseState* __r
   Accum A;
 #pragma unroll
   for (int k = 0; k < kLmTerms; ++k) A.v[k] = 0.0;
-  int my_corr = 0;
   const size_t cs = (size_t)2 * qcap;  // stride between the planes of corr
   for (int slot = blockIdx.x * kEvalThreads + threadIdx.x; slot < nde + nds; slot += gridDim.x * kEvalThreads) {
     const bool is_edge = slot < nde;
@@ -795,29 +760,9 @@ __global__ void __launch_bounds__(kEvalThreads) assoc_eval_kernel(PoseState* __r
     if (ok) {
       loss_correct(loss, r, J, cost_term);
       accumulate(A, r, J, cost_term);
-      my_corr++;
     }
   }
-  // correspondence count (needed for the "no residual blocks" exit)
-  for (int o = 16; o > 0; o >>= 1) my_corr += __shfl_xor_sync(0xffffffffu, my_corr, o);
-  if (lane_id() == 0 && my_corr) atomicAdd(&s_ncorr, my_corr);
-  __syncthreads();
-  if (threadIdx.x == 0 && s_ncorr) atomicAdd(&S->n_corr_acc, s_ncorr);
-  if (reduce_terms(A, partials, &S->ticket, s_sums)) {   // true in every thread of the last CTA
-    __shared__ PoseState st;
-    __shared__ int s_total_corr;
-    if (threadIdx.x == 0) s_total_corr = atomicExch(&S->n_corr_acc, 0);
-    __syncthreads();
-    state_load(&st, S);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      st.ticket = 0;        // reduce_terms re-armed it in global memory; keep the copy consistent whatever the copy-in saw
-      st.n_corr_acc = 0;
-      lm_start(st, s_sums, s_total_corr);
-    }
-    __syncthreads();
-    state_store(S, &st);
-  }
+  write_partials(A, partials);
 }
 
 // The whole ceres::Solve step loop (<= 4 attempts) of one outer iteration in ONE thread-block cluster (8 CTAs on 8 SMs), for the
@@ -836,26 +781,54 @@ struct ClusterShared {
 };
 __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClusterThreads)
     lm_cluster_kernel(PoseState* S, const P4* __restrict__ ds_edge, const int* __restrict__ d_nde, const P4* __restrict__ ds_surf,
-                      const int* __restrict__ d_nds, int qcap, const double* __restrict__ corr, const unsigned char* __restrict__ corr_ok, int loss) {
+                      const int* __restrict__ d_nds, int qcap, const double* __restrict__ corr, const unsigned char* __restrict__ corr_ok, int loss,
+                      const double* __restrict__ partials, int n_rows) {
   pdl_prologue();
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
-  // uniform across the cluster: decided from values the previous kernel wrote
-  if (S->skip_solve || S->lm_done) return;
+  // uniform across the cluster: decided from a value the previous kernels wrote
+  if (S->skip_solve) return;
   const int nde = *d_nde, nds = *d_nds;
   __shared__ ClusterShared sh;
   __shared__ PoseState st;   // CTA 0's working copy of the state
+  __shared__ double s_sums[kLmTerms];
   const unsigned int rank = cluster.block_rank();
-  if (rank == 0) state_load(&st, S);
   ClusterShared* sh0 = cluster.map_shared_rank(&sh, 0);
-  double x[7];
-#pragma unroll
-  for (int k = 0; k < 7; ++k) x[k] = S->x_cand[k];
   const size_t cs = (size_t)2 * qcap;
   const int w = warp_id(), l = lane_id();
+  // iteration 0 of ceres::Solve: CTA 0 adds up the per-CTA rows the association kernel left (thread (g, k): term k of rows g, g+8, ...;
+  // fixed order), starts the trust-region state and publishes the first candidate
+  if (rank == 0) {
+    state_load(&st, S);
+    double v = 0.0;
+    if (l < kLmTerms) {
+#pragma unroll 4
+      for (int r = w; r < n_rows; r += kClusterThreads / 32) v += __ldcg(partials + (size_t)r * kLmTerms + l);
+      sh.part[w][l] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < kLmTerms) {
+      double t = 0.0;
+#pragma unroll
+      for (int ww = 0; ww < kClusterThreads / 32; ++ww) t += sh.part[ww][threadIdx.x];
+      s_sums[threadIdx.x] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      lm_start(st, s_sums, (int)s_sums[28]);
+      sh.done = st.lm_done;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) sh.x[k] = st.x_cand[k];
+    }
+  }
+  cluster.sync();
+  double x[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) x[k] = sh0->x[k];
+  const bool finished_at_start = sh0->done != 0;
   const int tid = rank * kClusterThreads + threadIdx.x, nthreads = kClusterCtas * kClusterThreads;
   long long clk[6] = {0, 0, 0, 0, 0, 0};
-  for (int attempt = 0; attempt < 4; ++attempt) {
+  for (int attempt = 0; attempt < 4 && !finished_at_start; ++attempt) {
     clk[0] = clock64();
     Accum A;
 #pragma unroll
@@ -895,7 +868,6 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClusterT
     cluster.sync();   // every CTA's row is in place
     clk[3] = clock64();
     if (rank == 0) {
-      __shared__ double s_sums[kLmTerms];
       if (threadIdx.x < kLmTerms) {
         double v = 0.0;
 #pragma unroll
@@ -1086,7 +1058,7 @@ void odom_update_device(OdomDevice& od, const void* d_edge, const int* d_ne, con
     FLOAM_LAUNCH(K_ASSOC_EVAL, assoc_eval_kernel, kAssocBlocks, kEvalThreads, s, S, od.ds_edge, od.d_nds_edge, od.ds_surf, od.d_nds_surf, od.edge_map, od.surf_map,
                  od.qcap, od.corr, od.corr_ok, od.knn_ids, od.loss, od.partials);
     FLOAM_LAUNCH(K_LM_CLUSTER, lm_cluster_kernel, kClusterCtas, kClusterThreads, s, S, od.ds_edge, od.d_nds_edge, od.ds_surf, od.d_nds_surf, od.qcap, od.corr, od.corr_ok,
-                 od.loss);
+                 od.loss, od.partials, kAssocBlocks);
   }
   FLOAM_LAUNCH(K_FINISH, finish_kernel, 1, 32, s, S, update_type, od.scan_period, od.traj, od.traj_cap);
   if (update_type == FLOAM_INITIAL_ITERATION) return;

@@ -32,6 +32,7 @@ struct PoseState {
   int n_corr_acc;        // accumulator of the running association
   int frame_counter;     // frames completed (index of the next trajectory record)
   long long dbg_clk[8];  // clock64 stamps of the last lm_cluster_kernel attempt (development aid, FLOAM_DBG_CLOCKS)
+  long long dbg_clk2[8]; // clock64 stamps of the last CTA of assoc_eval_kernel
 };
 
 struct GridDims {
@@ -54,7 +55,7 @@ struct LocalMap {
   int cap, ncells_cap;
 };
 
-constexpr int kLmTerms = 28;  // 21 H (upper triangle) + 6 g + cost
+constexpr int kLmTerms = 29;  // 21 H (upper triangle) + 6 g + cost + number of correspondences
 
 struct OdomDevice {
   PoseState* state;
