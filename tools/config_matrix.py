@@ -1,0 +1,104 @@
+"""BASELINE.json configs[0..3] on one B200: frames/s of the CUDA path, parity against the oracle where the oracle finishes in
+seconds, and the oracle's own single-thread frames/s on the same frames. One JSON line per config (-> profiles/).
+
+  0  VLP-16, 100 frames, res 0.4, deskew off          (the reference's CPU-runnable case)
+  1  HDL-64, res 0.4, deskew off                      (bench.py's workload; shorter here)
+  2  HDL-64 + 200 Hz IMU: deskew + alignment + two-pass velocity deskew, Huber loss
+  3  OS1-128 (128 x 2048) at map_resolution 0.1 (surf leaf 0.2): dense local maps, kNN-heavy
+"""
+import json
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, ".")
+from floam_b200 import capi, synth          # noqa: E402
+from oracle import pyoracle as po            # noqa: E402
+
+
+def run(cfg):
+    name, sensor, frames, res, loss, deskew, imu, oracle_frames = cfg
+    seq = synth.Sequence(sensor, seed=0, distort=deskew)
+    scans, off = seq.scans(0, frames)
+    nl = seq.num_lines
+    prm = dict(num_lines=nl, map_resolution=res, loss=loss, max_scan_points=seq.max_points + 1024, max_map_points=1 << 22,
+               max_global_map_points=0, max_grid_cells=1 << 23)
+    ctx = capi.Context(**prm)
+    ext = po.euler2quat(0, 0, 180)
+    out = {"config": name, "sensor": sensor, "frames": frames, "map_resolution": res, "loss": loss, "deskew": deskew, "imu": imu,
+           "points_per_scan": float(np.mean(np.diff(off)))}
+    if imu:
+        for k in range(-40, 20 * frames + 40):
+            t = 100.0 + 0.005 * k
+            ctx.imu_push(t, seq.imu(max(t - 100.0, 0.0)))
+        poses = []; ms = []
+        for f in range(frames):
+            s = scans[off[f]:off[f + 1]].copy()
+            t0 = time.perf_counter()
+            rc, pose, _ = ctx.process_scan_imu(s, int((100.0 + 0.1 * f) * 1e6), ext, deskew)
+            ms.append((time.perf_counter() - t0) * 1e3); poses.append(pose)
+            assert rc == capi.OK
+        poses = np.array(poses)
+        steady = ms[12:]
+        out["frames_per_s_e2e_sync"] = 1e3 / float(np.mean(steady)); out["p50_ms"] = float(np.percentile(steady, 50)); out["p99_ms"] = float(np.percentile(steady, 99))
+    else:
+        ctx.stage_scans(scans, off)
+        p0, _ = ctx.replay_staged(0, 12)
+        p1, ms = ctx.replay_staged(12, frames - 12)
+        poses = np.concatenate([p0, p1])
+        out["frames_per_s_device"] = (frames - 12) / (ms * 1e-3); out["ms_per_frame"] = ms / (frames - 12)
+    d = ctx.debug()
+    ne, ns = ctx.odom_map_sizes()
+    out.update(map_points=[ne, ns], queries_last_frame=len(d["ds_edge"]) + len(d["ds_surf"]), correspondences_last_frame=d["n_corr"])
+    out["knn_queries_per_s"] = out["queries_last_frame"] * 2 * out.get("frames_per_s_device", out.get("frames_per_s_e2e_sync", 0.0))
+    ctx.close()
+    # oracle on a prefix of the same frames: parity + CPU frames/s
+    m = min(frames, oracle_frames)
+    if m > 1:
+        if imu:
+            h = po.Imu()
+            for k in range(-40, 20 * frames + 40):
+                t = 100.0 + 0.005 * k
+                h.add(t, seq.imu(max(t - 100.0, 0.0)))
+            orc = po.Odom(num_lines=nl, map_resolution=res, loss=loss, total_order=True, use_kdtree=False)
+            O = []; t0 = time.perf_counter()
+            for f in range(m):
+                s = scans[off[f]:off[f + 1]].copy()
+                h.deskew_align(s, int((100.0 + 0.1 * f) * 1e6), ext)
+                e, sf = po.feature_extract(s, nl, 2.0, 60.0, total_order=True)[:2]
+                if f == 0:
+                    orc.init_map(synth.to_xyzi(e), synth.to_xyzi(sf)); O.append(np.array([0, 0, 0, 1, 0, 0, 0.0]))
+                else:
+                    O.append(orc.update(e, sf, deskew))
+            cpu_s = time.perf_counter() - t0
+            O = np.array(O)
+        else:
+            orc = po.Odom(num_lines=nl, map_resolution=res, loss=loss, total_order=True, use_kdtree=False)
+            O = []; t0 = time.perf_counter()
+            for f in range(m):
+                e, sf = po.feature_extract(scans[off[f]:off[f + 1]], nl, 2.0, 60.0, total_order=True)[:2]
+                if f == 0:
+                    orc.init_map(synth.to_xyzi(e), synth.to_xyzi(sf)); O.append(np.array([0, 0, 0, 1, 0, 0, 0.0]))
+                else:
+                    O.append(orc.update(e, sf, deskew))
+            cpu_s = time.perf_counter() - t0
+            O = np.array(O)
+        out["oracle_frames"] = m
+        out["max_pose_diff_vs_oracle"] = float(np.abs(poses[:m] - O).max())
+        out["oracle_cpu_frames_per_s_1thread_bruteforce_knn"] = m / cpu_s
+    gt = [seq.pose(0.1 * f) for f in range(frames)]
+    out["ate_vs_ground_truth_m"] = synth.ate(poses, gt)[0]
+    print(json.dumps(out), flush=True)
+
+
+CONFIGS = [
+    ("0: VLP-16 100 frames", "vlp16", 100, 0.4, "cauchy", False, False, 100),
+    ("1: HDL-64 300 frames", "hdl64", 300, 0.4, "cauchy", False, False, 40),
+    ("2: HDL-64 + IMU deskew, Huber, 60 frames", "hdl64", 60, 0.4, "huber", True, True, 20),
+    ("3: OS1-128 dense map (res 0.1), 60 frames", "os1-128", 60, 0.1, "cauchy", False, False, 6),
+]
+if __name__ == "__main__":
+    which = [int(a) for a in sys.argv[1:]] or list(range(len(CONFIGS)))
+    for i in which:
+        run(CONFIGS[i])
