@@ -53,6 +53,7 @@ enum KernelSlot {
   K_LM_CLUSTER,
   K_FINISH,
   K_MAP_APPEND,
+  K_MAP_COMMIT,
   K_COMPENSATE_VELOCITY,
   K_KNN5,
   K_RADIX_HIST,

@@ -157,6 +157,14 @@ __global__ void map_bump_kernel(int* d_nmap, const int* d_nin, int cap, int repl
   if (base + *d_nin <= cap) *d_nmap = base + *d_nin;
 }
 
+// the filtered map goes back into its home buffer (a device-side pointer swap would need every consumer to chase a pointer)
+__global__ void __launch_bounds__(kThreads) map_commit_kernel(const P4* __restrict__ src, const int* __restrict__ d_n, P4* __restrict__ dst, const int* d_skip) {
+  pdl_prologue();
+  if (d_skip && *d_skip) return;
+  const int n = *d_n;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) dst[i] = __ldg(src + i);
+}
+
 // addPointsToMap :256-268: pointAssociateToMap (double transform, float store) and push_back
 __global__ void __launch_bounds__(kThreads) map_append_kernel(const P4* __restrict__ ds, const int* __restrict__ d_nds, P4* __restrict__ map,
                                                                const int* __restrict__ d_nmap, int cap, PoseState* S, const int* d_skip) {
@@ -1076,9 +1084,10 @@ void odom_update_device(OdomDevice& od, const void* d_edge, const int* d_ne, con
     cudaStream_t st = k == 0 ? s : a;
     VoxelWorkspace& ws = k == 0 ? *od.vws : *od.vws_aux;
     FLOAM_LAUNCH(K_MAP_APPEND, map_append_kernel, grid_for(od.qcap), kThreads, st, dss[k], nds[k], mp.pts, mp.d_n, mp.cap, S, skip);
-    // the appended points are counted in by the crop itself (no separate size bump); the voxel filter then rewrites *d_n
-    crop_box_device(mp.pts, mp.d_n, mp.cap, S->crop_bounds, mp.tmp, mp.d_ncrop, ws, skip, st, nds[k], mp.cap);
-    voxel_grid_device(mp.tmp, 16, mp.d_ncrop, mp.cap, leaf[k], mp.pts, mp.d_n, ws, skip, st);
+    // CropBox (:270-287) is folded into the VoxelGrid (:289-292); the appended points are counted in by the filter (no separate
+    // size bump). The filter gathers from mp.pts through the sorted index and writes mp.tmp; the two buffers then swap roles.
+    voxel_grid_device(mp.pts, 16, mp.d_n, mp.cap, leaf[k], mp.tmp, mp.d_n, ws, skip, st, S->crop_bounds, nds[k], mp.cap);
+    FLOAM_LAUNCH(K_MAP_COMMIT, map_commit_kernel, grid_for(mp.cap), kThreads, st, mp.tmp, mp.d_n, mp.pts, skip);
     rebuild_grid(od, mp, skip, st, &ws);
   }
   cudaEventRecord(od.ev_join, a);

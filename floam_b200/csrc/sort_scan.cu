@@ -41,6 +41,7 @@ static const char* const kSlotNames[K_NUM_SLOTS] = {
   "lm_cluster",
   "finish",
   "map_append",
+  "map_commit",
   "compensate_velocity",
   "knn5",
   "radix_hist",

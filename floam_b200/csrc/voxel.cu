@@ -19,14 +19,33 @@ __device__ __forceinline__ float4 load_xyzi(const char* base, int stride, int i)
   return make_float4(a.x, a.y, a.z, in);
 }
 
+// pcl::CropBox ahead of the VoxelGrid (addPointsToMap, src/odomEstimationClass.cpp:270-292) is folded into the filter itself: a point
+// outside the box contributes nothing to the bounding box, gets a key past the last voxel (so the sort parks it at the end) and the
+// run detection / centroid kernels only look at the first n_kept sorted entries. No separate crop pass, no scratch copy.
+__device__ __forceinline__ bool crop_out(const float4 p, const float* __restrict__ b) {
+  return (p.x < b[0] || p.y < b[1] || p.z < b[2]) || (p.x > b[3] || p.y > b[4] || p.z > b[5]);
+}
+// n = *d_n, plus *d_extra freshly appended points when they fitted into `cap` (addPointsToMap's push_backs)
+__device__ __forceinline__ int total_count(const int* __restrict__ d_n, const int* __restrict__ d_extra, int cap) {
+  int n = *d_n;
+  if (d_extra && n + *d_extra <= cap) n += *d_extra;
+  return n;
+}
+
+// counts[0] = points in the input (incl. d_extra), counts[1] = points kept by the crop (== counts[0] without a crop box)
 __global__ void __launch_bounds__(kThreads) voxel_bbox_kernel(const char* __restrict__ in, int stride, const int* __restrict__ d_n,
-                                                               unsigned int* __restrict__ bbox, const int* d_skip) {
+                                                               const int* __restrict__ d_extra, int cap, const float* __restrict__ crop,
+                                                               unsigned int* __restrict__ bbox, int* __restrict__ counts, const int* d_skip) {
   pdl_prologue();
   if (d_skip && *d_skip) return;
-  const int n = *d_n;
+  const int n = total_count(d_n, d_extra, cap);
+  if (blockIdx.x == 0 && threadIdx.x == 0) counts[0] = n;
   float mn[3] = {3.402823466e38f, 3.402823466e38f, 3.402823466e38f}, mx[3] = {-3.402823466e38f, -3.402823466e38f, -3.402823466e38f};
+  int kept = 0;
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
     const float4 p = load_xyzi(in, stride, i);
+    if (crop && crop_out(p, crop)) continue;
+    ++kept;
     mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
     mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
   }
@@ -38,12 +57,15 @@ __global__ void __launch_bounds__(kThreads) voxel_bbox_kernel(const char* __rest
       mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
     }
   }
-  if (lane_id() == 0 && blockIdx.x * kThreads + (threadIdx.x & ~31) < n) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) kept += __shfl_xor_sync(0xffffffffu, kept, o);
+  if (lane_id() == 0 && kept > 0) {
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
       atomicMin(&bbox[a], float_flip(mn[a]));
       atomicMax(&bbox[3 + a], float_flip(mx[a]));
     }
+    atomicAdd(&counts[1], kept);
   }
 }
 
@@ -53,17 +75,19 @@ __device__ __forceinline__ int bits_for(long long cells) {  // number of key bit
   return b;
 }
 
-__global__ void __launch_bounds__(kThreads) voxel_keys_kernel(const char* __restrict__ in, int stride, const int* __restrict__ d_n, float leaf,
-                                                               const unsigned int* __restrict__ bbox, unsigned int* __restrict__ keys,
-                                                               int* __restrict__ vals, int* d_nbits, int* d_passthrough, const int* d_skip) {
+__global__ void __launch_bounds__(kThreads) voxel_keys_kernel(const char* __restrict__ in, int stride, const int* __restrict__ counts, float leaf,
+                                                               const float* __restrict__ crop, const unsigned int* __restrict__ bbox,
+                                                               unsigned int* __restrict__ keys, int* __restrict__ vals, int* d_nbits, int* d_passthrough,
+                                                               const int* d_skip) {
   pdl_prologue();
   if (d_skip && *d_skip) return;
-  const int n = *d_n;
+  const int n = counts[0];
+  const bool none = counts[1] == 0;   // nothing survives the crop (or the input is empty): the bounding box is undefined
   // every thread derives the grid from the bbox exactly like VoxelGrid::applyFilter (float arithmetic, no contraction)
   const float inv = __fdiv_rn(1.0f, leaf);
   float mnp[3], mxp[3];
 #pragma unroll
-  for (int a = 0; a < 3; ++a) { mnp[a] = float_unflip(bbox[a]); mxp[a] = float_unflip(bbox[3 + a]); }
+  for (int a = 0; a < 3; ++a) { mnp[a] = none ? 0.f : float_unflip(bbox[a]); mxp[a] = none ? 0.f : float_unflip(bbox[3 + a]); }
   const long long dx = (long long)fmul(fsub(mxp[0], mnp[0]), inv) + 1;
   const long long dy = (long long)fmul(fsub(mxp[1], mnp[1]), inv) + 1;
   const long long dz = (long long)fmul(fsub(mxp[2], mnp[2]), inv) + 1;
@@ -76,16 +100,21 @@ __global__ void __launch_bounds__(kThreads) voxel_keys_kernel(const char* __rest
     div_b[a] = max_b - min_b[a] + 1;
   }
   const int mul1 = div_b[0], mul2 = div_b[0] * div_b[1];
+  // cropped-out points sort behind every voxel: key = number of voxels (or n in pass-through mode)
+  const long long ncells = (long long)div_b[0] * div_b[1] * div_b[2];
+  const unsigned int parked = pass ? (unsigned int)n : (unsigned int)ncells;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     *d_passthrough = pass ? 1 : 0;
-    *d_nbits = pass ? bits_for(n) : bits_for((long long)div_b[0] * div_b[1] * div_b[2]);
+    *d_nbits = pass ? bits_for((long long)n + 1) : bits_for(ncells + 1);
   }
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
     unsigned int key;
-    if (pass) {
+    const float4 p = load_xyzi(in, stride, i);
+    if (crop && crop_out(p, crop)) {
+      key = parked;
+    } else if (pass) {
       key = (unsigned int)i;  // every point its own voxel, order kept: the centroid of one point is the point
     } else {
-      const float4 p = load_xyzi(in, stride, i);
       const int ijk0 = (int)fsub(floorf(fmul(p.x, inv)), (float)min_b[0]);
       const int ijk1 = (int)fsub(floorf(fmul(p.y, inv)), (float)min_b[1]);
       const int ijk2 = (int)fsub(floorf(fmul(p.z, inv)), (float)min_b[2]);
@@ -103,14 +132,10 @@ __global__ void __launch_bounds__(kThreads) voxel_keys_kernel(const char* __rest
 __device__ __forceinline__ int is_head(const unsigned int* __restrict__ keys, int i) { return (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0; }
 
 __global__ void __launch_bounds__(kScanThreads) voxel_heads_kernel(const unsigned int* __restrict__ keys, const int* __restrict__ d_n,
-                                                                   int* __restrict__ tile_sums, unsigned int* bbox, const int* d_skip) {
+                                                                   int* __restrict__ tile_sums, const int* d_skip) {
   pdl_prologue();
   if (d_skip && *d_skip) return;
   const int n = *d_n;
-  if (blockIdx.x == 0 && threadIdx.x == 0) {  // every reader of the bounding box (voxel_keys_kernel) is done: re-arm it for the next filter
-    bbox[0] = bbox[1] = bbox[2] = 0xffffffffu;
-    bbox[3] = bbox[4] = bbox[5] = 0u;
-  }
   if (blockIdx.x * kScanTile >= n) return;
   __shared__ int smem[33];
   const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
@@ -153,11 +178,16 @@ constexpr int kShortRun = 32;
 constexpr int kStage = 256;
 __global__ void __launch_bounds__(kThreads) voxel_reduce_kernel(const char* __restrict__ in, int stride, const int* __restrict__ vals,
                                                                  const int* __restrict__ head_pos, const int* __restrict__ d_nout, P4* __restrict__ out,
-                                                                 const int* d_skip) {
+                                                                 unsigned int* bbox, int* counts, const int* d_skip) {
   pdl_prologue();
   if (d_skip && *d_skip) return;
   __shared__ float4 s_stage[kThreads / 32][kStage];
   const int nv = *d_nout;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {  // last kernel of the filter: re-arm the accumulators for the next one
+    bbox[0] = bbox[1] = bbox[2] = 0xffffffffu;
+    bbox[3] = bbox[4] = bbox[5] = 0u;
+    counts[1] = 0;
+  }
   for (int v = blockIdx.x * kThreads + threadIdx.x; v < nv; v += gridDim.x * kThreads) {
     const int b = __ldg(head_pos + v), e = __ldg(head_pos + v + 1);
     if (e - b > kShortRun) continue;
@@ -292,6 +322,7 @@ void voxel_workspace_bind(VoxelWorkspace& ws, void* mem, int n_max) {
   ws.bbox = (unsigned int*)take(32);
   ws.d_nbits = (int*)take(4);
   ws.d_passthrough = (int*)take(4);
+  ws.d_counts = (int*)take(16);
   sort_workspace_bind(ws.sort, take(sort_workspace_bytes(n_max)), n_max);
   scan_workspace_bind(ws.scan, take(scan_workspace_bytes(n_max + 1)), n_max + 1);
 }
@@ -300,24 +331,27 @@ int voxel_workspace_arm(VoxelWorkspace& ws, cudaStream_t s) {
   const unsigned int bb[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
   FLOAM_CUDA_OK(cudaMemcpyAsync(ws.bbox, bb, sizeof(bb), cudaMemcpyHostToDevice, s));
   if (sort_workspace_arm(ws.sort, s)) return FLOAM_ERR_CUDA;
+  FLOAM_CUDA_OK(cudaMemsetAsync(ws.d_counts, 0, 16, s));
   FLOAM_CUDA_OK(cudaStreamSynchronize(s));
   return FLOAM_OK;
 }
 
 void voxel_grid_device(const void* d_in, int stride_bytes, const int* d_n, int n_max, float leaf, P4* d_out, int* d_nout, VoxelWorkspace& ws,
-                       const int* d_skip, cudaStream_t s) {
+                       const int* d_skip, cudaStream_t s, const float* d_crop, const int* d_extra, int cap) {
   if (n_max > ws.n_max) n_max = ws.n_max;
   const char* in = (const char*)d_in;
   const int g = grid_for(n_max);
   const int gt = (n_max + kScanTile - 1) / kScanTile;
-  FLOAM_LAUNCH(K_VOXEL_BBOX, voxel_bbox_kernel, g, kThreads, s, in, stride_bytes, d_n, ws.bbox, d_skip);
-  FLOAM_LAUNCH(K_VOXEL_KEYS, voxel_keys_kernel, g, kThreads, s, in, stride_bytes, d_n, leaf, ws.bbox, ws.keys, ws.vals, ws.d_nbits, ws.d_passthrough, d_skip);
+  int* counts = ws.d_counts;   // [0] input points, [1] points kept by the crop
+  FLOAM_LAUNCH(K_VOXEL_BBOX, voxel_bbox_kernel, g, kThreads, s, in, stride_bytes, d_n, d_extra, cap, d_crop, ws.bbox, counts, d_skip);
+  FLOAM_LAUNCH(K_VOXEL_KEYS, voxel_keys_kernel, g, kThreads, s, in, stride_bytes, counts, leaf, d_crop, ws.bbox, ws.keys, ws.vals, ws.d_nbits, ws.d_passthrough,
+               d_skip);
   unsigned int* skeys = nullptr;
   int* svals = nullptr;
-  radix_sort_pairs(ws.keys, ws.vals, d_n, ws.d_nbits, n_max, ws.sort, d_skip, s, &skeys, &svals);
-  FLOAM_LAUNCH(K_VOXEL_HEADS, voxel_heads_kernel, gt, kScanThreads, s, skeys, d_n, ws.scan.block_sums, ws.bbox, d_skip);
-  FLOAM_LAUNCH(K_VOXEL_RANK, voxel_rank_kernel, gt, kScanThreads, s, skeys, d_n, ws.scan.block_sums, ws.flags, d_nout, d_skip);
-  FLOAM_LAUNCH(K_VOXEL_REDUCE, voxel_reduce_kernel, g, kThreads, s, in, stride_bytes, svals, ws.flags, d_nout, d_out, d_skip);
+  radix_sort_pairs(ws.keys, ws.vals, counts, ws.d_nbits, n_max, ws.sort, d_skip, s, &skeys, &svals);
+  FLOAM_LAUNCH(K_VOXEL_HEADS, voxel_heads_kernel, gt, kScanThreads, s, skeys, counts + 1, ws.scan.block_sums, d_skip);
+  FLOAM_LAUNCH(K_VOXEL_RANK, voxel_rank_kernel, gt, kScanThreads, s, skeys, counts + 1, ws.scan.block_sums, ws.flags, d_nout, d_skip);
+  FLOAM_LAUNCH(K_VOXEL_REDUCE, voxel_reduce_kernel, g, kThreads, s, in, stride_bytes, svals, ws.flags, d_nout, d_out, ws.bbox, counts, d_skip);
 }
 
 void repack_xyzi_device(const void* d_in32, const int* d_n, int n_max, P4* d_out, cudaStream_t s) {

@@ -11,6 +11,7 @@ struct VoxelWorkspace {
   unsigned int* bbox;   // 6 order-preserving-encoded floats: min xyz, max xyz
   int* d_nbits;         // key width of the current grid
   int* d_passthrough;   // Q13: leaf too small for the extent -> output = input
+  int* d_counts;        // [0] points of the running filter's input, [1] points its crop box kept
   SortWorkspace sort;
   ScanWorkspace scan;
   int n_max;
@@ -24,8 +25,10 @@ int voxel_workspace_arm(VoxelWorkspace& ws, cudaStream_t s);
 // (16 = float4 xyzi, 32 = PointXYZI / PointXYZIRT with intensity at +16). Output order = ascending voxel index; inside a
 // voxel the float accumulation runs in ascending input index (the stable stand-in for std::sort's unspecified order).
 // d_skip (optional): when *d_skip != 0 every kernel returns immediately (device-side "not a keyframe").
+// d_crop (optional, 6 floats on the device: min xyz, max xyz): pcl::CropBox folded in — points outside the inclusive box are ignored,
+// exactly as if CropBox::filter had run first. d_extra / cap: the input holds *d_n + *d_extra points when that fits into cap.
 void voxel_grid_device(const void* d_in, int stride_bytes, const int* d_n, int n_max, float leaf, P4* d_out, int* d_nout, VoxelWorkspace& ws,
-                       const int* d_skip, cudaStream_t s);
+                       const int* d_skip, cudaStream_t s, const float* d_crop = nullptr, const int* d_extra = nullptr, int cap = 0);
 
 // pcl::CropBox<PointXYZI>::filter, identity transform, negative=false, inclusive float bounds read from device memory
 // (d_bounds: min xyz, max xyz). Order-preserving compaction.
