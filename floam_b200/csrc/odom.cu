@@ -158,11 +158,40 @@ __global__ void map_bump_kernel(int* d_nmap, const int* d_nin, int cap, int repl
 }
 
 // the filtered map goes back into its home buffer (a device-side pointer swap would need every consumer to chase a pointer)
-__global__ void __launch_bounds__(kThreads) map_commit_kernel(const P4* __restrict__ src, const int* __restrict__ d_n, P4* __restrict__ dst, const int* d_skip) {
+// — and, since every map point passes through here, this is also where the bounding box of the search grid is accumulated.
+__device__ __forceinline__ void bbox_accumulate(float (&mn)[3], float (&mx)[3], bool any, unsigned int* __restrict__ bbox) {
+  if (!__any_sync(0xffffffffu, any)) return;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+      mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+    }
+  }
+  if (lane_id() == 0) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      atomicMin(&bbox[a], float_flip(mn[a]));
+      atomicMax(&bbox[3 + a], float_flip(mx[a]));
+    }
+  }
+}
+__global__ void __launch_bounds__(kThreads) map_commit_kernel(const P4* __restrict__ src, const int* __restrict__ d_n, P4* __restrict__ dst,
+                                                               unsigned int* __restrict__ bbox, const int* d_skip) {
   pdl_prologue();
   if (d_skip && *d_skip) return;
   const int n = *d_n;
-  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) dst[i] = __ldg(src + i);
+  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  bool any = false;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+    const float4 p = __ldg(src + i);
+    dst[i] = p;
+    mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
+    mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
+    any = true;
+  }
+  bbox_accumulate(mn, mx, any, bbox);
 }
 
 // addPointsToMap :256-268: pointAssociateToMap (double transform, float store) and push_back
@@ -198,32 +227,15 @@ __global__ void __launch_bounds__(kThreads) grid_bbox_kernel(const P4* __restric
     mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
     any = true;
   }
-  if (!__any_sync(0xffffffffu, any)) return;
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
-      mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
-    }
-  }
-  if (lane_id() == 0) {
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      atomicMin(&bbox[a], float_flip(mn[a]));
-      atomicMax(&bbox[3 + a], float_flip(mx[a]));
-    }
-  }
+  bbox_accumulate(mn, mx, any, bbox);
 }
 
-// one thread: grid extent from the bounding box; re-arms the bbox accumulators for the next build
-__global__ void grid_dims_kernel(unsigned int* bbox, const int* d_n, GridDims* dims, int ncells_cap, PoseState* S, const int* d_skip) {
-  pdl_prologue();
-  if (d_skip && *d_skip) return;
-  if (threadIdx.x != 0) return;
+// grid extent from the bounding box (every CTA of the count kernel derives it by itself; CTA 0 also stores it for the kernels after)
+__device__ __forceinline__ GridDims grid_dims_from_bbox(const unsigned int* bbox, int n, int ncells_cap, bool* overflow) {
   GridDims g;
   g.ix0 = g.iy0 = g.iz0 = 0; g.nx = g.ny = g.nz = 0; g.ncells = 0;
-  if (*d_n > 0) {
+  *overflow = false;
+  if (n > 0) {
     const float mnx = float_unflip(bbox[0]), mny = float_unflip(bbox[1]), mnz = float_unflip(bbox[2]);
     const float mxx = float_unflip(bbox[3]), mxy = float_unflip(bbox[4]), mxz = float_unflip(bbox[5]);
     g.ix0 = (int)floorf(mnx); g.iy0 = (int)floorf(mny); g.iz0 = (int)floorf(mnz);
@@ -231,12 +243,10 @@ __global__ void grid_dims_kernel(unsigned int* bbox, const int* d_n, GridDims* d
     if (nx * ny * nz <= (long long)ncells_cap) {
       g.nx = (int)nx; g.ny = (int)ny; g.nz = (int)nz; g.ncells = (int)(nx * ny * nz);
     } else {
-      atomicOr(&S->error_flags, 2);  // grid capacity exceeded: every query of this map is rejected
+      *overflow = true;  // grid capacity exceeded: every query of this map is rejected
     }
   }
-  *dims = g;
-  bbox[0] = bbox[1] = bbox[2] = 0xffffffffu;
-  bbox[3] = bbox[4] = bbox[5] = 0u;
+  return g;
 }
 
 __device__ __forceinline__ int cell_of(const GridDims& g, float x, float y, float z) {
@@ -244,13 +254,19 @@ __device__ __forceinline__ int cell_of(const GridDims& g, float x, float y, floa
   return cx + g.nx * (cy + g.ny * cz);
 }
 
-__global__ void __launch_bounds__(kThreads) grid_count_kernel(const P4* __restrict__ pts, const int* __restrict__ d_n, const GridDims* __restrict__ dims,
-                                                               int* __restrict__ cell_count, const int* d_skip) {
+__global__ void __launch_bounds__(kThreads) grid_count_kernel(const P4* __restrict__ pts, const int* __restrict__ d_n, const unsigned int* __restrict__ bbox,
+                                                               GridDims* __restrict__ dims, int ncells_cap, PoseState* S, int* __restrict__ cell_count,
+                                                               const int* d_skip) {
   pdl_prologue();
   if (d_skip && *d_skip) return;
-  const GridDims g = *dims;
-  if (g.ncells == 0) return;
   const int n = *d_n;
+  bool overflow;
+  const GridDims g = grid_dims_from_bbox(bbox, n, ncells_cap, &overflow);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    *dims = g;
+    if (overflow) atomicOr(&S->error_flags, 2);
+  }
+  if (g.ncells == 0) return;
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
     const float4 p = __ldg(pts + i);
     atomicAdd(&cell_count[cell_of(g, p.x, p.y, p.z)], 1);
@@ -261,9 +277,13 @@ __global__ void __launch_bounds__(kThreads) grid_count_kernel(const P4* __restri
 // The order of points inside a cell is arbitrary; the search orders candidates by (distance, index), so results do not depend on it.
 __global__ void __launch_bounds__(kThreads) grid_scatter_kernel(const P4* __restrict__ pts, const int* __restrict__ d_n, const GridDims* __restrict__ dims,
                                                                  const int* __restrict__ cell_start, int* __restrict__ cell_count,
-                                                                 float4* __restrict__ cell_pts, const int* d_skip) {
+                                                                 float4* __restrict__ cell_pts, unsigned int* bbox, const int* d_skip) {
   pdl_prologue();
   if (d_skip && *d_skip) return;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {  // every reader of the bounding box (grid_count_kernel) is done: re-arm it for the next build
+    bbox[0] = bbox[1] = bbox[2] = 0xffffffffu;
+    bbox[3] = bbox[4] = bbox[5] = 0u;
+  }
   const GridDims g = *dims;
   if (g.ncells == 0) return;
   const int n = *d_n;
@@ -952,14 +972,14 @@ __global__ void __launch_bounds__(kThreads) compensate_velocity_explicit_kernel(
 
 int* dims_ncells_ptr(GridDims* dims) { return reinterpret_cast<int*>(reinterpret_cast<char*>(dims) + offsetof(GridDims, ncells)); }
 
-void rebuild_grid(OdomDevice& od, LocalMap& map, const int* d_skip, cudaStream_t s, VoxelWorkspace* ws = nullptr) {
+// bbox_ready: the producer of map.pts (map_commit_kernel) has already accumulated the bounding box
+void rebuild_grid(OdomDevice& od, LocalMap& map, const int* d_skip, cudaStream_t s, VoxelWorkspace* ws = nullptr, bool bbox_ready = false) {
   if (!ws) ws = od.vws;
   const int g = grid_for(map.cap);
-  FLOAM_LAUNCH(K_GRID_BBOX, grid_bbox_kernel, g, kThreads, s, map.pts, map.d_n, map.bbox, d_skip);
-  FLOAM_LAUNCH(K_GRID_DIMS, grid_dims_kernel, 1, 32, s, map.bbox, map.d_n, map.dims, map.ncells_cap, od.state, d_skip);
-  FLOAM_LAUNCH(K_GRID_COUNT, grid_count_kernel, g, kThreads, s, map.pts, map.d_n, map.dims, map.cell_count, d_skip);
+  if (!bbox_ready) FLOAM_LAUNCH(K_GRID_BBOX, grid_bbox_kernel, g, kThreads, s, map.pts, map.d_n, map.bbox, d_skip);
+  FLOAM_LAUNCH(K_GRID_COUNT, grid_count_kernel, g, kThreads, s, map.pts, map.d_n, map.bbox, map.dims, map.ncells_cap, od.state, map.cell_count, d_skip);
   exclusive_scan_i32(map.cell_count, map.cell_start, dims_ncells_ptr(map.dims), 0, map.ncells_cap, ws->scan, d_skip, s);
-  FLOAM_LAUNCH(K_GRID_SCATTER, grid_scatter_kernel, g, kThreads, s, map.pts, map.d_n, map.dims, map.cell_start, map.cell_count, map.cell_pts, d_skip);
+  FLOAM_LAUNCH(K_GRID_SCATTER, grid_scatter_kernel, g, kThreads, s, map.pts, map.d_n, map.dims, map.cell_start, map.cell_count, map.cell_pts, map.bbox, d_skip);
 }
 
 }  // namespace
@@ -1087,8 +1107,8 @@ void odom_update_device(OdomDevice& od, const void* d_edge, const int* d_ne, con
     // CropBox (:270-287) is folded into the VoxelGrid (:289-292); the appended points are counted in by the filter (no separate
     // size bump). The filter gathers from mp.pts through the sorted index and writes mp.tmp; the two buffers then swap roles.
     voxel_grid_device(mp.pts, 16, mp.d_n, mp.cap, leaf[k], mp.tmp, mp.d_n, ws, skip, st, S->crop_bounds, nds[k], mp.cap);
-    FLOAM_LAUNCH(K_MAP_COMMIT, map_commit_kernel, grid_for(mp.cap), kThreads, st, mp.tmp, mp.d_n, mp.pts, skip);
-    rebuild_grid(od, mp, skip, st, &ws);
+    FLOAM_LAUNCH(K_MAP_COMMIT, map_commit_kernel, grid_for(mp.cap), kThreads, st, mp.tmp, mp.d_n, mp.pts, mp.bbox, skip);
+    rebuild_grid(od, mp, skip, st, &ws, true);
   }
   cudaEventRecord(od.ev_join, a);
   cudaStreamWaitEvent(s, od.ev_join, 0);
