@@ -132,7 +132,7 @@ def algorithmic_bytes(kernel, st):
         "voxel_keys": 16 * st["sort_n"] + 8 * st["sort_n"],
         "voxel_bbox": 16 * st["sort_n"],
         "grid_scatter": 32 * M, "grid_count": 16 * M, "grid_bbox": 16 * M,
-        "map_append": 32 * Q, "crop_flags": 16 * M, "crop_scatter": 32 * M,
+        "map_append": 32 * Q, "map_commit": 32 * M, "crop_flags": 16 * M, "crop_scatter": 32 * M,
     }
     return table.get(kernel)
 

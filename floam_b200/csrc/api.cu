@@ -424,6 +424,7 @@ int floam_compensate_velocity(floam_ctx* c, floam_point_xyzirt* pts, int n, cons
   if (!c || (!pts && n > 0) || n < 0 || !velocity) return FLOAM_ERR_ARG;
   if (n > c->prm.max_scan_points) return FLOAM_ERR_CAPACITY;
   if (n == 0) return FLOAM_OK;
+  if (c->inflight != 0) return FLOAM_ERR_ARG;  // frames submitted with floam_process_submit must be waited for first
   if (set_device(c)) return FLOAM_ERR_CUDA;
   int rc = upload_cloud(c, pts, n, c->d_scan[0], c->d_scan_n[0], 0);
   if (rc) return rc;
@@ -437,6 +438,7 @@ int floam_deskew_align_ex(floam_ctx* c, floam_point_xyzirt* pts, int n, uint64_t
   if (!c || !pts || !stamp_us || !extr_xyzw || n < 0) return FLOAM_ERR_ARG;
   if (n > c->prm.max_scan_points) return FLOAM_ERR_CAPACITY;
   if (n == 0) return FLOAM_NO_IMU;  // front()/back() on an empty cloud is undefined in the reference
+  if (c->inflight != 0) return FLOAM_ERR_ARG;  // frames submitted with floam_process_submit must be waited for first
   if (set_device(c)) return FLOAM_ERR_CUDA;
   DeskewPlan plan;
   deskew_plan(c->imu, *stamp_us, pts[0].time, pts[n - 1].time, extr_xyzw, flags, &plan);
@@ -455,6 +457,7 @@ int floam_feature_extract(floam_ctx* c, const floam_point_xyzirt* pts, int n, fl
                           int surf_cap, int* ns) {
   if (!c || (!pts && n > 0) || !ne || !ns || n < 0) return FLOAM_ERR_ARG;
   if (n > c->prm.max_scan_points) return FLOAM_ERR_CAPACITY;
+  if (c->inflight != 0) return FLOAM_ERR_ARG;  // frames submitted with floam_process_submit must be waited for first
   if (set_device(c)) return FLOAM_ERR_CUDA;
   FLOAM_CUDA_OK(cudaMemsetAsync(c->d_flags, 0, 4, c->stream));
   int rc = upload_cloud(c, pts, n, c->d_scan[0], c->d_scan_n[0], 0);
@@ -479,6 +482,7 @@ int floam_feature_extract(floam_ctx* c, const floam_point_xyzirt* pts, int n, fl
 static int load_maps(floam_ctx* c, const floam_point_xyzi* edge, int ne, const floam_point_xyzi* surf, int ns, int replace) {
   if (!c || ne < 0 || ns < 0 || (ne > 0 && !edge) || (ns > 0 && !surf)) return FLOAM_ERR_ARG;
   if (ne > c->stage_cap || ns > c->stage_cap) return FLOAM_ERR_CAPACITY;
+  if (c->inflight != 0) return FLOAM_ERR_ARG;  // frames submitted with floam_process_submit must be waited for first
   if (set_device(c)) return FLOAM_ERR_CUDA;
   OdomDevice& od = c->odom;
   int rc = upload_cloud(c, edge, ne, c->d_stage_in, c->d_stage_n, 0);
@@ -517,6 +521,7 @@ static int finish_update(floam_ctx* c, double pose_out[7]) {
 int floam_odom_update(floam_ctx* c, floam_point_xyzirt* edge, int ne, floam_point_xyzirt* surf, int ns, int deskew, double pose_out[7]) {
   if (!c || ne < 0 || ns < 0 || (ne > 0 && !edge) || (ns > 0 && !surf)) return FLOAM_ERR_ARG;
   if (ne > c->prm.max_scan_points || ns > c->prm.max_scan_points) return FLOAM_ERR_CAPACITY;
+  if (c->inflight != 0) return FLOAM_ERR_ARG;  // frames submitted with floam_process_submit must be waited for first
   if (set_device(c)) return FLOAM_ERR_CUDA;
   FLOAM_CUDA_OK(cudaEventRecord(c->ev_begin[0], c->stream));
   int rc = upload_cloud(c, edge, ne, c->d_edge, c->d_ne, 0);
@@ -533,6 +538,7 @@ int floam_odom_update(floam_ctx* c, floam_point_xyzirt* edge, int ne, floam_poin
 int floam_odom_update_xyzi(floam_ctx* c, const floam_point_xyzi* edge, int ne, const floam_point_xyzi* surf, int ns, int update_type, double pose_out[7]) {
   if (!c || ne < 0 || ns < 0 || (ne > 0 && !edge) || (ns > 0 && !surf) || update_type < 0 || update_type > 2) return FLOAM_ERR_ARG;
   if (ne > c->prm.max_scan_points || ns > c->prm.max_scan_points) return FLOAM_ERR_CAPACITY;
+  if (c->inflight != 0) return FLOAM_ERR_ARG;  // frames submitted with floam_process_submit must be waited for first
   if (set_device(c)) return FLOAM_ERR_CUDA;
   FLOAM_CUDA_OK(cudaEventRecord(c->ev_begin[0], c->stream));
   int rc = upload_cloud(c, edge, ne, c->d_edge, c->d_ne, 0);
@@ -591,6 +597,7 @@ int floam_odom_set_state(floam_ctx* c, const double odom_rowmajor[16], const dou
 
 int floam_odom_map_sizes(floam_ctx* c, int* n_edge, int* n_surf) {
   if (!c) return FLOAM_ERR_ARG;
+  if (c->inflight != 0) return FLOAM_ERR_ARG;  // frames submitted with floam_process_submit must be waited for first
   if (set_device(c)) return FLOAM_ERR_CUDA;
   FLOAM_CUDA_OK(cudaMemcpyAsync(c->h_ints + 16, c->odom.edge_map.d_n, 4, cudaMemcpyDeviceToHost, c->stream));
   FLOAM_CUDA_OK(cudaMemcpyAsync(c->h_ints + 17, c->odom.surf_map.d_n, 4, cudaMemcpyDeviceToHost, c->stream));
@@ -711,6 +718,7 @@ int floam_process_scan(floam_ctx* c, const floam_point_xyzirt* pts, int n, int d
 
 int floam_stage_scans(floam_ctx* c, const floam_point_xyzirt* pts, const int64_t* offsets, int n_frames) {
   if (!c || !pts || !offsets || n_frames < 1) return FLOAM_ERR_ARG;
+  if (c->inflight != 0) return FLOAM_ERR_ARG;  // frames submitted with floam_process_submit must be waited for first
   if (set_device(c)) return FLOAM_ERR_CUDA;
   for (int f = 0; f < n_frames; ++f)
     if (offsets[f + 1] < offsets[f] || offsets[f + 1] - offsets[f] > c->prm.max_scan_points) return FLOAM_ERR_CAPACITY;
@@ -746,6 +754,7 @@ int floam_process_staged(floam_ctx* c, int frame, int deskew, double pose_out[7]
 int floam_voxel_grid(floam_ctx* c, const floam_point_xyzi* pts, int n, float leaf, floam_point_xyzi* out, int cap, int* n_out) {
   if (!c || (!pts && n > 0) || !n_out || n < 0 || !(leaf > 0.f)) return FLOAM_ERR_ARG;
   if (n > c->stage_cap) return FLOAM_ERR_CAPACITY;
+  if (c->inflight != 0) return FLOAM_ERR_ARG;  // frames submitted with floam_process_submit must be waited for first
   if (set_device(c)) return FLOAM_ERR_CUDA;
   int rc = upload_cloud(c, pts, n, c->d_stage_in, c->d_stage_n, 0);
   if (rc) return rc;
@@ -762,6 +771,7 @@ int floam_voxel_grid(floam_ctx* c, const floam_point_xyzi* pts, int n, float lea
 int floam_crop_box(floam_ctx* c, const floam_point_xyzi* pts, int n, const float min_xyz[3], const float max_xyz[3], floam_point_xyzi* out, int cap, int* n_out) {
   if (!c || (!pts && n > 0) || !n_out || n < 0 || !min_xyz || !max_xyz) return FLOAM_ERR_ARG;
   if (n > c->stage_cap) return FLOAM_ERR_CAPACITY;
+  if (c->inflight != 0) return FLOAM_ERR_ARG;  // frames submitted with floam_process_submit must be waited for first
   if (set_device(c)) return FLOAM_ERR_CUDA;
   int rc = upload_cloud(c, pts, n, c->d_stage_in, c->d_stage_n, 0);
   if (rc) return rc;
@@ -782,6 +792,7 @@ int floam_crop_box(floam_ctx* c, const floam_point_xyzi* pts, int n, const float
 int floam_knn5(floam_ctx* c, const floam_point_xyzi* map, int m, const floam_point_xyzi* queries, int nq, int* ids, float* sqdist) {
   if (!c || !map || !queries || m < 0 || nq < 0 || !ids || !sqdist) return FLOAM_ERR_ARG;
   if (m > c->stage_cap || nq > c->stage_cap) return FLOAM_ERR_CAPACITY;
+  if (c->inflight != 0) return FLOAM_ERR_ARG;  // frames submitted with floam_process_submit must be waited for first
   if (set_device(c)) return FLOAM_ERR_CUDA;
   if (!c->knn_map_ready) {
     int rc = local_map_alloc(c->knn_map, c->prm.max_map_points, c->prm.max_grid_cells, ctx_alloc, c, c->stream);
@@ -813,6 +824,7 @@ int floam_mapping_update(floam_ctx* c, const floam_point_xyzi* pts, int n, const
   if (!c || (!pts && n > 0) || n < 0 || !pose_rowmajor) return FLOAM_ERR_ARG;
   if (!c->mapping.enabled) return FLOAM_ERR_ARG;
   if (n > c->stage_cap) return FLOAM_ERR_CAPACITY;
+  if (c->inflight != 0) return FLOAM_ERR_ARG;  // frames submitted with floam_process_submit must be waited for first
   if (set_device(c)) return FLOAM_ERR_CUDA;
   int rc = upload_cloud(c, pts, n, c->d_stage_in, c->d_stage_n, 0);
   if (rc) return rc;
@@ -826,6 +838,7 @@ int floam_mapping_update(floam_ctx* c, const floam_point_xyzi* pts, int n, const
 int floam_mapping_get_map(floam_ctx* c, floam_point_xyzi* out, int cap, int* n) {
   if (!c || !n) return FLOAM_ERR_ARG;
   if (!c->mapping.enabled) return FLOAM_ERR_ARG;
+  if (c->inflight != 0) return FLOAM_ERR_ARG;  // frames submitted with floam_process_submit must be waited for first
   if (set_device(c)) return FLOAM_ERR_CUDA;
   P4* d_out = nullptr;
   int* d_n = nullptr;
@@ -929,11 +942,10 @@ int floam_debug_fetch(floam_ctx* c, int what, void* out, size_t cap_bytes, size_
       return FLOAM_OK;
     }
     case FLOAM_DBG_CLOCKS: {
-      *n_bytes = sizeof(S->dbg_clk) + sizeof(S->dbg_clk2);
+      *n_bytes = sizeof(S->dbg_clk);
       if (!out) return FLOAM_OK;
       if (*n_bytes > cap_bytes) return FLOAM_ERR_CAPACITY;
       std::memcpy(out, S->dbg_clk, sizeof(S->dbg_clk));
-      std::memcpy((char*)out + sizeof(S->dbg_clk), S->dbg_clk2, sizeof(S->dbg_clk2));
       return FLOAM_OK;
     }
     case FLOAM_DBG_FEATURE_SRC_EDGE: return copy_dev(c->d_edge_src, (size_t)ne * 4);

@@ -41,7 +41,6 @@ enum KernelSlot {
   K_CELL_KEYS,
   K_GATHER,
   K_GRID_BBOX,
-  K_GRID_DIMS,
   K_GRID_COUNT,
   K_GRID_SCATTER,
   K_STATE_INIT,

@@ -32,7 +32,6 @@ struct PoseState {
   int n_corr_acc;        // accumulator of the running association
   int frame_counter;     // frames completed (index of the next trajectory record)
   long long dbg_clk[8];  // clock64 stamps of the last lm_cluster_kernel attempt (development aid, FLOAM_DBG_CLOCKS)
-  long long dbg_clk2[8]; // clock64 stamps of the last CTA of assoc_eval_kernel
 };
 
 struct GridDims {

@@ -29,7 +29,6 @@ static const char* const kSlotNames[K_NUM_SLOTS] = {
   "cell_keys",
   "gather",
   "grid_bbox",
-  "grid_dims",
   "grid_count",
   "grid_scatter",
   "state_init",

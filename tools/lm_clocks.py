@@ -14,4 +14,3 @@ for f in range(30):
         d = ctx.debug()
         print("frame", f, "corr", d["n_corr"], "cycles: eval %d  block-reduce %d  sync1 %d  dsmem+LM %d  sync2 %d  total %d" % (
             c[1] - c[0], c[2] - c[1], c[3] - c[2], c[4] - c[3], c[5] - c[4], c[5] - c[0]), " dev ms", ctx.last_frame_ms())
-        print("      assoc_eval last CTA: fit+eval loop %d  reduce+ticket+final %d  state copy+lm_start %d  total %d" % (c[9] - c[8], c[10] - c[9], c[11] - c[10], c[11] - c[8]))
