@@ -110,45 +110,50 @@ namespace {
 // 262,144 keys) and the ranking scatter.
 constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
-constexpr int kSortRounds = 4;                                 // keys per lane
-constexpr int kSortItemsPerWarp = 32 * kSortRounds;            // 128: a warp owns a contiguous chunk (stability)
-constexpr int kSortTile = kSortWarps * kSortItemsPerWarp;      // 1024 keys per CTA
-constexpr int kDirectTiles = 256;                              // <= 262,144 keys: scatter CTAs scan the count table themselves
+constexpr int kSortMinRounds = 4;                              // keys per lane: 4 (tile = 1024 keys) for small inputs ...
+constexpr int kSortMaxRounds = 32;                             // ... up to 32 (tile = 8192 keys) for large ones
+constexpr int kSortTile = kSortThreads * kSortMinRounds;       // smallest tile: the launch grid is sized for it
+constexpr int kDirectTiles = 256;                              // up to this many tiles the scatter CTAs scan the count table themselves
 constexpr int kMaxBins = 2048;                                 // 11-bit digits at most (3 x 11 >= 31 key bits)
 
-__device__ __forceinline__ int sort_tiles(int n) { return (n + kSortTile - 1) / kSortTile; }
+// Keys per lane, decided on the device from the live element count: the tile grows with the input so that the [tile][digit] count
+// table stays around 128 rows — every scatter CTA reads all of it, which is quadratic in the number of tiles (at a fixed 1024-key
+// tile a 236k-key sort spent 47 us per pass there).
+__device__ __forceinline__ int sort_rounds(int n) {
+  int r = kSortMinRounds;
+  while (r < kSortMaxRounds && n > 128 * kSortThreads * r) r <<= 1;
+  return r;
+}
+__device__ __forceinline__ int sort_tiles(int n, int rounds) { const int tile = kSortThreads * rounds; return (n + tile - 1) / tile; }
 __device__ __forceinline__ int digit_bits(int nbits) {
   const int b = (nbits + 2) / 3;
   return b < 1 ? 1 : b;
 }
 
 // counts of this tile's digits -> hist. Layout [tile][digit] (direct mode) or [digit][tile], which the last CTA then scans in place.
-__global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const unsigned int* __restrict__ keys, const int* __restrict__ d_n,
+template <int MAXR>
+__device__ __forceinline__ void radix_hist_body(const unsigned int* __restrict__ keys, const int* __restrict__ d_n,
                                                                   const int* __restrict__ d_nbits, int pass, int* __restrict__ hist, unsigned int* ticket,
-                                                                  const int* d_skip) {
-  pdl_prologue();
-  if (d_skip && *d_skip) return;
+                                                                  int* s_hist, int* s_scan, int& s_last) {
   const int n = *d_n;
-  const int tile0 = blockIdx.x * kSortTile;
+  const int R = MAXR;
+  const int tile0 = blockIdx.x * kSortThreads * R;
   if (tile0 >= n) return;
   const int bits = digit_bits(*d_nbits), shift = pass * bits, nbins = 1 << bits;
   const unsigned int dmask = (unsigned int)nbins - 1u;
-  const int nb = sort_tiles(n);
-  __shared__ int s_hist[kMaxBins];
-  __shared__ int s_scan[33];
-  __shared__ int s_last;
-  unsigned int k[kSortRounds];
+  const int nb = sort_tiles(n, R);
+  unsigned int k[MAXR];
 #pragma unroll
-  for (int r = 0; r < kSortRounds; ++r) {
+  for (int r = 0; r < MAXR; ++r) {
     const int i = tile0 + r * kSortThreads + threadIdx.x;
-    k[r] = (i < n) ? keys[i] : 0xffffffffu;
+    k[r] = (r < R && i < n) ? keys[i] : 0xffffffffu;
   }
   for (int d = threadIdx.x; d < nbins; d += kSortThreads) s_hist[d] = 0;
   __syncthreads();
 #pragma unroll
-  for (int r = 0; r < kSortRounds; ++r) {
+  for (int r = 0; r < MAXR; ++r) {
     const int i = tile0 + r * kSortThreads + threadIdx.x;
-    if (i < n) atomicAdd(&s_hist[(k[r] >> shift) & dmask], 1);
+    if (r < R && i < n) atomicAdd(&s_hist[(k[r] >> shift) & dmask], 1);
   }
   __syncthreads();
   if (nb <= kDirectTiles) {
@@ -180,6 +185,22 @@ __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const unsigned
   if (threadIdx.x == 0) *ticket = 0;
 }
 
+__global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const unsigned int* __restrict__ keys, const int* __restrict__ d_n,
+                                                                  const int* __restrict__ d_nbits, int pass, int* __restrict__ hist, unsigned int* ticket,
+                                                                  const int* d_skip) {
+  pdl_prologue();
+  if (d_skip && *d_skip) return;
+  __shared__ int s_hist[kMaxBins];
+  __shared__ int s_scan[33];
+  __shared__ int s_last;
+  switch (sort_rounds(*d_n)) {   // one fully unrolled variant per tile size; the small-input one stays as tight as a fixed-size kernel
+    case 4: radix_hist_body<4>(keys, d_n, d_nbits, pass, hist, ticket, s_hist, s_scan, s_last); break;
+    case 8: radix_hist_body<8>(keys, d_n, d_nbits, pass, hist, ticket, s_hist, s_scan, s_last); break;
+    case 16: radix_hist_body<16>(keys, d_n, d_nbits, pass, hist, ticket, s_hist, s_scan, s_last); break;
+    default: radix_hist_body<32>(keys, d_n, d_nbits, pass, hist, ticket, s_hist, s_scan, s_last); break;
+  }
+}
+
 // in-place exclusive scan of a small array by one block
 __global__ void __launch_bounds__(1024) single_block_scan_kernel(int* __restrict__ data, int n) {
   pdl_prologue();
@@ -196,40 +217,38 @@ __global__ void __launch_bounds__(1024) single_block_scan_kernel(int* __restrict
   }
 }
 
-__global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const unsigned int* __restrict__ keys_in, const int* __restrict__ vals_in,
+template <int MAXR>
+__device__ __forceinline__ void radix_scatter_body(const unsigned int* __restrict__ keys_in, const int* __restrict__ vals_in,
                                                                      unsigned int* __restrict__ keys_out, int* __restrict__ vals_out,
                                                                      const int* __restrict__ d_n, const int* __restrict__ d_nbits, int pass,
-                                                                     const int* __restrict__ hist, const int* d_skip) {
-  pdl_prologue();
-  if (d_skip && *d_skip) return;
+                                                                     const int* __restrict__ hist, int (*s_cnt)[256], int* s_base, int* s_scan) {
   const int n = *d_n;
-  const int tile0 = blockIdx.x * kSortTile;
+  const int R = MAXR;
+  const int tile0 = blockIdx.x * kSortThreads * R;
   if (tile0 >= n) return;
   const int w = warp_id(), l = lane_id();
-  const int begin = tile0 + w * kSortItemsPerWarp;
+  const int begin = tile0 + w * 32 * R;   // a warp owns a contiguous chunk of the tile (stability)
   // every load of the tile is in flight before anything is ranked
-  unsigned int k[kSortRounds];
-  int v[kSortRounds];
+  unsigned int k[MAXR];
+  int v[MAXR];
 #pragma unroll
-  for (int r = 0; r < kSortRounds; ++r) {
+  for (int r = 0; r < MAXR; ++r) {
     const int i = begin + r * 32 + l;
     k[r] = 0; v[r] = 0;
-    if (i < n) { k[r] = keys_in[i]; v[r] = vals_in[i]; }
+    if (r < R && i < n) { k[r] = keys_in[i]; v[r] = vals_in[i]; }
   }
   const int bits = digit_bits(*d_nbits), shift = pass * bits, nbins = 1 << bits;
   const unsigned int dmask = (unsigned int)nbins - 1u;
-  const int nb = sort_tiles(n);
-  __shared__ int s_cnt[kSortWarps][256];   // narrow digits: per-warp counters / running offsets
-  __shared__ int s_base[kMaxBins];         // wide digits: one running offset per bin, warps take turns
-  __shared__ int s_scan[33];
+  const int nb = sort_tiles(n, R);
   const bool narrow = nbins <= 256;
-  unsigned int mask[kSortRounds];
+  unsigned int mask[MAXR];
   int* cnt = s_cnt[w];
   if (narrow) {
     for (int i = threadIdx.x; i < kSortWarps * 256; i += kSortThreads) (&s_cnt[0][0])[i] = 0;
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < kSortRounds; ++r) {
+    for (int r = 0; r < MAXR; ++r) {
+      if (r >= R) break;
       const bool valid = begin + r * 32 + l < n;
       const unsigned int d = valid ? ((k[r] >> shift) & dmask) : 0xffffffffu;
       mask[r] = __match_any_sync(0xffffffffu, d);
@@ -280,7 +299,8 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const unsig
   __syncthreads();
   if (narrow) {
 #pragma unroll
-    for (int r = 0; r < kSortRounds; ++r) {
+    for (int r = 0; r < MAXR; ++r) {
+      if (r >= R) break;
       const bool valid = begin + r * 32 + l < n;
       const unsigned int d = (k[r] >> shift) & dmask;
       int pos = 0;
@@ -295,7 +315,8 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const unsig
     for (int ww = 0; ww < kSortWarps; ++ww) {
       if (w == ww) {
 #pragma unroll
-        for (int r = 0; r < kSortRounds; ++r) {
+        for (int r = 0; r < MAXR; ++r) {
+          if (r >= R) break;
           const bool valid = begin + r * 32 + l < n;
           const unsigned int d = valid ? ((k[r] >> shift) & dmask) : 0xffffffffu;
           const unsigned int m = __match_any_sync(0xffffffffu, d);
@@ -309,6 +330,23 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const unsig
       }
       __syncthreads();
     }
+  }
+}
+
+__global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const unsigned int* __restrict__ keys_in, const int* __restrict__ vals_in,
+                                                                     unsigned int* __restrict__ keys_out, int* __restrict__ vals_out,
+                                                                     const int* __restrict__ d_n, const int* __restrict__ d_nbits, int pass,
+                                                                     const int* __restrict__ hist, const int* d_skip) {
+  pdl_prologue();
+  if (d_skip && *d_skip) return;
+  __shared__ int s_cnt[kSortWarps][256];   // narrow digits: per-warp counters / running offsets
+  __shared__ int s_base[kMaxBins];         // wide digits: one running offset per bin, warps take turns
+  __shared__ int s_scan[33];
+  switch (sort_rounds(*d_n)) {
+    case 4: radix_scatter_body<4>(keys_in, vals_in, keys_out, vals_out, d_n, d_nbits, pass, hist, s_cnt, s_base, s_scan); break;
+    case 8: radix_scatter_body<8>(keys_in, vals_in, keys_out, vals_out, d_n, d_nbits, pass, hist, s_cnt, s_base, s_scan); break;
+    case 16: radix_scatter_body<16>(keys_in, vals_in, keys_out, vals_out, d_n, d_nbits, pass, hist, s_cnt, s_base, s_scan); break;
+    default: radix_scatter_body<32>(keys_in, vals_in, keys_out, vals_out, d_n, d_nbits, pass, hist, s_cnt, s_base, s_scan); break;
   }
 }
 
