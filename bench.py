@@ -114,6 +114,24 @@ def measured_peak_gbs():
         return 6650.0, "fallback"
 
 
+def ncu_traffic_bytes(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full` capture
+    (profiles/r1e_ncu_full_top_kernels.csv), or None when the kernel was not captured."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r1e_ncu_full_top_kernels.csv")
+    try:
+        with open(path) as f:
+            rows = list(csv.reader(f))
+        hdr, units = rows[0], rows[1]
+        ir, iw, ik = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        vals = [float(r[ir].replace(",", "")) * scale.get(units[ir], 1.0) + float(r[iw].replace(",", "")) * scale.get(units[iw], 1.0)
+                for r in rows[2:] if r[ik].replace("_kernel", "") == kernel]
+        return float(np.mean(vals)) if vals else None
+    except Exception:
+        return None
+
+
 def algorithmic_bytes(kernel, st):
     """Compulsory bytes one launch of `kernel` moves (DESIGN.md 'Kernels and rooflines'; SURVEY.md 8d per-unit figures x the units
     of the frame). st: per-frame averages — N scan points, F features, Q downsampled queries, C correspondences, M map points."""
@@ -244,7 +262,7 @@ def main():
     import torch.distributed as dist
     from floam_b200 import capi
     K = max(1, args.steps); W = max(3, args.warmup)
-    K = min(K, 6000)
+    K = min(K, 2500)   # bounds host + pinned + device copies of the sequence (3.8 MB per frame each)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local)
@@ -357,7 +375,7 @@ def main():
     ab = algorithmic_bytes(top, stats)
     top_us = kt[top][0]
     roofline = {"bound": "hbm", "kernel": top, "achieved": (ab / (top_us * 1e-6) / 1e9) if ab else None, "peak": peak, "peak_kind": peak_kind,
-                "unit": "GB/s", "frac": (ab / (top_us * 1e-6) / 1e9 / peak) if ab else None, "traffic": None,
+                "unit": "GB/s", "frac": (ab / (top_us * 1e-6) / 1e9 / peak) if ab else None, "traffic": ncu_traffic_bytes(top),
                 "algorithmic_bytes_per_launch": ab, "avg_launch_us": top_us, "event_pair_overhead_us": overhead_us,
                 "share_of_frame": shares[0][1], "launches_per_frame": shares[0][3],
                 "sum_of_kernel_us_per_frame": total_us,
