@@ -516,3 +516,75 @@ def test_fused_imu_frame_path(capi, po, synth, sensor, deskew):
     rc, _, _ = ctx.process_scan_imu(seq.scan(frames), int(9000.0 * 1e6), ext, deskew)
     assert rc == capi.NO_IMU
     ctx.close()
+
+
+# ------------------------------------------------------------------------------------------------ randomised sweeps -----
+def random_scan(capi, rng, num_lines, sizes, jump_prob=0.05, noise=0.01):
+    """Firing-order scan with the given per-ring point counts, range jumps (corners) and occasional out-of-gate returns."""
+    parts = []
+    for ring, n in enumerate(sizes):
+        p = np.zeros(n, capi.POINT_IRT)
+        az = np.sort(rng.uniform(-np.pi, np.pi, n))
+        r = rng.uniform(3, 40) + np.cumsum(rng.choice([0.0, 1.0], n, p=[1 - jump_prob, jump_prob]) * rng.normal(0, 1.5, n)) + noise * rng.standard_normal(n)
+        r = np.abs(r) + 0.5
+        far = rng.random(n) < 0.02
+        r[far] = rng.choice([0.5, 90.0], far.sum())          # outside [min_dis, max_dis]
+        p["x"] = r * np.cos(az); p["y"] = r * np.sin(az); p["z"] = rng.uniform(-2, 2) + 0.01 * rng.standard_normal(n)
+        p["ring"] = ring; p["pad0"] = 1; p["intensity"] = rng.random(n); p["time"] = np.linspace(0, 0.1, n, endpoint=False)
+        parts.append(p)
+    pts = np.concatenate(parts) if parts else np.zeros(0, capi.POINT_IRT)
+    keys = np.concatenate([np.arange(n) * num_lines + ring for ring, n in enumerate(sizes)]) if parts else np.zeros(0)
+    return pts[np.argsort(keys, kind="stable")]
+
+
+def test_feature_randomised_ring_sizes(capi, po, ctxs):
+    # ring sizes across the 131-point rule, sector arithmetic remainders (n - 10 mod 6) and the shared-memory sector capacity
+    rng = np.random.default_rng(2024)
+    ctx = ctxs(16)
+    for trial in range(25):
+        sizes = rng.choice([0, 5, 130, 131, 132, 137, 143, 200, 611, 1000, 1800, 2047, 2100, 4000], 16).tolist()
+        pts = random_scan(capi, rng, 16, sizes)
+        _, _, es, ss = ctx.feature_extract(pts, with_src=True)
+        _, _, oes, oss, _ = po.feature_extract(pts, 16, 2.0, 60.0, total_order=True)
+        assert np.array_equal(es, oes) and np.array_equal(ss, oss), (trial, sizes)
+
+
+def test_voxel_and_crop_randomised(capi, po, ctxs):
+    rng = np.random.default_rng(77)
+    ctx = ctxs(16)
+    for trial in range(20):
+        n = int(rng.choice([1, 2, 31, 33, 1023, 1025, 4096, 4097, 70000, 140000, 300000]))
+        ext = float(rng.choice([0.5, 5.0, 60.0, 400.0]))
+        leaf = float(rng.choice([0.1, 0.2, 0.4, 0.8, 3.0]))
+        pts = cloud(capi, rng, n, lo=(-ext, -ext, -ext / 8), hi=(ext, ext, ext / 8))
+        if trial % 3 == 0:
+            pts[: n // 2] = pts[n // 2: n // 2 + n // 2]       # heavy duplication: long voxel runs
+        g = ctx.voxel_grid(pts, leaf); o, _ = po.voxel_grid(pts, leaf, total_order=True)
+        assert len(g) == len(o) and np.array_equal(xyzi(g), xyzi(o)), (trial, n, ext, leaf)
+        mn = rng.uniform(-ext, 0, 3).astype(np.float32); mx = rng.uniform(0, ext, 3).astype(np.float32)
+        g = ctx.crop_box(pts, mn, mx); o = po.crop_box(pts, mn, mx)
+        assert len(g) == len(o) and np.array_equal(xyzi(g), xyzi(o)), (trial, n)
+
+
+def test_lm_solve_randomised_against_oracle(capi, po, synth, sequences):
+    # the on-device trust-region loop against the Ceres restatement from many starting poses, both losses: same step decisions
+    # (iterations, accepted steps, termination), same pose to 1e-9
+    rng = np.random.default_rng(5)
+    for loss in ("cauchy", "huber"):
+        ctx, orc, e, s = prepare_state(capi, po, synth, sequences, "vlp16", loss)
+        em, sm = orc.get_map(); T, L, _, oc = orc.get()
+        for trial in range(6):
+            dT = np.eye(4)
+            from scipy.spatial.transform import Rotation
+            dT[:3, :3] = Rotation.from_rotvec(rng.normal(0, 0.01, 3)).as_matrix(); dT[:3, 3] = rng.normal(0, 0.05, 3)
+            T2 = T @ dT
+            for side in (ctx, orc):
+                side.odom_set_map(em, sm) if side is ctx else side.set_map(em, sm)
+            ctx.odom_set_state(T2, L, 4); orc.set_state(T2, L, 4)
+            pose = ctx.odom_update_xyzi(e, s, capi.INITIAL_ITERATION); opose = orc.update_xyzi(e, s, 1)
+            d, od = ctx.debug(), orc.debug()
+            assert d["outer_iterations"] == od["outer_iterations"] == 3
+            for k in ("iterations", "accepted", "termination"):
+                assert d["lm"][k] == od["lm"][k], (loss, trial, k)
+            assert np.abs(pose - opose).max() < 1e-9, (loss, trial)
+        ctx.close()
