@@ -491,7 +491,7 @@ __device__ __forceinline__ double warp_reduce_terms(const Accum& A) {
 }
 
 // PoseSE3Parameterization gradient projection used for gradient_max_norm: |x - Plus(x, -g)|_inf
-__device__ double gradient_max_norm(const double* x, const double* g) {
+__device__ __noinline__ double gradient_max_norm(const double* x, const double* g) {
   // Only ever compared with gradient_tolerance = 1e-10. With max|g| >= 1e-3 the projected step moves x by far more than that
   // (quaternion part by |g_w|/4 at least; if g_w is below 4e-10 the translation part moves by |g_v| - |g_w x t| > 1e-3 - 4e-5),
   // so the exact value (a full se3 exponential) is only worth computing for tiny gradients.
@@ -526,7 +526,8 @@ __device__ void lm_finish(PoseState& S, int termination) {
 
 // Ceres TrustRegionMinimizer loop head up to the point where a candidate has to be evaluated.
 // Everything is a function of H = J^T J, g = J^T r and the cost at the current point.
-__device__ void lm_next_candidate(PoseState& S) {
+// __noinline__: called from lm_start and lm_after_candidate; one copy keeps the cluster kernel's instruction footprint down
+__device__ __noinline__ void lm_next_candidate(PoseState& S) {
   for (;;) {
     if (S.iteration >= 4) { lm_finish(S, 0); return; }                                 // max_num_iterations
     if (S.last_successful && S.gmax <= 1e-10) { lm_finish(S, 3); return; }             // gradient_tolerance
