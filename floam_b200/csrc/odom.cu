@@ -549,11 +549,12 @@ __device__ __noinline__ void lm_next_candidate(PoseState& S) {
 #pragma unroll
       for (int b = 0; b <= a; ++b) A[a * 6 + b] = S.scale[a] * S.scale[b] * S.H[tri(b, a)];
     }
+    // D^2 = diag / radius (Ceres forms sqrt(diag / radius) and the QR squares it again; one reciprocal serves the six entries)
+    const double inv_radius = 1.0 / S.radius;
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
       hs_diag[j] = A[j * 6 + j];
-      const double lm_diagonal = sqrt(S.diag[j] / S.radius);
-      A[j * 6 + j] += lm_diagonal * lm_diagonal;
+      A[j * 6 + j] += S.diag[j] * inv_radius;
     }
     const bool ok = m::cholesky6_solve(A, gs, y);
     S.reuse_diag = 1;

@@ -92,29 +92,33 @@ FM_HD void se3_plus(const double* x, const double* delta, double* out) {
   const V3 omega{delta[0], delta[1], delta[2]}, upsilon{delta[3], delta[4], delta[5]};
   const double theta = norm(omega);
   const double half_theta = 0.5 * theta;
+  // one sincos of the half angle serves all four trigonometric values (double-angle identities); one reciprocal of theta serves
+  // the three divisions. Same functions as the reference's getTransformFromSe3, evaluated with fewer long-latency operations.
+  double sh, ch;
+  sincos(half_theta, &sh, &ch);
   double imag_factor;
-  const double real_factor = cos(half_theta);
+  const double real_factor = ch;
+  V3 dt;
   if (theta < 1e-10) {
     const double theta_sq = theta * theta, theta_po4 = theta_sq * theta_sq;
     imag_factor = 0.5 - 0.0208333 * theta_sq + 0.000260417 * theta_po4;
-  } else {
-    imag_factor = sin(half_theta) / theta;
-  }
-  const double dq[4] = {imag_factor * omega.x, imag_factor * omega.y, imag_factor * omega.z, real_factor};
-  V3 dt;
-  if (theta < 1e-10) {
+    const double dq0[4] = {imag_factor * omega.x, imag_factor * omega.y, imag_factor * omega.z, real_factor};
     double R[9];
-    quat_to_matrix(dq, R);
+    quat_to_matrix(dq0, R);
     dt = {R[0] * upsilon.x + R[1] * upsilon.y + R[2] * upsilon.z, R[3] * upsilon.x + R[4] * upsilon.y + R[5] * upsilon.z,
           R[6] * upsilon.x + R[7] * upsilon.y + R[8] * upsilon.z};
   } else {
+    const double inv_theta = 1.0 / theta;
+    imag_factor = sh * inv_theta;
+    const double sin_theta = 2.0 * sh * ch, one_minus_cos = 2.0 * sh * sh;
     // J = I + c1 * Omega + c2 * Omega^2 ; J*u = u + c1 (omega x u) + c2 (omega x (omega x u))
-    const double c1 = (1 - cos(theta)) / (theta * theta);
-    const double c2 = (theta - sin(theta)) / (theta * theta * theta);
+    const double c1 = one_minus_cos * inv_theta * inv_theta;
+    const double c2 = (theta - sin_theta) * inv_theta * inv_theta * inv_theta;
     const V3 wu = cross(omega, upsilon);
     const V3 wwu = cross(omega, wu);
     dt = add(upsilon, add(scale(c1, wu), scale(c2, wwu)));
   }
+  const double dq[4] = {imag_factor * omega.x, imag_factor * omega.y, imag_factor * omega.z, real_factor};
   quat_mul(dq, x, out);
   const V3 tp = add(quat_rotate(dq, V3{x[4], x[5], x[6]}), dt);
   out[4] = tp.x; out[5] = tp.y; out[6] = tp.z;
@@ -359,9 +363,8 @@ FM_HD bool cholesky6_solve(const double* A, const double* b, double* y) {
 #pragma unroll
     for (int k = 0; k < j; ++k) s = fma(-L[j * 6 + k], L[j * 6 + k], s);
     if (!(s > 0.0)) return false;
-    const double d = sqrt(s);
-    L[j * 6 + j] = d;
-    inv[j] = 1.0 / d;
+    inv[j] = rsqrt(s);          // one reciprocal square root instead of sqrt + divide on the serial critical path
+    L[j * 6 + j] = s * inv[j];
 #pragma unroll
     for (int i = j + 1; i < 6; ++i) {
       double t = A[i * 6 + j];
