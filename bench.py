@@ -6,10 +6,12 @@ of a synthetic HDL-64-shaped sequence (64 rings x 1875 azimuths, ~118k returns/s
 Before the timed region the sequence is pre-rolled (map-seeding frame + 11 frames in which the reference's outer-iteration count
 decays 11 -> 2) and W warm-up frames are run; then EXACTLY K frames are timed.
 
-  value     frames/s, scans already resident in HBM, frames enqueued back to back (floam_replay_staged), CUDA events on the stream
+  value     frames/s, scans already resident in HBM, frames enqueued back to back (floam_replay_staged: the pose-independent half of
+            frame k+1 overlaps the solve / map update of frame k), CUDA events on the context's streams
   e2e       frames/s through the public C-ABI call a node would make (floam_process_submit / floam_process_wait) with HOST scans in
             pinned memory: H2D upload of every scan and D2H of every pose inside the timed region
-  roofline  the kernel class with the largest share of the frame, timed live with CUDA event pairs (floam_set_kernel_timing)
+  roofline  the kernel class with the largest share of the frame, timed live with CUDA event pairs recorded as nodes of the frame
+            graphs (floam_set_kernel_timing), pair overhead calibrated with an empty kernel and subtracted
   cpu_baseline  the oracle port of the reference classes on one host thread over a bounded sample of the same sequence
 
 N > 1 (torchrun): every rank replays its own independent sequence on its own GPU (replicas, no collective on the data path);

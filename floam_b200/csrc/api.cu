@@ -276,7 +276,6 @@ int floam_create(const floam_params* params, int device, floam_ctx** out) {
   for (int k = 0; k < 2; ++k) {
     if (cudaEventCreate(&c->ev_begin[k]) != cudaSuccess || cudaEventCreate(&c->ev_end[k]) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_upload[k], cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c->ev_consumed[k], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_front_done[k], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_back_done[k], cudaEventDisableTiming) != cudaSuccess)
       return fail(FLOAM_ERR_CUDA);
@@ -334,8 +333,7 @@ int floam_create(const floam_params* params, int device, floam_ctx** out) {
   for (int k = 0; k < 2; ++k) {
     c->h_state[k] = (PoseState*)host_alloc(c, sizeof(PoseState));
     c->h_flags[k] = (int*)host_alloc(c, 64);
-    c->h_pinned_scan[k] = host_alloc(c, (size_t)ns * 32);
-    if (!c->h_state[k] || !c->h_flags[k] || !c->h_pinned_scan[k]) return fail(FLOAM_ERR_CUDA);
+    if (!c->h_state[k] || !c->h_flags[k]) return fail(FLOAM_ERR_CUDA);
     std::memset(c->h_state[k], 0, sizeof(PoseState));
     c->h_state[k]->x[3] = 1.0;
     *c->h_flags[k] = 0;
@@ -371,7 +369,6 @@ void floam_destroy(floam_ctx* c) {
     if (c->ev_begin[k]) cudaEventDestroy(c->ev_begin[k]);
     if (c->ev_end[k]) cudaEventDestroy(c->ev_end[k]);
     if (c->ev_upload[k]) cudaEventDestroy(c->ev_upload[k]);
-    if (c->ev_consumed[k]) cudaEventDestroy(c->ev_consumed[k]);
     if (c->ev_front_done[k]) cudaEventDestroy(c->ev_front_done[k]);
     if (c->ev_back_done[k]) cudaEventDestroy(c->ev_back_done[k]);
   }
@@ -652,7 +649,6 @@ static int submit_common(floam_ctx* c, const floam_point_xyzirt* pts, int n, int
   FLOAM_CUDA_OK(cudaEventRecord(c->ev_upload[slot], c->copy_stream));
   FLOAM_CUDA_OK(cudaStreamWaitEvent(c->front_stream, c->ev_upload[slot], 0));
   FLOAM_CUDA_OK(cudaEventRecord(c->ev_begin[slot], c->front_stream));
-  c->frame_was_init[slot] = !c->map_initialised;
   int rc = launch_frame(c, deskew, slot, plan != nullptr);
   if (rc) return rc;
   FLOAM_CUDA_OK(cudaEventRecord(c->ev_end[slot], c->stream));

@@ -35,9 +35,9 @@ struct floam_ctx {
   cudaStream_t stream = nullptr;       // all kernels
   cudaStream_t copy_stream = nullptr;  // uploads of the next scan
   cudaEvent_t ev_begin[2] = {nullptr, nullptr}, ev_end[2] = {nullptr, nullptr};
-  cudaEvent_t ev_upload[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+  cudaEvent_t ev_upload[2] = {nullptr, nullptr};
   cudaEvent_t ev_replay_begin = nullptr, ev_replay_end = nullptr;
-  bool consumed_valid[2] = {false, false};
+  bool consumed_valid[2] = {false, false};   // a FRONT has read d_scan[slot] before (ev_front_done[slot] is meaningful)
   std::vector<void*> allocs;           // everything cudaMalloc'ed
   std::vector<void*> host_allocs;      // everything cudaMallocHost'ed
 
@@ -85,7 +85,6 @@ struct floam_ctx {
   double* h_doubles = nullptr;           // 64 doubles
   floam::PoseState* h_state[2] = {nullptr, nullptr};
   int* h_flags[2] = {nullptr, nullptr};
-  void* h_pinned_scan[2] = {nullptr, nullptr};  // pinned bounce buffers for pageable callers
 
   // staged scans for device-resident replay
   floam::PointIRT* d_staged = nullptr;
@@ -95,7 +94,6 @@ struct floam_ctx {
 
   // submit/wait pipeline
   int inflight = 0, submit_slot = 0, wait_slot = 0;
-  bool frame_was_init[2] = {false, false};
   bool map_initialised = false;
   bool use_graphs = true;
   std::map<floam_graph_key, floam_graph_entry> graphs;
