@@ -14,7 +14,7 @@ CUDA_LIB = os.path.join(LIB_DIR, "libfloam_b200.so")
 SYNTH_LIB = os.path.join(LIB_DIR, "libfloam_synth.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
-              "-Xcompiler", "-Wall", "--expt-relaxed-constexpr",
+              "-Xcompiler", "-Wall", "-Xcompiler", "-Wno-unknown-pragmas", "--expt-relaxed-constexpr",
               # no FMA contraction: float/double arithmetic must round like the reference's x86 build
               "-fmad=false"]
 

@@ -105,19 +105,33 @@ __device__ __forceinline__ void pdl_prologue() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 template <typename... KArgs, typename... Args>
-inline void launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t s, Args&&... args) {
+inline void launch_kernel_dyn(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t dyn_smem, cudaStream_t s, Args&&... args) {
   if (!g_use_pdl) {
-    kern<<<grid, block, 0, s>>>(KArgs(args)...);
+    kern<<<grid, block, dyn_smem, s>>>(KArgs(args)...);
     return;
   }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = s;
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = dyn_smem; cfg.stream = s;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
   cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
+
+template <typename... KArgs, typename... Args>
+inline void launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t s, Args&&... args) {
+  launch_kernel_dyn(kern, grid, block, 0, s, static_cast<Args&&>(args)...);
+}
+
+// dynamic shared memory variant (the kernel's cudaFuncAttributeMaxDynamicSharedMemorySize is raised by its owner, once)
+#define FLOAM_LAUNCH_DYN(slot, kern, grid, block, smem, stream, ...)       \
+  do {                                                                     \
+    ::floam::g_launches++;                                                 \
+    if (::floam::g_timer) ::floam::launch_timer_begin(slot, stream);       \
+    ::floam::launch_kernel_dyn(kern, dim3(grid), dim3(block), smem, stream, __VA_ARGS__); \
+    if (::floam::g_timer) ::floam::launch_timer_end(stream);               \
+  } while (0)
 
 #define FLOAM_LAUNCH(slot, kern, grid, block, stream, ...)                 \
   do {                                                                     \

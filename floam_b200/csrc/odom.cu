@@ -804,6 +804,11 @@ __global__ void __launch_bounds__(kEvalThreads) assoc_eval_kernel(PoseState* __r
 constexpr int kClusterCtas = 8;    // portable cluster size; 16 CTAs (non-portable) was measured: evaluation 3.8k instead of 5.7k cycles per
                                    // attempt, but the cluster barrier doubled (1.8k) and the frame got slower
 constexpr int kClusterThreads = 256;
+// Accepted correspondences of a CTA's share are staged in shared memory once per solve (stable compaction of its contiguous slot
+// range: edge slots first, then surf): 6 double planes (a, b | n, d) + 3 float planes (the query point). Every step attempt then
+// evaluates dense items out of shared memory instead of striding over the ~55 % rejected slots with dependent L2 loads.
+constexpr int kStageCap = 3072;
+constexpr size_t kLmStageBytes = (size_t)kStageCap * (6 * sizeof(double) + 3 * sizeof(float));   // 180 KB
 struct ClusterShared {
   double part[kClusterThreads / 32][kLmTerms];
   double row[kLmTerms];   // this CTA's 28 totals
@@ -827,6 +832,64 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClusterT
   ClusterShared* sh0 = cluster.map_shared_rank(&sh, 0);
   const size_t cs = (size_t)2 * qcap;
   const int w = warp_id(), l = lane_id();
+  // ---- stage this CTA's share: slots [lo, hi) of the cluster-wide slot range, warp ww owning the ww-th eighth of it ----
+  extern __shared__ __align__(16) unsigned char lm_dyn[];
+  double* sc = reinterpret_cast<double*>(lm_dyn);                                        // [6][kStageCap]
+  float* sp = reinterpret_cast<float*>(lm_dyn + (size_t)6 * kStageCap * sizeof(double));  // [3][kStageCap]
+  __shared__ int s_wtot[kClusterThreads / 32], s_wedge[kClusterThreads / 32], s_over_lo;
+  const int total = nde + nds;
+  const int chunk = (total + kClusterCtas - 1) / kClusterCtas;
+  const int lo = min((int)rank * chunk, total), hi = min(lo + chunk, total);
+  const int sub = (hi - lo + kClusterThreads / 32 - 1) / (kClusterThreads / 32);
+  const int wlo = min(lo + w * sub, hi), whi = min(wlo + sub, hi);
+  {
+    int cnt = 0, cnt_edge = 0;
+    for (int s0 = wlo; s0 < whi; s0 += 32) {
+      const int slot = s0 + l;
+      const bool ok = slot < whi && corr_ok[slot < nde ? slot : qcap + slot - nde] != 0;
+      cnt += __popc(__ballot_sync(0xffffffffu, ok));
+      cnt_edge += __popc(__ballot_sync(0xffffffffu, ok && slot < nde));
+    }
+    if (l == 0) { s_wtot[w] = cnt; s_wedge[w] = cnt_edge; }
+    if (threadIdx.x == 0) s_over_lo = hi;
+  }
+  __syncthreads();
+  int n_staged = 0, n_staged_edge = 0;
+  {
+    int base = 0;
+#pragma unroll
+    for (int ww = 0; ww < kClusterThreads / 32; ++ww) {
+      if (ww < w) base += s_wtot[ww];
+      n_staged += s_wtot[ww];
+      n_staged_edge += s_wedge[ww];
+    }
+    n_staged = min(n_staged, kStageCap);
+    n_staged_edge = min(n_staged_edge, kStageCap);
+    for (int s0 = wlo; s0 < whi; s0 += 32) {
+      const int slot = s0 + l;
+      const bool is_edge = slot < nde;
+      const int qi = is_edge ? slot : slot - nde;
+      const int out = is_edge ? qi : qcap + qi;
+      const bool ok = slot < whi && corr_ok[out] != 0;
+      const unsigned int b = __ballot_sync(0xffffffffu, ok);
+      const int pos = base + __popc(b & ((1u << l) - 1u));
+      if (ok) {
+        if (pos < kStageCap) {
+          const float4 p = __ldg((is_edge ? ds_edge : ds_surf) + qi);
+          sp[pos] = p.x; sp[kStageCap + pos] = p.y; sp[2 * kStageCap + pos] = p.z;
+          const int planes = is_edge ? 6 : 4;
+#pragma unroll
+          for (int k = 0; k < 6; ++k)
+            if (k < planes) sc[(size_t)k * kStageCap + pos] = corr[k * cs + out];
+        } else if (pos == kStageCap) {
+          s_over_lo = slot;   // first accepted slot that did not fit: [over_lo, hi) is evaluated from global memory
+        }
+      }
+      base += __popc(b);
+    }
+  }
+  __syncthreads();
+  const int over_lo = s_over_lo;
   // iteration 0 of ceres::Solve: CTA 0 adds up the per-CTA rows the association kernel left (thread (g, k): term k of rows g, g+8, ...;
   // fixed order), starts the trust-region state and publishes the first candidate
   if (rank == 0) {
@@ -857,14 +920,27 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClusterT
 #pragma unroll
   for (int k = 0; k < 7; ++k) x[k] = sh0->x[k];
   const bool finished_at_start = sh0->done != 0;
-  const int tid = rank * kClusterThreads + threadIdx.x, nthreads = kClusterCtas * kClusterThreads;
   long long clk[6] = {0, 0, 0, 0, 0, 0};
   for (int attempt = 0; attempt < 4 && !finished_at_start; ++attempt) {
     clk[0] = clock64();
     Accum A;
 #pragma unroll
     for (int k = 0; k < kLmTerms; ++k) A.v[k] = 0.0;
-    for (int slot = tid; slot < nde + nds; slot += nthreads) {
+    for (int k = threadIdx.x; k < n_staged; k += kClusterThreads) {   // staged items: [0, n_staged_edge) edge, then surf
+      const m::V3 pc{(double)sp[k], (double)sp[kStageCap + k], (double)sp[2 * kStageCap + k]};
+      double r, J[6], cost_term;
+      if (k < n_staged_edge) {
+        const m::V3 a{sc[k], sc[kStageCap + k], sc[2 * kStageCap + k]};
+        const m::V3 b{sc[3 * kStageCap + k], sc[4 * kStageCap + k], sc[5 * kStageCap + k]};
+        eval_edge(x, pc, a, b, r, J);
+      } else {
+        const m::V3 n{sc[k], sc[kStageCap + k], sc[2 * kStageCap + k]};
+        eval_surf(x, pc, n, sc[3 * kStageCap + k], r, J);
+      }
+      loss_correct(loss, r, J, cost_term);
+      accumulate(A, r, J, cost_term);
+    }
+    for (int slot = over_lo + threadIdx.x; slot < hi; slot += kClusterThreads) {   // beyond the staging capacity (dense maps): from global
       const bool is_edge = slot < nde;
       const int qi = is_edge ? slot : slot - nde;
       const int out = is_edge ? qi : qcap + qi;
@@ -1013,6 +1089,7 @@ int odom_device_init(OdomDevice& od, const floam_params& prm, VoxelWorkspace* vw
   od.vws = vws;
   od.vws_aux = vws_aux;
   od.aux_stream = aux;
+  FLOAM_CUDA_OK(cudaFuncSetAttribute(lm_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLmStageBytes));
   FLOAM_CUDA_OK(cudaEventCreateWithFlags(&od.ev_fork, cudaEventDisableTiming));
   FLOAM_CUDA_OK(cudaEventCreateWithFlags(&od.ev_join, cudaEventDisableTiming));
   od.leaf_edge = (float)prm.map_resolution;        // setLeafSize(float...) :13-14
@@ -1088,7 +1165,7 @@ void odom_update_device(OdomDevice& od, const void* d_edge, const int* d_ne, con
                  od.qcap, od.knn_ids, od.knn_d2);
     FLOAM_LAUNCH(K_ASSOC_EVAL, assoc_eval_kernel, kAssocBlocks, kEvalThreads, s, S, od.ds_edge, od.d_nds_edge, od.ds_surf, od.d_nds_surf, od.edge_map, od.surf_map,
                  od.qcap, od.corr, od.corr_ok, od.knn_ids, od.loss, od.partials);
-    FLOAM_LAUNCH(K_LM_CLUSTER, lm_cluster_kernel, kClusterCtas, kClusterThreads, s, S, od.ds_edge, od.d_nds_edge, od.ds_surf, od.d_nds_surf, od.qcap, od.corr, od.corr_ok,
+    FLOAM_LAUNCH_DYN(K_LM_CLUSTER, lm_cluster_kernel, kClusterCtas, kClusterThreads, kLmStageBytes, s, S, od.ds_edge, od.d_nds_edge, od.ds_surf, od.d_nds_surf, od.qcap, od.corr, od.corr_ok,
                  od.loss, od.partials, kAssocBlocks);
   }
   FLOAM_LAUNCH(K_FINISH, finish_kernel, 1, 32, s, S, update_type, od.scan_period, od.traj, od.traj_cap);
