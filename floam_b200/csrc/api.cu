@@ -1,6 +1,7 @@
 // C ABI of the B200-native FLOAM odometry path (include/floam_b200.h). Thin host layer: argument checks, uploads, kernel
 // sequencing (captured into CUDA graphs for the per-frame path) and the small pinned mailboxes results come back through.
 // There is no CPU fallback anywhere in this file: without a usable sm_100 device floam_create fails.
+#include <chrono>
 #include <algorithm>
 #include <cctype>
 #include <cmath>
@@ -972,12 +973,18 @@ int floam_replay_staged(floam_ctx* c, int first, int count, int deskew, double* 
   const int counter0 = c->h_state[0]->frame_counter;
   FLOAM_CUDA_OK(cudaEventRecord(c->ev_replay_begin, c->front_stream));
   int last_slot = 0;
+  const auto t_host0 = std::chrono::steady_clock::now();
   for (int f = first; f < first + count; ++f) {
     last_slot = c->submit_slot;
     if ((rc = enqueue_staged_frame(c, f, deskew))) return rc;
   }
   FLOAM_CUDA_OK(cudaEventRecord(c->ev_replay_end, c->stream));
+  const auto t_host1 = std::chrono::steady_clock::now();
   FLOAM_CUDA_OK(cudaStreamSynchronize(c->stream));
+  if (getenv("FLOAM_DBG_ENQUEUE"))   // development aid: is the replay bound by the host's enqueue rate or by the device?
+    fprintf(stderr, "replay_staged: %d frames enqueued in %.3f ms of host time (%.4f ms/frame)\n", count,
+            std::chrono::duration<double, std::milli>(t_host1 - t_host0).count(),
+            std::chrono::duration<double, std::milli>(t_host1 - t_host0).count() / count);
   if ((rc = check_async("replay_staged"))) return rc;
   cudaEventElapsedTime(&c->last_frame_ms, c->ev_replay_begin, c->ev_replay_end);
   if (total_ms) *total_ms = c->last_frame_ms;

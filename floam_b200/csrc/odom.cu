@@ -808,6 +808,7 @@ constexpr int kClusterThreads = 256;
 // range: edge slots first, then surf): 6 double planes (a, b | n, d) + 3 float planes (the query point). Every step attempt then
 // evaluates dense items out of shared memory instead of striding over the ~55 % rejected slots with dependent L2 loads.
 constexpr int kStageCap = 3072;
+constexpr int kCoordinatorOnlyBelow = 16384;   // query slots
 constexpr size_t kLmStageBytes = (size_t)kStageCap * (6 * sizeof(double) + 3 * sizeof(float));   // 180 KB
 struct ClusterShared {
   double part[kClusterThreads / 32][kLmTerms];
@@ -832,14 +833,43 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClusterT
   ClusterShared* sh0 = cluster.map_shared_rank(&sh, 0);
   const size_t cs = (size_t)2 * qcap;
   const int w = warp_id(), l = lane_id();
+  // iteration 0 of ceres::Solve: CTA 0 adds up the per-CTA rows the association kernel left (thread (g, k): term k of rows g, g+8, ...;
+  // fixed order), starts the trust-region state and publishes the first candidate
+  if (rank == 0) {
+    state_load(&st, S);
+    double v = 0.0;
+    if (l < kLmTerms) {
+#pragma unroll 4
+      for (int r = w; r < n_rows; r += kClusterThreads / 32) v += __ldcg(partials + (size_t)r * kLmTerms + l);
+      sh.part[w][l] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < kLmTerms) {
+      double t = 0.0;
+#pragma unroll
+      for (int ww = 0; ww < kClusterThreads / 32; ++ww) t += sh.part[ww][threadIdx.x];
+      s_sums[threadIdx.x] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      lm_start(st, s_sums, (int)s_sums[28]);
+      sh.done = st.lm_done;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) sh.x[k] = st.x_cand[k];
+    }
+  }
   // ---- stage this CTA's share: slots [lo, hi) of the cluster-wide slot range, warp ww owning the ww-th eighth of it ----
+  // Small problems (the usual case) leave CTA 0 without a share: its iteration-0 bookkeeping above is the critical path of the
+  // prologue, and the other seven CTAs stage their correspondences meanwhile.
   extern __shared__ __align__(16) unsigned char lm_dyn[];
   double* sc = reinterpret_cast<double*>(lm_dyn);                                        // [6][kStageCap]
   float* sp = reinterpret_cast<float*>(lm_dyn + (size_t)6 * kStageCap * sizeof(double));  // [3][kStageCap]
   __shared__ int s_wtot[kClusterThreads / 32], s_wedge[kClusterThreads / 32], s_over_lo;
   const int total = nde + nds;
-  const int chunk = (total + kClusterCtas - 1) / kClusterCtas;
-  const int lo = min((int)rank * chunk, total), hi = min(lo + chunk, total);
+  const int n_eval = total <= kCoordinatorOnlyBelow ? kClusterCtas - 1 : kClusterCtas;
+  const int erank = (int)rank - (kClusterCtas - n_eval);   // -1: no share
+  const int chunk = (total + n_eval - 1) / n_eval;
+  const int lo = erank < 0 ? total : min(erank * chunk, total), hi = min(lo + chunk, total);
   const int sub = (hi - lo + kClusterThreads / 32 - 1) / (kClusterThreads / 32);
   const int wlo = min(lo + w * sub, hi), whi = min(wlo + sub, hi);
   {
@@ -890,31 +920,6 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClusterT
   }
   __syncthreads();
   const int over_lo = s_over_lo;
-  // iteration 0 of ceres::Solve: CTA 0 adds up the per-CTA rows the association kernel left (thread (g, k): term k of rows g, g+8, ...;
-  // fixed order), starts the trust-region state and publishes the first candidate
-  if (rank == 0) {
-    state_load(&st, S);
-    double v = 0.0;
-    if (l < kLmTerms) {
-#pragma unroll 4
-      for (int r = w; r < n_rows; r += kClusterThreads / 32) v += __ldcg(partials + (size_t)r * kLmTerms + l);
-      sh.part[w][l] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x < kLmTerms) {
-      double t = 0.0;
-#pragma unroll
-      for (int ww = 0; ww < kClusterThreads / 32; ++ww) t += sh.part[ww][threadIdx.x];
-      s_sums[threadIdx.x] = t;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      lm_start(st, s_sums, (int)s_sums[28]);
-      sh.done = st.lm_done;
-#pragma unroll
-      for (int k = 0; k < 7; ++k) sh.x[k] = st.x_cand[k];
-    }
-  }
   cluster.sync();
   double x[7];
 #pragma unroll
