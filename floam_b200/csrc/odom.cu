@@ -317,40 +317,50 @@ __device__ __forceinline__ void knn5_insert(Knn5& k, float dist, int idx) {
   }
 }
 
-__device__ __forceinline__ void knn5_search(const GridDims& g, const int* __restrict__ cell_start, const float4* __restrict__ cell_pts, float qx, float qy,
-                                            float qz, Knn5& k) {
+// Upper bound of the warp-wide 5th smallest distance seen so far: the private lists are ascending, so five rounds of
+// {redux.min over the list heads, lowest lane holding the minimum pops} walk the five smallest distances of the union.
+__device__ __forceinline__ float knn5_warp_bound(const Knn5& k) {
+  const int l = lane_id();
+  unsigned int v0 = __float_as_uint(k.d[0]), v1 = __float_as_uint(k.d[1]), v2 = __float_as_uint(k.d[2]), v3 = __float_as_uint(k.d[3]),
+               v4 = __float_as_uint(k.d[4]);   // distances are >= 0: the bit patterns order like the floats
+  unsigned int m = 0;
 #pragma unroll
-  for (int j = 0; j < 5; ++j) { k.d[j] = FLT_MAX; k.id[j] = 0x7fffffff; }
-  if (g.ncells == 0) return;
-  // float -> int conversion saturates, so far-away queries simply find no cell
-  const int cx = (int)floorf(qx) - g.ix0, cy = (int)floorf(qy) - g.iy0, cz = (int)floorf(qz) - g.iz0;
-  const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
-  if (x0 > x1) return;
-  for (int z = max(cz - 1, 0); z <= min(cz + 1, g.nz - 1); ++z) {
-    for (int y = max(cy - 1, 0); y <= min(cy + 1, g.ny - 1); ++y) {
-      const int row = g.nx * (y + g.ny * z);
-      const int b = __ldg(cell_start + row + x0), e = __ldg(cell_start + row + x1 + 1);  // the three x-cells are contiguous
-      for (int i = b; i < e; ++i) {
-        const float4 p = __ldg(cell_pts + i);
-        // flann::L2_Simple: ((0 + dx^2) + dy^2) + dz^2 in float, no contraction
-        const float dx = fsub(qx, p.x), dy = fsub(qy, p.y), dz = fsub(qz, p.z);
-        const float dist = fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
-        knn5_insert(k, dist, __float_as_int(p.w));
-      }
-    }
+  for (int j = 0; j < 5; ++j) {
+    m = __reduce_min_sync(0xffffffffu, v0);
+    const unsigned int who = __ballot_sync(0xffffffffu, v0 == m);
+    if (l == __ffs(who) - 1) { v0 = v1; v1 = v2; v2 = v3; v3 = v4; v4 = __float_as_uint(FLT_MAX); }
+  }
+  return __uint_as_float(m);
+}
+
+__device__ __forceinline__ void knn5_scan_range(int b, int e, float qx, float qy, float qz, float bound, const float4* __restrict__ cell_pts, Knn5& k) {
+  for (int i = b + lane_id(); i < e; i += 32) {
+    const float4 p = __ldg(cell_pts + i);
+    // flann::L2_Simple: ((0 + dx^2) + dy^2) + dz^2 in float, no contraction
+    const float dx = fsub(qx, p.x), dy = fsub(qy, p.y), dz = fsub(qz, p.z);
+    const float dist = fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
+    if (dist <= bound) knn5_insert(k, dist, __float_as_int(p.w));
   }
 }
 
-// The same search by a whole warp for ONE query: the nine x-contiguous cell runs are fetched up front (lanes 0..8 load the run
-// bounds), lanes stride over the candidates of each run keeping a private top-5, and five rounds of warp arg-min over the packed
+// The same search by a whole warp for ONE query. Lanes 0..8 load the bounds of the nine x-contiguous cell runs, lanes 0..26 the
+// bounds of the 27 cells; lanes stride over candidates keeping a private top-5, and five rounds of warp arg-min over the packed
 // (distance, index) heads merge the 32 lists. Every lane returns the final set.
+//  * few candidates (sparse maps, the usual case): the nine runs are scanned whole.
+//  * many candidates (dense maps): the query's own cell is scanned first and gives an upper bound of the 5th distance; a
+//    neighbouring cell is skipped when the distance from the query to the cell, computed with the SAME rounded operations as a
+//    candidate distance (per axis q - floor(q) or floor(q) + 1 - q, or 0), exceeds the bound. Rounding is monotonic, so every
+//    candidate of a skipped cell has a computed distance >= that figure > bound >= the final 5th distance: the result is the
+//    same set, ties included, as the exhaustive scan.
+constexpr int kKnnPruneAbove = 256;   // candidates in the 27 cells
 __device__ __forceinline__ void knn5_search_warp(const GridDims& g, const int* __restrict__ cell_start, const float4* __restrict__ cell_pts, float qx,
                                                  float qy, float qz, Knn5& out) {
   const int l = lane_id();
   Knn5 k;
 #pragma unroll
   for (int j = 0; j < 5; ++j) { k.d[j] = FLT_MAX; k.id[j] = 0x7fffffff; }
-  const int cx = (int)floorf(qx) - g.ix0, cy = (int)floorf(qy) - g.iy0, cz = (int)floorf(qz) - g.iz0;
+  const float flx = floorf(qx), fly = floorf(qy), flz = floorf(qz);
+  const int cx = (int)flx - g.ix0, cy = (int)fly - g.iy0, cz = (int)flz - g.iz0;   // float -> int saturates: far-away queries find no cell
   const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
   int rb = 0, re = 0;  // lane r < 9 owns run r = (dz+1)*3 + (dy+1)
   if (l < 9 && g.ncells != 0 && x0 <= x1) {
@@ -361,14 +371,38 @@ __device__ __forceinline__ void knn5_search_warp(const GridDims& g, const int* _
       re = __ldg(cell_start + row + x1 + 1);
     }
   }
+  int cb = 0, ce = 0;  // lane c < 27 owns cell c = (dz+1)*9 + (dy+1)*3 + (dx+1)
+  float cdm = FLT_MAX; // ... and its distance from the query
+  if (l < 27 && g.ncells != 0) {
+    const int ox = l % 3 - 1, oy = (l / 3) % 3 - 1, oz = l / 9 - 1;
+    const int X = cx + ox, Y = cy + oy, Z = cz + oz;
+    if (X >= 0 && X < g.nx && Y >= 0 && Y < g.ny && Z >= 0 && Z < g.nz) {
+      const int cell = X + g.nx * (Y + g.ny * Z);
+      cb = __ldg(cell_start + cell);
+      ce = __ldg(cell_start + cell + 1);
+    }
+    const float gx = ox < 0 ? fsub(qx, flx) : ox > 0 ? fsub(fadd(flx, 1.0f), qx) : 0.0f;
+    const float gy = oy < 0 ? fsub(qy, fly) : oy > 0 ? fsub(fadd(fly, 1.0f), qy) : 0.0f;
+    const float gz = oz < 0 ? fsub(qz, flz) : oz > 0 ? fsub(fadd(flz, 1.0f), qz) : 0.0f;
+    cdm = fadd(fadd(fmul(gx, gx), fmul(gy, gy)), fmul(gz, gz));
+  }
+  const int total = __reduce_add_sync(0xffffffffu, re - rb);
+  if (total <= kKnnPruneAbove) {
 #pragma unroll
-  for (int r = 0; r < 9; ++r) {
-    const int b = __shfl_sync(0xffffffffu, rb, r), e = __shfl_sync(0xffffffffu, re, r);
-    for (int i = b + l; i < e; i += 32) {
-      const float4 p = __ldg(cell_pts + i);
-      const float dx = fsub(qx, p.x), dy = fsub(qy, p.y), dz = fsub(qz, p.z);
-      const float dist = fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
-      knn5_insert(k, dist, __float_as_int(p.w));
+    for (int r = 0; r < 9; ++r) {
+      const int b = __shfl_sync(0xffffffffu, rb, r), e = __shfl_sync(0xffffffffu, re, r);
+      knn5_scan_range(b, e, qx, qy, qz, FLT_MAX, cell_pts, k);
+    }
+  } else {
+    knn5_scan_range(__shfl_sync(0xffffffffu, cb, 13), __shfl_sync(0xffffffffu, ce, 13), qx, qy, qz, FLT_MAX, cell_pts, k);
+    float bound = knn5_warp_bound(k);
+#pragma unroll 1
+    for (int c = 0; c < 27; ++c) {
+      const int b = __shfl_sync(0xffffffffu, cb, c), e = __shfl_sync(0xffffffffu, ce, c);
+      const float dm = __shfl_sync(0xffffffffu, cdm, c);
+      if (c == 13 || e <= b || dm > bound) continue;   // warp-uniform
+      knn5_scan_range(b, e, qx, qy, qz, bound, cell_pts, k);
+      if (e - b >= 32 || bound == FLT_MAX) bound = knn5_warp_bound(k);
     }
   }
 #pragma unroll
@@ -1011,18 +1045,24 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClusterT
 }
 
 // stand-alone 5-NN (floam_knn5): queries are used as given (no pose transform)
-__global__ void __launch_bounds__(kEvalThreads) knn5_kernel(const P4* __restrict__ queries, const int* __restrict__ d_nq, LocalMap map, int* __restrict__ ids,
-                                                             float* __restrict__ d2) {
+__global__ void __launch_bounds__(kKnnThreads) knn5_kernel(const P4* __restrict__ queries, const int* __restrict__ d_nq, LocalMap map, int* __restrict__ ids,
+                                                            float* __restrict__ d2) {
   pdl_prologue();
   const int nq = *d_nq;
   const GridDims g = *map.dims;
-  for (int i = blockIdx.x * kEvalThreads + threadIdx.x; i < nq; i += gridDim.x * kEvalThreads) {
+  const int warps_total = gridDim.x * (kKnnThreads / 32);
+  for (int i = blockIdx.x * (kKnnThreads / 32) + warp_id(); i < nq; i += warps_total) {   // one warp per query, like the association
     const float4 q = __ldg(queries + i);
     Knn5 nn;
-    knn5_search(g, map.cell_start, map.cell_pts, q.x, q.y, q.z, nn);
+    knn5_search_warp(g, map.cell_start, map.cell_pts, q.x, q.y, q.z, nn);
     const bool near = nn.d[4] < 1.0f;
-#pragma unroll
-    for (int j = 0; j < 5; ++j) { ids[(size_t)i * 5 + j] = near ? nn.id[j] : -1; d2[(size_t)i * 5 + j] = near ? nn.d[j] : 0.f; }
+    if (lane_id() < 5) {
+      const int j = lane_id();
+      const int id = j == 0 ? nn.id[0] : j == 1 ? nn.id[1] : j == 2 ? nn.id[2] : j == 3 ? nn.id[3] : nn.id[4];
+      const float d = j == 0 ? nn.d[0] : j == 1 ? nn.d[1] : j == 2 ? nn.d[2] : j == 3 ? nn.d[3] : nn.d[4];
+      ids[(size_t)i * 5 + j] = near ? id : -1;
+      d2[(size_t)i * 5 + j] = near ? d : 0.f;
+    }
   }
 }
 
@@ -1224,10 +1264,10 @@ void compensate_velocity_explicit_device(PointIRT* d_pts, const int* d_n, int n_
 }
 
 void knn5_device(OdomDevice& od, LocalMap& map, const P4* d_queries, const int* d_nq, int nq_max, int* d_ids, float* d_d2, cudaStream_t s) {
-  int g = (nq_max + kEvalThreads - 1) / kEvalThreads;
-  if (g > kNumSMs * 16) g = kNumSMs * 16;
+  int g = (nq_max + kKnnThreads / 32 - 1) / (kKnnThreads / 32);
+  if (g > kKnnBlocks) g = kKnnBlocks;
   if (g < 1) g = 1;
-  FLOAM_LAUNCH(K_KNN5, knn5_kernel, g, kEvalThreads, s, d_queries, d_nq, map, d_ids, d_d2);
+  FLOAM_LAUNCH(K_KNN5, knn5_kernel, g, kKnnThreads, s, d_queries, d_nq, map, d_ids, d_d2);
 }
 
 }  // namespace floam

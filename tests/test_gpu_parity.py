@@ -224,6 +224,32 @@ def test_knn_dense_map_stress(capi, po, ctxs):
     assert np.array_equal(ids[sample], oids) and np.array_equal(d2[sample], od2)
 
 
+def test_knn_pruned_search_is_exhaustive(capi, po, ctxs):
+    # Dense cells (hundreds of candidates per query) take the pruned path of the warp search: it must return exactly what brute
+    # force returns, including for queries on cell faces / corners, on map points, in sparse pockets next to dense cells, and
+    # with duplicated map points (ties by index).
+    ctx = ctxs(16)
+    rng = np.random.default_rng(77)
+    dense = cloud(capi, rng, 150000, lo=(-4, -4, -1), hi=(4, 4, 2))                   # ~780 points / m^3
+    lattice = cloud(capi, rng, 20000, lo=(-4, -4, -1), hi=(4, 4, 2))
+    for k in "xyz":
+        lattice[k] = np.round(lattice[k] * 4) / 4                                     # quarter-metre lattice: many exact ties, points on cell faces
+    sparse = cloud(capi, rng, 300, lo=(4, -4, -1), hi=(9, 4, 2))                      # a sparse pocket next to the dense block
+    m = np.concatenate([dense, lattice, sparse, dense[:3000]])
+    q = cloud(capi, rng, 3000, lo=(-5, -5, -2), hi=(9.5, 5, 3))
+    qi = q[:600].copy()
+    for k in "xyz":
+        qi[k] = np.round(qi[k])                                                        # queries on cell corners
+    qf = q[600:1200].copy(); qf["x"] = np.round(qf["x"])                               # ... and on cell faces
+    qp = m[rng.choice(len(m), 600, replace=False)].copy()                              # ... and on map points
+    q = np.concatenate([q, qi, qf, qp])
+    ids, d2 = ctx.knn5(m, q)
+    oids, od2 = po.knn(m, q, 5, use_kdtree=False)
+    near = od2[:, 4] < 1.0
+    assert near.sum() > 3000 and (~near).sum() > 10
+    assert np.array_equal(ids[near], oids[near]) and np.array_equal(d2[near], od2[near]) and (ids[~near] == -1).all()
+
+
 # ------------------------------------------------------------------------------------------------ odometry stages -------
 def prepare_state(capi, po, synth, sequences, sensor, loss):
     """Both sides get the same map / pose state and the same next frame; returns (ctx, oracle, edge, surf)."""
