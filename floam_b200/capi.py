@@ -36,10 +36,39 @@ SYMBOLS = [
     "floam_process_wait", "floam_stage_scans", "floam_process_staged", "floam_mapping_update", "floam_mapping_get_map", "floam_voxel_grid",
     "floam_crop_box", "floam_knn5", "floam_debug_fetch", "floam_launch_count", "floam_last_frame_ms", "floam_replay_staged",
     "floam_set_kernel_timing", "floam_kernel_slots", "floam_kernel_name", "floam_kernel_timing", "floam_deskew_align_ex",
-    "floam_compensate_velocity", "floam_process_submit_imu", "floam_process_scan_imu",
+    "floam_compensate_velocity", "floam_process_submit_imu", "floam_process_scan_imu", "floam_unpack_pointcloud2", "floam_process_submit_pc2",
 ]
 
 _lib = None
+
+
+class Pc2Layout(C.Structure):
+    """floam_pc2_layout: where the PointXYZIRT fields sit inside a sensor_msgs/PointCloud2 point (offset -1 = field absent)."""
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("point_step", C.c_uint32), ("row_step", C.c_uint32),
+                ("off_x", C.c_int32), ("off_y", C.c_int32), ("off_z", C.c_int32), ("off_intensity", C.c_int32), ("off_ring", C.c_int32),
+                ("off_time", C.c_int32), ("is_bigendian", C.c_int32)]
+
+
+def pc2_layout(n, point_step, x=0, y=4, z=8, intensity=12, ring=16, time=18, height=1, row_step=None, bigendian=False):
+    """Defaults: the Velodyne driver's XYZIRT message (22 bytes per point)."""
+    width = n // height
+    return Pc2Layout(width, height, point_step, width * point_step if row_step is None else row_step, x, y, z, intensity, ring, time, int(bigendian))
+
+
+def pack_pointcloud2(pts, layout):
+    """Test/bench helper: the msg.data bytes a driver would publish for `pts` (POINT_IRT) in the given layout; padding bytes are 0xAB."""
+    n = len(pts)
+    assert n == layout.width * layout.height
+    raw = np.full((layout.height, layout.row_step), 0xAB, np.uint8)
+    body = np.full((n, layout.point_step), 0xAB, np.uint8)
+    order = ">" if layout.is_bigendian else "<"
+    for name, off, dt in (("x", layout.off_x, "f4"), ("y", layout.off_y, "f4"), ("z", layout.off_z, "f4"), ("intensity", layout.off_intensity, "f4"),
+                          ("ring", layout.off_ring, "u2"), ("time", layout.off_time, "f4")):
+        if off >= 0:
+            b = np.ascontiguousarray(pts[name].astype(order + dt)).view(np.uint8).reshape(n, -1)
+            body[:, off:off + b.shape[1]] = b
+    raw[:, :layout.width * layout.point_step] = body.reshape(layout.height, layout.width * layout.point_step)
+    return np.ascontiguousarray(raw.reshape(-1))
 
 
 class FloamError(RuntimeError):
@@ -246,6 +275,24 @@ class Context:
         """pts must stay alive (ideally a PinnedBuffer.array slice) until the matching process_wait returns."""
         assert pts.dtype == POINT_IRT and pts.flags.c_contiguous
         _check(lib().floam_process_submit(self.h, _p(pts), len(pts) if n is None else int(n), int(deskew)), "floam_process_submit")
+
+    def unpack_pointcloud2(self, raw, layout):
+        """pcl::fromROSMsg on the device: raw msg.data bytes -> POINT_IRT array."""
+        raw = np.ascontiguousarray(raw, np.uint8)
+        out = np.zeros(layout.width * layout.height, POINT_IRT)
+        _check(lib().floam_unpack_pointcloud2(self.h, _p(raw), C.byref(layout), _p(out)), "floam_unpack_pointcloud2")
+        return out
+
+    def process_submit_pc2(self, raw, layout, deskew=False, stamp_us=None, extrinsics_xyzw=None):
+        """raw must stay alive until the matching process_wait returns. With stamp_us / extrinsics the IMU steps run too; returns the
+        re-centred stamp in that case."""
+        assert raw.dtype == np.uint8 and raw.flags.c_contiguous
+        if stamp_us is None:
+            _check(lib().floam_process_submit_pc2(self.h, _p(raw), C.byref(layout), None, None, int(deskew)), "floam_process_submit_pc2")
+            return None
+        st = C.c_uint64(int(stamp_us)); ex = np.ascontiguousarray(extrinsics_xyzw, np.float64)
+        _check(lib().floam_process_submit_pc2(self.h, _p(raw), C.byref(layout), C.byref(st), _p(ex), int(deskew)), "floam_process_submit_pc2")
+        return st.value
 
     def process_wait(self):
         pose = np.zeros(7)

@@ -10,6 +10,7 @@
 #include <string>
 
 #include "context.cuh"
+#include "ingest.cuh"
 #include "odom_math.cuh"
 
 using namespace floam;
@@ -632,15 +633,42 @@ int floam_odom_get_map(floam_ctx* c, floam_point_xyzi* edge, int edge_cap, floam
 }
 
 // ---- fused frame path ---------------------------------------------------------------------------------------------
-static int submit_common(floam_ctx* c, const floam_point_xyzirt* pts, int n, int deskew, DeskewPlan* plan) {
-  if (!c || (!pts && n > 0) || n < 0) return FLOAM_ERR_ARG;
+static int pc2_layout_check(const floam_pc2_layout* L, long long* n_out) {
+  if (!L || L->point_step == 0 || L->width == 0) return FLOAM_ERR_ARG;
+  if ((unsigned long long)L->row_step < (unsigned long long)L->width * L->point_step) return FLOAM_ERR_ARG;
+  const int32_t offs[6] = {L->off_x, L->off_y, L->off_z, L->off_intensity, L->off_ring, L->off_time};
+  for (int k = 0; k < 6; ++k)
+    if (offs[k] >= 0 && (uint32_t)offs[k] + (k == 4 ? 2u : 4u) > L->point_step) return FLOAM_ERR_ARG;
+  *n_out = (long long)L->width * L->height;
+  return FLOAM_OK;
+}
+static int raw_reserve(floam_ctx* c, size_t bytes) {
+  if (bytes <= c->raw_cap) return FLOAM_OK;
+  if (c->raw_cap != 0) return FLOAM_ERR_CAPACITY;   // sized by the first message: max_scan_points of its point_step (at least 64 B)
+  for (int k = 0; k < 2; ++k)
+    if (!(c->d_raw[k] = (unsigned char*)ctx_alloc(c, bytes))) return FLOAM_ERR_CUDA;
+  c->raw_cap = bytes;
+  return FLOAM_OK;
+}
+
+// pts: packed 32-byte points, or (raw, layout): PointCloud2 bytes unpacked on the device
+static int submit_common(floam_ctx* c, const floam_point_xyzirt* pts, int n, int deskew, DeskewPlan* plan, const uint8_t* raw = nullptr,
+                         const floam_pc2_layout* layout = nullptr) {
+  if (!c || (!pts && !raw && n > 0) || n < 0) return FLOAM_ERR_ARG;
   if (n > c->prm.max_scan_points) return FLOAM_ERR_CAPACITY;
   if (c->inflight >= 2) return FLOAM_ERR_ARG;
   if (set_device(c)) return FLOAM_ERR_CUDA;
   const int slot = c->submit_slot;
   // upload on the copy stream once the FRONT that read this scan buffer two frames ago is done
   if (c->consumed_valid[slot]) FLOAM_CUDA_OK(cudaStreamWaitEvent(c->copy_stream, c->ev_front_done[slot], 0));
-  if (n > 0) FLOAM_CUDA_OK(cudaMemcpyAsync(c->d_scan[slot], pts, (size_t)n * 32, cudaMemcpyHostToDevice, c->copy_stream));
+  if (raw && n > 0) {
+    const size_t bytes = (size_t)layout->row_step * layout->height;
+    const size_t step = layout->point_step > 64 ? layout->point_step : 64;
+    int rc = raw_reserve(c, bytes > step * c->prm.max_scan_points ? bytes : step * c->prm.max_scan_points);
+    if (rc) return rc;
+    FLOAM_CUDA_OK(cudaMemcpyAsync(c->d_raw[slot], raw, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+    unpack_pointcloud2_device(c->d_raw[slot], *layout, c->d_scan[slot], c->copy_stream);
+  } else if (n > 0) FLOAM_CUDA_OK(cudaMemcpyAsync(c->d_scan[slot], pts, (size_t)n * 32, cudaMemcpyHostToDevice, c->copy_stream));
   c->h_ints[32 + slot] = n;
   FLOAM_CUDA_OK(cudaMemcpyAsync(c->d_scan_n[slot], &c->h_ints[32 + slot], 4, cudaMemcpyHostToDevice, c->copy_stream));
   if (plan) {
@@ -685,6 +713,51 @@ int floam_process_submit_imu(floam_ctx* c, const floam_point_xyzirt* pts, int n,
   *stamp_us = plan.stamp_us_new;
   if (!plan.can_compensate) return FLOAM_NO_IMU;  // "cannot compensate - no IMU data": the node drops the scan (src/laserProcessingNode.cpp:108-112)
   return submit_common(c, pts, n, deskew, &plan);
+}
+
+// the time field of point i of a raw message, read on the host (the deskew plan needs the first and the last point's)
+static float pc2_time_at(const uint8_t* data, const floam_pc2_layout* L, long long i) {
+  if (L->off_time < 0) return 0.f;
+  const uint8_t* p = data + (size_t)(i / L->width) * L->row_step + (size_t)(i % L->width) * L->point_step + L->off_time;
+  uint32_t u = L->is_bigendian ? ((uint32_t)p[0] << 24 | (uint32_t)p[1] << 16 | (uint32_t)p[2] << 8 | p[3])
+                               : ((uint32_t)p[3] << 24 | (uint32_t)p[2] << 16 | (uint32_t)p[1] << 8 | p[0]);
+  float f;
+  std::memcpy(&f, &u, 4);
+  return f;
+}
+
+int floam_process_submit_pc2(floam_ctx* c, const uint8_t* data, const floam_pc2_layout* layout, uint64_t* stamp_us, const double extr_xyzw[4], int deskew) {
+  long long n = 0;
+  if (!c || !data || (stamp_us == nullptr) != (extr_xyzw == nullptr)) return FLOAM_ERR_ARG;
+  int rc = pc2_layout_check(layout, &n);
+  if (rc) return rc;
+  if (n > c->prm.max_scan_points) return FLOAM_ERR_CAPACITY;
+  if (n < 1) return FLOAM_ERR_ARG;
+  if (!stamp_us) return submit_common(c, nullptr, (int)n, deskew, nullptr, data, layout);
+  DeskewPlan plan;
+  deskew_plan(c->imu, *stamp_us, pc2_time_at(data, layout, 0), pc2_time_at(data, layout, n - 1), extr_xyzw,
+              FLOAM_DESKEW_CENTER_TIME | FLOAM_DESKEW_COMPENSATE | FLOAM_DESKEW_ALIGN, &plan);
+  *stamp_us = plan.stamp_us_new;
+  if (!plan.can_compensate) return FLOAM_NO_IMU;
+  return submit_common(c, nullptr, (int)n, deskew, &plan, data, layout);
+}
+
+int floam_unpack_pointcloud2(floam_ctx* c, const uint8_t* data, const floam_pc2_layout* layout, floam_point_xyzirt* out) {
+  long long n = 0;
+  if (!c || !data || !out || c->inflight != 0) return FLOAM_ERR_ARG;
+  int rc = pc2_layout_check(layout, &n);
+  if (rc) return rc;
+  if (n > c->prm.max_scan_points) return FLOAM_ERR_CAPACITY;
+  if (n < 1) return FLOAM_OK;
+  if (set_device(c)) return FLOAM_ERR_CUDA;
+  const size_t bytes = (size_t)layout->row_step * layout->height;
+  const size_t step = layout->point_step > 64 ? layout->point_step : 64;
+  if ((rc = raw_reserve(c, bytes > step * c->prm.max_scan_points ? bytes : step * c->prm.max_scan_points))) return rc;
+  FLOAM_CUDA_OK(cudaMemcpyAsync(c->d_raw[0], data, bytes, cudaMemcpyHostToDevice, c->stream));
+  unpack_pointcloud2_device(c->d_raw[0], *layout, c->d_scan[0], c->stream);
+  FLOAM_CUDA_OK(cudaMemcpyAsync(out, c->d_scan[0], (size_t)n * 32, cudaMemcpyDeviceToHost, c->stream));
+  FLOAM_CUDA_OK(cudaStreamSynchronize(c->stream));
+  return check_async("unpack_pointcloud2");
 }
 
 int floam_process_scan_imu(floam_ctx* c, const floam_point_xyzirt* pts, int n, uint64_t* stamp_us, const double extr_xyzw[4], int deskew, double pose_out[7]) {

@@ -69,6 +69,7 @@ enum KernelSlot {
   K_CROP_FLAGS,
   K_CROP_SCATTER,
   K_RECORD_POSE,
+  K_UNPACK_PC2,
   K_NOOP,
   K_NUM_SLOTS
 };

@@ -43,6 +43,8 @@ struct floam_ctx {
 
   // scan + features (device)
   floam::PointIRT* d_scan[2] = {nullptr, nullptr};  // double-buffered upload target
+  unsigned char* d_raw[2] = {nullptr, nullptr};     // raw PointCloud2 bytes (floam_process_submit_pc2), allocated on first use
+  size_t raw_cap = 0;
   int* d_scan_n[2] = {nullptr, nullptr};
   // feature clouds: two buffer sets (frame parity); the unsuffixed names alias the set of the frame being enqueued / last completed
   floam::PointIRT *d_edge = nullptr, *d_surf = nullptr;

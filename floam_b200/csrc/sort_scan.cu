@@ -57,6 +57,7 @@ static const char* const kSlotNames[K_NUM_SLOTS] = {
   "crop_flags",
   "crop_scatter",
   "record_pose",
+  "unpack_pc2",
   "noop"
 };
 const char* kernel_slot_name(int slot) { return (slot >= 0 && slot < K_NUM_SLOTS) ? kSlotNames[slot] : "?"; }

@@ -14,6 +14,7 @@
 #include <Eigen/Dense>
 #include <Eigen/Geometry>
 #include <sensor_msgs/Imu.h>
+#include <sensor_msgs/PointCloud2.h>
 #else
 namespace Eigen {
 struct Vector3d {
@@ -77,6 +78,23 @@ struct PointCloud {
 }  // namespace pcl
 
 namespace sensor_msgs {
+struct PointField {
+  enum { INT8 = 1, UINT8 = 2, INT16 = 3, UINT16 = 4, INT32 = 5, UINT32 = 6, FLOAT32 = 7, FLOAT64 = 8 };
+  std::string name;
+  std::uint32_t offset = 0;
+  std::uint8_t datatype = 0;
+  std::uint32_t count = 1;
+};
+struct PointCloud2 {
+  struct { struct { double t = 0; double toSec() const { return t; } } stamp; std::string frame_id; } header;
+  std::uint32_t height = 1, width = 0;
+  std::vector<PointField> fields;
+  bool is_bigendian = false;
+  std::uint32_t point_step = 0, row_step = 0;
+  std::vector<std::uint8_t> data;
+  bool is_dense = true;
+  typedef std::shared_ptr<const PointCloud2> ConstPtr;
+};
 struct Imu {
   struct { struct { double t = 0; double toSec() const { return t; } } stamp; } header;
   struct { double x = 0, y = 0, z = 0, w = 0; } orientation;  // default message: all-zero quaternion

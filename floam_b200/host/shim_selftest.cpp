@@ -7,6 +7,8 @@
 #include "laserMappingClass.h"
 #include "laserProcessingClass.h"
 #include "odomEstimationClass.h"
+#include "pointCloud2Adapter.h"
+#include <cstring>
 
 static pcl::PointCloud<vel_point::PointXYZIRT>::Ptr make_scan(double shift) {
   pcl::PointCloud<vel_point::PointXYZIRT>::Ptr c(new pcl::PointCloud<vel_point::PointXYZIRT>());
@@ -23,6 +25,27 @@ static pcl::PointCloud<vel_point::PointXYZIRT>::Ptr make_scan(double shift) {
       c->push_back(p);
     }
   return c;
+}
+
+// the message the Velodyne driver would publish for a scan: XYZIRT, 22 bytes per point
+static sensor_msgs::PointCloud2 to_msg(const pcl::PointCloud<vel_point::PointXYZIRT>& c, double stamp) {
+  sensor_msgs::PointCloud2 m;
+  m.header.stamp.t = stamp;
+  m.width = (std::uint32_t)c.size(); m.height = 1; m.point_step = 22; m.row_step = m.width * 22; m.is_bigendian = false;
+  const char* names[6] = {"x", "y", "z", "intensity", "ring", "time"};
+  const std::uint32_t offs[6] = {0, 4, 8, 12, 16, 18};
+  for (int k = 0; k < 6; ++k) {
+    sensor_msgs::PointField f;
+    f.name = names[k]; f.offset = offs[k]; f.datatype = k == 4 ? sensor_msgs::PointField::UINT16 : sensor_msgs::PointField::FLOAT32;
+    m.fields.push_back(f);
+  }
+  m.data.resize((size_t)m.row_step);
+  for (size_t i = 0; i < c.size(); ++i) {
+    std::uint8_t* p = m.data.data() + i * 22;
+    std::memcpy(p, &c.points[i].x, 4); std::memcpy(p + 4, &c.points[i].y, 4); std::memcpy(p + 8, &c.points[i].z, 4);
+    std::memcpy(p + 12, &c.points[i].intensity, 4); std::memcpy(p + 16, &c.points[i].ring, 2); std::memcpy(p + 18, &c.points[i].time, 4);
+  }
+  return m;
 }
 
 int main() {
@@ -61,6 +84,22 @@ int main() {
   std::printf("local map %zu points, global map %zu points\n", local->size(), global->size());
   const double x = odomEstimation.odom.translation().x();
   if (!(std::fabs(x - 0.2) < 0.05) || local->size() == 0 || global->size() == 0) { std::printf("shim_selftest: FAILED\n"); return 1; }
+  // the same five scans as PointCloud2 messages through the fused node adapter (own context): same kernels, same pose
+  floam_b200_host::FloamContext fused;
+  fused.prm = shared.prm;
+  fused.set_lidar(lidar_param);
+  fused.ensure();
+  if (!fused.ctx) { std::printf("shim_selftest: FAILED (second context)\n"); return 1; }
+  floam_b200_host::FusedOdometryNode node(fused.ctx, false, false, Eigen::Quaterniond(1, 0, 0, 0));
+  std::vector<sensor_msgs::PointCloud2> msgs;
+  for (int f = 0; f < 5; ++f) msgs.push_back(to_msg(*make_scan(0.05 * f), 0.1 * f));
+  double pose[7] = {0, 0, 0, 1, 0, 0, 0};
+  bool have = false;
+  for (int f = 0; f < 5; ++f)
+    if (node.velodyneHandler(msgs[f], pose, &have) != FLOAM_OK) { std::printf("shim_selftest: FAILED (fused submit %d)\n", f); return 1; }
+  while (node.flush(pose) == FLOAM_OK) {}
+  std::printf("fused PointCloud2 path: t = %.4f %.4f %.4f\n", pose[4], pose[5], pose[6]);
+  if (!(std::fabs(pose[4] - x) < 1e-9)) { std::printf("shim_selftest: FAILED (fused path differs: %.17g vs %.17g)\n", pose[4], x); return 1; }
   std::printf("shim_selftest: ok\n");
   return 0;
 }

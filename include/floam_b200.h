@@ -140,6 +140,25 @@ int floam_process_wait(floam_ctx* ctx, double pose_out[7]);
 int floam_process_submit_imu(floam_ctx* ctx, const floam_point_xyzirt* pts, int n, uint64_t* stamp_us, const double extrinsics_xyzw[4], int deskew);
 int floam_process_scan_imu(floam_ctx* ctx, const floam_point_xyzirt* pts, int n, uint64_t* stamp_us, const double extrinsics_xyzw[4], int deskew,
                            double pose_out[7]);
+/* sensor_msgs/PointCloud2 ingestion: what pcl::fromROSMsg(*msg, *pointcloud_in) does on the host in the reference
+ * (src/laserProcessingNode.cpp:98).  The raw message bytes (msg.data, row_step * height of them) are uploaded as they are — 22 bytes
+ * per point for the Velodyne driver's XYZIRT layout instead of 32 — and re-packed into floam_point_xyzirt on the device.
+ * off_* = byte offset inside a point of the message field with that NAME and the registered DATATYPE (FLOAT32; UINT16 for ring:
+ * include/lidar.h:25-31), or -1 when the message has no such field; like fromROSMsg, an unmatched field stays 0. */
+typedef struct floam_pc2_layout {
+  uint32_t width, height;   /* msg.width, msg.height: n = width * height points */
+  uint32_t point_step;      /* msg.point_step */
+  uint32_t row_step;        /* msg.row_step (>= width * point_step) */
+  int32_t off_x, off_y, off_z, off_intensity, off_ring, off_time;
+  int32_t is_bigendian;     /* msg.is_bigendian */
+} floam_pc2_layout;
+/* stage entry point: unpack only (out has width * height elements) */
+int floam_unpack_pointcloud2(floam_ctx* ctx, const uint8_t* data, const floam_pc2_layout* layout, floam_point_xyzirt* out);
+/* floam_process_submit / floam_process_submit_imu fed with the raw message. stamp_us and extrinsics_xyzw are either both NULL
+ * (no IMU steps) or both given (CenterTime + Compensate + alignment as in floam_process_submit_imu; FLOAM_NO_IMU drops the scan).
+ * data must stay valid until the matching floam_process_wait returns. */
+int floam_process_submit_pc2(floam_ctx* ctx, const uint8_t* data, const floam_pc2_layout* layout, uint64_t* stamp_us,
+                             const double extrinsics_xyzw[4], int deskew);
 /* Device-resident replay for kernel-only timing: the scans already sit in HBM (uploaded once with floam_stage_scans). */
 int floam_stage_scans(floam_ctx* ctx, const floam_point_xyzirt* pts, const int64_t* offsets, int n_frames);
 int floam_process_staged(floam_ctx* ctx, int frame, int deskew, double pose_out[7]);

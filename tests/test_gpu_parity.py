@@ -417,6 +417,49 @@ def test_all_entry_paths_give_identical_poses(capi, synth, sequences):
     assert np.array_equal(A, np.array(E))
 
 
+def test_pointcloud2_ingestion(capi, synth, sequences):
+    # pcl::fromROSMsg on the device (src/laserProcessingNode.cpp:98): raw message bytes -> PointXYZIRT, bit-exact against a numpy unpack,
+    # for the Velodyne 22-byte layout, a padded 48-byte layout with shuffled fields and row padding, big-endian data and missing fields
+    seq, scans, off = sequences("vlp16", 6)
+    pts = scans[off[0]:off[1]]
+    n = len(pts) - len(pts) % 16
+    pts = pts[:n]
+    ctx = fresh(capi, 16)
+    expect = np.zeros(n, capi.POINT_IRT)
+    for k in ("x", "y", "z", "intensity", "ring", "time"):
+        expect[k] = pts[k]
+    layouts = [capi.pc2_layout(n, 22),
+               capi.pc2_layout(n, 48, x=16, y=20, z=24, intensity=4, ring=10, time=40, height=16, row_step=(n // 16) * 48 + 20),
+               capi.pc2_layout(n, 26, x=1, y=5, z=9, intensity=13, ring=17, time=21, bigendian=True)]
+    for L in layouts:
+        raw = capi.pack_pointcloud2(pts, L)
+        out = ctx.unpack_pointcloud2(raw, L)
+        assert out.tobytes() == expect.tobytes()
+    L = capi.pc2_layout(n, 22, time=-1, intensity=-1)        # fields the message does not carry stay zero, like fromROSMsg
+    out = ctx.unpack_pointcloud2(capi.pack_pointcloud2(pts, L), L)
+    e2 = expect.copy(); e2["time"] = 0; e2["intensity"] = 0
+    assert out.tobytes() == e2.tobytes()
+    with pytest.raises(capi.FloamError):                      # a field reaching past point_step is rejected
+        ctx.unpack_pointcloud2(np.zeros(n * 22, np.uint8), capi.pc2_layout(n, 22, time=20))
+    ctx.close()
+    # the fused frame path fed with raw messages gives the poses of the packed-point path, bit for bit
+    a = fresh(capi, 16); b = fresh(capi, 16)
+    raws = []
+    for f in range(6):
+        s = scans[off[f]:off[f + 1]]
+        L = capi.pc2_layout(len(s), 22)
+        raws.append((capi.pack_pointcloud2(s, L), L))
+    Pa = np.array([a.process_scan(scans[off[f]:off[f + 1]]) for f in range(6)])
+    Pb = []
+    for f in range(6):
+        b.process_submit_pc2(raws[f][0], raws[f][1])
+        if f >= 1:
+            Pb.append(b.process_wait())
+    Pb.append(b.process_wait())
+    assert np.array_equal(Pa, np.array(Pb))
+    a.close(); b.close()
+
+
 def test_two_contexts_are_independent_replicas(capi, sequences):
     seq, scans, off = sequences("vlp16", 8)
     a, b = fresh(capi, 16), fresh(capi, 16)
