@@ -157,8 +157,6 @@ __global__ void map_bump_kernel(int* d_nmap, const int* d_nin, int cap, int repl
   if (base + *d_nin <= cap) *d_nmap = base + *d_nin;
 }
 
-// the filtered map goes back into its home buffer (a device-side pointer swap would need every consumer to chase a pointer)
-// — and, since every map point passes through here, this is also where the bounding box of the search grid is accumulated.
 __device__ __forceinline__ void bbox_accumulate(float (&mn)[3], float (&mx)[3], bool any, unsigned int* __restrict__ bbox) {
   if (!__any_sync(0xffffffffu, any)) return;
 #pragma unroll
@@ -177,43 +175,6 @@ __device__ __forceinline__ void bbox_accumulate(float (&mn)[3], float (&mx)[3], 
     }
   }
 }
-__global__ void __launch_bounds__(kThreads) map_commit_kernel(const P4* __restrict__ src, const int* __restrict__ d_n, P4* __restrict__ dst,
-                                                               unsigned int* __restrict__ bbox, const int* d_skip) {
-  pdl_prologue();
-  if (d_skip && *d_skip) return;
-  const int n = *d_n;
-  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-  bool any = false;
-  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
-    const float4 p = __ldg(src + i);
-    dst[i] = p;
-    mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
-    mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
-    any = true;
-  }
-  bbox_accumulate(mn, mx, any, bbox);
-}
-
-// addPointsToMap :256-268: pointAssociateToMap (double transform, float store) and push_back
-__global__ void __launch_bounds__(kThreads) map_append_kernel(const P4* __restrict__ ds, const int* __restrict__ d_nds, P4* __restrict__ map,
-                                                               const int* __restrict__ d_nmap, int cap, PoseState* S, const int* d_skip) {
-  pdl_prologue();
-  if (*d_skip) return;
-  const int nds = *d_nds, base = *d_nmap;
-  if (base + nds > cap) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&S->error_flags, 1);
-    return;
-  }
-  double x[7];
-#pragma unroll
-  for (int k = 0; k < 7; ++k) x[k] = S->x[k];
-  for (int i = blockIdx.x * kThreads + threadIdx.x; i < nds; i += gridDim.x * kThreads) {
-    const float4 p = __ldg(ds + i);
-    const m::V3 w = m::add(m::quat_rotate(x, m::V3{(double)p.x, (double)p.y, (double)p.z}), m::V3{x[4], x[5], x[6]});
-    map[base + i] = make_float4((float)w.x, (float)w.y, (float)w.z, p.w);
-  }
-}
-
 __global__ void __launch_bounds__(kThreads) grid_bbox_kernel(const P4* __restrict__ pts, const int* __restrict__ d_n, unsigned int* __restrict__ bbox,
                                                               const int* d_skip) {
   pdl_prologue();
@@ -277,7 +238,8 @@ __global__ void __launch_bounds__(kThreads) grid_count_kernel(const P4* __restri
 // The order of points inside a cell is arbitrary; the search orders candidates by (distance, index), so results do not depend on it.
 __global__ void __launch_bounds__(kThreads) grid_scatter_kernel(const P4* __restrict__ pts, const int* __restrict__ d_n, const GridDims* __restrict__ dims,
                                                                  const int* __restrict__ cell_start, int* __restrict__ cell_count,
-                                                                 float4* __restrict__ cell_pts, unsigned int* bbox, const int* d_skip) {
+                                                                 float4* __restrict__ cell_pts, unsigned int* bbox, P4* __restrict__ home,
+                                                                 const int* d_skip) {
   pdl_prologue();
   if (d_skip && *d_skip) return;
   if (blockIdx.x == 0 && threadIdx.x == 0) {  // every reader of the bounding box (grid_count_kernel) is done: re-arm it for the next build
@@ -285,10 +247,13 @@ __global__ void __launch_bounds__(kThreads) grid_scatter_kernel(const P4* __rest
     bbox[3] = bbox[4] = bbox[5] = 0u;
   }
   const GridDims g = *dims;
-  if (g.ncells == 0) return;
   const int n = *d_n;
+  // home (optional): pts is the filter's output buffer; every point passes through here, so this is also where the cloud goes back
+  // into the map's home buffer (a device-side pointer swap would need every consumer to chase a pointer)
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
     const float4 p = __ldg(pts + i);
+    if (home) home[i] = p;
+    if (g.ncells == 0) continue;
     const int c = cell_of(g, p.x, p.y, p.z);
     const int pos = cell_start[c] + atomicSub(&cell_count[c], 1) - 1;
     cell_pts[pos] = make_float4(p.x, p.y, p.z, __int_as_float(i));
@@ -1095,14 +1060,17 @@ __global__ void __launch_bounds__(kThreads) compensate_velocity_explicit_kernel(
 
 int* dims_ncells_ptr(GridDims* dims) { return reinterpret_cast<int*>(reinterpret_cast<char*>(dims) + offsetof(GridDims, ncells)); }
 
-// bbox_ready: the producer of map.pts (map_commit_kernel) has already accumulated the bounding box
-void rebuild_grid(OdomDevice& od, LocalMap& map, const int* d_skip, cudaStream_t s, VoxelWorkspace* ws = nullptr, bool bbox_ready = false) {
+// from_tmp: the cloud sits in map.tmp (output of the keyframe filter, which has also accumulated its bounding box); the scatter kernel
+// copies it home into map.pts on the way
+void rebuild_grid(OdomDevice& od, LocalMap& map, const int* d_skip, cudaStream_t s, VoxelWorkspace* ws = nullptr, bool from_tmp = false) {
   if (!ws) ws = od.vws;
   const int g = grid_for(map.cap);
-  if (!bbox_ready) FLOAM_LAUNCH(K_GRID_BBOX, grid_bbox_kernel, g, kThreads, s, map.pts, map.d_n, map.bbox, d_skip);
-  FLOAM_LAUNCH(K_GRID_COUNT, grid_count_kernel, g, kThreads, s, map.pts, map.d_n, map.bbox, map.dims, map.ncells_cap, od.state, map.cell_count, d_skip);
+  const P4* src = from_tmp ? map.tmp : map.pts;
+  if (!from_tmp) FLOAM_LAUNCH(K_GRID_BBOX, grid_bbox_kernel, g, kThreads, s, map.pts, map.d_n, map.bbox, d_skip);
+  FLOAM_LAUNCH(K_GRID_COUNT, grid_count_kernel, g, kThreads, s, src, map.d_n, map.bbox, map.dims, map.ncells_cap, od.state, map.cell_count, d_skip);
   exclusive_scan_i32(map.cell_count, map.cell_start, dims_ncells_ptr(map.dims), 0, map.ncells_cap, ws->scan, d_skip, s);
-  FLOAM_LAUNCH(K_GRID_SCATTER, grid_scatter_kernel, g, kThreads, s, map.pts, map.d_n, map.dims, map.cell_start, map.cell_count, map.cell_pts, map.bbox, d_skip);
+  FLOAM_LAUNCH(K_GRID_SCATTER, grid_scatter_kernel, g, kThreads, s, src, map.d_n, map.dims, map.cell_start, map.cell_count, map.cell_pts, map.bbox,
+               from_tmp ? map.pts : (P4*)nullptr, d_skip);
 }
 
 }  // namespace
@@ -1227,11 +1195,11 @@ void odom_update_device(OdomDevice& od, const void* d_edge, const int* d_ne, con
     LocalMap& mp = *maps[k];
     cudaStream_t st = k == 0 ? s : a;
     VoxelWorkspace& ws = k == 0 ? *od.vws : *od.vws_aux;
-    FLOAM_LAUNCH(K_MAP_APPEND, map_append_kernel, grid_for(od.qcap), kThreads, st, dss[k], nds[k], mp.pts, mp.d_n, mp.cap, S, skip);
-    // CropBox (:270-287) is folded into the VoxelGrid (:289-292); the appended points are counted in by the filter (no separate
-    // size bump). The filter gathers from mp.pts through the sorted index and writes mp.tmp; the two buffers then swap roles.
-    voxel_grid_device(mp.pts, 16, mp.d_n, mp.cap, leaf[k], mp.tmp, mp.d_n, ws, skip, st, S->crop_bounds, nds[k], mp.cap);
-    FLOAM_LAUNCH(K_MAP_COMMIT, map_commit_kernel, grid_for(mp.cap), kThreads, st, mp.tmp, mp.d_n, mp.pts, mp.bbox, skip);
+    // One filter does it all: its first kernel appends the transformed features (:256-268) while it takes the bounding box, CropBox
+    // (:270-287) is folded into the VoxelGrid (:289-292), and its last kernel leaves the bounding box of the new map for the search
+    // grid. The filter gathers from mp.pts through the sorted index into mp.tmp; the grid's scatter kernel copies the cloud home.
+    const VoxelAppend app{dss[k], S->x, &S->error_flags};
+    voxel_grid_device(mp.pts, 16, mp.d_n, mp.cap, leaf[k], mp.tmp, mp.d_n, ws, skip, st, S->crop_bounds, nds[k], mp.cap, &app, mp.bbox);
     rebuild_grid(od, mp, skip, st, &ws, true);
   }
   cudaEventRecord(od.ev_join, a);

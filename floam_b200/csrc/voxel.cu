@@ -6,6 +6,8 @@
 // Appendix A.2): predicate -> scan -> order-preserving scatter.
 #include "voxel.cuh"
 
+#include "odom_math.cuh"
+
 namespace floam {
 namespace {
 
@@ -33,17 +35,35 @@ __device__ __forceinline__ int total_count(const int* __restrict__ d_n, const in
 }
 
 // counts[0] = points in the input (incl. d_extra), counts[1] = points kept by the crop (== counts[0] without a crop box)
-__global__ void __launch_bounds__(kThreads) voxel_bbox_kernel(const char* __restrict__ in, int stride, const int* __restrict__ d_n,
+__global__ void __launch_bounds__(kThreads) voxel_bbox_kernel(const char* in, int stride, const int* __restrict__ d_n,
                                                                const int* __restrict__ d_extra, int cap, const float* __restrict__ crop,
-                                                               unsigned int* __restrict__ bbox, int* __restrict__ counts, const int* d_skip) {
+                                                               unsigned int* __restrict__ bbox, int* __restrict__ counts, VoxelAppend app,
+                                                               const int* d_skip) {
   pdl_prologue();
   if (d_skip && *d_skip) return;
   const int n = total_count(d_n, d_extra, cap);
-  if (blockIdx.x == 0 && threadIdx.x == 0) counts[0] = n;
+  const int n_old = *d_n;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    counts[0] = n;
+    if (app.src && n_old + *d_extra > cap) atomicOr(app.err_flags, 1);   // the new points do not fit: they are dropped, the flag is sticky
+  }
+  double x[7];
+  if (app.src) {
+#pragma unroll
+    for (int k = 0; k < 7; ++k) x[k] = app.pose7[k];
+  }
   float mn[3] = {3.402823466e38f, 3.402823466e38f, 3.402823466e38f}, mx[3] = {-3.402823466e38f, -3.402823466e38f, -3.402823466e38f};
   int kept = 0;
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
-    const float4 p = load_xyzi(in, stride, i);
+    float4 p;
+    if (app.src && i >= n_old) {   // addPointsToMap :256-268: pointAssociateToMap (double transform, float store) and push_back
+      const float4 q = __ldg(app.src + (i - n_old));
+      const m::V3 w = m::add(m::quat_rotate(x, m::V3{(double)q.x, (double)q.y, (double)q.z}), m::V3{x[4], x[5], x[6]});
+      p = make_float4((float)w.x, (float)w.y, (float)w.z, q.w);
+      *reinterpret_cast<float4*>(const_cast<char*>(in) + (size_t)i * stride) = p;   // stride is 16 for the map clouds
+    } else {
+      p = load_xyzi(in, stride, i);
+    }
     if (crop && crop_out(p, crop)) continue;
     ++kept;
     mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
@@ -178,11 +198,13 @@ constexpr int kShortRun = 32;
 constexpr int kStage = 256;
 __global__ void __launch_bounds__(kThreads) voxel_reduce_kernel(const char* __restrict__ in, int stride, const int* __restrict__ vals,
                                                                  const int* __restrict__ head_pos, const int* __restrict__ d_nout, P4* __restrict__ out,
-                                                                 unsigned int* bbox, int* counts, const int* d_skip) {
+                                                                 unsigned int* bbox, int* counts, unsigned int* out_bbox, const int* d_skip) {
   pdl_prologue();
   if (d_skip && *d_skip) return;
   __shared__ float4 s_stage[kThreads / 32][kStage];
   const int nv = *d_nout;
+  float omn[3] = {3.402823466e38f, 3.402823466e38f, 3.402823466e38f}, omx[3] = {-3.402823466e38f, -3.402823466e38f, -3.402823466e38f};
+  bool wrote = false;
   if (blockIdx.x == 0 && threadIdx.x == 0) {  // last kernel of the filter: re-arm the accumulators for the next one
     bbox[0] = bbox[1] = bbox[2] = 0xffffffffu;
     bbox[3] = bbox[4] = bbox[5] = 0u;
@@ -205,7 +227,11 @@ __global__ void __launch_bounds__(kThreads) voxel_reduce_kernel(const char* __re
         if (idx[u] >= 0) { sx = fadd(sx, p[u].x); sy = fadd(sy, p[u].y); sz = fadd(sz, p[u].z); si = fadd(si, p[u].w); }
     }
     const float cnt = (float)(e - b);
-    out[v] = make_float4(__fdiv_rn(sx, cnt), __fdiv_rn(sy, cnt), __fdiv_rn(sz, cnt), __fdiv_rn(si, cnt));
+    const float4 c = make_float4(__fdiv_rn(sx, cnt), __fdiv_rn(sy, cnt), __fdiv_rn(sz, cnt), __fdiv_rn(si, cnt));
+    out[v] = c;
+    omn[0] = fminf(omn[0], c.x); omn[1] = fminf(omn[1], c.y); omn[2] = fminf(omn[2], c.z);
+    omx[0] = fmaxf(omx[0], c.x); omx[1] = fmaxf(omx[1], c.y); omx[2] = fmaxf(omx[2], c.z);
+    wrote = true;
   }
   const int w = warp_id(), l = lane_id();
   const int warps_total = gridDim.x * (kThreads / 32);
@@ -233,7 +259,29 @@ __global__ void __launch_bounds__(kThreads) voxel_reduce_kernel(const char* __re
     }
     if (l == 0) {
       const float cnt = (float)(e - b);
-      out[v] = make_float4(__fdiv_rn(sx, cnt), __fdiv_rn(sy, cnt), __fdiv_rn(sz, cnt), __fdiv_rn(si, cnt));
+      const float4 c = make_float4(__fdiv_rn(sx, cnt), __fdiv_rn(sy, cnt), __fdiv_rn(sz, cnt), __fdiv_rn(si, cnt));
+      out[v] = c;
+      omn[0] = fminf(omn[0], c.x); omn[1] = fminf(omn[1], c.y); omn[2] = fminf(omn[2], c.z);
+      omx[0] = fmaxf(omx[0], c.x); omx[1] = fmaxf(omx[1], c.y); omx[2] = fmaxf(omx[2], c.z);
+      wrote = true;
+    }
+  }
+  // bounding box of the output cloud for the caller's search grid (only warps that produced a centroid vote)
+  if (out_bbox && __any_sync(0xffffffffu, wrote)) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        omn[a] = fminf(omn[a], __shfl_xor_sync(0xffffffffu, omn[a], o));
+        omx[a] = fmaxf(omx[a], __shfl_xor_sync(0xffffffffu, omx[a], o));
+      }
+    }
+    if (l == 0) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        atomicMin(&out_bbox[a], float_flip(omn[a]));
+        atomicMax(&out_bbox[3 + a], float_flip(omx[a]));
+      }
     }
   }
 }
@@ -337,13 +385,15 @@ int voxel_workspace_arm(VoxelWorkspace& ws, cudaStream_t s) {
 }
 
 void voxel_grid_device(const void* d_in, int stride_bytes, const int* d_n, int n_max, float leaf, P4* d_out, int* d_nout, VoxelWorkspace& ws,
-                       const int* d_skip, cudaStream_t s, const float* d_crop, const int* d_extra, int cap) {
+                       const int* d_skip, cudaStream_t s, const float* d_crop, const int* d_extra, int cap, const VoxelAppend* append,
+                       unsigned int* out_bbox) {
+  const VoxelAppend app = append ? *append : VoxelAppend{nullptr, nullptr, nullptr};
   if (n_max > ws.n_max) n_max = ws.n_max;
   const char* in = (const char*)d_in;
   const int g = grid_for(n_max);
   const int gt = (n_max + kScanTile - 1) / kScanTile;
   int* counts = ws.d_counts;   // [0] input points, [1] points kept by the crop
-  FLOAM_LAUNCH(K_VOXEL_BBOX, voxel_bbox_kernel, g, kThreads, s, in, stride_bytes, d_n, d_extra, cap, d_crop, ws.bbox, counts, d_skip);
+  FLOAM_LAUNCH(K_VOXEL_BBOX, voxel_bbox_kernel, g, kThreads, s, in, stride_bytes, d_n, d_extra, cap, d_crop, ws.bbox, counts, app, d_skip);
   FLOAM_LAUNCH(K_VOXEL_KEYS, voxel_keys_kernel, g, kThreads, s, in, stride_bytes, counts, leaf, d_crop, ws.bbox, ws.keys, ws.vals, ws.d_nbits, ws.d_passthrough,
                d_skip);
   unsigned int* skeys = nullptr;
@@ -351,7 +401,7 @@ void voxel_grid_device(const void* d_in, int stride_bytes, const int* d_n, int n
   radix_sort_pairs(ws.keys, ws.vals, counts, ws.d_nbits, n_max, ws.sort, d_skip, s, &skeys, &svals);
   FLOAM_LAUNCH(K_VOXEL_HEADS, voxel_heads_kernel, gt, kScanThreads, s, skeys, counts + 1, ws.scan.block_sums, d_skip);
   FLOAM_LAUNCH(K_VOXEL_RANK, voxel_rank_kernel, gt, kScanThreads, s, skeys, counts + 1, ws.scan.block_sums, ws.flags, d_nout, d_skip);
-  FLOAM_LAUNCH(K_VOXEL_REDUCE, voxel_reduce_kernel, g, kThreads, s, in, stride_bytes, svals, ws.flags, d_nout, d_out, ws.bbox, counts, d_skip);
+  FLOAM_LAUNCH(K_VOXEL_REDUCE, voxel_reduce_kernel, g, kThreads, s, in, stride_bytes, svals, ws.flags, d_nout, d_out, ws.bbox, counts, out_bbox, d_skip);
 }
 
 void repack_xyzi_device(const void* d_in32, const int* d_n, int n_max, P4* d_out, cudaStream_t s) {

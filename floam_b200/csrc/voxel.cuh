@@ -27,8 +27,18 @@ int voxel_workspace_arm(VoxelWorkspace& ws, cudaStream_t s);
 // d_skip (optional): when *d_skip != 0 every kernel returns immediately (device-side "not a keyframe").
 // d_crop (optional, 6 floats on the device: min xyz, max xyz): pcl::CropBox folded in — points outside the inclusive box are ignored,
 // exactly as if CropBox::filter had run first. d_extra / cap: the input holds *d_n + *d_extra points when that fits into cap.
+// append (optional; addPointsToMap :256-268 folded into the first kernel of the filter): the *d_extra points are not in the input yet —
+// the bounding-box kernel reads them from append->src, applies pointAssociateToMap (double q * p + t, float store) with the pose
+// at append->pose7 and stores them at d_in[*d_n ...] on the way. When they do not fit into cap, bit 0 of *append->err_flags is set.
+// out_bbox (optional): flipped-float min/max accumulators that receive the bounding box of the OUTPUT cloud (the search grid's extent).
+struct VoxelAppend {
+  const P4* src;
+  const double* pose7;   // qx qy qz qw tx ty tz on the device
+  int* err_flags;
+};
 void voxel_grid_device(const void* d_in, int stride_bytes, const int* d_n, int n_max, float leaf, P4* d_out, int* d_nout, VoxelWorkspace& ws,
-                       const int* d_skip, cudaStream_t s, const float* d_crop = nullptr, const int* d_extra = nullptr, int cap = 0);
+                       const int* d_skip, cudaStream_t s, const float* d_crop = nullptr, const int* d_extra = nullptr, int cap = 0,
+                       const VoxelAppend* append = nullptr, unsigned int* out_bbox = nullptr);
 
 // pcl::CropBox<PointXYZI>::filter, identity transform, negative=false, inclusive float bounds read from device memory
 // (d_bounds: min xyz, max xyz). Order-preserving compaction.
