@@ -18,7 +18,7 @@ OK, ERR_NO_DEVICE, ERR_CUDA, ERR_CAPACITY, ERR_ARG, NO_IMU, ERR_NONFINITE = rang
 LOSS_TRIVIAL, LOSS_HUBER, LOSS_CAUCHY_TRUE = 0, 1, 2
 VANILLA, INITIAL_ITERATION, REFINEMENT_AND_UPDATE = 0, 1, 2
 (DBG_DS_EDGE, DBG_DS_SURF, DBG_EDGE_KNN, DBG_SURF_KNN, DBG_EDGE_D2, DBG_SURF_D2, DBG_EDGE_OK, DBG_SURF_OK, DBG_RESIDUALS, DBG_LM,
- DBG_SCALARS, DBG_FEATURE_SRC_EDGE, DBG_FEATURE_SRC_SURF, DBG_CLOCKS) = range(14)
+ DBG_SCALARS, DBG_FEATURE_SRC_EDGE, DBG_FEATURE_SRC_SURF, DBG_CLOCKS, DBG_TIMELINE) = range(15)
 
 
 class Params(C.Structure):

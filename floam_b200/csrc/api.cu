@@ -140,7 +140,7 @@ void enqueue_back(floam_ctx* c, int deskew, int slot, bool first) {
     enqueue_selector(c, c->d_edge, c->d_ne, c->d_surf, c->d_ns, c->prm.max_scan_points, deskew, !deskew);
   }
   if (c->timer.enabled) launch_noop(c->stream);   // calibration of the event-pair overhead (kernel-timing mode only)
-  fetch_state(c, slot);
+  odom_mail_state(c->odom, c->d_flags, c->h_state[slot], c->h_flags[slot], c->stream);
 }
 
 // Capture-or-replay of one half. Graphs are keyed by everything that changes the launch sequence or the buffers it touches.
@@ -1016,6 +1016,14 @@ int floam_debug_fetch(floam_ctx* c, int what, void* out, size_t cap_bytes, size_
       if (!out) return FLOAM_OK;
       if (*n_bytes > cap_bytes) return FLOAM_ERR_CAPACITY;
       std::memcpy(out, S->dbg_clk, sizeof(S->dbg_clk));
+      return FLOAM_OK;
+    }
+    case FLOAM_DBG_TIMELINE: {
+      long long tl[8] = {S->tl_sum[0], S->tl_sum[1], S->tl_sum[2], S->tl_sum[3], S->tl_predict, S->tl_finish, S->tl_end[0], S->tl_end[1]};
+      *n_bytes = sizeof(tl);
+      if (!out) return FLOAM_OK;
+      if (*n_bytes > cap_bytes) return FLOAM_ERR_CAPACITY;
+      std::memcpy(out, tl, sizeof(tl));
       return FLOAM_OK;
     }
     case FLOAM_DBG_FEATURE_SRC_EDGE: return copy_dev(c->d_edge_src, (size_t)ne * 4);

@@ -66,9 +66,23 @@ __global__ void state_init_kernel(PoseState* S) {
 }
 
 // updatePointsToMap :62-71. The motion prediction is unconditional (Q2).
+__device__ __forceinline__ long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return (long long)t;
+}
+
 __global__ void predict_kernel(PoseState* S, const int* n_edge_map, const int* n_surf_map) {
   pdl_prologue();
   if (threadIdx.x != 0) return;
+  {
+    const long long now = global_ns();
+    if (S->tl_predict != 0 && S->tl_end[0] != 0) {
+      const long long end = S->tl_end[0] > S->tl_end[1] ? S->tl_end[0] : S->tl_end[1];
+      S->tl_sum[0] += end - S->tl_predict; S->tl_sum[1] += now - end; S->tl_sum[2] += S->tl_finish - S->tl_predict; S->tl_sum[3] += 1;
+    }
+    S->tl_predict = now; S->tl_end[0] = S->tl_end[1] = 0;
+  }
   double inv[12], rel[12], pred[12];
   m::iso_inverse(S->last_odom, inv);
   m::iso_mul(inv, S->odom, rel);
@@ -92,6 +106,7 @@ __global__ void predict_kernel(PoseState* S, const int* n_edge_map, const int* n
 __global__ void finish_kernel(PoseState* S, int update_type, double scan_period, double* traj, int traj_cap) {
   pdl_prologue();
   if (threadIdx.x != 0) return;
+  S->tl_finish = global_ns();
   double R[9];
   m::quat_to_matrix(S->x, R);
   for (int i = 0; i < 9; ++i) S->odom[i] = R[i];
@@ -239,9 +254,10 @@ __global__ void __launch_bounds__(kThreads) grid_count_kernel(const P4* __restri
 __global__ void __launch_bounds__(kThreads) grid_scatter_kernel(const P4* __restrict__ pts, const int* __restrict__ d_n, const GridDims* __restrict__ dims,
                                                                  const int* __restrict__ cell_start, int* __restrict__ cell_count,
                                                                  float4* __restrict__ cell_pts, unsigned int* bbox, P4* __restrict__ home,
-                                                                 const int* d_skip) {
+                                                                 long long* stamp, const int* d_skip) {
   pdl_prologue();
   if (d_skip && *d_skip) return;
+  if (stamp && blockIdx.x == 0 && threadIdx.x == 0) *stamp = global_ns();
   if (blockIdx.x == 0 && threadIdx.x == 0) {  // every reader of the bounding box (grid_count_kernel) is done: re-arm it for the next build
     bbox[0] = bbox[1] = bbox[2] = 0xffffffffu;
     bbox[3] = bbox[4] = bbox[5] = 0u;
@@ -1062,7 +1078,8 @@ int* dims_ncells_ptr(GridDims* dims) { return reinterpret_cast<int*>(reinterpret
 
 // from_tmp: the cloud sits in map.tmp (output of the keyframe filter, which has also accumulated its bounding box); the scatter kernel
 // copies it home into map.pts on the way
-void rebuild_grid(OdomDevice& od, LocalMap& map, const int* d_skip, cudaStream_t s, VoxelWorkspace* ws = nullptr, bool from_tmp = false) {
+void rebuild_grid(OdomDevice& od, LocalMap& map, const int* d_skip, cudaStream_t s, VoxelWorkspace* ws = nullptr, bool from_tmp = false,
+                  long long* stamp = nullptr) {
   if (!ws) ws = od.vws;
   const int g = grid_for(map.cap);
   const P4* src = from_tmp ? map.tmp : map.pts;
@@ -1070,7 +1087,7 @@ void rebuild_grid(OdomDevice& od, LocalMap& map, const int* d_skip, cudaStream_t
   FLOAM_LAUNCH(K_GRID_COUNT, grid_count_kernel, g, kThreads, s, src, map.d_n, map.bbox, map.dims, map.ncells_cap, od.state, map.cell_count, d_skip);
   exclusive_scan_i32(map.cell_count, map.cell_start, dims_ncells_ptr(map.dims), 0, map.ncells_cap, ws->scan, d_skip, s);
   FLOAM_LAUNCH(K_GRID_SCATTER, grid_scatter_kernel, g, kThreads, s, src, map.d_n, map.dims, map.cell_start, map.cell_count, map.cell_pts, map.bbox,
-               from_tmp ? map.pts : (P4*)nullptr, d_skip);
+               from_tmp ? map.pts : (P4*)nullptr, stamp, d_skip);
 }
 
 }  // namespace
@@ -1146,6 +1163,18 @@ void odom_reset_state(OdomDevice& od, cudaStream_t s) {
   od.optimization_count = 2;
 }
 
+__global__ void mail_state_kernel(const PoseState* __restrict__ S, const int* __restrict__ d_flags, PoseState* h_state, int* h_flags) {
+  pdl_prologue();
+  const unsigned int* src = reinterpret_cast<const unsigned int*>(S);
+  unsigned int* dst = reinterpret_cast<unsigned int*>(h_state);
+  for (int i = threadIdx.x; i < (int)(sizeof(PoseState) / 4); i += blockDim.x) dst[i] = __ldcg(src + i);
+  if (threadIdx.x == 0) *h_flags = *d_flags;
+  __threadfence_system();
+}
+void odom_mail_state(OdomDevice& od, const int* d_flags, PoseState* h_state, int* h_flags, cudaStream_t s) {
+  FLOAM_LAUNCH(K_RECORD_POSE, mail_state_kernel, 1, 128, s, od.state, d_flags, h_state, h_flags);
+}
+
 void odom_record_pose(OdomDevice& od, cudaStream_t s) { FLOAM_LAUNCH(K_RECORD_POSE, record_pose_kernel, 1, 32, s, od.state, od.traj, od.traj_cap); }
 
 void odom_rebuild_grids(OdomDevice& od, cudaStream_t s) {
@@ -1200,7 +1229,7 @@ void odom_update_device(OdomDevice& od, const void* d_edge, const int* d_ne, con
     // grid. The filter gathers from mp.pts through the sorted index into mp.tmp; the grid's scatter kernel copies the cloud home.
     const VoxelAppend app{dss[k], S->x, &S->error_flags};
     voxel_grid_device(mp.pts, 16, mp.d_n, mp.cap, leaf[k], mp.tmp, mp.d_n, ws, skip, st, S->crop_bounds, nds[k], mp.cap, &app, mp.bbox);
-    rebuild_grid(od, mp, skip, st, &ws, true);
+    rebuild_grid(od, mp, skip, st, &ws, true, &S->tl_end[k]);
   }
   cudaEventRecord(od.ev_join, a);
   cudaStreamWaitEvent(s, od.ev_join, 0);

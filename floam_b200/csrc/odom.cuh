@@ -31,6 +31,9 @@ struct PoseState {
   int n_corr;            // accepted correspondences of the last association
   int n_corr_acc;        // accumulator of the running association
   int frame_counter;     // frames completed (index of the next trajectory record)
+  // development aid (FLOAM_DBG_TIMELINE): globaltimer stamps of the BACK half — predict start, finish start, start of the two grid
+  // scatters (its last kernels) — and their running sums: [0] BACK duration, [1] gap between consecutive BACKs, [2] solve part, [3] frames
+  long long tl_predict, tl_finish, tl_end[2], tl_sum[4];
   long long dbg_clk[8];  // clock64 stamps of the last lm_cluster_kernel attempt (development aid, FLOAM_DBG_CLOCKS)
 };
 
@@ -88,6 +91,9 @@ int odom_device_init(OdomDevice& od, const floam_params& prm, VoxelWorkspace* vw
 void odom_reset_state(OdomDevice& od, cudaStream_t s);
 // appends the current pose to the device trajectory log (first frame: the update path does it in its finish kernel)
 void odom_record_pose(OdomDevice& od, cudaStream_t s);
+// End-of-frame mailbox: the state (and the feature-extraction flags word) written straight into pinned, device-mapped host memory by
+// a kernel — posted stores instead of two copy-engine nodes at the tail of the frame graph.
+void odom_mail_state(OdomDevice& od, const int* d_flags, PoseState* h_state, int* h_flags, cudaStream_t s);
 
 // append (replace = 0) or overwrite (replace = 1) a map with a strided device cloud and rebuild its grid
 void local_map_load(OdomDevice& od, LocalMap& map, const void* d_pts, const int* d_n, int stride, int n_max, int replace, cudaStream_t s);

@@ -189,7 +189,8 @@ enum floam_debug_what {
   FLOAM_DBG_LM = 9,                                   /* double[47]: iterations, accepted, initial_cost, final_cost, termination, H0[36], g0[6] */
   FLOAM_DBG_SCALARS = 10,                             /* int[6]: outer_iterations, keyframe, n_ds_edge, n_ds_surf, n_correspondences, solve_skipped */
   FLOAM_DBG_FEATURE_SRC_EDGE = 11, FLOAM_DBG_FEATURE_SRC_SURF = 12, /* int[]: input indices of the last feature extraction's outputs */
-  FLOAM_DBG_CLOCKS = 13                               /* int64[8]: SM clock stamps inside the last solve's final step attempt — profiling aid */
+  FLOAM_DBG_CLOCKS = 13,                              /* int64[8]: SM clock stamps inside the last solve's final step attempt — profiling aid */
+  FLOAM_DBG_TIMELINE = 14                             /* int64[8]: ns sums over frames {pose-dependent half, gap to the next one, solve part, frames} + last stamps — profiling aid */
 };
 int floam_debug_fetch(floam_ctx* ctx, int what, void* out, size_t cap_bytes, size_t* n_bytes);
 

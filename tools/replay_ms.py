@@ -16,3 +16,6 @@ for rep in range(3):
     res.append(ms / n)
     p0 = np.concatenate([p0, p])
 print("ms/frame per third:", np.round(res, 4), " fps:", np.round(1e3 / np.array(res), 1), " pose crc %08x" % (zlib.crc32(p0.tobytes()) & 0xffffffff), " last t", np.round(p0[-1, 4:], 4))
+tl = ctx.debug_fetch(capi.DBG_TIMELINE, np.int64)
+if tl[3] > 0:
+    print("pose-dependent half: %.1f us/frame (solve part %.1f us), gap to the next frame's %.1f us, over %d frames" % (tl[0] / tl[3] / 1e3, tl[2] / tl[3] / 1e3, tl[1] / tl[3] / 1e3, tl[3]))
