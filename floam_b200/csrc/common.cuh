@@ -244,7 +244,8 @@ __device__ __forceinline__ int tile_offset(const int* __restrict__ tile_sums, in
 struct SortWorkspace {
   unsigned int* keys_alt;   // capacity n_max
   int* vals_alt;            // capacity n_max
-  int* hist;                // 2048 * max_blocks digit counts
+  int* hist;                // three digit-count tables (one per pass), table_stride ints apart
+  int table_stride;
   unsigned int* ticket;     // last-CTA-done counter of the count kernel
   int max_blocks;
   int n_max;

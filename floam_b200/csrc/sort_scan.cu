@@ -131,11 +131,38 @@ __device__ __forceinline__ int digit_bits(int nbits) {
   return b < 1 ? 1 : b;
 }
 
-// counts of this tile's digits -> hist. Layout [tile][digit] (direct mode) or [digit][tile], which the last CTA then scans in place.
+// The last CTA to finish (ticket) turns a [digit][tile] count table into exclusive offsets in place: large inputs only.
+__device__ __forceinline__ void scan_table_by_last_cta(int* __restrict__ hist, int total_entries, unsigned int* ticket, int nb, int* s_scan, int& s_last) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == (unsigned int)nb - 1u) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  int carry = 0;
+  for (int base = 0; base < total_entries; base += kSortThreads * 4) {
+    const int i = base + threadIdx.x * 4;
+    int v[4], sum = 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { v[u] = (i + u < total_entries) ? __ldcg(hist + i + u) : 0; sum += v[u]; }
+    int total;
+    int ex = block_excl_scan(sum, s_scan, &total) + carry;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { if (i + u < total_entries) hist[i + u] = ex; ex += v[u]; }
+    carry += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *ticket = 0;
+}
+
+// Pass 0 only: counts of this tile's digits -> hist. Layout [tile][digit] (direct mode) or [digit][tile], which the last CTA then scans
+// in place. The count tables of passes 1 and 2 (hist + table_stride, hist + 2 * table_stride) are filled by the scatter kernel of the
+// pass before them — every key adds itself to the (tile, digit) cell of the position it is written to — so this kernel zeroes this
+// tile's cells in both.
 template <int MAXR>
 __device__ __forceinline__ void radix_hist_body(const unsigned int* __restrict__ keys, const int* __restrict__ d_n,
-                                                                  const int* __restrict__ d_nbits, int pass, int* __restrict__ hist, unsigned int* ticket,
-                                                                  int* s_hist, int* s_scan, int& s_last) {
+                                                                  const int* __restrict__ d_nbits, int pass, int* __restrict__ hist, int table_stride,
+                                                                  unsigned int* ticket, int* s_hist, int* s_scan, int& s_last) {
   const int n = *d_n;
   const int R = MAXR;
   const int tile0 = blockIdx.x * kSortThreads * R;
@@ -158,47 +185,36 @@ __device__ __forceinline__ void radix_hist_body(const unsigned int* __restrict__
   }
   __syncthreads();
   if (nb <= kDirectTiles) {
-    for (int d = threadIdx.x; d < nbins; d += kSortThreads) hist[blockIdx.x * nbins + d] = s_hist[d];
+    for (int d = threadIdx.x; d < nbins; d += kSortThreads) {
+      const int cell = blockIdx.x * nbins + d;
+      hist[cell] = s_hist[d];
+      hist[table_stride + cell] = 0;
+      hist[2 * table_stride + cell] = 0;
+    }
     return;
   }
-  for (int d = threadIdx.x; d < nbins; d += kSortThreads) hist[d * nb + blockIdx.x] = s_hist[d];
-  // large inputs: the last CTA to finish turns the [digit][tile] counts into exclusive offsets (no separate scan launch)
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == (unsigned int)nb - 1u) ? 1 : 0;
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  const int total_entries = nbins * nb;
-  int carry = 0;
-  for (int base = 0; base < total_entries; base += kSortThreads * 4) {
-    const int i = base + threadIdx.x * 4;
-    int v[4], sum = 0;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) { v[u] = (i + u < total_entries) ? __ldcg(hist + i + u) : 0; sum += v[u]; }
-    int total;
-    int ex = block_excl_scan(sum, s_scan, &total) + carry;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) { if (i + u < total_entries) hist[i + u] = ex; ex += v[u]; }
-    carry += total;
-    __syncthreads();
+  for (int d = threadIdx.x; d < nbins; d += kSortThreads) {
+    const int cell = d * nb + blockIdx.x;
+    hist[cell] = s_hist[d];
+    hist[table_stride + cell] = 0;
+    hist[2 * table_stride + cell] = 0;
   }
-  if (threadIdx.x == 0) *ticket = 0;
+  scan_table_by_last_cta(hist, nbins * nb, ticket, nb, s_scan, s_last);
 }
 
 __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const unsigned int* __restrict__ keys, const int* __restrict__ d_n,
-                                                                  const int* __restrict__ d_nbits, int pass, int* __restrict__ hist, unsigned int* ticket,
-                                                                  const int* d_skip) {
+                                                                  const int* __restrict__ d_nbits, int pass, int* __restrict__ hist, int table_stride,
+                                                                  unsigned int* ticket, const int* d_skip) {
   pdl_prologue();
   if (d_skip && *d_skip) return;
   __shared__ int s_hist[kMaxBins];
   __shared__ int s_scan[33];
   __shared__ int s_last;
   switch (sort_rounds(*d_n)) {   // one fully unrolled variant per tile size; the small-input one stays as tight as a fixed-size kernel
-    case 4: radix_hist_body<4>(keys, d_n, d_nbits, pass, hist, ticket, s_hist, s_scan, s_last); break;
-    case 8: radix_hist_body<8>(keys, d_n, d_nbits, pass, hist, ticket, s_hist, s_scan, s_last); break;
-    case 16: radix_hist_body<16>(keys, d_n, d_nbits, pass, hist, ticket, s_hist, s_scan, s_last); break;
-    default: radix_hist_body<32>(keys, d_n, d_nbits, pass, hist, ticket, s_hist, s_scan, s_last); break;
+    case 4: radix_hist_body<4>(keys, d_n, d_nbits, pass, hist, table_stride, ticket, s_hist, s_scan, s_last); break;
+    case 8: radix_hist_body<8>(keys, d_n, d_nbits, pass, hist, table_stride, ticket, s_hist, s_scan, s_last); break;
+    case 16: radix_hist_body<16>(keys, d_n, d_nbits, pass, hist, table_stride, ticket, s_hist, s_scan, s_last); break;
+    default: radix_hist_body<32>(keys, d_n, d_nbits, pass, hist, table_stride, ticket, s_hist, s_scan, s_last); break;
   }
 }
 
@@ -222,11 +238,13 @@ template <int MAXR>
 __device__ __forceinline__ void radix_scatter_body(const unsigned int* __restrict__ keys_in, const int* __restrict__ vals_in,
                                                                      unsigned int* __restrict__ keys_out, int* __restrict__ vals_out,
                                                                      const int* __restrict__ d_n, const int* __restrict__ d_nbits, int pass,
-                                                                     const int* __restrict__ hist, int (*s_cnt)[256], int* s_base, int* s_scan) {
+                                                                     const int* __restrict__ hist, int* __restrict__ hist_next, unsigned int* ticket,
+                                                                     int (*s_cnt)[256], int* s_base, int* s_scan, int& s_last) {
   const int n = *d_n;
   const int R = MAXR;
   const int tile0 = blockIdx.x * kSortThreads * R;
   if (tile0 >= n) return;
+  constexpr int kTileShift = MAXR == 4 ? 10 : MAXR == 8 ? 11 : MAXR == 16 ? 12 : 13;   // log2(kSortThreads * MAXR)
   const int w = warp_id(), l = lane_id();
   const int begin = tile0 + w * 32 * R;   // a warp owns a contiguous chunk of the tile (stability)
   // every load of the tile is in flight before anything is ranked
@@ -241,6 +259,7 @@ __device__ __forceinline__ void radix_scatter_body(const unsigned int* __restric
   const int bits = digit_bits(*d_nbits), shift = pass * bits, nbins = 1 << bits;
   const unsigned int dmask = (unsigned int)nbins - 1u;
   const int nb = sort_tiles(n, R);
+  const bool direct = nb <= kDirectTiles;
   const bool narrow = nbins <= 256;
   unsigned int mask[MAXR];
   int* cnt = s_cnt[w];
@@ -309,7 +328,13 @@ __device__ __forceinline__ void radix_scatter_body(const unsigned int* __restric
       __syncwarp();
       if (valid && (__ffs(mask[r]) - 1) == l) cnt[d] += __popc(mask[r]);
       __syncwarp();
-      if (valid) { keys_out[pos] = k[r]; vals_out[pos] = v[r]; }
+      if (valid) {
+        keys_out[pos] = k[r]; vals_out[pos] = v[r];
+        if (hist_next) {   // this key counts itself into the next pass's table, at the tile it lands in
+          const int dn = (int)((k[r] >> (shift + bits)) & dmask), tn = pos >> kTileShift;
+          atomicAdd(hist_next + (direct ? tn * nbins + dn : dn * nb + tn), 1);
+        }
+      }
     }
   } else {
     // wide digits (keys above 24 bits): the warps of the tile rank one after the other against the shared running offsets
@@ -326,36 +351,49 @@ __device__ __forceinline__ void radix_scatter_body(const unsigned int* __restric
           __syncwarp();
           if (valid && (__ffs(m) - 1) == l) s_base[d] += __popc(m);
           __syncwarp();
-          if (valid) { keys_out[pos] = k[r]; vals_out[pos] = v[r]; }
+          if (valid) {
+            keys_out[pos] = k[r]; vals_out[pos] = v[r];
+            if (hist_next) {
+              const int dn = (int)((k[r] >> (shift + bits)) & dmask), tn = pos >> kTileShift;
+              atomicAdd(hist_next + (direct ? tn * nbins + dn : dn * nb + tn), 1);
+            }
+          }
         }
       }
       __syncthreads();
     }
   }
+  if (hist_next && !direct) scan_table_by_last_cta(hist_next, nbins * nb, ticket, nb, s_scan, s_last);
 }
 
 __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const unsigned int* __restrict__ keys_in, const int* __restrict__ vals_in,
                                                                      unsigned int* __restrict__ keys_out, int* __restrict__ vals_out,
                                                                      const int* __restrict__ d_n, const int* __restrict__ d_nbits, int pass,
-                                                                     const int* __restrict__ hist, const int* d_skip) {
+                                                                     const int* __restrict__ hist, int* __restrict__ hist_next, unsigned int* ticket,
+                                                                     const int* d_skip) {
   pdl_prologue();
   if (d_skip && *d_skip) return;
   __shared__ int s_cnt[kSortWarps][256];   // narrow digits: per-warp counters / running offsets
   __shared__ int s_base[kMaxBins];         // wide digits: one running offset per bin, warps take turns
   __shared__ int s_scan[33];
+  __shared__ int s_last;
   switch (sort_rounds(*d_n)) {
-    case 4: radix_scatter_body<4>(keys_in, vals_in, keys_out, vals_out, d_n, d_nbits, pass, hist, s_cnt, s_base, s_scan); break;
-    case 8: radix_scatter_body<8>(keys_in, vals_in, keys_out, vals_out, d_n, d_nbits, pass, hist, s_cnt, s_base, s_scan); break;
-    case 16: radix_scatter_body<16>(keys_in, vals_in, keys_out, vals_out, d_n, d_nbits, pass, hist, s_cnt, s_base, s_scan); break;
-    default: radix_scatter_body<32>(keys_in, vals_in, keys_out, vals_out, d_n, d_nbits, pass, hist, s_cnt, s_base, s_scan); break;
+    case 4: radix_scatter_body<4>(keys_in, vals_in, keys_out, vals_out, d_n, d_nbits, pass, hist, hist_next, ticket, s_cnt, s_base, s_scan, s_last); break;
+    case 8: radix_scatter_body<8>(keys_in, vals_in, keys_out, vals_out, d_n, d_nbits, pass, hist, hist_next, ticket, s_cnt, s_base, s_scan, s_last); break;
+    case 16: radix_scatter_body<16>(keys_in, vals_in, keys_out, vals_out, d_n, d_nbits, pass, hist, hist_next, ticket, s_cnt, s_base, s_scan, s_last); break;
+    default: radix_scatter_body<32>(keys_in, vals_in, keys_out, vals_out, d_n, d_nbits, pass, hist, hist_next, ticket, s_cnt, s_base, s_scan, s_last); break;
   }
 }
 
 }  // namespace
 
+// rows of one count table: the tile grows with the input (sort_rounds), so at most 128 tiles up to 128 * 8192 keys, n / 8192 beyond
+static int table_rows(int n_max) {
+  const int big = (n_max + kSortThreads * kSortMaxRounds - 1) / (kSortThreads * kSortMaxRounds);
+  return (big > 128 ? big : 128) + 1;
+}
 size_t sort_workspace_bytes(int n_max) {
-  const int nblocks = (n_max + kSortTile - 1) / kSortTile;
-  return (size_t)n_max * 8 + (size_t)kMaxBins * nblocks * 4 + 512;
+  return (size_t)n_max * 8 + (size_t)3 * kMaxBins * table_rows(n_max) * 4 + 512;
 }
 void sort_workspace_bind(SortWorkspace& ws, void* mem, int n_max) {
   char* p = (char*)mem;
@@ -365,6 +403,7 @@ void sort_workspace_bind(SortWorkspace& ws, void* mem, int n_max) {
   ws.vals_alt = (int*)p; p += (size_t)n_max * 4;
   ws.ticket = (unsigned int*)p; p += 256;
   ws.hist = (int*)p;
+  ws.table_stride = kMaxBins * table_rows(n_max);
 }
 int sort_workspace_arm(SortWorkspace& ws, cudaStream_t s) {
   FLOAM_CUDA_OK(cudaMemsetAsync(ws.ticket, 0, 256, s));
@@ -377,9 +416,11 @@ void radix_sort_pairs_from(unsigned int* keys, int* vals, unsigned int* keys_alt
   const int nblocks = (n_max + kSortTile - 1) / kSortTile;
   unsigned int* kin = keys; int* vin = vals;
   unsigned int* kout = keys_alt; int* vout = vals_alt;
+  // four launches: digit counts of pass 0, then three scatters, each of which also counts the digits of the pass after it
+  FLOAM_LAUNCH(K_RADIX_HIST, radix_hist_kernel, nblocks, kSortThreads, s, kin, d_n, d_nbits, 0, ws.hist, ws.table_stride, ws.ticket, d_skip);
   for (int pass = 0; pass < 3; ++pass) {
-    FLOAM_LAUNCH(K_RADIX_HIST, radix_hist_kernel, nblocks, kSortThreads, s, kin, d_n, d_nbits, pass, ws.hist, ws.ticket, d_skip);
-    FLOAM_LAUNCH(K_RADIX_SCATTER, radix_scatter_kernel, nblocks, kSortThreads, s, kin, vin, kout, vout, d_n, d_nbits, pass, ws.hist, d_skip);
+    FLOAM_LAUNCH(K_RADIX_SCATTER, radix_scatter_kernel, nblocks, kSortThreads, s, kin, vin, kout, vout, d_n, d_nbits, pass, ws.hist + (size_t)pass * ws.table_stride,
+                 pass < 2 ? ws.hist + (size_t)(pass + 1) * ws.table_stride : (int*)nullptr, ws.ticket, d_skip);
     unsigned int* tk = kin; kin = kout; kout = tk;
     int* tv = vin; vin = vout; vout = tv;
   }

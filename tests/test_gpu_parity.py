@@ -141,6 +141,16 @@ def test_voxel_grid_wide_keys(capi, po, ctxs, n):
     assert not passthrough and len(g) == len(o) and np.array_equal(xyzi(g), xyzi(o))
 
 
+def test_voxel_grid_above_two_million_points(capi, po):
+    # > 256 sort tiles of 8192 keys: the count tables switch to the [digit][tile] layout scanned by the last CTA to finish, for the
+    # counts of pass 0 (count kernel) and for those the scatter kernels of passes 0 and 1 leave for the pass after them
+    ctx = fresh(capi, 16, max_map_points=1 << 22, max_global_map_points=0)
+    pts = cloud(capi, np.random.default_rng(123), 2600000, lo=(-80, -80, -4), hi=(80, 80, 8))
+    g = ctx.voxel_grid(pts, 0.3); o, passthrough = po.voxel_grid(pts, 0.3, total_order=True)
+    ctx.close()
+    assert not passthrough and len(g) == len(o) and np.array_equal(xyzi(g), xyzi(o))
+
+
 def test_voxel_grid_duplicates_and_negative_coordinates(capi, po, ctxs):
     rng = np.random.default_rng(5)
     pts = cloud(capi, rng, 3000, lo=(-3, -3, -3), hi=(3, 3, 3))
