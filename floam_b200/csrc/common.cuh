@@ -268,6 +268,8 @@ struct ScanWorkspace {
   int* block_sums;  // one total per 4096-element tile
   int n_max;
 };
+// second half of exclusive_scan_i32 alone, for a caller that already holds the sums of every kScanTile-element tile of `in`
+void exclusive_scan_with_tile_sums(const int* in, int* out, const int* d_n, int n_max, const int* tile_sums, const int* d_skip, cudaStream_t s);
 size_t scan_workspace_bytes(int n_max);
 void scan_workspace_bind(ScanWorkspace& ws, void* mem, int n_max);
 // out[i] = sum_{j<i} in[j] for i in [0, n]; out has n+1 entries (out[n] = total). n read from *d_n (or n_fixed if d_n==nullptr).

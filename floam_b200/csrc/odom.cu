@@ -232,9 +232,10 @@ __device__ __forceinline__ int cell_of(const GridDims& g, float x, float y, floa
 
 __global__ void __launch_bounds__(kThreads) grid_count_kernel(const P4* __restrict__ pts, const int* __restrict__ d_n, const unsigned int* __restrict__ bbox,
                                                                GridDims* __restrict__ dims, int ncells_cap, PoseState* S, int* __restrict__ cell_count,
-                                                               const int* d_skip) {
+                                                               int* __restrict__ tile_sums, const int* d_skip) {
   pdl_prologue();
   if (d_skip && *d_skip) return;
+  static_assert(kScanTile == 4096, "tile_sums index is cell >> 12");
   const int n = *d_n;
   bool overflow;
   const GridDims g = grid_dims_from_bbox(bbox, n, ncells_cap, &overflow);
@@ -245,7 +246,12 @@ __global__ void __launch_bounds__(kThreads) grid_count_kernel(const P4* __restri
   if (g.ncells == 0) return;
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
     const float4 p = __ldg(pts + i);
-    atomicAdd(&cell_count[cell_of(g, p.x, p.y, p.z)], 1);
+    const int c = cell_of(g, p.x, p.y, p.z);
+    atomicAdd(&cell_count[c], 1);
+    // the scan's per-tile sums come for free here (one atomic per group of lanes that hit the same tile)
+    const int t = c >> 12;
+    const unsigned int peers = __match_any_sync(__activemask(), t);
+    if (lane_id() == __ffs(peers) - 1) atomicAdd(&tile_sums[t], __popc(peers));
   }
 }
 
@@ -253,8 +259,8 @@ __global__ void __launch_bounds__(kThreads) grid_count_kernel(const P4* __restri
 // The order of points inside a cell is arbitrary; the search orders candidates by (distance, index), so results do not depend on it.
 __global__ void __launch_bounds__(kThreads) grid_scatter_kernel(const P4* __restrict__ pts, const int* __restrict__ d_n, const GridDims* __restrict__ dims,
                                                                  const int* __restrict__ cell_start, int* __restrict__ cell_count,
-                                                                 float4* __restrict__ cell_pts, unsigned int* bbox, P4* __restrict__ home,
-                                                                 long long* stamp, const int* d_skip) {
+                                                                 float4* __restrict__ cell_pts, unsigned int* bbox, int* __restrict__ tile_sums,
+                                                                 P4* __restrict__ home, long long* stamp, const int* d_skip) {
   pdl_prologue();
   if (d_skip && *d_skip) return;
   if (stamp && blockIdx.x == 0 && threadIdx.x == 0) *stamp = global_ns();
@@ -264,6 +270,8 @@ __global__ void __launch_bounds__(kThreads) grid_scatter_kernel(const P4* __rest
   }
   const GridDims g = *dims;
   const int n = *d_n;
+  // the scan before this kernel was the only reader of the tile sums: back to zero for the next build
+  for (int t = blockIdx.x * kThreads + threadIdx.x; t * kScanTile < g.ncells; t += gridDim.x * kThreads) tile_sums[t] = 0;
   // home (optional): pts is the filter's output buffer; every point passes through here, so this is also where the cloud goes back
   // into the map's home buffer (a device-side pointer swap would need every consumer to chase a pointer)
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
@@ -1084,10 +1092,11 @@ void rebuild_grid(OdomDevice& od, LocalMap& map, const int* d_skip, cudaStream_t
   const int g = grid_for(map.cap);
   const P4* src = from_tmp ? map.tmp : map.pts;
   if (!from_tmp) FLOAM_LAUNCH(K_GRID_BBOX, grid_bbox_kernel, g, kThreads, s, map.pts, map.d_n, map.bbox, d_skip);
-  FLOAM_LAUNCH(K_GRID_COUNT, grid_count_kernel, g, kThreads, s, src, map.d_n, map.bbox, map.dims, map.ncells_cap, od.state, map.cell_count, d_skip);
-  exclusive_scan_i32(map.cell_count, map.cell_start, dims_ncells_ptr(map.dims), 0, map.ncells_cap, ws->scan, d_skip, s);
+  FLOAM_LAUNCH(K_GRID_COUNT, grid_count_kernel, g, kThreads, s, src, map.d_n, map.bbox, map.dims, map.ncells_cap, od.state, map.cell_count, map.tile_sums,
+               d_skip);
+  exclusive_scan_with_tile_sums(map.cell_count, map.cell_start, dims_ncells_ptr(map.dims), map.ncells_cap, map.tile_sums, d_skip, s);
   FLOAM_LAUNCH(K_GRID_SCATTER, grid_scatter_kernel, g, kThreads, s, src, map.d_n, map.dims, map.cell_start, map.cell_count, map.cell_pts, map.bbox,
-               from_tmp ? map.pts : (P4*)nullptr, stamp, d_skip);
+               map.tile_sums, from_tmp ? map.pts : (P4*)nullptr, stamp, d_skip);
 }
 
 }  // namespace
@@ -1100,12 +1109,16 @@ int local_map_alloc(LocalMap& map, int cap, int ncells_cap, void* (*alloc)(void*
   map.cell_pts = (float4*)alloc(actx, (size_t)cap * sizeof(float4));
   map.cell_start = (int*)alloc(actx, ((size_t)ncells_cap + 1) * 4);
   map.cell_count = (int*)alloc(actx, (size_t)ncells_cap * 4);
+  const size_t tile_bytes = ((size_t)ncells_cap / kScanTile + 2) * 4;
+  map.tile_sums = (int*)alloc(actx, tile_bytes);
   map.dims = (GridDims*)alloc(actx, sizeof(GridDims));
   map.bbox = (unsigned int*)alloc(actx, 32);
   int* ints = (int*)alloc(actx, 4 * 4);
   if (!map.pts || !map.tmp || !map.cell_pts || !map.cell_start || !map.cell_count || !map.dims || !map.bbox || !ints) return FLOAM_ERR_CUDA;
   map.d_n = ints; map.d_ntmp = ints + 1; map.d_ncrop = ints + 2; map.d_ncells = ints + 3;
+  if (!map.tile_sums) return FLOAM_ERR_CUDA;
   FLOAM_CUDA_OK(cudaMemsetAsync(map.cell_count, 0, (size_t)ncells_cap * 4, s));
+  FLOAM_CUDA_OK(cudaMemsetAsync(map.tile_sums, 0, tile_bytes, s));
   FLOAM_CUDA_OK(cudaMemsetAsync(map.dims, 0, sizeof(GridDims), s));
   FLOAM_CUDA_OK(cudaMemsetAsync(ints, 0, 16, s));
   const unsigned int bb[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};

@@ -51,6 +51,7 @@ struct LocalMap {
   float4* cell_pts; // points bucketed by 1 m cell: xyz + map index (as int bits in w)
   int* cell_start;  // [ncells_cap + 1]
   int* cell_count;  // [ncells_cap]
+  int* tile_sums;   // points per kScanTile cells: filled by the count kernel, consumed by the scan, zeroed again by the scatter kernel
   GridDims* dims;
   unsigned int* bbox;
   int* d_ncells;

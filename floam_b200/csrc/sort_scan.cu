@@ -492,4 +492,9 @@ void exclusive_scan_i32(const int* in, int* out, const int* d_n, int n_fixed, in
   FLOAM_LAUNCH(K_SCAN_ADD, scan_add_kernel, nblocks, kScanThreads, s, in, out, d_n, n_fixed, ws.block_sums, d_skip);
 }
 
+void exclusive_scan_with_tile_sums(const int* in, int* out, const int* d_n, int n_max, const int* tile_sums, const int* d_skip, cudaStream_t s) {
+  const int nblocks = (n_max + kScanTile - 1) / kScanTile;
+  FLOAM_LAUNCH(K_SCAN_ADD, scan_add_kernel, nblocks, kScanThreads, s, in, out, d_n, 0, tile_sums, d_skip);
+}
+
 }  // namespace floam
