@@ -103,9 +103,15 @@ __global__ void predict_kernel(PoseState* S, const int* n_edge_map, const int* n
 }
 
 // :114-121 + KeyFrameUpdate :320-343 + the CropBox bounds of addPointsToMap :270-279
-__global__ void finish_kernel(PoseState* S, int update_type, double scan_period, double* traj, int traj_cap) {
-  pdl_prologue();
-  if (threadIdx.x != 0) return;
+// One thread. S may be the global state or CTA 0's shared-memory copy inside the cluster kernel (generic pointer).
+struct FinishArgs {
+  int enabled;       // the cluster kernel of the last outer iteration runs the write-back itself (no separate launch)
+  int update_type;
+  double scan_period;
+  double* traj;
+  int traj_cap;
+};
+__device__ __noinline__ void finish_body(PoseState* S, int update_type, double scan_period, double* traj, int traj_cap) {
   S->tl_finish = global_ns();
   double R[9];
   m::quat_to_matrix(S->x, R);
@@ -140,6 +146,11 @@ __global__ void finish_kernel(PoseState* S, int update_type, double scan_period,
     for (int k = 0; k < 7; ++k) rec[k] = S->x[k];
     S->frame_counter++;
   }
+}
+__global__ void finish_kernel(PoseState* S, int update_type, double scan_period, double* traj, int traj_cap) {
+  pdl_prologue();
+  if (threadIdx.x != 0) return;
+  finish_body(S, update_type, scan_period, traj, traj_cap);
 }
 
 __global__ void record_pose_kernel(PoseState* S, double* traj, int traj_cap) {
@@ -842,12 +853,15 @@ struct ClusterShared {
 __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClusterThreads)
     lm_cluster_kernel(PoseState* S, const P4* __restrict__ ds_edge, const int* __restrict__ d_nde, const P4* __restrict__ ds_surf,
                       const int* __restrict__ d_nds, int qcap, const double* __restrict__ corr, const unsigned char* __restrict__ corr_ok, int loss,
-                      const double* __restrict__ partials, int n_rows) {
+                      const double* __restrict__ partials, int n_rows, FinishArgs fin) {
   pdl_prologue();
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   // uniform across the cluster: decided from a value the previous kernels wrote
-  if (S->skip_solve) return;
+  if (S->skip_solve) {
+    if (fin.enabled && cluster.block_rank() == 0 && threadIdx.x == 0) finish_body(S, fin.update_type, fin.scan_period, fin.traj, fin.traj_cap);
+    return;
+  }
   const int nde = *d_nde, nds = *d_nds;
   __shared__ ClusterShared sh;
   __shared__ PoseState st;   // CTA 0's working copy of the state
@@ -1029,7 +1043,12 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClusterT
     // no third barrier: row[] is rewritten only after this barrier pair, and CTA 0 rewrites x/done only after the next round's first
     // barrier, which every CTA reaches after it has read this round's values
   }
-  if (rank == 0) state_store(S, &st);   // ordered after thread 0's last update by the barrier pair above
+  if (rank == 0) {
+    // odom write-back, KeyFrameUpdate and the crop bounds (:114-121, :320-343) on the shared copy, after the last outer iteration
+    if (fin.enabled && threadIdx.x == 0) finish_body(&st, fin.update_type, fin.scan_period, fin.traj, fin.traj_cap);
+    __syncthreads();
+    state_store(S, &st);   // ordered after thread 0's last update by the barrier pair above (and this barrier)
+  }
   cluster.sync();     // CTA 0's shared memory must outlive the last remote read
 }
 
@@ -1221,9 +1240,9 @@ void odom_update_device(OdomDevice& od, const void* d_edge, const int* d_ne, con
     FLOAM_LAUNCH(K_ASSOC_EVAL, assoc_eval_kernel, kAssocBlocks, kEvalThreads, s, S, od.ds_edge, od.d_nds_edge, od.ds_surf, od.d_nds_surf, od.edge_map, od.surf_map,
                  od.qcap, od.corr, od.corr_ok, od.knn_ids, od.loss, od.partials);
     FLOAM_LAUNCH_DYN(K_LM_CLUSTER, lm_cluster_kernel, kClusterCtas, kClusterThreads, kLmStageBytes, s, S, od.ds_edge, od.d_nds_edge, od.ds_surf, od.d_nds_surf, od.qcap, od.corr, od.corr_ok,
-                 od.loss, od.partials, kAssocBlocks);
+                 od.loss, od.partials, kAssocBlocks, FinishArgs{it + 1 == od.optimization_count ? 1 : 0, update_type, od.scan_period, od.traj, od.traj_cap});
   }
-  FLOAM_LAUNCH(K_FINISH, finish_kernel, 1, 32, s, S, update_type, od.scan_period, od.traj, od.traj_cap);
+  if (od.optimization_count <= 0) FLOAM_LAUNCH(K_FINISH, finish_kernel, 1, 32, s, S, update_type, od.scan_period, od.traj, od.traj_cap);
   if (update_type == FLOAM_INITIAL_ITERATION) return;
   // addPointsToMap :253-294, predicated on the device-side keyframe decision
   const int* skip = &S->not_keyframe;

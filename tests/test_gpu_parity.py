@@ -488,7 +488,7 @@ def test_kernel_timing_reports_every_frame_kernel(capi, sequences):
     ctx.set_kernel_timing(True)
     P = [ctx.process_scan(scans[off[f]:off[f + 1]]) for f in range(3, 6)]
     t = ctx.kernel_timing(); ctx.set_kernel_timing(False)
-    for k in ("ring_count", "sector", "assoc_eval", "assoc_knn", "lm_cluster", "radix_scatter", "voxel_reduce", "finish"):
+    for k in ("ring_count", "sector", "assoc_eval", "assoc_knn", "lm_cluster", "radix_scatter", "voxel_reduce", "grid_scatter"):
         assert k in t and t[k][0] > 0
     ctx.close()
 
