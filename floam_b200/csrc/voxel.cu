@@ -98,10 +98,12 @@ __device__ __forceinline__ int bits_for(long long cells) {  // number of key bit
 __global__ void __launch_bounds__(kThreads) voxel_keys_kernel(const char* __restrict__ in, int stride, const int* __restrict__ counts, float leaf,
                                                                const float* __restrict__ crop, const unsigned int* __restrict__ bbox,
                                                                unsigned int* __restrict__ keys, int* __restrict__ vals, int* d_nbits, int* d_passthrough,
-                                                               const int* d_skip) {
+                                                               int* __restrict__ tile_state, const int* d_skip) {
   pdl_prologue();
   if (d_skip && *d_skip) return;
   const int n = counts[0];
+  // look-back states of voxel_rank_kernel (one per kScanTile sorted keys), armed here
+  for (int t = blockIdx.x * kThreads + threadIdx.x; t * kScanTile < n; t += gridDim.x * kThreads) tile_state[t] = 0;
   const bool none = counts[1] == 0;   // nothing survives the crop (or the input is empty): the bounding box is undefined
   // every thread derives the grid from the bbox exactly like VoxelGrid::applyFilter (float arithmetic, no contraction)
   const float inv = __fdiv_rn(1.0f, leaf);
@@ -151,37 +153,44 @@ __global__ void __launch_bounds__(kThreads) voxel_keys_kernel(const char* __rest
 // run are independent of the loop control and pipeline.
 __device__ __forceinline__ int is_head(const unsigned int* __restrict__ keys, int i) { return (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0; }
 
-__global__ void __launch_bounds__(kScanThreads) voxel_heads_kernel(const unsigned int* __restrict__ keys, const int* __restrict__ d_n,
-                                                                   int* __restrict__ tile_sums, const int* d_skip) {
-  pdl_prologue();
-  if (d_skip && *d_skip) return;
-  const int n = *d_n;
-  if (blockIdx.x * kScanTile >= n) return;
-  __shared__ int smem[33];
-  const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
-  int sum = 0;
-#pragma unroll
-  for (int k = 0; k < kScanItems; ++k) sum += (base + k < n) ? is_head(keys, base + k) : 0;
-  const int total = block_sum(sum, smem);
-  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
-}
-
+// Single pass: every tile counts and ranks its run heads, then finds the number of heads before it by decoupled look-back over the
+// tiles' published states (state = value << 2 | 1: this tile's own count; value << 2 | 2: inclusive prefix up to this tile). The
+// states are zeroed by voxel_keys_kernel, two launches earlier. Lower-numbered tiles are dispatched first, so the wait is short.
 __global__ void __launch_bounds__(kScanThreads) voxel_rank_kernel(const unsigned int* __restrict__ keys, const int* __restrict__ d_n,
-                                                                  const int* __restrict__ tile_sums, int* __restrict__ head_pos, int* d_nout, const int* d_skip) {
+                                                                  int* tile_state, int* __restrict__ head_pos, int* d_nout, const int* d_skip) {
   pdl_prologue();
   if (d_skip && *d_skip) return;
   const int n = *d_n;
   if (n == 0) { if (blockIdx.x == 0 && threadIdx.x == 0) { *d_nout = 0; head_pos[0] = 0; } return; }
   if (blockIdx.x * kScanTile >= n) return;
   __shared__ int smem[33];
-  const int offset = tile_offset(tile_sums, blockIdx.x, smem);
+  __shared__ int s_offset;
   const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
   int h[kScanItems];
   int sum = 0;
 #pragma unroll
   for (int k = 0; k < kScanItems; ++k) { h[k] = (base + k < n) ? is_head(keys, base + k) : 0; sum += h[k]; }
   int total;
-  int rank = block_excl_scan(sum, smem, &total) + offset;
+  int rank = block_excl_scan(sum, smem, &total);
+  if (threadIdx.x == 0) {
+    volatile int* st = tile_state;
+    int before = 0;
+    if (blockIdx.x > 0) {
+      st[blockIdx.x] = (total << 2) | 1;
+      for (int t = (int)blockIdx.x - 1; t >= 0; --t) {
+        int v;
+        while (((v = st[t]) & 3) == 0) __nanosleep(20);
+        before += v >> 2;
+        if ((v & 3) == 2) break;
+      }
+    }
+    __threadfence();
+    st[blockIdx.x] = ((before + total) << 2) | 2;
+    s_offset = before;
+  }
+  __syncthreads();
+  const int offset = s_offset;
+  rank += offset;
 #pragma unroll
   for (int k = 0; k < kScanItems; ++k)
     if (h[k]) head_pos[rank++] = base + k;
@@ -395,11 +404,10 @@ void voxel_grid_device(const void* d_in, int stride_bytes, const int* d_n, int n
   int* counts = ws.d_counts;   // [0] input points, [1] points kept by the crop
   FLOAM_LAUNCH(K_VOXEL_BBOX, voxel_bbox_kernel, g, kThreads, s, in, stride_bytes, d_n, d_extra, cap, d_crop, ws.bbox, counts, app, d_skip);
   FLOAM_LAUNCH(K_VOXEL_KEYS, voxel_keys_kernel, g, kThreads, s, in, stride_bytes, counts, leaf, d_crop, ws.bbox, ws.keys, ws.vals, ws.d_nbits, ws.d_passthrough,
-               d_skip);
+               ws.scan.block_sums, d_skip);
   unsigned int* skeys = nullptr;
   int* svals = nullptr;
   radix_sort_pairs(ws.keys, ws.vals, counts, ws.d_nbits, n_max, ws.sort, d_skip, s, &skeys, &svals);
-  FLOAM_LAUNCH(K_VOXEL_HEADS, voxel_heads_kernel, gt, kScanThreads, s, skeys, counts + 1, ws.scan.block_sums, d_skip);
   FLOAM_LAUNCH(K_VOXEL_RANK, voxel_rank_kernel, gt, kScanThreads, s, skeys, counts + 1, ws.scan.block_sums, ws.flags, d_nout, d_skip);
   FLOAM_LAUNCH(K_VOXEL_REDUCE, voxel_reduce_kernel, g, kThreads, s, in, stride_bytes, svals, ws.flags, d_nout, d_out, ws.bbox, counts, out_bbox, d_skip);
 }
