@@ -117,10 +117,14 @@ def measured_peak_gbs():
 
 
 def ncu_traffic_bytes(kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full` capture
-    (profiles/r1e_ncu_full_top_kernels.csv), or None when the kernel was not captured."""
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the newest committed `ncu --set full` capture
+    (profiles/*_ncu_full_top_kernels.csv), or None when the kernel was not captured."""
     import csv
-    path = os.path.join(ROOT, "profiles", "r1e_ncu_full_top_kernels.csv")
+    import glob
+    found = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_full_top_kernels.csv")))
+    if not found:
+        return None
+    path = found[-1]
     try:
         with open(path) as f:
             rows = list(csv.reader(f))
@@ -309,7 +313,7 @@ def main():
     def run_e2e(f0, f1, lat=None):
         poses = np.zeros((f1 - f0, 7)); pending = []
         for f in range(f0, f1):
-            if len(pending) == 2:
+            if len(pending) == 3:   # the API keeps up to three frames in flight: upload + FRONT of k+2 run under the BACK of k and k+1
                 g = pending.pop(0); poses[g - f0] = ctx2.process_wait()
                 if lat is not None:
                     lat.append(ctx2.last_frame_ms())

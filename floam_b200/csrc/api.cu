@@ -130,7 +130,7 @@ void enqueue_front(floam_ctx* c, PointIRT* d_scan, const int* d_scan_n, int desk
                            c->ev_ffork, c->ev_fjoin);
 }
 
-void enqueue_back(floam_ctx* c, int deskew, int slot, bool first) {
+void enqueue_back(floam_ctx* c, int deskew, int ring, bool first) {
   if (first) {
     // odomEstimationNode.cpp:219-224: first frame only seeds the map (raw features, Q11); odom stays identity
     odom_init_map_device(c->odom, c->d_edge, c->d_ne, c->d_surf, c->d_ns, 32, c->prm.max_scan_points, 0, c->stream);
@@ -140,7 +140,7 @@ void enqueue_back(floam_ctx* c, int deskew, int slot, bool first) {
     enqueue_selector(c, c->d_edge, c->d_ne, c->d_surf, c->d_ns, c->prm.max_scan_points, deskew, !deskew);
   }
   if (c->timer.enabled) launch_noop(c->stream);   // calibration of the event-pair overhead (kernel-timing mode only)
-  odom_mail_state(c->odom, c->d_flags, c->h_state[slot], c->h_flags[slot], c->stream);
+  odom_mail_state(c->odom, c->d_flags, c->h_state[ring], c->h_flags[ring], c->stream);
 }
 
 // Capture-or-replay of one half. Graphs are keyed by everything that changes the launch sequence or the buffers it touches.
@@ -176,8 +176,10 @@ int launch_half(floam_ctx* c, const floam_graph_key& key, cudaStream_t s, Body b
   return FLOAM_OK;
 }
 
-// Both halves of the frame whose scan sits in d_scan[slot] (slot = frame parity). The caller has made front_stream wait for the scan.
-int launch_frame(floam_ctx* c, int deskew, int slot, bool imu) {
+// Both halves of the frame whose scan sits in d_scan[slot] (slot = frame parity = ring & 1; ring = the frame's mailbox). The caller has
+// made front_stream wait for the scan.
+int launch_frame(floam_ctx* c, int deskew, int ring, bool imu) {
+  const int slot = ring & 1;
   const bool first = !c->map_initialised;
   OdomDevice& od = c->odom;
   const bool timing = c->timer.enabled;
@@ -192,7 +194,7 @@ int launch_frame(floam_ctx* c, int deskew, int slot, bool imu) {
   FLOAM_CUDA_OK(cudaEventRecord(c->ev_front_done[slot], c->front_stream));
   FLOAM_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_front_done[slot], 0));
   const int saved_count = od.optimization_count;
-  rc = launch_half(c, floam_graph_key{flags, outer, first ? 0 : (deskew ? 1 : 0), slot}, c->stream, [&]() { enqueue_back(c, deskew, slot, first); });
+  rc = launch_half(c, floam_graph_key{flags, outer, first ? 0 : (deskew ? 1 : 0), ring}, c->stream, [&]() { enqueue_back(c, deskew, ring, first); });
   if (rc) return rc;
   FLOAM_CUDA_OK(cudaEventRecord(c->ev_back_done[slot], c->stream));
   c->back_valid[slot] = true;
@@ -275,9 +277,10 @@ int floam_create(const floam_params* params, int device, floam_ctx** out) {
   if (cudaStreamCreateWithFlags(&c->front_aux, cudaStreamNonBlocking) != cudaSuccess) return fail(FLOAM_ERR_CUDA);
   if (cudaEventCreateWithFlags(&c->ev_ffork, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_fjoin, cudaEventDisableTiming) != cudaSuccess)
     return fail(FLOAM_ERR_CUDA);
+  for (int k = 0; k < 4; ++k)
+    if (cudaEventCreate(&c->ev_begin[k]) != cudaSuccess || cudaEventCreate(&c->ev_end[k]) != cudaSuccess) return fail(FLOAM_ERR_CUDA);
   for (int k = 0; k < 2; ++k) {
-    if (cudaEventCreate(&c->ev_begin[k]) != cudaSuccess || cudaEventCreate(&c->ev_end[k]) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c->ev_upload[k], cudaEventDisableTiming) != cudaSuccess ||
+    if (cudaEventCreateWithFlags(&c->ev_upload[k], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_front_done[k], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_back_done[k], cudaEventDisableTiming) != cudaSuccess)
       return fail(FLOAM_ERR_CUDA);
@@ -332,7 +335,7 @@ int floam_create(const floam_params* params, int device, floam_ctx** out) {
 
   c->h_ints = (int*)host_alloc(c, 64 * sizeof(int));
   c->h_doubles = (double*)host_alloc(c, 64 * sizeof(double));
-  for (int k = 0; k < 2; ++k) {
+  for (int k = 0; k < 4; ++k) {
     c->h_state[k] = (PoseState*)host_alloc(c, sizeof(PoseState));
     c->h_flags[k] = (int*)host_alloc(c, 64);
     if (!c->h_state[k] || !c->h_flags[k]) return fail(FLOAM_ERR_CUDA);
@@ -367,9 +370,11 @@ void floam_destroy(floam_ctx* c) {
   for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second.exec);
   for (void* p : c->allocs) cudaFree(p);
   for (void* p : c->host_allocs) cudaFreeHost(p);
-  for (int k = 0; k < 2; ++k) {
+  for (int k = 0; k < 4; ++k) {
     if (c->ev_begin[k]) cudaEventDestroy(c->ev_begin[k]);
     if (c->ev_end[k]) cudaEventDestroy(c->ev_end[k]);
+  }
+  for (int k = 0; k < 2; ++k) {
     if (c->ev_upload[k]) cudaEventDestroy(c->ev_upload[k]);
     if (c->ev_front_done[k]) cudaEventDestroy(c->ev_front_done[k]);
     if (c->ev_back_done[k]) cudaEventDestroy(c->ev_back_done[k]);
@@ -656,9 +661,9 @@ static int submit_common(floam_ctx* c, const floam_point_xyzirt* pts, int n, int
                          const floam_pc2_layout* layout = nullptr) {
   if (!c || (!pts && !raw && n > 0) || n < 0) return FLOAM_ERR_ARG;
   if (n > c->prm.max_scan_points) return FLOAM_ERR_CAPACITY;
-  if (c->inflight >= 2) return FLOAM_ERR_ARG;
+  if (c->inflight >= 3) return FLOAM_ERR_ARG;
   if (set_device(c)) return FLOAM_ERR_CUDA;
-  const int slot = c->submit_slot;
+  const int ring = c->submit_slot, slot = ring & 1;
   // upload on the copy stream once the FRONT that read this scan buffer two frames ago is done
   if (c->consumed_valid[slot]) FLOAM_CUDA_OK(cudaStreamWaitEvent(c->copy_stream, c->ev_front_done[slot], 0));
   if (raw && n > 0) {
@@ -669,37 +674,37 @@ static int submit_common(floam_ctx* c, const floam_point_xyzirt* pts, int n, int
     FLOAM_CUDA_OK(cudaMemcpyAsync(c->d_raw[slot], raw, bytes, cudaMemcpyHostToDevice, c->copy_stream));
     unpack_pointcloud2_device(c->d_raw[slot], *layout, c->d_scan[slot], c->copy_stream);
   } else if (n > 0) FLOAM_CUDA_OK(cudaMemcpyAsync(c->d_scan[slot], pts, (size_t)n * 32, cudaMemcpyHostToDevice, c->copy_stream));
-  c->h_ints[32 + slot] = n;
-  FLOAM_CUDA_OK(cudaMemcpyAsync(c->d_scan_n[slot], &c->h_ints[32 + slot], 4, cudaMemcpyHostToDevice, c->copy_stream));
+  c->h_ints[32 + ring] = n;
+  FLOAM_CUDA_OK(cudaMemcpyAsync(c->d_scan_n[slot], &c->h_ints[32 + ring], 4, cudaMemcpyHostToDevice, c->copy_stream));
   if (plan) {
     const int rc = deskew_upload(c->imu, *plan, c->d_plan[slot], c->copy_stream);
     if (rc) return rc;
   }
   FLOAM_CUDA_OK(cudaEventRecord(c->ev_upload[slot], c->copy_stream));
   FLOAM_CUDA_OK(cudaStreamWaitEvent(c->front_stream, c->ev_upload[slot], 0));
-  FLOAM_CUDA_OK(cudaEventRecord(c->ev_begin[slot], c->front_stream));
-  int rc = launch_frame(c, deskew, slot, plan != nullptr);
+  FLOAM_CUDA_OK(cudaEventRecord(c->ev_begin[ring], c->front_stream));
+  int rc = launch_frame(c, deskew, ring, plan != nullptr);
   if (rc) return rc;
-  FLOAM_CUDA_OK(cudaEventRecord(c->ev_end[slot], c->stream));
+  FLOAM_CUDA_OK(cudaEventRecord(c->ev_end[ring], c->stream));
   c->consumed_valid[slot] = true;
-  c->submit_slot ^= 1;
+  c->submit_slot = (ring + 1) & 3;
   c->inflight++;
   return FLOAM_OK;
 }
 
 // same for a scan that already sits in device memory (staged replay): the copy into the frame's scan buffer rides on the front stream
 static int enqueue_staged_frame(floam_ctx* c, int frame, int deskew) {
-  const int slot = c->submit_slot;
+  const int ring = c->submit_slot, slot = ring & 1;
   const int n = (int)(c->staged_offsets[frame + 1] - c->staged_offsets[frame]);
-  FLOAM_CUDA_OK(cudaEventRecord(c->ev_begin[slot], c->front_stream));
+  FLOAM_CUDA_OK(cudaEventRecord(c->ev_begin[ring], c->front_stream));
   if (n > 0)
     FLOAM_CUDA_OK(cudaMemcpyAsync(c->d_scan[slot], c->d_staged + c->staged_offsets[frame], (size_t)n * 32, cudaMemcpyDeviceToDevice, c->front_stream));
   FLOAM_CUDA_OK(cudaMemcpyAsync(c->d_scan_n[slot], c->d_staged_counts + frame, 4, cudaMemcpyDeviceToDevice, c->front_stream));
-  const int rc = launch_frame(c, deskew, slot, false);
+  const int rc = launch_frame(c, deskew, ring, false);
   if (rc) return rc;
-  FLOAM_CUDA_OK(cudaEventRecord(c->ev_end[slot], c->stream));
+  FLOAM_CUDA_OK(cudaEventRecord(c->ev_end[ring], c->stream));
   c->consumed_valid[slot] = true;
-  c->submit_slot ^= 1;
+  c->submit_slot = (ring + 1) & 3;
   c->wait_slot = c->submit_slot;   // nothing stays in flight across these calls: keep the submit / wait slots aligned
   return FLOAM_OK;
 }
@@ -773,7 +778,7 @@ int floam_process_wait(floam_ctx* c, double pose_out[7]) {
   const int slot = c->wait_slot;
   FLOAM_CUDA_OK(cudaEventSynchronize(c->ev_end[slot]));
   cudaEventElapsedTime(&c->last_frame_ms, c->ev_begin[slot], c->ev_end[slot]);
-  c->wait_slot ^= 1;
+  c->wait_slot = (slot + 1) & 3;
   c->inflight--;
   if (pose_out) pose_out_from_state(c->h_state[slot], pose_out);
   return status_from_flags(c, slot);
@@ -1075,7 +1080,7 @@ int floam_replay_staged(floam_ctx* c, int first, int count, int deskew, double* 
       FLOAM_CUDA_OK(cudaMemcpy(poses_out + (size_t)k * 7, c->odom.traj + (size_t)((counter0 + k) % cap) * 7, 56, cudaMemcpyDeviceToHost));
   }
   // status of the last frame's mailbox; earlier frames' sticky error flags are part of the same state
-  if (c->h_state[last_slot]->error_flags == 0 && c->h_state[last_slot ^ 1]->error_flags != 0 && count > 1) return FLOAM_ERR_CAPACITY;
+  if (c->h_state[last_slot]->error_flags == 0 && c->h_state[(last_slot + 3) & 3]->error_flags != 0 && count > 1) return FLOAM_ERR_CAPACITY;
   return status_from_flags(c, last_slot);
 }
 

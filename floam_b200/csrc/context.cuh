@@ -34,7 +34,7 @@ struct floam_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;       // all kernels
   cudaStream_t copy_stream = nullptr;  // uploads of the next scan
-  cudaEvent_t ev_begin[2] = {nullptr, nullptr}, ev_end[2] = {nullptr, nullptr};
+  cudaEvent_t ev_begin[4] = {nullptr, nullptr, nullptr, nullptr}, ev_end[4] = {nullptr, nullptr, nullptr, nullptr};   // per mailbox (frame ring index)
   cudaEvent_t ev_upload[2] = {nullptr, nullptr};
   cudaEvent_t ev_replay_begin = nullptr, ev_replay_end = nullptr;
   bool consumed_valid[2] = {false, false};   // a FRONT has read d_scan[slot] before (ev_front_done[slot] is meaningful)
@@ -85,8 +85,8 @@ struct floam_ctx {
   // pinned host mailboxes
   int* h_ints = nullptr;                 // 64 ints
   double* h_doubles = nullptr;           // 64 doubles
-  floam::PoseState* h_state[2] = {nullptr, nullptr};
-  int* h_flags[2] = {nullptr, nullptr};
+  floam::PoseState* h_state[4] = {nullptr, nullptr, nullptr, nullptr};   // ring of four: up to three frames in flight
+  int* h_flags[4] = {nullptr, nullptr, nullptr, nullptr};
 
   // staged scans for device-resident replay
   floam::PointIRT* d_staged = nullptr;
@@ -95,7 +95,7 @@ struct floam_ctx {
   std::vector<long long> staged_offsets;
 
   // submit/wait pipeline
-  int inflight = 0, submit_slot = 0, wait_slot = 0;
+  int inflight = 0, submit_slot = 0, wait_slot = 0;   // frame ring indices 0..3: mailbox = index, buffer parity = index & 1
   bool map_initialised = false;
   bool use_graphs = true;
   std::map<floam_graph_key, floam_graph_entry> graphs;

@@ -1201,7 +1201,7 @@ __global__ void mail_state_kernel(const PoseState* __restrict__ S, const int* __
   unsigned int* dst = reinterpret_cast<unsigned int*>(h_state);
   for (int i = threadIdx.x; i < (int)(sizeof(PoseState) / 4); i += blockDim.x) dst[i] = __ldcg(src + i);
   if (threadIdx.x == 0) *h_flags = *d_flags;
-  __threadfence_system();
+  // no system fence: the host reads the mailbox only after an event recorded behind this kernel, and kernel completion flushes the stores
 }
 void odom_mail_state(OdomDevice& od, const int* d_flags, PoseState* h_state, int* h_flags, cudaStream_t s) {
   FLOAM_LAUNCH(K_RECORD_POSE, mail_state_kernel, 1, 128, s, od.state, d_flags, h_state, h_flags);

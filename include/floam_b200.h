@@ -131,7 +131,7 @@ int floam_odom_set_map(floam_ctx* ctx, const floam_point_xyzi* edge, int ne, con
  * without the TCPROS hops. Only the scan goes up and only the 7-double pose comes down. */
 int floam_process_scan(floam_ctx* ctx, const floam_point_xyzirt* pts, int n, int deskew, double pose_out[7]);
 /* Same, split so the upload of frame k+1 overlaps the kernels of frame k. pts must stay valid (ideally pinned) until
- * the matching floam_process_wait returns. At most two submissions may be in flight. */
+ * the matching floam_process_wait returns. At most three submissions may be in flight (results come back in order). */
 int floam_process_submit(floam_ctx* ctx, const floam_point_xyzirt* pts, int n, int deskew);
 int floam_process_wait(floam_ctx* ctx, double pose_out[7]);
 /* The same with the IMU steps of laser_processing() folded in: CenterTime + dmapping::Compensate + IMU alignment run on the

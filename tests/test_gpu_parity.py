@@ -413,18 +413,22 @@ def test_all_entry_paths_give_identical_poses(capi, synth, sequences):
     ctx = fresh(capi, 16); ctx.stage_scans(scans, off)
     D = np.array([ctx.process_staged(f) for f in range(16)]); ctx.close()
     assert np.array_equal(A, D)
-    ctx = fresh(capi, 16)
-    bufs = [capi.PinnedBuffer(seq.max_points) for _ in range(3)]
-    E = []; pending = 0
-    for f in range(16):
-        n = int(off[f + 1] - off[f]); bufs[f % 3].array[:n] = scans[off[f]:off[f + 1]]
-        if pending == 2:
+    for depth in (2, 3):                       # frames in flight (the API allows three)
+        ctx = fresh(capi, 16)
+        bufs = [capi.PinnedBuffer(seq.max_points) for _ in range(4)]
+        E = []; pending = 0
+        for f in range(16):
+            n = int(off[f + 1] - off[f]); bufs[f % 4].array[:n] = scans[off[f]:off[f + 1]]
+            if pending == depth:
+                E.append(ctx.process_wait()); pending -= 1
+            ctx.process_submit(bufs[f % 4].array[:n], n); pending += 1
+        if depth == 3:                         # a fourth submission is refused, and refusing it disturbs nothing
+            with pytest.raises(capi.FloamError):
+                ctx.process_submit(bufs[0].array[:n], n)
+        while pending:
             E.append(ctx.process_wait()); pending -= 1
-        ctx.process_submit(bufs[f % 3].array[:n], n); pending += 1
-    while pending:
-        E.append(ctx.process_wait()); pending -= 1
-    ctx.close()
-    assert np.array_equal(A, np.array(E))
+        ctx.close()
+        assert np.array_equal(A, np.array(E))
 
 
 def test_pointcloud2_ingestion(capi, synth, sequences):
