@@ -79,13 +79,41 @@ __global__ void __launch_bounds__(kThreads) voxel_bbox_kernel(const char* in, in
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) kept += __shfl_xor_sync(0xffffffffu, kept, o);
-  if (lane_id() == 0 && kept > 0) {
+  // one set of atomics per CTA, not per warp: the seven accumulators are single addresses every voting warp would queue on
+  __shared__ float s_mn[kThreads / 32][3], s_mx[kThreads / 32][3];
+  __shared__ int s_kept[kThreads / 32];
+  const int w = warp_id(), l = lane_id();
+  if (l == 0) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { s_mn[w][a] = mn[a]; s_mx[w][a] = mx[a]; }
+    s_kept[w] = kept;
+  }
+  __syncthreads();
+  if (w == 0) {
+    int k = l < kThreads / 32 ? s_kept[l] : 0;
+    float vmn[3], vmx[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-      atomicMin(&bbox[a], float_flip(mn[a]));
-      atomicMax(&bbox[3 + a], float_flip(mx[a]));
+      vmn[a] = l < kThreads / 32 ? s_mn[l][a] : 3.402823466e38f;
+      vmx[a] = l < kThreads / 32 ? s_mx[l][a] : -3.402823466e38f;
     }
-    atomicAdd(&counts[1], kept);
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      k += __shfl_xor_sync(0xffffffffu, k, o);
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        vmn[a] = fminf(vmn[a], __shfl_xor_sync(0xffffffffu, vmn[a], o));
+        vmx[a] = fmaxf(vmx[a], __shfl_xor_sync(0xffffffffu, vmx[a], o));
+      }
+    }
+    if (l == 0 && k > 0) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        atomicMin(&bbox[a], float_flip(vmn[a]));
+        atomicMax(&bbox[3 + a], float_flip(vmx[a]));
+      }
+      atomicAdd(&counts[1], k);
+    }
   }
 }
 
@@ -275,8 +303,10 @@ __global__ void __launch_bounds__(kThreads) voxel_reduce_kernel(const char* __re
       wrote = true;
     }
   }
-  // bounding box of the output cloud for the caller's search grid (only warps that produced a centroid vote)
-  if (out_bbox && __any_sync(0xffffffffu, wrote)) {
+  // bounding box of the output cloud for the caller's search grid: warp, then CTA reduction, one set of atomics per CTA
+  if (out_bbox) {   // uniform: kernel argument
+    float* s_box = reinterpret_cast<float*>(&s_stage[0][0]);   // the staging area is idle now: [warp][6]
+    __syncthreads();
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
 #pragma unroll
@@ -285,12 +315,19 @@ __global__ void __launch_bounds__(kThreads) voxel_reduce_kernel(const char* __re
         omx[a] = fmaxf(omx[a], __shfl_xor_sync(0xffffffffu, omx[a], o));
       }
     }
+    const bool any = __any_sync(0xffffffffu, wrote);
     if (l == 0) {
 #pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        atomicMin(&out_bbox[a], float_flip(omn[a]));
-        atomicMax(&out_bbox[3 + a], float_flip(omx[a]));
-      }
+      for (int a = 0; a < 3; ++a) { s_box[w * 6 + a] = any ? omn[a] : 3.402823466e38f; s_box[w * 6 + 3 + a] = any ? omx[a] : -3.402823466e38f; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+      const int a = threadIdx.x;
+      float v = s_box[a];
+#pragma unroll
+      for (int ww = 1; ww < kThreads / 32; ++ww) v = a < 3 ? fminf(v, s_box[ww * 6 + a]) : fmaxf(v, s_box[ww * 6 + a]);
+      if (a < 3) { if (v != 3.402823466e38f) atomicMin(&out_bbox[a], float_flip(v)); }
+      else if (v != -3.402823466e38f) atomicMax(&out_bbox[a], float_flip(v));
     }
   }
 }
