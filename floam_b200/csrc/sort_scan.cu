@@ -162,10 +162,10 @@ __device__ __forceinline__ void scan_table_by_last_cta(int* __restrict__ hist, i
 template <int MAXR>
 __device__ __forceinline__ void radix_hist_body(const unsigned int* __restrict__ keys, const int* __restrict__ d_n,
                                                                   const int* __restrict__ d_nbits, int pass, int* __restrict__ hist, int table_stride,
-                                                                  unsigned int* ticket, int* s_hist, int* s_scan, int& s_last) {
+                                                                  unsigned int* ticket, int* s_hist, int* s_scan, int& s_last, int tile) {
   const int n = *d_n;
   const int R = MAXR;
-  const int tile0 = blockIdx.x * kSortThreads * R;
+  const int tile0 = tile * kSortThreads * R;
   if (tile0 >= n) return;
   const int bits = digit_bits(*d_nbits), shift = pass * bits, nbins = 1 << bits;
   const unsigned int dmask = (unsigned int)nbins - 1u;
@@ -186,7 +186,7 @@ __device__ __forceinline__ void radix_hist_body(const unsigned int* __restrict__
   __syncthreads();
   if (nb <= kDirectTiles) {
     for (int d = threadIdx.x; d < nbins; d += kSortThreads) {
-      const int cell = blockIdx.x * nbins + d;
+      const int cell = tile * nbins + d;
       hist[cell] = s_hist[d];
       hist[table_stride + cell] = 0;
       hist[2 * table_stride + cell] = 0;
@@ -194,7 +194,7 @@ __device__ __forceinline__ void radix_hist_body(const unsigned int* __restrict__
     return;
   }
   for (int d = threadIdx.x; d < nbins; d += kSortThreads) {
-    const int cell = d * nb + blockIdx.x;
+    const int cell = d * nb + tile;
     hist[cell] = s_hist[d];
     hist[table_stride + cell] = 0;
     hist[2 * table_stride + cell] = 0;
@@ -210,11 +210,19 @@ __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const unsigned
   __shared__ int s_hist[kMaxBins];
   __shared__ int s_scan[33];
   __shared__ int s_last;
-  switch (sort_rounds(*d_n)) {   // one fully unrolled variant per tile size; the small-input one stays as tight as a fixed-size kernel
-    case 4: radix_hist_body<4>(keys, d_n, d_nbits, pass, hist, table_stride, ticket, s_hist, s_scan, s_last); break;
-    case 8: radix_hist_body<8>(keys, d_n, d_nbits, pass, hist, table_stride, ticket, s_hist, s_scan, s_last); break;
-    case 16: radix_hist_body<16>(keys, d_n, d_nbits, pass, hist, table_stride, ticket, s_hist, s_scan, s_last); break;
-    default: radix_hist_body<32>(keys, d_n, d_nbits, pass, hist, table_stride, ticket, s_hist, s_scan, s_last); break;
+  // The grid is sized for the hardware (one wave), not for the capacity: CTA b takes tiles b, b + gridDim.x, ... of the live input.
+  // (A capacity-sized grid spent most of the kernel draining thousands of CTAs that load two words and exit.)
+  const int n = *d_n;
+  const int rounds = sort_rounds(n);
+  const int nb = sort_tiles(n, rounds);
+  for (int tile = blockIdx.x; tile < nb; tile += gridDim.x) {
+    switch (rounds) {   // one fully unrolled variant per tile size; the small-input one stays as tight as a fixed-size kernel
+      case 4: radix_hist_body<4>(keys, d_n, d_nbits, pass, hist, table_stride, ticket, s_hist, s_scan, s_last, tile); break;
+      case 8: radix_hist_body<8>(keys, d_n, d_nbits, pass, hist, table_stride, ticket, s_hist, s_scan, s_last, tile); break;
+      case 16: radix_hist_body<16>(keys, d_n, d_nbits, pass, hist, table_stride, ticket, s_hist, s_scan, s_last, tile); break;
+      default: radix_hist_body<32>(keys, d_n, d_nbits, pass, hist, table_stride, ticket, s_hist, s_scan, s_last, tile); break;
+    }
+    __syncthreads();   // the shared arrays are reused by the next tile
   }
 }
 
@@ -239,10 +247,10 @@ __device__ __forceinline__ void radix_scatter_body(const unsigned int* __restric
                                                                      unsigned int* __restrict__ keys_out, int* __restrict__ vals_out,
                                                                      const int* __restrict__ d_n, const int* __restrict__ d_nbits, int pass,
                                                                      const int* __restrict__ hist, int* __restrict__ hist_next, unsigned int* ticket,
-                                                                     int (*s_cnt)[256], int* s_base, int* s_scan, int& s_last) {
+                                                                     int (*s_cnt)[256], int* s_base, int* s_scan, int& s_last, int tile) {
   const int n = *d_n;
   const int R = MAXR;
-  const int tile0 = blockIdx.x * kSortThreads * R;
+  const int tile0 = tile * kSortThreads * R;
   if (tile0 >= n) return;
   constexpr int kTileShift = MAXR == 4 ? 10 : MAXR == 8 ? 11 : MAXR == 16 ? 12 : 13;   // log2(kSortThreads * MAXR)
   const int w = warp_id(), l = lane_id();
@@ -285,7 +293,7 @@ __device__ __forceinline__ void radix_scatter_body(const unsigned int* __restric
     if (nb <= kDirectTiles) {
       if (d < nbins) {
         int before = 0;
-        const int b = blockIdx.x;
+        const int b = tile;
         // nb independent L2 reads per thread: unrolled 16-deep so that 16 are in flight (at 4 this loop WAS the kernel: 57 tiles ->
         // 14 dependent round trips)
 #pragma unroll 16
@@ -301,7 +309,7 @@ __device__ __forceinline__ void radix_scatter_body(const unsigned int* __restric
       carry += grand;
       __syncthreads();
     } else if (d < nbins) {
-      base = hist[d * nb + blockIdx.x];
+      base = hist[d * nb + tile];
     }
     if (d < nbins) {
       if (narrow) {
@@ -377,11 +385,17 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const unsig
   __shared__ int s_base[kMaxBins];         // wide digits: one running offset per bin, warps take turns
   __shared__ int s_scan[33];
   __shared__ int s_last;
-  switch (sort_rounds(*d_n)) {
-    case 4: radix_scatter_body<4>(keys_in, vals_in, keys_out, vals_out, d_n, d_nbits, pass, hist, hist_next, ticket, s_cnt, s_base, s_scan, s_last); break;
-    case 8: radix_scatter_body<8>(keys_in, vals_in, keys_out, vals_out, d_n, d_nbits, pass, hist, hist_next, ticket, s_cnt, s_base, s_scan, s_last); break;
-    case 16: radix_scatter_body<16>(keys_in, vals_in, keys_out, vals_out, d_n, d_nbits, pass, hist, hist_next, ticket, s_cnt, s_base, s_scan, s_last); break;
-    default: radix_scatter_body<32>(keys_in, vals_in, keys_out, vals_out, d_n, d_nbits, pass, hist, hist_next, ticket, s_cnt, s_base, s_scan, s_last); break;
+  const int n = *d_n;
+  const int rounds = sort_rounds(n);
+  const int nb = sort_tiles(n, rounds);
+  for (int tile = blockIdx.x; tile < nb; tile += gridDim.x) {   // one wave of CTAs, each looping over its tiles (see radix_hist_kernel)
+    switch (rounds) {
+      case 4: radix_scatter_body<4>(keys_in, vals_in, keys_out, vals_out, d_n, d_nbits, pass, hist, hist_next, ticket, s_cnt, s_base, s_scan, s_last, tile); break;
+      case 8: radix_scatter_body<8>(keys_in, vals_in, keys_out, vals_out, d_n, d_nbits, pass, hist, hist_next, ticket, s_cnt, s_base, s_scan, s_last, tile); break;
+      case 16: radix_scatter_body<16>(keys_in, vals_in, keys_out, vals_out, d_n, d_nbits, pass, hist, hist_next, ticket, s_cnt, s_base, s_scan, s_last, tile); break;
+      default: radix_scatter_body<32>(keys_in, vals_in, keys_out, vals_out, d_n, d_nbits, pass, hist, hist_next, ticket, s_cnt, s_base, s_scan, s_last, tile); break;
+    }
+    __syncthreads();
   }
 }
 
@@ -413,7 +427,8 @@ int sort_workspace_arm(SortWorkspace& ws, cudaStream_t s) {
 void radix_sort_pairs_from(unsigned int* keys, int* vals, unsigned int* keys_alt, int* vals_alt, const int* d_n, const int* d_nbits, int n_max,
                            SortWorkspace& ws, const int* d_skip, cudaStream_t s, unsigned int** sorted_keys, int** sorted_vals) {
   if (n_max > ws.n_max) n_max = ws.n_max;
-  const int nblocks = (n_max + kSortTile - 1) / kSortTile;
+  int nblocks = (n_max + kSortTile - 1) / kSortTile;
+  if (nblocks > 2 * kNumSMs) nblocks = 2 * kNumSMs;   // one wave (the scatter kernel fits two CTAs per SM); CTAs loop over tiles
   unsigned int* kin = keys; int* vin = vals;
   unsigned int* kout = keys_alt; int* vout = vals_alt;
   // four launches: digit counts of pass 0, then three scatters, each of which also counts the digits of the pass after it
@@ -440,24 +455,28 @@ void exclusive_scan_small(int* data, int n, cudaStream_t s) {
 // ---- generic exclusive scan: two kernels, no serial single-CTA step -------------------------------------------------------------
 namespace {
 
+// Both kernels run one wave of CTAs that loop over the live tiles (grids sized for the hardware, not for the capacity).
 __global__ void __launch_bounds__(kScanThreads) scan_tiles_kernel(const int* __restrict__ in, const int* __restrict__ d_n, int n_fixed,
                                                                   int* __restrict__ block_sums, const int* d_skip) {
   pdl_prologue();
   if (d_skip && *d_skip) return;
   const int n = d_n ? *d_n : n_fixed;
-  if (blockIdx.x * kScanTile >= n) return;
   __shared__ int smem[33];
-  const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
-  int sum = 0;
-  if (base + kScanItems <= n) {
-    const int4 q = *reinterpret_cast<const int4*>(in + base);
-    sum = q.x + q.y + q.z + q.w;
-  } else {
+  const int ntiles = (n + kScanTile - 1) / kScanTile;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int base = tile * kScanTile + threadIdx.x * kScanItems;
+    int sum = 0;
+    if (base + kScanItems <= n) {
+      const int4 q = *reinterpret_cast<const int4*>(in + base);
+      sum = q.x + q.y + q.z + q.w;
+    } else {
 #pragma unroll
-    for (int k = 0; k < kScanItems; ++k) sum += (base + k < n) ? in[base + k] : 0;
+      for (int k = 0; k < kScanItems; ++k) sum += (base + k < n) ? in[base + k] : 0;
+    }
+    const int total = block_sum(sum, smem);
+    if (threadIdx.x == 0) block_sums[tile] = total;
+    __syncthreads();
   }
-  const int total = block_sum(sum, smem);
-  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
 }
 
 __global__ void __launch_bounds__(kScanThreads) scan_add_kernel(const int* __restrict__ in, int* __restrict__ out, const int* __restrict__ d_n, int n_fixed,
@@ -466,19 +485,22 @@ __global__ void __launch_bounds__(kScanThreads) scan_add_kernel(const int* __res
   if (d_skip && *d_skip) return;
   const int n = d_n ? *d_n : n_fixed;
   if (n == 0) { if (blockIdx.x == 0 && threadIdx.x == 0) out[0] = 0; return; }
-  if (blockIdx.x * kScanTile >= n) return;
   __shared__ int smem[33];
-  const int offset = tile_offset(block_sums, blockIdx.x, smem);
-  const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
-  int v[kScanItems];
-  int sum = 0;
+  const int ntiles = (n + kScanTile - 1) / kScanTile;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int offset = tile_offset(block_sums, tile, smem);
+    const int base = tile * kScanTile + threadIdx.x * kScanItems;
+    int v[kScanItems];
+    int sum = 0;
 #pragma unroll
-  for (int k = 0; k < kScanItems; ++k) { v[k] = (base + k < n) ? in[base + k] : 0; sum += v[k]; }
-  int total;
-  int ex = block_excl_scan(sum, smem, &total) + offset;
+    for (int k = 0; k < kScanItems; ++k) { v[k] = (base + k < n) ? in[base + k] : 0; sum += v[k]; }
+    int total;
+    int ex = block_excl_scan(sum, smem, &total) + offset;
 #pragma unroll
-  for (int k = 0; k < kScanItems; ++k) { if (base + k < n) out[base + k] = ex; ex += v[k]; }
-  if (blockIdx.x == (n - 1) / kScanTile && threadIdx.x == 0) out[n] = offset + total;  // grand total
+    for (int k = 0; k < kScanItems; ++k) { if (base + k < n) out[base + k] = ex; ex += v[k]; }
+    if (tile == ntiles - 1 && threadIdx.x == 0) out[n] = offset + total;  // grand total
+    __syncthreads();
+  }
 }
 
 }  // namespace
@@ -486,14 +508,18 @@ __global__ void __launch_bounds__(kScanThreads) scan_add_kernel(const int* __res
 size_t scan_workspace_bytes(int n_max) { return ((size_t)(n_max + kScanTile - 1) / kScanTile + 2) * 4 + 256; }
 void scan_workspace_bind(ScanWorkspace& ws, void* mem, int n_max) { ws.block_sums = (int*)mem; ws.n_max = n_max; }
 
-void exclusive_scan_i32(const int* in, int* out, const int* d_n, int n_fixed, int n_max, ScanWorkspace& ws, const int* d_skip, cudaStream_t s) {
+static int scan_grid(int n_max) {
   const int nblocks = (n_max + kScanTile - 1) / kScanTile;
+  return nblocks > 2 * kNumSMs ? 2 * kNumSMs : nblocks;
+}
+void exclusive_scan_i32(const int* in, int* out, const int* d_n, int n_fixed, int n_max, ScanWorkspace& ws, const int* d_skip, cudaStream_t s) {
+  const int nblocks = scan_grid(n_max);
   FLOAM_LAUNCH(K_SCAN_TILES, scan_tiles_kernel, nblocks, kScanThreads, s, in, d_n, n_fixed, ws.block_sums, d_skip);
   FLOAM_LAUNCH(K_SCAN_ADD, scan_add_kernel, nblocks, kScanThreads, s, in, out, d_n, n_fixed, ws.block_sums, d_skip);
 }
 
 void exclusive_scan_with_tile_sums(const int* in, int* out, const int* d_n, int n_max, const int* tile_sums, const int* d_skip, cudaStream_t s) {
-  const int nblocks = (n_max + kScanTile - 1) / kScanTile;
+  const int nblocks = scan_grid(n_max);
   FLOAM_LAUNCH(K_SCAN_ADD, scan_add_kernel, nblocks, kScanThreads, s, in, out, d_n, 0, tile_sums, d_skip);
 }
 

@@ -190,39 +190,44 @@ __global__ void __launch_bounds__(kScanThreads) voxel_rank_kernel(const unsigned
   if (d_skip && *d_skip) return;
   const int n = *d_n;
   if (n == 0) { if (blockIdx.x == 0 && threadIdx.x == 0) { *d_nout = 0; head_pos[0] = 0; } return; }
-  if (blockIdx.x * kScanTile >= n) return;
   __shared__ int smem[33];
   __shared__ int s_offset;
-  const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
-  int h[kScanItems];
-  int sum = 0;
+  const int ntiles = (n + kScanTile - 1) / kScanTile;
+  // one wave of CTAs (the grid is sized for the hardware, not the capacity), each taking tiles b, b + gridDim.x, ...: a tile only
+  // ever waits for lower-numbered tiles, which belong to CTAs that are resident or done
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int base = tile * kScanTile + threadIdx.x * kScanItems;
+    int h[kScanItems];
+    int sum = 0;
 #pragma unroll
-  for (int k = 0; k < kScanItems; ++k) { h[k] = (base + k < n) ? is_head(keys, base + k) : 0; sum += h[k]; }
-  int total;
-  int rank = block_excl_scan(sum, smem, &total);
-  if (threadIdx.x == 0) {
-    volatile int* st = tile_state;
-    int before = 0;
-    if (blockIdx.x > 0) {
-      st[blockIdx.x] = (total << 2) | 1;
-      for (int t = (int)blockIdx.x - 1; t >= 0; --t) {
-        int v;
-        while (((v = st[t]) & 3) == 0) __nanosleep(20);
-        before += v >> 2;
-        if ((v & 3) == 2) break;
+    for (int k = 0; k < kScanItems; ++k) { h[k] = (base + k < n) ? is_head(keys, base + k) : 0; sum += h[k]; }
+    int total;
+    int rank = block_excl_scan(sum, smem, &total);
+    if (threadIdx.x == 0) {
+      volatile int* st = tile_state;
+      int before = 0;
+      if (tile > 0) {
+        st[tile] = (total << 2) | 1;
+        for (int t = tile - 1; t >= 0; --t) {
+          int v;
+          while (((v = st[t]) & 3) == 0) __nanosleep(20);
+          before += v >> 2;
+          if ((v & 3) == 2) break;
+        }
       }
+      __threadfence();
+      st[tile] = ((before + total) << 2) | 2;
+      s_offset = before;
     }
-    __threadfence();
-    st[blockIdx.x] = ((before + total) << 2) | 2;
-    s_offset = before;
-  }
-  __syncthreads();
-  const int offset = s_offset;
-  rank += offset;
+    __syncthreads();
+    const int offset = s_offset;
+    rank += offset;
 #pragma unroll
-  for (int k = 0; k < kScanItems; ++k)
-    if (h[k]) head_pos[rank++] = base + k;
-  if (blockIdx.x == (n - 1) / kScanTile && threadIdx.x == 0) { *d_nout = offset + total; head_pos[offset + total] = n; }
+    for (int k = 0; k < kScanItems; ++k)
+      if (h[k]) head_pos[rank++] = base + k;
+    if (tile == ntiles - 1 && threadIdx.x == 0) { *d_nout = offset + total; head_pos[offset + total] = n; }
+    __syncthreads();   // s_offset / smem are reused by the next tile
+  }
 }
 
 // pcl::CentroidPoint<PointXYZI>: float sums in run order (ascending input index), then / n. The ORDER of the additions is fixed, so
@@ -437,7 +442,8 @@ void voxel_grid_device(const void* d_in, int stride_bytes, const int* d_n, int n
   if (n_max > ws.n_max) n_max = ws.n_max;
   const char* in = (const char*)d_in;
   const int g = grid_for(n_max);
-  const int gt = (n_max + kScanTile - 1) / kScanTile;
+  int gt = (n_max + kScanTile - 1) / kScanTile;
+  if (gt > 2 * kNumSMs) gt = 2 * kNumSMs;   // voxel_rank_kernel loops over tiles
   int* counts = ws.d_counts;   // [0] input points, [1] points kept by the crop
   FLOAM_LAUNCH(K_VOXEL_BBOX, voxel_bbox_kernel, g, kThreads, s, in, stride_bytes, d_n, d_extra, cap, d_crop, ws.bbox, counts, app, d_skip);
   FLOAM_LAUNCH(K_VOXEL_KEYS, voxel_keys_kernel, g, kThreads, s, in, stride_bytes, counts, leaf, d_crop, ws.bbox, ws.keys, ws.vals, ws.d_nbits, ws.d_passthrough,
@@ -446,7 +452,8 @@ void voxel_grid_device(const void* d_in, int stride_bytes, const int* d_n, int n
   int* svals = nullptr;
   radix_sort_pairs(ws.keys, ws.vals, counts, ws.d_nbits, n_max, ws.sort, d_skip, s, &skeys, &svals);
   FLOAM_LAUNCH(K_VOXEL_RANK, voxel_rank_kernel, gt, kScanThreads, s, skeys, counts + 1, ws.scan.block_sums, ws.flags, d_nout, d_skip);
-  FLOAM_LAUNCH(K_VOXEL_REDUCE, voxel_reduce_kernel, g, kThreads, s, in, stride_bytes, svals, ws.flags, d_nout, d_out, ws.bbox, counts, out_bbox, d_skip);
+  const int gr = g < 3 * kNumSMs ? g : 3 * kNumSMs;   // 80 registers + 33 KB shared memory: three CTAs per SM make one wave; the kernel strides
+  FLOAM_LAUNCH(K_VOXEL_REDUCE, voxel_reduce_kernel, gr, kThreads, s, in, stride_bytes, svals, ws.flags, d_nout, d_out, ws.bbox, counts, out_bbox, d_skip);
 }
 
 void repack_xyzi_device(const void* d_in32, const int* d_n, int n_max, P4* d_out, cudaStream_t s) {

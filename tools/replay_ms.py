@@ -6,7 +6,7 @@ from floam_b200 import capi, synth
 frames = int(sys.argv[1]) if len(sys.argv) > 1 else 212
 seq = synth.Sequence("hdl64", seed=0)
 scans, off = seq.scans(0, frames)
-ctx = capi.Context(num_lines=64, loss="cauchy", max_scan_points=seq.max_points + 1024, max_map_points=1 << 21, max_global_map_points=0, max_grid_cells=1 << 23)
+ctx = capi.Context(num_lines=64, loss="cauchy", max_scan_points=seq.max_points + 1024, max_map_points=1 << int(__import__("os").environ.get("MAPBITS", "21")), max_global_map_points=0, max_grid_cells=1 << int(__import__("os").environ.get("CELLBITS", "23")))
 ctx.stage_scans(scans, off)
 p0, _ = ctx.replay_staged(0, 12)
 res = []
