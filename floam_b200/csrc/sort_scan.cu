@@ -115,14 +115,18 @@ constexpr int kSortMinRounds = 4;                              // keys per lane:
 constexpr int kSortMaxRounds = 32;                             // ... up to 32 (tile = 8192 keys) for large ones
 constexpr int kSortTile = kSortThreads * kSortMinRounds;       // smallest tile: the launch grid is sized for it
 constexpr int kDirectTiles = 256;                              // up to this many tiles the scatter CTAs scan the count table themselves
-constexpr int kMaxBins = 2048;                                 // 11-bit digits at most (3 x 11 >= 31 key bits)
+constexpr int kMaxBins = 2048;
+constexpr int kNarrowBins = 1024;                              // digits up to 10 bits (keys up to 30 bits) rank with per-warp counters                                 // 11-bit digits at most (3 x 11 >= 31 key bits)
 
 // Keys per lane, decided on the device from the live element count: the tile grows with the input so that the [tile][digit] count
 // table stays around 128 rows — every scatter CTA reads all of it, which is quadratic in the number of tiles (at a fixed 1024-key
 // tile a 236k-key sort spent 47 us per pass there).
-__device__ __forceinline__ int sort_rounds(int n) {
+// Wide digits (keys above 24 bits: 512 or 1024 bins) widen the rows, so they get proportionally fewer of them.
+__device__ __forceinline__ int sort_rounds(int n, int nbits) {
+  const int bits = (nbits + 2) / 3;
+  const int rows = bits <= 8 ? 128 : (bits == 9 ? 64 : 32);
   int r = kSortMinRounds;
-  while (r < kSortMaxRounds && n > 128 * kSortThreads * r) r <<= 1;
+  while (r < kSortMaxRounds && n > rows * kSortThreads * r) r <<= 1;
   return r;
 }
 __device__ __forceinline__ int sort_tiles(int n, int rounds) { const int tile = kSortThreads * rounds; return (n + tile - 1) / tile; }
@@ -213,7 +217,7 @@ __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const unsigned
   // The grid is sized for the hardware (one wave), not for the capacity: CTA b takes tiles b, b + gridDim.x, ... of the live input.
   // (A capacity-sized grid spent most of the kernel draining thousands of CTAs that load two words and exit.)
   const int n = *d_n;
-  const int rounds = sort_rounds(n);
+  const int rounds = sort_rounds(n, *d_nbits);
   const int nb = sort_tiles(n, rounds);
   for (int tile = blockIdx.x; tile < nb; tile += gridDim.x) {
     switch (rounds) {   // one fully unrolled variant per tile size; the small-input one stays as tight as a fixed-size kernel
@@ -247,7 +251,7 @@ __device__ __forceinline__ void radix_scatter_body(const unsigned int* __restric
                                                                      unsigned int* __restrict__ keys_out, int* __restrict__ vals_out,
                                                                      const int* __restrict__ d_n, const int* __restrict__ d_nbits, int pass,
                                                                      const int* __restrict__ hist, int* __restrict__ hist_next, unsigned int* ticket,
-                                                                     int (*s_cnt)[256], int* s_base, int* s_scan, int& s_last, int tile) {
+                                                                     int (*s_cnt)[kNarrowBins], int* s_base, int* s_scan, int& s_last, int tile) {
   const int n = *d_n;
   const int R = MAXR;
   const int tile0 = tile * kSortThreads * R;
@@ -268,11 +272,12 @@ __device__ __forceinline__ void radix_scatter_body(const unsigned int* __restric
   const unsigned int dmask = (unsigned int)nbins - 1u;
   const int nb = sort_tiles(n, R);
   const bool direct = nb <= kDirectTiles;
-  const bool narrow = nbins <= 256;
+  const bool narrow = nbins <= kNarrowBins;
   unsigned int mask[MAXR];
   int* cnt = s_cnt[w];
   if (narrow) {
-    for (int i = threadIdx.x; i < kSortWarps * 256; i += kSortThreads) (&s_cnt[0][0])[i] = 0;
+    for (int ww = 0; ww < kSortWarps; ++ww)
+      for (int d = threadIdx.x; d < nbins; d += kSortThreads) s_cnt[ww][d] = 0;
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < MAXR; ++r) {
@@ -381,12 +386,12 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const unsig
                                                                      const int* d_skip) {
   pdl_prologue();
   if (d_skip && *d_skip) return;
-  __shared__ int s_cnt[kSortWarps][256];   // narrow digits: per-warp counters / running offsets
+  __shared__ int s_cnt[kSortWarps][kNarrowBins];   // digits up to 10 bits: per-warp counters / running offsets (32 KB)
   __shared__ int s_base[kMaxBins];         // wide digits: one running offset per bin, warps take turns
   __shared__ int s_scan[33];
   __shared__ int s_last;
   const int n = *d_n;
-  const int rounds = sort_rounds(n);
+  const int rounds = sort_rounds(n, *d_nbits);
   const int nb = sort_tiles(n, rounds);
   for (int tile = blockIdx.x; tile < nb; tile += gridDim.x) {   // one wave of CTAs, each looping over its tiles (see radix_hist_kernel)
     switch (rounds) {
