@@ -124,7 +124,7 @@ constexpr int kNarrowBins = 1024;                              // digits up to 1
 // Wide digits (keys above 24 bits: 512 or 1024 bins) widen the rows, so they get proportionally fewer of them.
 __device__ __forceinline__ int sort_rounds(int n, int nbits) {
   const int bits = (nbits + 2) / 3;
-  const int rows = bits <= 8 ? 128 : (bits == 9 ? 64 : 32);
+  const int rows = bits <= 8 ? 128 : 64;
   int r = kSortMinRounds;
   while (r < kSortMaxRounds && n > rows * kSortThreads * r) r <<= 1;
   return r;
