@@ -433,7 +433,7 @@ void radix_sort_pairs_from(unsigned int* keys, int* vals, unsigned int* keys_alt
                            SortWorkspace& ws, const int* d_skip, cudaStream_t s, unsigned int** sorted_keys, int** sorted_vals) {
   if (n_max > ws.n_max) n_max = ws.n_max;
   int nblocks = (n_max + kSortTile - 1) / kSortTile;
-  if (nblocks > 2 * kNumSMs) nblocks = 2 * kNumSMs;   // one wave (the scatter kernel fits two CTAs per SM); CTAs loop over tiles
+  if (nblocks > kNumSMs) nblocks = kNumSMs;   // one wave (the scatter kernel's registers allow one CTA per SM); CTAs loop over tiles
   unsigned int* kin = keys; int* vin = vals;
   unsigned int* kout = keys_alt; int* vout = vals_alt;
   // four launches: digit counts of pass 0, then three scatters, each of which also counts the digits of the pass after it
