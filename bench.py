@@ -155,8 +155,10 @@ def algorithmic_bytes(kernel, st):
         "voxel_reduce": 24 * st["sort_n"] + 16 * st["sort_out"],
         "voxel_keys": 16 * st["sort_n"] + 8 * st["sort_n"],
         "voxel_bbox": 16 * st["sort_n"],
+        "voxel_rank": 4 * st["sort_n"] + 4 * st["sort_out"],   # sorted keys in, run starts out
+        "scan_add": 8 * M, "unpack_pc2": 22 * N + 32 * N,
         "grid_scatter": 32 * M, "grid_count": 16 * M, "grid_bbox": 16 * M,
-        "map_append": 32 * Q, "map_commit": 32 * M, "crop_flags": 16 * M, "crop_scatter": 32 * M,
+        "crop_flags": 16 * M, "crop_scatter": 32 * M,
     }
     return table.get(kernel)
 

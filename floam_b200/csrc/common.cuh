@@ -51,8 +51,6 @@ enum KernelSlot {
   K_ASSOC_EVAL,
   K_LM_CLUSTER,
   K_FINISH,
-  K_MAP_APPEND,
-  K_MAP_COMMIT,
   K_COMPENSATE_VELOCITY,
   K_KNN5,
   K_RADIX_HIST,
@@ -63,12 +61,12 @@ enum KernelSlot {
   K_VOXEL_RANK,
   K_VOXEL_BBOX,
   K_VOXEL_KEYS,
-  K_VOXEL_HEADS,
   K_VOXEL_REDUCE,
   K_REPACK,
   K_CROP_FLAGS,
   K_CROP_SCATTER,
   K_RECORD_POSE,
+  K_MAIL_STATE,
   K_UNPACK_PC2,
   K_NOOP,
   K_NUM_SLOTS

@@ -37,7 +37,7 @@ static_assert(kAssocBlocks <= 1024, "partials rows");
 
 inline int grid_for(int n_max) {
   int g = (n_max + kThreads - 1) / kThreads;
-  const int cap = kNumSMs * 8;
+  const int cap = kNumSMs * 4;   // the kernels stride; empty CTAs of a capacity-sized grid are not free
   return g < 1 ? 1 : (g > cap ? cap : g);
 }
 
@@ -1204,7 +1204,7 @@ __global__ void mail_state_kernel(const PoseState* __restrict__ S, const int* __
   // no system fence: the host reads the mailbox only after an event recorded behind this kernel, and kernel completion flushes the stores
 }
 void odom_mail_state(OdomDevice& od, const int* d_flags, PoseState* h_state, int* h_flags, cudaStream_t s) {
-  FLOAM_LAUNCH(K_RECORD_POSE, mail_state_kernel, 1, 128, s, od.state, d_flags, h_state, h_flags);
+  FLOAM_LAUNCH(K_MAIL_STATE, mail_state_kernel, 1, 128, s, od.state, d_flags, h_state, h_flags);
 }
 
 void odom_record_pose(OdomDevice& od, cudaStream_t s) { FLOAM_LAUNCH(K_RECORD_POSE, record_pose_kernel, 1, 32, s, od.state, od.traj, od.traj_cap); }

@@ -39,8 +39,6 @@ static const char* const kSlotNames[K_NUM_SLOTS] = {
   "assoc_eval",
   "lm_cluster",
   "finish",
-  "map_append",
-  "map_commit",
   "compensate_velocity",
   "knn5",
   "radix_hist",
@@ -51,12 +49,12 @@ static const char* const kSlotNames[K_NUM_SLOTS] = {
   "voxel_rank",
   "voxel_bbox",
   "voxel_keys",
-  "voxel_heads",
   "voxel_reduce",
   "repack",
   "crop_flags",
   "crop_scatter",
   "record_pose",
+  "mail_state",
   "unpack_pc2",
   "noop"
 };

@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(kThreads) repack_kernel(const char* __restrict
 
 inline int grid_for(int n_max) {
   int g = (n_max + kThreads - 1) / kThreads;
-  const int cap = kNumSMs * 8;
+  const int cap = kNumSMs * 4;   // the kernels stride; empty CTAs of a capacity-sized grid are not free
   return g < 1 ? 1 : (g > cap ? cap : g);
 }
 

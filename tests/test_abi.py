@@ -53,6 +53,36 @@ def test_point_layouts(capi):
     assert capi.POINT_I.fields["intensity"][1] == 16
 
 
+def test_pointcloud2_layout_and_packing_helper(capi):
+    # floam_pc2_layout is 11 32-bit words; the helper that builds msg.data for the GPU tests is checked here against a hand-built
+    # Velodyne XYZIRT point (22 bytes: x y z intensity f32 @0/4/8/12, ring u16 @16, time f32 @18) and a big-endian, row-padded layout
+    import ctypes
+    import struct
+    import numpy as np
+    assert ctypes.sizeof(capi.Pc2Layout) == 44
+    pts = np.zeros(4, capi.POINT_IRT)
+    pts["x"] = [1.5, -2.0, 3.25, 0.0]; pts["y"] = [0.5, 8.0, -1.0, 2.0]; pts["z"] = [9.0, 0.25, 0.0, -4.0]
+    pts["intensity"] = [0.1, 0.2, 0.3, 0.4]; pts["ring"] = [0, 7, 63, 15]; pts["time"] = [0.0, 0.01, 0.05, 0.099]
+    L = capi.pc2_layout(4, 22)
+    raw = capi.pack_pointcloud2(pts, L)
+    assert raw.dtype == np.uint8 and len(raw) == 4 * 22
+    for i in range(4):
+        x, y, z, it, ring, t = struct.unpack_from("<ffffHf", raw.tobytes(), i * 22)
+        assert (x, y, z, ring) == (pts["x"][i], pts["y"][i], pts["z"][i], pts["ring"][i])
+        assert np.float32(it) == pts["intensity"][i] and np.float32(t) == pts["time"][i]
+    L = capi.pc2_layout(4, 24, x=4, y=8, z=12, intensity=16, ring=0, time=20, height=2, row_step=2 * 24 + 8, bigendian=True)
+    raw = capi.pack_pointcloud2(pts, L).tobytes()
+    assert len(raw) == 2 * (2 * 24 + 8)
+    for i in range(4):
+        base = (i // 2) * L.row_step + (i % 2) * 24
+        assert struct.unpack_from(">H", raw, base)[0] == pts["ring"][i] and struct.unpack_from(">f", raw, base + 12)[0] == pts["z"][i]
+    assert raw[2 * 24:2 * 24 + 8] == b"\xab" * 8          # row padding is left alone
+    # the library refuses a call without a context before it looks at anything else (no GPU here)
+    out = np.zeros(4, capi.POINT_IRT)
+    rc = capi.lib().floam_unpack_pointcloud2(None, raw, ctypes.byref(L), out.ctypes.data_as(ctypes.c_void_p))
+    assert rc == capi.ERR_ARG
+
+
 def test_no_cpu_fallback_without_device(capi):
     import torch
     if torch.cuda.is_available():
