@@ -271,6 +271,14 @@ class Context:
         rc = _check(lib().floam_process_scan_imu(self.h, _p(pts), len(pts), C.byref(st), _p(ex), int(deskew), _p(pose)), "floam_process_scan_imu", allow=(NO_IMU,))
         return rc, pose, st.value
 
+    def process_submit_imu(self, pts, stamp_us, extr_xyzw, deskew=False):
+        """floam_process_submit with the IMU steps folded in; returns (status, new_stamp_us). status NO_IMU = nothing was submitted.
+        pts must stay alive until the matching process_wait returns."""
+        assert pts.dtype == POINT_IRT and pts.flags.c_contiguous
+        st = C.c_uint64(int(stamp_us)); ex = np.ascontiguousarray(extr_xyzw, np.float64)
+        rc = _check(lib().floam_process_submit_imu(self.h, _p(pts), len(pts), C.byref(st), _p(ex), int(deskew)), "floam_process_submit_imu", allow=(NO_IMU,))
+        return rc, st.value
+
     def process_submit(self, pts, n=None, deskew=False):
         """pts must stay alive (ideally a PinnedBuffer.array slice) until the matching process_wait returns."""
         assert pts.dtype == POINT_IRT and pts.flags.c_contiguous

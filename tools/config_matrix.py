@@ -42,6 +42,28 @@ def run(cfg):
         poses = np.array(poses)
         steady = ms[12:]
         out["frames_per_s_e2e_sync"] = 1e3 / float(np.mean(steady)); out["p50_ms"] = float(np.percentile(steady, 50)); out["p99_ms"] = float(np.percentile(steady, 99))
+        # the same frames again through the pipelined calls (three in flight) on a fresh context: throughput figure, poses must be identical
+        ctx.close()
+        ctx = capi.Context(**prm)
+        for k in range(-40, 20 * frames + 40):
+            t = 100.0 + 0.005 * k
+            ctx.imu_push(t, seq.imu(max(t - 100.0, 0.0)))
+        keep = [scans[off[f]:off[f + 1]].copy() for f in range(frames)]
+        Q = []; pending = 0; t12 = None
+        for f in range(frames):
+            if f == 12:
+                while pending:
+                    Q.append(ctx.process_wait()); pending -= 1
+                t12 = time.perf_counter()
+            if pending == 3:
+                Q.append(ctx.process_wait()); pending -= 1
+            rc, _ = ctx.process_submit_imu(keep[f], int((100.0 + 0.1 * f) * 1e6), ext, deskew)
+            assert rc == capi.OK
+            pending += 1
+        while pending:
+            Q.append(ctx.process_wait()); pending -= 1
+        out["frames_per_s_e2e_pipelined"] = (frames - 12) / (time.perf_counter() - t12)
+        out["pipelined_poses_identical"] = bool(np.array_equal(np.array(Q), poses))
     else:
         ctx.stage_scans(scans, off)
         p0, _ = ctx.replay_staged(0, 12)
