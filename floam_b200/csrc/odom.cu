@@ -714,12 +714,14 @@ __global__ void __launch_bounds__(kKnnThreads) assoc_knn_kernel(const PoseState*
                                                                  const P4* __restrict__ ds_surf, const int* __restrict__ d_nds, LocalMap emap, LocalMap smap,
                                                                  int qcap, int* __restrict__ knn_ids, float* __restrict__ knn_d2) {
   pdl_prologue();
-  if (S->skip_solve) return;
+  // every scalar this kernel needs is requested before the first one is looked at: one L2 round trip, not three
+  const int skip = S->skip_solve;
   const int nde = *d_nde, nds = *d_nds;
   double x[7];
 #pragma unroll
   for (int k = 0; k < 7; ++k) x[k] = S->x[k];
   const GridDims ge = *emap.dims, gs = *smap.dims;
+  if (skip) return;
   const int warps_total = gridDim.x * (kKnnThreads / 32);
   for (int slot = blockIdx.x * (kKnnThreads / 32) + warp_id(); slot < nde + nds; slot += warps_total) {
     const bool is_edge = slot < nde;
@@ -749,11 +751,12 @@ __global__ void __launch_bounds__(kEvalThreads) assoc_eval_kernel(PoseState* __r
                                                                    int qcap, double* __restrict__ corr, unsigned char* __restrict__ corr_ok,
                                                                    const int* __restrict__ knn_ids, int loss, double* __restrict__ partials) {
   pdl_prologue();
-  if (S->skip_solve) return;
+  const int skip = S->skip_solve;   // scalars requested together (see assoc_knn_kernel)
   const int nde = *d_nde, nds = *d_nds;
   double x[7];
 #pragma unroll
   for (int k = 0; k < 7; ++k) x[k] = S->x[k];
+  if (skip) return;
   Accum A;
 #pragma unroll
   for (int k = 0; k < kLmTerms; ++k) A.v[k] = 0.0;
