@@ -269,6 +269,7 @@ int floam_create(const floam_params* params, int device, floam_ctx** out) {
   c->device = device;
   c->use_graphs = std::getenv("FLOAM_NO_GRAPHS") == nullptr;
   if (const char* e = std::getenv("FLOAM_PDL")) g_use_pdl = std::atoi(e) != 0;   // programmatic dependent launch (common.cuh)
+  if (const char* e = std::getenv("FLOAM_PDL_SOLVE")) g_pdl_solve = std::atoi(e) != 0;
   auto fail = [&](int rc) { floam_destroy(c); return rc; };
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(FLOAM_ERR_CUDA);
   if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(FLOAM_ERR_CUDA);

@@ -98,14 +98,21 @@ void launch_timer_fold(LaunchTimer* t, int first, int last);  // folds the pairs
 // (griddepcontrol.wait) before touching memory. With the launch attribute below, the launch latency of kernel k+1 overlaps the
 // execution of kernel k; without it both instructions are no-ops. The frame is a chain of ~60 dependent, microsecond-sized
 // kernels, so this is where the time goes.
-extern bool g_use_pdl;
+extern bool g_use_pdl;         // FLOAM_PDL=1: every launch (measured slower: early-launched CTAs of wide kernels crowd the SMs)
+extern bool g_pdl_solve;       // the serial solve chain only (prediction -> kNN -> fit -> LM, narrow kernels): FLOAM_PDL_SOLVE, default on
+extern thread_local bool t_pdl_scope;   // set around the launches of that chain (PdlSolveScope)
+struct PdlSolveScope {
+  bool saved;
+  PdlSolveScope() : saved(t_pdl_scope) { t_pdl_scope = g_pdl_solve; }
+  ~PdlSolveScope() { t_pdl_scope = saved; }
+};
 __device__ __forceinline__ void pdl_prologue() {
   asm volatile("griddepcontrol.launch_dependents;");
   asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 template <typename... KArgs, typename... Args>
 inline void launch_kernel_dyn(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t dyn_smem, cudaStream_t s, Args&&... args) {
-  if (!g_use_pdl) {
+  if (!g_use_pdl && !t_pdl_scope) {
     kern<<<grid, block, dyn_smem, s>>>(KArgs(args)...);
     return;
   }

@@ -1238,6 +1238,7 @@ void odom_update_device(OdomDevice& od, const void* d_edge, const int* d_ne, con
   // downSamplingToMap :137-142, unless the frame pipeline already did it ahead of time
   if (!ds_ready) odom_downsample_device(od, d_edge, d_ne, d_surf, d_ns, stride, n_max, *od.vws, *od.vws_aux, s, a, od.ev_fork, od.ev_join);
   for (int it = 0; it < od.optimization_count; ++it) {
+    PdlSolveScope pdl;   // kNN, fit and LM may be scheduled while their predecessor drains (griddepcontrol.wait orders the data)
     FLOAM_LAUNCH(K_ASSOC_KNN, assoc_knn_kernel, kKnnBlocks, kKnnThreads, s, S, od.ds_edge, od.d_nds_edge, od.ds_surf, od.d_nds_surf, od.edge_map, od.surf_map,
                  od.qcap, od.knn_ids, od.knn_d2);
     FLOAM_LAUNCH(K_ASSOC_EVAL, assoc_eval_kernel, kAssocBlocks, kEvalThreads, s, S, od.ds_edge, od.d_nds_edge, od.ds_surf, od.d_nds_surf, od.edge_map, od.surf_map,

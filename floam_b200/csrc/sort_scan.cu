@@ -10,6 +10,8 @@ namespace floam {
 thread_local long long g_launches = 0;
 thread_local LaunchTimer* g_timer = nullptr;
 bool g_use_pdl = false;
+bool g_pdl_solve = false;
+thread_local bool t_pdl_scope = false;
 
 static const char* const kSlotNames[K_NUM_SLOTS] = {
   "ring_count",
