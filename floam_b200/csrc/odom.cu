@@ -303,8 +303,11 @@ struct Knn5 {
   int id[5];
 };
 
-__device__ __forceinline__ void knn5_insert(Knn5& k, float dist, int idx) {
-  if (dist > k.d[4] || (dist == k.d[4] && idx > k.id[4])) return;
+// rej: smallest distance this lane has seen and does NOT hold in its list (rejected candidates and evicted entries); with the heads
+// left over after the merge it yields the 6th distance, which is what lets the next outer iteration reuse the neighbour set
+__device__ __forceinline__ void knn5_insert(Knn5& k, float dist, int idx, float& rej) {
+  if (dist > k.d[4] || (dist == k.d[4] && idx > k.id[4])) { rej = fminf(rej, dist); return; }
+  rej = fminf(rej, k.d[4]);
   // replace the current worst, then bubble up by (distance, index); static indices keep the set in registers
   k.d[4] = dist; k.id[4] = idx;
 #pragma unroll
@@ -333,13 +336,15 @@ __device__ __forceinline__ float knn5_warp_bound(const Knn5& k) {
   return __uint_as_float(m);
 }
 
-__device__ __forceinline__ void knn5_scan_range(int b, int e, float qx, float qy, float qz, float bound, const float4* __restrict__ cell_pts, Knn5& k) {
+__device__ __forceinline__ void knn5_scan_range(int b, int e, float qx, float qy, float qz, float bound, const float4* __restrict__ cell_pts, Knn5& k,
+                                                float& rej) {
   for (int i = b + lane_id(); i < e; i += 32) {
     const float4 p = __ldg(cell_pts + i);
     // flann::L2_Simple: ((0 + dx^2) + dy^2) + dz^2 in float, no contraction
     const float dx = fsub(qx, p.x), dy = fsub(qy, p.y), dz = fsub(qz, p.z);
     const float dist = fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
-    if (dist <= bound) knn5_insert(k, dist, __float_as_int(p.w));
+    if (dist <= bound) knn5_insert(k, dist, __float_as_int(p.w), rej);
+    else rej = fminf(rej, dist);
   }
 }
 
@@ -353,9 +358,11 @@ __device__ __forceinline__ void knn5_scan_range(int b, int e, float qx, float qy
 //    candidate of a skipped cell has a computed distance >= that figure > bound >= the final 5th distance: the result is the
 //    same set, ties included, as the exhaustive scan.
 constexpr int kKnnPruneAbove = 256;   // candidates in the 27 cells
+// others_min: lower bound of the computed distance of every map point that is inside the 27 cells and NOT in the result.
 __device__ __forceinline__ void knn5_search_warp(const GridDims& g, const int* __restrict__ cell_start, const float4* __restrict__ cell_pts, float qx,
-                                                 float qy, float qz, Knn5& out) {
+                                                 float qy, float qz, Knn5& out, float& others_min) {
   const int l = lane_id();
+  float rej = FLT_MAX, skipped = FLT_MAX;
   Knn5 k;
 #pragma unroll
   for (int j = 0; j < 5; ++j) { k.d[j] = FLT_MAX; k.id[j] = 0x7fffffff; }
@@ -391,17 +398,18 @@ __device__ __forceinline__ void knn5_search_warp(const GridDims& g, const int* _
 #pragma unroll
     for (int r = 0; r < 9; ++r) {
       const int b = __shfl_sync(0xffffffffu, rb, r), e = __shfl_sync(0xffffffffu, re, r);
-      knn5_scan_range(b, e, qx, qy, qz, FLT_MAX, cell_pts, k);
+      knn5_scan_range(b, e, qx, qy, qz, FLT_MAX, cell_pts, k, rej);
     }
   } else {
-    knn5_scan_range(__shfl_sync(0xffffffffu, cb, 13), __shfl_sync(0xffffffffu, ce, 13), qx, qy, qz, FLT_MAX, cell_pts, k);
+    knn5_scan_range(__shfl_sync(0xffffffffu, cb, 13), __shfl_sync(0xffffffffu, ce, 13), qx, qy, qz, FLT_MAX, cell_pts, k, rej);
     float bound = knn5_warp_bound(k);
 #pragma unroll 1
     for (int c = 0; c < 27; ++c) {
       const int b = __shfl_sync(0xffffffffu, cb, c), e = __shfl_sync(0xffffffffu, ce, c);
       const float dm = __shfl_sync(0xffffffffu, cdm, c);
-      if (c == 13 || e <= b || dm > bound) continue;   // warp-uniform
-      knn5_scan_range(b, e, qx, qy, qz, bound, cell_pts, k);
+      if (c == 13 || e <= b) continue;                 // warp-uniform
+      if (dm > bound) { skipped = fminf(skipped, dm); continue; }
+      knn5_scan_range(b, e, qx, qy, qz, bound, cell_pts, k, rej);
       if (e - b >= 32 || bound == FLT_MAX) bound = knn5_warp_bound(k);
     }
   }
@@ -422,6 +430,9 @@ __device__ __forceinline__ void knn5_search_warp(const GridDims& g, const int* _
       k.d[3] = k.d[4]; k.id[3] = k.id[4]; k.d[4] = FLT_MAX; k.id[4] = 0x7fffffff;
     }
   }
+  // what is left: every lane's unpopped head and whatever it turned away, plus the cells that were pruned whole
+  const float mine_other = fminf(rej, k.d[0]);
+  others_min = fminf(__uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(mine_other))), skipped);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -710,9 +721,17 @@ __device__ void write_partials(const Accum& A, double* __restrict__ partials) {
 // (1) assoc_knn_kernel: pointAssociateToMap + nearestKSearch(5), one WARP per query (lanes share the candidate scan).
 //     Slots [0, nde) are edge queries against the edge map, [nde, nde+nds) surf queries against the surf map.
 constexpr int kKnnThreads = 256;
+// Later outer iterations of the same update (reuse != 0; the maps do not change in between) first try to KEEP the previous neighbour
+// set: the previous search left, per query, the query position q_s and a lower bound B of the true distance from q_s to every map
+// point outside the stored five (from the 6th computed distance; points outside the 27 searched cells are more than 1 m away). The
+// pose moved the query by delta, so every other point is at least B - delta from the new position q'. If that, squared and shaved by
+// the float rounding of a computed distance, still exceeds the largest computed distance D5' from q' to the stored five — and the
+// five still lie in the 27 cells around q' — no other point can enter: the exhaustive search would return exactly these five, and
+// they are re-sorted by (distance, index). Otherwise the full search runs. Either way the outputs are those of the full search.
 __global__ void __launch_bounds__(kKnnThreads) assoc_knn_kernel(const PoseState* __restrict__ S, const P4* __restrict__ ds_edge, const int* __restrict__ d_nde,
                                                                  const P4* __restrict__ ds_surf, const int* __restrict__ d_nds, LocalMap emap, LocalMap smap,
-                                                                 int qcap, int* __restrict__ knn_ids, float* __restrict__ knn_d2) {
+                                                                 int qcap, int* __restrict__ knn_ids, float* __restrict__ knn_d2, float4* __restrict__ knn_q,
+                                                                 int reuse) {
   pdl_prologue();
   // every scalar this kernel needs is requested before the first one is looked at: one L2 round trip, not three
   const int skip = S->skip_solve;
@@ -722,6 +741,7 @@ __global__ void __launch_bounds__(kKnnThreads) assoc_knn_kernel(const PoseState*
   for (int k = 0; k < 7; ++k) x[k] = S->x[k];
   const GridDims ge = *emap.dims, gs = *smap.dims;
   if (skip) return;
+  const int l = lane_id();
   const int warps_total = gridDim.x * (kKnnThreads / 32);
   for (int slot = blockIdx.x * (kKnnThreads / 32) + warp_id(); slot < nde + nds; slot += warps_total) {
     const bool is_edge = slot < nde;
@@ -730,16 +750,60 @@ __global__ void __launch_bounds__(kKnnThreads) assoc_knn_kernel(const PoseState*
     const float4 p = __ldg((is_edge ? ds_edge : ds_surf) + qi);
     // pointAssociateToMap :126-135: double transform, float store
     const m::V3 pw = m::add(m::quat_rotate(x, m::V3{(double)p.x, (double)p.y, (double)p.z}), m::V3{x[4], x[5], x[6]});
-    Knn5 nn;
+    const float qx = (float)pw.x, qy = (float)pw.y, qz = (float)pw.z;
     const LocalMap& map = is_edge ? emap : smap;
-    knn5_search_warp(is_edge ? ge : gs, map.cell_start, map.cell_pts, (float)pw.x, (float)pw.y, (float)pw.z, nn);
+    if (reuse) {
+      const float4 qs = knn_q[out];
+      const int pid = l < 5 ? knn_ids[(size_t)out * 5 + l] : 0;
+      if (qs.w > 0.f && __shfl_sync(0xffffffffu, pid, 0) >= 0) {   // warp-uniform
+        float dist = 0.f;
+        bool inside = true;
+        if (l < 5) {
+          const float4 mp = __ldg(map.pts + pid);
+          const float dx = fsub(qx, mp.x), dy = fsub(qy, mp.y), dz = fsub(qz, mp.z);
+          dist = fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
+          inside = fabsf(floorf(mp.x) - floorf(qx)) <= 1.f && fabsf(floorf(mp.y) - floorf(qy)) <= 1.f && fabsf(floorf(mp.z) - floorf(qz)) <= 1.f;
+        }
+        const float d5 = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(dist)));   // distances >= 0: bit patterns order like floats
+        const bool all_inside = __all_sync(0xffffffffu, inside);
+        const double ddx = (double)qx - (double)qs.x, ddy = (double)qy - (double)qs.y, ddz = (double)qz - (double)qs.z;
+        const double delta = sqrt(ddx * ddx + ddy * ddy + ddz * ddz);
+        const double slack = (double)qs.w - delta * (1.0 + 1e-6) - 1e-9;
+        if (all_inside && slack > 0.0 && slack * slack * (1.0 - 1e-6) > (double)d5) {
+          int rank = 0;
+#pragma unroll
+          for (int k = 0; k < 5; ++k) {
+            const float dk = __shfl_sync(0xffffffffu, dist, k);
+            const int ik = __shfl_sync(0xffffffffu, pid, k);
+            rank += (dk < dist || (dk == dist && ik < pid)) ? 1 : 0;
+          }
+          const bool near = d5 < 1.0f;
+          if (l < 5) {
+            knn_ids[(size_t)out * 5 + rank] = near ? pid : -1;
+            knn_d2[(size_t)out * 5 + rank] = near ? dist : 0.f;
+          }
+          if (l == 0) knn_q[out] = make_float4(qx, qy, qz, near ? __double2float_rd(slack) : -1.f);
+          continue;
+        }
+      }
+    }
+    Knn5 nn;
+    float others;
+    knn5_search_warp(is_edge ? ge : gs, map.cell_start, map.cell_pts, qx, qy, qz, nn, others);
     const bool near = nn.d[4] < 1.0f;  // pointSearchSqDis[4] < 1.0 : the only queries the reference uses
-    if (lane_id() < 5) {
-      const int j = lane_id();
+    if (l < 5) {
+      const int j = l;
       const int id = j == 0 ? nn.id[0] : j == 1 ? nn.id[1] : j == 2 ? nn.id[2] : j == 3 ? nn.id[3] : nn.id[4];
       const float d = j == 0 ? nn.d[0] : j == 1 ? nn.d[1] : j == 2 ? nn.d[2] : j == 3 ? nn.d[3] : nn.d[4];
       knn_ids[(size_t)out * 5 + j] = near ? id : -1;
       knn_d2[(size_t)out * 5 + j] = near ? d : 0.f;
+    }
+    if (l == 0 && knn_q) {
+      // lower bound of the TRUE distance to every point outside the result: the 6th computed distance (less its rounding), and one
+      // cell width for everything outside the 27 cells
+      double lb = 1.0 - 1e-6;
+      if (others < FLT_MAX) lb = fmin(lb, sqrt((double)others) * (1.0 - 1e-6));
+      knn_q[out] = make_float4(qx, qy, qz, near ? __double2float_rd(lb) : -1.f);
     }
   }
 }
@@ -1065,7 +1129,8 @@ __global__ void __launch_bounds__(kKnnThreads) knn5_kernel(const P4* __restrict_
   for (int i = blockIdx.x * (kKnnThreads / 32) + warp_id(); i < nq; i += warps_total) {   // one warp per query, like the association
     const float4 q = __ldg(queries + i);
     Knn5 nn;
-    knn5_search_warp(g, map.cell_start, map.cell_pts, q.x, q.y, q.z, nn);
+    float others;
+    knn5_search_warp(g, map.cell_start, map.cell_pts, q.x, q.y, q.z, nn, others);
     const bool near = nn.d[4] < 1.0f;
     if (lane_id() < 5) {
       const int j = lane_id();
@@ -1179,11 +1244,12 @@ int odom_device_init(OdomDevice& od, const floam_params& prm, VoxelWorkspace* vw
   od.corr = (double*)alloc(actx, (size_t)6 * 2 * od.qcap * sizeof(double));
   od.corr_ok = (unsigned char*)alloc(actx, (size_t)2 * od.qcap);
   od.knn_ids = (int*)alloc(actx, (size_t)2 * od.qcap * 5 * 4);
+  od.knn_q = (float4*)alloc(actx, (size_t)2 * od.qcap * sizeof(float4));
   od.knn_d2 = (float*)alloc(actx, (size_t)2 * od.qcap * 5 * 4);
   od.partials = (double*)alloc(actx, (size_t)kAssocBlocks * kLmTerms * sizeof(double));
   od.traj_cap = 1 << 16;
   od.traj = (double*)alloc(actx, (size_t)od.traj_cap * 7 * sizeof(double));
-  if (!ints || !od.corr || !od.corr_ok || !od.knn_ids || !od.knn_d2 || !od.partials || !od.traj) return FLOAM_ERR_CUDA;
+  if (!ints || !od.corr || !od.corr_ok || !od.knn_ids || !od.knn_d2 || !od.knn_q || !od.partials || !od.traj) return FLOAM_ERR_CUDA;
   od.d_nds_edge_b[0] = ints; od.d_nds_surf_b[0] = ints + 1; od.d_nds_edge_b[1] = ints + 2; od.d_nds_surf_b[1] = ints + 3;
   odom_select_buffers(od, 0);
   FLOAM_CUDA_OK(cudaMemsetAsync(ints, 0, 16, s));
@@ -1240,7 +1306,7 @@ void odom_update_device(OdomDevice& od, const void* d_edge, const int* d_ne, con
   for (int it = 0; it < od.optimization_count; ++it) {
     PdlSolveScope pdl;   // kNN, fit and LM may be scheduled while their predecessor drains (griddepcontrol.wait orders the data)
     FLOAM_LAUNCH(K_ASSOC_KNN, assoc_knn_kernel, kKnnBlocks, kKnnThreads, s, S, od.ds_edge, od.d_nds_edge, od.ds_surf, od.d_nds_surf, od.edge_map, od.surf_map,
-                 od.qcap, od.knn_ids, od.knn_d2);
+                 od.qcap, od.knn_ids, od.knn_d2, od.knn_q, it > 0 ? 1 : 0);
     FLOAM_LAUNCH(K_ASSOC_EVAL, assoc_eval_kernel, kAssocBlocks, kEvalThreads, s, S, od.ds_edge, od.d_nds_edge, od.ds_surf, od.d_nds_surf, od.edge_map, od.surf_map,
                  od.qcap, od.corr, od.corr_ok, od.knn_ids, od.loss, od.partials);
     FLOAM_LAUNCH_DYN(K_LM_CLUSTER, lm_cluster_kernel, kClusterCtas, kClusterThreads, kLmStageBytes, s, S, od.ds_edge, od.d_nds_edge, od.ds_surf, od.d_nds_surf, od.qcap, od.corr, od.corr_ok,

@@ -73,6 +73,7 @@ struct OdomDevice {
   unsigned char* corr_ok;      // [2*qcap]
   int* knn_ids;                // [2*qcap*5] debug taps / floam_knn5
   float* knn_d2;               // [2*qcap*5]
+  float4* knn_q;               // [2*qcap] query position of the last search + lower bound of the distance to every other map point
   double* partials;            // [CTAs of the association kernel][kLmTerms]
   VoxelWorkspace* vws;         // main-branch workspace (surf side)
   VoxelWorkspace* vws_aux;     // second workspace: the edge side runs as a parallel branch of the frame graph
