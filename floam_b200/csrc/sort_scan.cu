@@ -3,6 +3,8 @@
 // Everything here is sized for latency on SMALL inputs (5k - 200k elements per frame, all L2-resident): tiles of 1024 keys so
 // that even a 20k-element sort spreads over 20+ CTAs, every global load issued before its first use, and — up to 262,144 keys —
 // no separate scan kernel: each scatter CTA derives its digit bases straight from the [tile][digit] count table.
+#include <cstdint>
+
 #include "common.cuh"
 
 namespace floam {
@@ -116,6 +118,7 @@ constexpr int kSortMaxRounds = 32;                             // ... up to 32 (
 constexpr int kSortTile = kSortThreads * kSortMinRounds;       // smallest tile: the launch grid is sized for it
 constexpr int kDirectTiles = 256;                              // up to this many tiles the scatter CTAs scan the count table themselves
 constexpr int kMaxBins = 2048;
+constexpr int kStageTableBytes = 128 * 1024;                    // count table staged in shared memory when it fits (128 rows x 256 bins)
 constexpr int kNarrowBins = 1024;                              // digits up to 10 bits (keys up to 30 bits) rank with per-warp counters                                 // 11-bit digits at most (3 x 11 >= 31 key bits)
 
 // Keys per lane, decided on the device from the live element count: the tile grows with the input so that the [tile][digit] count
@@ -251,7 +254,8 @@ __device__ __forceinline__ void radix_scatter_body(const unsigned int* __restric
                                                                      unsigned int* __restrict__ keys_out, int* __restrict__ vals_out,
                                                                      const int* __restrict__ d_n, const int* __restrict__ d_nbits, int pass,
                                                                      const int* __restrict__ hist, int* __restrict__ hist_next, unsigned int* ticket,
-                                                                     int (*s_cnt)[kNarrowBins], int* s_base, int* s_scan, int& s_last, int tile) {
+                                                                     int (*s_cnt)[kNarrowBins], int* s_base, int* s_scan, int& s_last, int tile,
+                                                                     const int* s_table, unsigned int bar_addr, bool& table_ready) {
   const int n = *d_n;
   const int R = MAXR;
   const int tile0 = tile * kSortThreads * R;
@@ -290,6 +294,12 @@ __device__ __forceinline__ void radix_scatter_body(const unsigned int* __restric
     }
     __syncthreads();
   }
+  // the count table staged by the bulk copy (issued before the tile's loads) must have landed by now
+  if (s_table && !table_ready) {
+    asm volatile("{\n .reg .pred p;\n WAIT_TABLE:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n @p bra TABLE_DONE;\n bra WAIT_TABLE;\n TABLE_DONE:\n}"
+                 :: "r"(bar_addr) : "memory");
+    table_ready = true;
+  }
   // global base of (digit, this tile): everything with a smaller digit, plus the same digit in earlier tiles
   int carry = 0;
   for (int d0 = 0; d0 < nbins; d0 += kSortThreads) {
@@ -301,11 +311,20 @@ __device__ __forceinline__ void radix_scatter_body(const unsigned int* __restric
         const int b = tile;
         // nb independent L2 reads per thread: unrolled 16-deep so that 16 are in flight (at 4 this loop WAS the kernel: 57 tiles ->
         // 14 dependent round trips)
+        if (s_table) {   // shared-memory copy of the whole table: consecutive digits, no bank conflicts
+#pragma unroll 8
+          for (int t = 0; t < nb; ++t) {
+            const int c = s_table[t * nbins + d];
+            total += c;
+            before += (t < b) ? c : 0;
+          }
+        } else {
 #pragma unroll 16
-        for (int t = 0; t < nb; ++t) {
-          const int c = __ldg(hist + t * nbins + d);
-          total += c;
-          before += (t < b) ? c : 0;
+          for (int t = 0; t < nb; ++t) {
+            const int c = __ldg(hist + t * nbins + d);
+            total += c;
+            before += (t < b) ? c : 0;
+          }
         }
         base = before;
       }
@@ -391,14 +410,37 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const unsig
   __shared__ int s_scan[33];
   __shared__ int s_last;
   const int n = *d_n;
-  const int rounds = sort_rounds(n, *d_nbits);
+  const int nbits = *d_nbits;
+  const int rounds = sort_rounds(n, nbits);
   const int nb = sort_tiles(n, rounds);
+  // The [tile][digit] count table of this pass (every scatter CTA needs all of it) comes in with ONE bulk copy (TMA, cp.async.bulk
+  // global -> shared, completion on an mbarrier) issued before the tile's own loads, instead of nb dependent batches of L2 reads.
+  extern __shared__ __align__(128) unsigned char s_dyn[];
+  __shared__ __align__(8) unsigned long long s_bar;
+  const int table_bytes = (nb * (1 << digit_bits(nbits)) * 4 + 15) & ~15;
+  const bool staged = nb <= kDirectTiles && table_bytes <= kStageTableBytes && (int)blockIdx.x < nb;
+  const unsigned int bar_addr = (unsigned int)__cvta_generic_to_shared(&s_bar);
+  if (staged) {
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_addr));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned int dst = (unsigned int)__cvta_generic_to_shared(s_dyn);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar_addr), "r"(table_bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   :: "r"(dst), "l"(hist), "r"(table_bytes), "r"(bar_addr) : "memory");
+    }
+  }
+  const int* s_table = staged ? reinterpret_cast<const int*>(s_dyn) : nullptr;
+  bool table_ready = false;
   for (int tile = blockIdx.x; tile < nb; tile += gridDim.x) {   // one wave of CTAs, each looping over its tiles (see radix_hist_kernel)
     switch (rounds) {
-      case 4: radix_scatter_body<4>(keys_in, vals_in, keys_out, vals_out, d_n, d_nbits, pass, hist, hist_next, ticket, s_cnt, s_base, s_scan, s_last, tile); break;
-      case 8: radix_scatter_body<8>(keys_in, vals_in, keys_out, vals_out, d_n, d_nbits, pass, hist, hist_next, ticket, s_cnt, s_base, s_scan, s_last, tile); break;
-      case 16: radix_scatter_body<16>(keys_in, vals_in, keys_out, vals_out, d_n, d_nbits, pass, hist, hist_next, ticket, s_cnt, s_base, s_scan, s_last, tile); break;
-      default: radix_scatter_body<32>(keys_in, vals_in, keys_out, vals_out, d_n, d_nbits, pass, hist, hist_next, ticket, s_cnt, s_base, s_scan, s_last, tile); break;
+      case 4: radix_scatter_body<4>(keys_in, vals_in, keys_out, vals_out, d_n, d_nbits, pass, hist, hist_next, ticket, s_cnt, s_base, s_scan, s_last, tile, s_table, bar_addr, table_ready); break;
+      case 8: radix_scatter_body<8>(keys_in, vals_in, keys_out, vals_out, d_n, d_nbits, pass, hist, hist_next, ticket, s_cnt, s_base, s_scan, s_last, tile, s_table, bar_addr, table_ready); break;
+      case 16: radix_scatter_body<16>(keys_in, vals_in, keys_out, vals_out, d_n, d_nbits, pass, hist, hist_next, ticket, s_cnt, s_base, s_scan, s_last, tile, s_table, bar_addr, table_ready); break;
+      default: radix_scatter_body<32>(keys_in, vals_in, keys_out, vals_out, d_n, d_nbits, pass, hist, hist_next, ticket, s_cnt, s_base, s_scan, s_last, tile, s_table, bar_addr, table_ready); break;
     }
     __syncthreads();
   }
@@ -412,7 +454,7 @@ static int table_rows(int n_max) {
   return (big > 128 ? big : 128) + 1;
 }
 size_t sort_workspace_bytes(int n_max) {
-  return (size_t)n_max * 8 + (size_t)3 * kMaxBins * table_rows(n_max) * 4 + 512;
+  return (size_t)n_max * 8 + (size_t)3 * kMaxBins * table_rows(n_max) * 4 + 1024;
 }
 void sort_workspace_bind(SortWorkspace& ws, void* mem, int n_max) {
   char* p = (char*)mem;
@@ -420,11 +462,14 @@ void sort_workspace_bind(SortWorkspace& ws, void* mem, int n_max) {
   ws.max_blocks = (n_max + kSortTile - 1) / kSortTile;
   ws.keys_alt = (unsigned int*)p; p += (size_t)n_max * 4;
   ws.vals_alt = (int*)p; p += (size_t)n_max * 4;
+  p = (char*)(((uintptr_t)p + 255) & ~(uintptr_t)255);
   ws.ticket = (unsigned int*)p; p += 256;
-  ws.hist = (int*)p;
+  ws.hist = (int*)p;   // 256-byte aligned: the scatter kernel bulk-copies whole tables
   ws.table_stride = kMaxBins * table_rows(n_max);
 }
 int sort_workspace_arm(SortWorkspace& ws, cudaStream_t s) {
+  // per device: the scatter kernel stages its count table in up to 128 KB of dynamic shared memory
+  FLOAM_CUDA_OK(cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageTableBytes));
   FLOAM_CUDA_OK(cudaMemsetAsync(ws.ticket, 0, 256, s));
   return FLOAM_OK;
 }
@@ -439,7 +484,7 @@ void radix_sort_pairs_from(unsigned int* keys, int* vals, unsigned int* keys_alt
   // four launches: digit counts of pass 0, then three scatters, each of which also counts the digits of the pass after it
   FLOAM_LAUNCH(K_RADIX_HIST, radix_hist_kernel, nblocks, kSortThreads, s, kin, d_n, d_nbits, 0, ws.hist, ws.table_stride, ws.ticket, d_skip);
   for (int pass = 0; pass < 3; ++pass) {
-    FLOAM_LAUNCH(K_RADIX_SCATTER, radix_scatter_kernel, nblocks, kSortThreads, s, kin, vin, kout, vout, d_n, d_nbits, pass, ws.hist + (size_t)pass * ws.table_stride,
+    FLOAM_LAUNCH_DYN(K_RADIX_SCATTER, radix_scatter_kernel, nblocks, kSortThreads, kStageTableBytes, s, kin, vin, kout, vout, d_n, d_nbits, pass, ws.hist + (size_t)pass * ws.table_stride,
                  pass < 2 ? ws.hist + (size_t)(pass + 1) * ws.table_stride : (int*)nullptr, ws.ticket, d_skip);
     unsigned int* tk = kin; kin = kout; kout = tk;
     int* tv = vin; vin = vout; vout = tv;

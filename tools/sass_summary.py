@@ -42,7 +42,7 @@ if cur:
 with open(os.path.join(ROOT, "profiles", "r1_sass_summary.md"), "w") as f:
     f.write("# SASS instruction mix per kernel (sm_100a), from `cuobjdump -sass floam_b200/lib/libfloam_b200.so`\n\n")
     f.write("Full listing: `r1_sass.txt.gz` (regenerate both with `python tools/sass_summary.py`). Static instruction counts.\n")
-    f.write("No tensor-core or TMA instructions appear anywhere: nothing on this path is a dense contraction, and the gathers are\n")
+    f.write("No tensor-core instructions appear anywhere (nothing on this path is a dense contraction); the one TMA instruction is the bulk copy\nof the count table in `radix_scatter_kernel` (`UBLKCP`). The kNN gathers are\n")
     f.write("short runs read through `LDG` (see DESIGN.md section 4). Float arithmetic of the bit-exact stages is `FADD`/`FMUL` (never `FFMA`).\n\n")
     f.write("| kernel | instructions | " + " | ".join(g for g, _ in GROUPS) + " |\n|---|---|" + "---|" * len(GROUPS) + "\n")
     for name, n, c in sorted(rows, key=lambda r: -r[1]):
