@@ -642,6 +642,57 @@ def test_fused_imu_frame_path(capi, po, synth, sensor, deskew):
     ctx.close()
 
 
+def test_imu_frames_pipelined_and_from_raw_messages(capi, po, synth):
+    # the IMU-folded frame path through (a) synchronous calls, (b) three submissions in flight, (c) raw PointCloud2 bytes in the
+    # Velodyne 22-byte layout with three in flight: one set of kernels, identical poses and identical re-centred stamps
+    frames = 10
+    seq = synth.Sequence("vlp16", seed=4, distort=True)
+    ext = po.euler2quat(0, 0, 180)
+    scans = [seq.scan(f) for f in range(frames)]
+    stamps = [int((700.0 + 0.1 * f) * 1e6) for f in range(frames)]
+
+    def make():
+        ctx = fresh(capi, 16, loss="huber")
+        for k in range(-40, 40 + 20 * frames):
+            t = 700.0 + 0.005 * k
+            ctx.imu_push(t, seq.imu(max(t - 700.0, 0.0)))
+        return ctx
+    a = make()
+    A = []; SA = []
+    for f in range(frames):
+        rc, pose, st = a.process_scan_imu(scans[f].copy(), stamps[f], ext, True)
+        assert rc == capi.OK
+        A.append(pose); SA.append(st)
+    a.close()
+
+    def pipelined(submit):
+        ctx = make(); P = []; S = []; pending = 0
+        for f in range(frames):
+            if pending == 3:
+                P.append(ctx.process_wait()); pending -= 1
+            S.append(submit(ctx, f)); pending += 1
+        while pending:
+            P.append(ctx.process_wait()); pending -= 1
+        # a scan the IMU buffer does not cover is refused without disturbing the pipeline
+        rc, _ = ctx.process_submit_imu(scans[0].copy(), int(9000.0 * 1e6), ext, True)
+        assert rc == capi.NO_IMU
+        ctx.close()
+        return np.array(P), S
+    keep = [s.copy() for s in scans]
+
+    def submit_points(ctx, f):
+        rc, st = ctx.process_submit_imu(keep[f], stamps[f], ext, True)
+        assert rc == capi.OK
+        return st
+    B, SB = pipelined(submit_points)
+    raws = []
+    for s in scans:
+        L = capi.pc2_layout(len(s), 22)
+        raws.append((capi.pack_pointcloud2(s, L), L))
+    C_, SC = pipelined(lambda ctx, f: ctx.process_submit_pc2(raws[f][0], raws[f][1], True, stamps[f], ext))
+    assert np.array_equal(np.array(A), B) and np.array_equal(B, C_) and SA == SB == SC
+
+
 # ------------------------------------------------------------------------------------------------ randomised sweeps -----
 def random_scan(capi, rng, num_lines, sizes, jump_prob=0.05, noise=0.01):
     """Firing-order scan with the given per-ring point counts, range jumps (corners) and occasional out-of-gate returns."""
