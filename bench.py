@@ -243,13 +243,14 @@ def cpu_baseline(scans, off, num_lines, n_frames):
     from oracle import pyoracle as po
     po.build()
     last = min(len(off) - 1, PREROLL + n_frames)
-    sec, poses, ms, q = po.replay_sequence(scans[:off[last]], off[:last + 1], num_lines, min_dis=ODOM["min_distance"], max_dis=ODOM["max_distance"],
-                                           map_resolution=ODOM["map_resolution"], loss=ODOM["loss"], deskew=False)
+    sec, poses, ms, q, stages = po.replay_sequence_stages(scans[:off[last]], off[:last + 1], num_lines, PREROLL, min_dis=ODOM["min_distance"],
+                                                          max_dis=ODOM["max_distance"], map_resolution=ODOM["map_resolution"], loss=ODOM["loss"], deskew=False)
     steady = ms[PREROLL:]
     fps = 1e3 / float(np.mean(steady)) if len(steady) else 0.0
     return {"value": fps, "unit": UNIT, "cores": 1, "kind": "port",
             "sample": "frames %d..%d of the same sequence (after the same pre-roll), featureExtraction + odometry, one thread" % (PREROLL, last - 1),
-            "p50_ms": float(np.percentile(steady, 50)) if len(steady) else None}, poses
+            "p50_ms": float(np.percentile(steady, 50)) if len(steady) else None,
+            "stage_ms_per_frame": {k: round(v, 3) for k, v in stages.items()}}, poses
 
 
 def main():

@@ -265,20 +265,24 @@ int fo_mapping_get_map(void* m, PointXYZI* out, int cap) { return copy_out(((Las
 // ---------- timed whole-sequence replay (cpu_baseline / --impl reference): featureExtraction + odometry per frame ----------
 // scans: concatenated frames, offsets[f]..offsets[f+1]. Returns seconds of wall-clock over the replayed frames
 // (steady_clock, single thread like the reference's one worker thread per class). poses_out: 7 doubles per frame.
-double fo_replay_sequence(const PointXYZIRT* scans, const long long* offsets, int n_frames, int num_lines, double scan_period, double min_dis,
+}  // extern "C"
+
+static double replay_sequence_impl(const PointXYZIRT* scans, const long long* offsets, int n_frames, int num_lines, double scan_period, double min_dis,
                           double max_dis, double map_resolution, const char* loss, int deskew, double* poses_out, double* per_frame_ms,
-                          long* knn_queries) {
+                          long* knn_queries, int stage_skip, double* stage_ms_out) {
   LaserProcessing lp;
   LidarParam p; p.num_lines = num_lines; p.scan_period = scan_period; p.min_distance = min_dis; p.max_distance = max_dis;
   lp.init(p);
   OdomEstimation est;
   est.init(p, map_resolution, loss);
   bool inited = false;
-  double total = 0;
+  double total = 0, feature_s = 0;
   for (int f = 0; f < n_frames; ++f) {
+    est.stage_timing = stage_ms_out && f >= stage_skip;
     auto t0 = std::chrono::steady_clock::now();
     CloudIRT in(scans + offsets[f], scans + offsets[f + 1]), e, s;
     lp.featureExtraction(in, e, s);
+    if (est.stage_timing) feature_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (!inited) {  // src/odomEstimationNode.cpp:219-224
       est.initMapWithPoints(VelToIntensityCopy(e), VelToIntensityCopy(s));
       inited = true;
@@ -296,7 +300,26 @@ double fo_replay_sequence(const PointXYZIRT* scans, const long long* offsets, in
     }
   }
   if (knn_queries) *knn_queries = est.stat_knn_queries;
+  if (stage_ms_out) {   // milliseconds per frame over frames [stage_skip, n_frames): features, downsample, kd build, association, solve, map update
+    const double nf = n_frames > stage_skip ? (double)(n_frames - stage_skip) : 1.0;
+    stage_ms_out[0] = feature_s * 1e3 / nf;
+    for (int k = 0; k < 5; ++k) stage_ms_out[1 + k] = est.stage_s[k] * 1e3 / nf;
+  }
   return total * 1e-3;
+}
+
+extern "C" {
+
+double fo_replay_sequence(const PointXYZIRT* scans, const long long* offsets, int n_frames, int num_lines, double scan_period, double min_dis,
+                          double max_dis, double map_resolution, const char* loss, int deskew, double* poses_out, double* per_frame_ms,
+                          long* knn_queries) {
+  return replay_sequence_impl(scans, offsets, n_frames, num_lines, scan_period, min_dis, max_dis, map_resolution, loss, deskew, poses_out, per_frame_ms, knn_queries, 0, nullptr);
+}
+
+double fo_replay_sequence_stages(const PointXYZIRT* scans, const long long* offsets, int n_frames, int num_lines, double scan_period, double min_dis,
+                          double max_dis, double map_resolution, const char* loss, int deskew, double* poses_out, double* per_frame_ms,
+                          long* knn_queries, int stage_skip, double* stage_ms_out) {
+  return replay_sequence_impl(scans, offsets, n_frames, num_lines, scan_period, min_dis, max_dis, map_resolution, loss, deskew, poses_out, per_frame_ms, knn_queries, stage_skip, stage_ms_out);
 }
 
 }  // extern "C"

@@ -164,6 +164,10 @@ class OdomEstimation {
   Iso3 last_odom;
   int optimization_count = 2;
   long stat_knn_queries = 0;
+  // wall-clock seconds per stage, accumulated while stage_timing is set (bench.py's per-stage CPU baseline):
+  // [0] downSamplingToMap, [1] kd-tree builds, [2] addEdge/SurfCostFactor (kNN + fits), [3] ceres solve, [4] addPointsToMap
+  bool stage_timing = false;
+  double stage_s[5] = {0, 0, 0, 0, 0};
 
  private:
   void pointAssociateToMap(const PointXYZI& pi, PointXYZI& po) const;                                   // :126-135

@@ -1,6 +1,8 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see types.h).  parity unpinned.
 // Restates src/odomEstimationClass.cpp:7-343 line by line (quirks Q1-Q4, Q10-Q12 of SURVEY.md §0 kept verbatim).
 #include "floam_oracle.h"
+
+#include <chrono>
 #include <algorithm>
 #include <cctype>
 #include <cstdio>
@@ -63,8 +65,16 @@ void OdomEstimation::updatePointsToMap(const CloudI& edge_in, const CloudI& surf
   parameters[0] = q_w_curr.x; parameters[1] = q_w_curr.y; parameters[2] = q_w_curr.z; parameters[3] = q_w_curr.w;
   parameters[4] = odom.t.x; parameters[5] = odom.t.y; parameters[6] = odom.t.z;
 
+  auto now = []() { return std::chrono::steady_clock::now(); };
+  auto lap = [&](std::chrono::steady_clock::time_point& t0, int stage) {   // test infrastructure only: per-stage CPU time
+    const auto t1 = now();
+    if (stage_timing) stage_s[stage] += std::chrono::duration<double>(t1 - t0).count();
+    t0 = t1;
+  };
+  auto tick = now();
   CloudI downsampledEdgeCloud, downsampledSurfCloud;
   downSamplingToMap(edge_in, downsampledEdgeCloud, surf_in, downsampledSurfCloud);
+  lap(tick, 0);
   if (debug) { debug->outer_iterations = 0; debug->residuals.clear(); debug->lm = LmSummary(); }
 
   if (laserCloudCornerMap.size() > 10 && laserCloudSurfMap.size() > 50) {
@@ -72,14 +82,17 @@ void OdomEstimation::updatePointsToMap(const CloudI& edge_in, const CloudI& surf
       kdtreeEdgeMap.setInputCloud(laserCloudCornerMap);
       kdtreeSurfMap.setInputCloud(laserCloudSurfMap);
     }
+    lap(tick, 1);
     LossKind loss = (loss_function_ == "huber") ? LOSS_HUBER : (loss_function_ == "cauchy_true" ? LOSS_CAUCHY_TRUE : LOSS_TRIVIAL);  // Q1
     for (int iterCount = 0; iterCount < optimization_count; iterCount++) {
       std::vector<Residual> problem;
       const bool tap = debug && (iterCount == optimization_count - 1);
       addEdgeCostFactor(downsampledEdgeCloud, laserCloudCornerMap, problem, tap);
       addSurfCostFactor(downsampledSurfCloud, laserCloudSurfMap, problem, tap);
+      lap(tick, 2);
       LmSummary sm;
       ceres_solve_pose(problem, loss, parameters, &sm, 4);
+      lap(tick, 3);
       if (debug) { debug->outer_iterations++; if (tap) { debug->residuals = problem; debug->lm = sm; } }
     }
   } else {
@@ -92,7 +105,9 @@ void OdomEstimation::updatePointsToMap(const CloudI& edge_in, const CloudI& surf
   bool kf = false;
   if (update_type == VANILLA || update_type == REFINEMENT_AND_UPDATE) {
     kf = KeyFrameUpdate(odom);
+    tick = now();
     if (kf) addPointsToMap(downsampledEdgeCloud, downsampledSurfCloud);
+    lap(tick, 4);
   }
   if (debug) { debug->ds_edge = downsampledEdgeCloud; debug->ds_surf = downsampledSurfCloud; debug->keyframe = kf; }
 }

@@ -256,3 +256,18 @@ def replay_sequence(scans, offsets, num_lines, scan_period=0.1, min_dis=2.0, max
     sec = lib().fo_replay_sequence(_p(scans), _p(offsets), nf, int(num_lines), C.c_double(scan_period), C.c_double(min_dis), C.c_double(max_dis),
                                    C.c_double(map_resolution), loss.encode(), int(deskew), _p(poses), _p(ms), C.byref(q))
     return sec, poses, ms, q.value
+
+
+STAGES = ("featureExtraction", "downSamplingToMap", "kdtree_build", "association_knn_fit", "ceres_solve", "addPointsToMap")
+
+
+def replay_sequence_stages(scans, offsets, num_lines, skip, scan_period=0.1, min_dis=2.0, max_dis=60.0, map_resolution=0.4, loss="cauchy", deskew=False):
+    """replay_sequence plus wall-clock milliseconds per frame and stage over frames [skip, n): dict stage -> ms."""
+    scans = np.ascontiguousarray(scans, POINT_IRT); offsets = np.ascontiguousarray(offsets, np.int64)
+    nf = len(offsets) - 1
+    poses = np.zeros((nf, 7)); ms = np.zeros(nf); q = C.c_long(); st = np.zeros(6)
+    L = lib()
+    L.fo_replay_sequence_stages.restype = C.c_double
+    sec = L.fo_replay_sequence_stages(_p(scans), _p(offsets), nf, int(num_lines), C.c_double(scan_period), C.c_double(min_dis), C.c_double(max_dis),
+                                      C.c_double(map_resolution), loss.encode(), int(deskew), _p(poses), _p(ms), C.byref(q), int(skip), _p(st))
+    return sec, poses, ms, q.value, dict(zip(STAGES, [float(x) for x in st]))
