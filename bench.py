@@ -181,51 +181,62 @@ def run_reference(args, rank):
     po.build()
     K = max(1, min(args.steps, 120)); W = max(0, min(args.warmup, 10))
     frames = PREROLL + W + K
-    seq, scans, off = build_sequence(0, frames)
-    nl = seq.num_lines
-    q1, q2 = queue.Queue(maxsize=4), queue.Queue(maxsize=4)
-    stamps = {}
+    S = max(1, args.gpus)   # the N-GPU workload is N independent sequences (configs[4]): the host runs as many pipelines side by side
+    spans = [None] * S
 
-    def node_features():
-        for f in range(frames):
-            e, s, _, _, _ = po.feature_extract(scans[off[f]:off[f + 1]], nl, ODOM["min_distance"], ODOM["max_distance"])
-            q1.put((f, e, s))
-        q1.put(None)
+    def pipeline(si):
+        seq, scans, off = build_sequence(si, frames)
+        nl = seq.num_lines
+        q1, q2 = queue.Queue(maxsize=4), queue.Queue(maxsize=4)
+        stamps = {}
 
-    def node_odom():
-        od = po.Odom(num_lines=nl, map_resolution=ODOM["map_resolution"], loss=ODOM["loss"])
-        while True:
-            item = q1.get()
-            if item is None:
-                break
-            f, e, s = item
-            if f == 0:
-                od.init_map(synth.to_xyzi(e), synth.to_xyzi(s)); T = np.eye(4)
-            else:
-                od.update(e, s, False); T = od.get()[0]
-            stamps[f] = time.perf_counter()
-            q2.put((f, T))
-        q2.put(None)
+        def node_features():
+            for f in range(frames):
+                e, s, _, _, _ = po.feature_extract(scans[off[f]:off[f + 1]], nl, ODOM["min_distance"], ODOM["max_distance"])
+                q1.put((f, e, s))
+            q1.put(None)
 
-    def node_mapping():
-        mp = po.Mapping(map_resolution=ODOM["map_resolution"])
-        while True:
-            item = q2.get()
-            if item is None:
-                break
-            f, T = item
-            mp.update(synth.to_xyzi(scans[off[f]:off[f + 1]][::4]), T)   # the reference maps the filtered cloud; a quarter keeps it off the critical path
+        def node_odom():
+            od = po.Odom(num_lines=nl, map_resolution=ODOM["map_resolution"], loss=ODOM["loss"])
+            while True:
+                item = q1.get()
+                if item is None:
+                    break
+                f, e, s = item
+                if f == 0:
+                    od.init_map(synth.to_xyzi(e), synth.to_xyzi(s)); T = np.eye(4)
+                else:
+                    od.update(e, s, False); T = od.get()[0]
+                stamps[f] = time.perf_counter()
+                q2.put((f, T))
+            q2.put(None)
 
-    th = [threading.Thread(target=t) for t in (node_features, node_odom, node_mapping)]
-    [t.start() for t in th]
-    [t.join() for t in th]
-    t0 = stamps[PREROLL + W - 1]; t1 = stamps[frames - 1]
-    fps = K / (t1 - t0)
+        def node_mapping():
+            mp = po.Mapping(map_resolution=ODOM["map_resolution"])
+            while True:
+                item = q2.get()
+                if item is None:
+                    break
+                f, T = item
+                mp.update(synth.to_xyzi(scans[off[f]:off[f + 1]][::4]), T)   # the reference maps the filtered cloud; a quarter keeps it off the critical path
+
+        th = [threading.Thread(target=t) for t in (node_features, node_odom, node_mapping)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        spans[si] = (stamps[PREROLL + W - 1], stamps[frames - 1])
+
+    pipes = [threading.Thread(target=pipeline, args=(si,)) for si in range(S)]
+    [t.start() for t in pipes]
+    [t.join() for t in pipes]
+    t0 = min(sp[0] for sp in spans); t1 = max(sp[1] for sp in spans)
+    fps = S * K / (t1 - t0)
+    cores = min(3 * S, os.cpu_count() or 1)
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
-            "ms_per_step": 1e3 / fps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "ms_per_step": 1e3 * S / fps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(),
-            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": 3, "kind": "port",
-                             "sample": "frames %d..%d of sequence 0 (oracle port of the reference classes; 3 pipelined host threads)" % (PREROLL + W, frames - 1)},
+            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "frames %d..%d of %d sequence(s) (oracle port of the reference classes; 3 pipelined host threads per sequence, "
+                                       "%d host cores)" % (PREROLL + W, frames - 1, S, os.cpu_count() or 1)},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
     return 0
