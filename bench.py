@@ -378,6 +378,21 @@ def main():
     timing = ctx3.kernel_timing()
     ctx3.set_kernel_timing(False)
     ctx3.close()
+    # ---- single-frame latency: one scan in flight at a time (host scan in, pose out), what a live 10 Hz sensor would see ----
+    NL = min(50, K)
+    ctx4 = capi.Context(device=local, **prm)
+    ctx4.stage_scans(scans[:off[frames - NL]], off[:frames - NL + 1])
+    ctx4.replay_staged(0, frames - NL)
+    single = []
+    one = capi.PinnedBuffer(int(np.max(np.diff(off))))
+    for f in range(frames - NL, frames):
+        n_f = int(off[f + 1] - off[f])
+        one.array[:n_f] = scans[off[f]:off[f + 1]]      # the capture driver's buffer: filling it is not part of the latency
+        t_s = time.perf_counter()
+        ctx4.process_scan(one.array[:n_f])
+        single.append((time.perf_counter() - t_s) * 1e3)
+    ctx4.close()
+    one.close()
     for k in stats:
         stats[k] /= TF
     # every kernel is bracketed by an event pair inside the frame graph; the pair itself costs a few microseconds, measured by an
@@ -419,6 +434,8 @@ def main():
                     "poses_identical_to_device_replay": identical},
             "gpu_launches": int(launches), "launches_per_frame": launches / K,
             "p50_ms_per_frame": float(np.percentile(lat, 50)), "p99_ms_per_frame": float(np.percentile(lat, 99)),
+            "single_frame_latency_ms": {"p50": float(np.percentile(single, 50)), "p99": float(np.percentile(single, 99)), "frames": NL,
+                                        "note": "floam_process_scan with nothing else in flight: upload + FRONT + BACK + pose read-back, host wall clock"},
             "knn_queries_per_s": float(stats["Q"] * 2 * value / world),
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "frame_stats": {k: round(v, 1) for k, v in stats.items()}, "final_map_points": [ne_map, ns_map],
