@@ -130,6 +130,31 @@ inline void launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStr
   launch_kernel_dyn(kern, grid, block, 0, s, static_cast<Args&&>(args)...);
 }
 
+// one thread-block cluster of `cluster` CTAs (runtime cluster dimension; 16 needs cudaFuncAttributeNonPortableClusterSizeAllowed)
+template <typename... KArgs, typename... Args>
+inline void launch_cluster_kernel(void (*kern)(KArgs...), int cluster, dim3 block, size_t dyn_smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cluster); cfg.blockDim = block; cfg.dynamicSmemBytes = dyn_smem; cfg.stream = s;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  int n = 1;
+  if (g_use_pdl || t_pdl_scope) {
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    n = 2;
+  }
+  cfg.attrs = at; cfg.numAttrs = n;
+  cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+#define FLOAM_LAUNCH_CLUSTER(slot, kern, cluster, block, smem, stream, ...) \
+  do {                                                                     \
+    ::floam::g_launches++;                                                 \
+    if (::floam::g_timer) ::floam::launch_timer_begin(slot, stream);       \
+    ::floam::launch_cluster_kernel(kern, cluster, dim3(block), smem, stream, __VA_ARGS__); \
+    if (::floam::g_timer) ::floam::launch_timer_end(stream);               \
+  } while (0)
+
 // dynamic shared memory variant (the kernel's cudaFuncAttributeMaxDynamicSharedMemorySize is raised by its owner, once)
 #define FLOAM_LAUNCH_DYN(slot, kern, grid, block, smem, stream, ...)       \
   do {                                                                     \

@@ -22,6 +22,7 @@
 
 #include <cfloat>
 #include <cstddef>
+#include <cstdlib>
 
 #include <cooperative_groups.h>
 
@@ -917,7 +918,7 @@ struct ClusterShared {
   double x[7];            // candidate pose (valid in CTA 0, read remotely)
   int done;
 };
-__global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClusterThreads)
+__global__ void __launch_bounds__(kClusterThreads)   // launched as ONE cluster of 8 (portable) or 16 CTAs (od.lm_cluster_ctas)
     lm_cluster_kernel(PoseState* S, const P4* __restrict__ ds_edge, const int* __restrict__ d_nde, const P4* __restrict__ ds_surf,
                       const int* __restrict__ d_nds, int qcap, const double* __restrict__ corr, const unsigned char* __restrict__ corr_ok, int loss,
                       const double* __restrict__ partials, int n_rows, FinishArgs fin) {
@@ -970,8 +971,9 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClusterT
   float* sp = reinterpret_cast<float*>(lm_dyn + (size_t)6 * kStageCap * sizeof(double));  // [3][kStageCap]
   __shared__ int s_wtot[kClusterThreads / 32], s_wedge[kClusterThreads / 32], s_over_lo;
   const int total = nde + nds;
-  const int n_eval = total <= kCoordinatorOnlyBelow ? kClusterCtas - 1 : kClusterCtas;
-  const int erank = (int)rank - (kClusterCtas - n_eval);   // -1: no share
+  const int n_ctas = (int)cluster.num_blocks();
+  const int n_eval = total <= kCoordinatorOnlyBelow ? n_ctas - 1 : n_ctas;
+  const int erank = (int)rank - (n_ctas - n_eval);   // -1: no share
   const int chunk = (total + n_eval - 1) / n_eval;
   const int lo = erank < 0 ? total : min(erank * chunk, total), hi = min(lo + chunk, total);
   const int sub = (hi - lo + kClusterThreads / 32 - 1) / (kClusterThreads / 32);
@@ -1087,7 +1089,7 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClusterT
       if (threadIdx.x < kLmTerms) {
         double v = 0.0;
 #pragma unroll
-        for (int c = 0; c < kClusterCtas; ++c) v += cluster.map_shared_rank(&sh, c)->row[threadIdx.x];
+        for (int c = 0; c < n_ctas; ++c) v += cluster.map_shared_rank(&sh, c)->row[threadIdx.x];
         s_sums[threadIdx.x] = v;
       }
       __syncthreads();
@@ -1220,6 +1222,12 @@ int odom_device_init(OdomDevice& od, const floam_params& prm, VoxelWorkspace* vw
   od.vws_aux = vws_aux;
   od.aux_stream = aux;
   FLOAM_CUDA_OK(cudaFuncSetAttribute(lm_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLmStageBytes));
+  FLOAM_CUDA_OK(cudaFuncSetAttribute(lm_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  // Cluster size of the solve: 8 CTAs (portable) for the usual few thousand correspondences; dense configurations (128-line sensors,
+  // map resolution <= 0.2 m: tens of thousands of correspondences, FP64-issue bound on 8 SMs) get 16. A property of the context,
+  // so that every entry path adds the normal equations up in the same order. FLOAM_LM_CLUSTER overrides (8 or 16).
+  od.lm_cluster_ctas = (prm.num_lines >= 128 || prm.map_resolution <= 0.2) ? 16 : kClusterCtas;
+  if (const char* e = std::getenv("FLOAM_LM_CLUSTER")) od.lm_cluster_ctas = std::atoi(e) == 16 ? 16 : kClusterCtas;
   FLOAM_CUDA_OK(cudaEventCreateWithFlags(&od.ev_fork, cudaEventDisableTiming));
   FLOAM_CUDA_OK(cudaEventCreateWithFlags(&od.ev_join, cudaEventDisableTiming));
   od.leaf_edge = (float)prm.map_resolution;        // setLeafSize(float...) :13-14
@@ -1309,7 +1317,7 @@ void odom_update_device(OdomDevice& od, const void* d_edge, const int* d_ne, con
                  od.qcap, od.knn_ids, od.knn_d2, od.knn_q, it > 0 ? 1 : 0);
     FLOAM_LAUNCH(K_ASSOC_EVAL, assoc_eval_kernel, kAssocBlocks, kEvalThreads, s, S, od.ds_edge, od.d_nds_edge, od.ds_surf, od.d_nds_surf, od.edge_map, od.surf_map,
                  od.qcap, od.corr, od.corr_ok, od.knn_ids, od.loss, od.partials);
-    FLOAM_LAUNCH_DYN(K_LM_CLUSTER, lm_cluster_kernel, kClusterCtas, kClusterThreads, kLmStageBytes, s, S, od.ds_edge, od.d_nds_edge, od.ds_surf, od.d_nds_surf, od.qcap, od.corr, od.corr_ok,
+    FLOAM_LAUNCH_CLUSTER(K_LM_CLUSTER, lm_cluster_kernel, od.lm_cluster_ctas, kClusterThreads, kLmStageBytes, s, S, od.ds_edge, od.d_nds_edge, od.ds_surf, od.d_nds_surf, od.qcap, od.corr, od.corr_ok,
                  od.loss, od.partials, kAssocBlocks, FinishArgs{it + 1 == od.optimization_count ? 1 : 0, update_type, od.scan_period, od.traj, od.traj_cap});
   }
   if (od.optimization_count <= 0) FLOAM_LAUNCH(K_FINISH, finish_kernel, 1, 32, s, S, update_type, od.scan_period, od.traj, od.traj_cap);

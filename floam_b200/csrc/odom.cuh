@@ -79,6 +79,7 @@ struct OdomDevice {
   VoxelWorkspace* vws_aux;     // second workspace: the edge side runs as a parallel branch of the frame graph
   cudaStream_t aux_stream;     // fork/join partner of the context stream
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int lm_cluster_ctas = 8;     // CTAs of the solve's thread-block cluster (8, or 16 for dense configurations)
   float leaf_edge, leaf_surf;
   double scan_period;
   int loss;
