@@ -167,6 +167,17 @@ bool evaluate_program(const std::vector<Residual>& blocks, LossKind loss, const 
   return true;
 }
 
+struct BlockProgram : LmProgram {  // the restated cost functions + loss (evaluate_program above)
+  const std::vector<Residual>& blocks;
+  LossKind loss;
+  BlockProgram(const std::vector<Residual>& b, LossKind l) : blocks(b), loss(l) {}
+  size_t num_residuals() const override { return blocks.size(); }
+  bool evaluate(const double x[7], double* cost, std::vector<double>* residuals, std::vector<double>* jacobian, double gradient[6]) override {
+    return evaluate_program(blocks, loss, x, cost, residuals, jacobian, gradient);
+  }
+  void plus(const double x[7], const double delta[6], double out[7]) override { se3_plus(x, delta, out); }
+};
+
 double norm7(const double a[7]) {
   double s = 0;
   for (int i = 0; i < 7; ++i) s += a[i] * a[i];
@@ -176,12 +187,20 @@ double norm7(const double a[7]) {
 }  // namespace
 
 void ceres_solve_pose(const std::vector<Residual>& blocks, LossKind loss, double x_io[7], LmSummary* summary, int max_num_iterations) {
+  BlockProgram program(blocks, loss);
+  trust_region_lm(program, x_io, summary, max_num_iterations);
+}
+
+// TrustRegionMinimizer + LevenbergMarquardtStrategy + DenseQRSolver (Ceres 1.13/1.14) for ONE parameter block of global size 7
+// and local size 6.  Shared by the restated problem above and by oracle/stubs/ceres/ceres.h, where the program calls the
+// reference's own cost functions and parameterization through their virtual interfaces.
+void trust_region_lm(LmProgram& program, double x_io[7], LmSummary* summary, int max_num_iterations) {
   LmSummary local;
   LmSummary& S = summary ? *summary : local;
   S = LmSummary();
   std::memset(S.H0, 0, sizeof(S.H0));
   std::memset(S.g0, 0, sizeof(S.g0));
-  const size_t C = blocks.size();
+  const size_t C = program.num_residuals();
   if (C == 0) { S.termination = 5; return; }
 
   // Solver::Options defaults in force (Appendix A.5)
@@ -201,7 +220,7 @@ void ceres_solve_pose(const std::vector<Residual>& blocks, LossKind loss, double
 
   int iteration = 0;
   auto evaluate_gradient_and_jacobian = [&]() -> bool {  // TrustRegionMinimizer::EvaluateGradientAndJacobian
-    if (!evaluate_program(blocks, loss, x, &x_cost, &residuals, &jacobian, gradient)) return false;
+    if (!program.evaluate(x, &x_cost, &residuals, &jacobian, gradient)) return false;
     if (iteration == 0) {
       for (int j = 0; j < 6; ++j) {
         double s = 0;
@@ -222,7 +241,7 @@ void ceres_solve_pose(const std::vector<Residual>& blocks, LossKind loss, double
     // gradient_max_norm = |x - Plus(x, -g)|_inf
     double ng[6], proj[7];
     for (int j = 0; j < 6; ++j) ng[j] = -gradient[j];
-    se3_plus(x, ng, proj);
+    program.plus(x, ng, proj);
     gradient_max_norm = 0.0;
     for (int j = 0; j < 7; ++j) gradient_max_norm = std::max(gradient_max_norm, std::fabs(x[j] - proj[j]));
     return true;
@@ -288,8 +307,8 @@ void ceres_solve_pose(const std::vector<Residual>& blocks, LossKind loss, double
 
     // ComputeCandidatePointAndEvaluateCost
     double candidate_x[7], candidate_cost;
-    se3_plus(x, delta, candidate_x);
-    if (!evaluate_program(blocks, loss, candidate_x, &candidate_cost, nullptr, nullptr, nullptr))
+    program.plus(x, delta, candidate_x);
+    if (!program.evaluate(candidate_x, &candidate_cost, nullptr, nullptr, nullptr))
       candidate_cost = std::numeric_limits<double>::max();
 
     if (getenv("FO_LM_DEBUG")) fprintf(stderr, "it %d radius %g step %g %g %g %g %g %g delta %g %g %g %g %g %g model %g cost %g cand %g\n", iteration, radius, step[0], step[1], step[2], step[3], step[4], step[5], delta[0], delta[1], delta[2], delta[3], delta[4], delta[5], model_cost_change, x_cost, candidate_cost);

@@ -47,14 +47,19 @@ class LaserProcessing {
 // pcl::VoxelGrid<PointXYZI>::filter, leaf as given to setLeafSize (cast to float there).
 // total_order=false: std::sort on idx only (PCL 1.8.1, unstable inside a voxel);
 // total_order=true : stable (ascending point index inside a voxel) — the CUDA path's contract.
-void voxel_grid_filter(const CloudI& in, float leaf, CloudI& out, bool total_order = false, bool* passthrough = nullptr);
+void voxel_grid_filter(const PointXYZI* in, size_t n, float leaf, CloudI& out, bool total_order = false, bool* passthrough = nullptr);
+inline void voxel_grid_filter(const CloudI& in, float leaf, CloudI& out, bool total_order = false, bool* passthrough = nullptr) {
+  voxel_grid_filter(in.data(), in.size(), leaf, out, total_order, passthrough);
+}
 // pcl::CropBox<PointXYZI>::filter, min/max already cast to float, negative=false.
-void crop_box_filter(const CloudI& in, const float mn[3], const float mx[3], CloudI& out);
+void crop_box_filter(const PointXYZI* in, size_t n, const float mn[3], const float mx[3], CloudI& out);
+inline void crop_box_filter(const CloudI& in, const float mn[3], const float mx[3], CloudI& out) { crop_box_filter(in.data(), in.size(), mn, mx, out); }
 
 // ---- pcl::KdTreeFLANN<PointXYZI> (Appendix A.3) ----
 class KdTreeFlann {
  public:
-  void setInputCloud(const CloudI& cloud);
+  void setInputCloud(const PointXYZI* cloud, size_t n);
+  void setInputCloud(const CloudI& cloud) { setInputCloud(cloud.data(), cloud.size()); }
   // returns number of neighbours found (min(k, N)); ids/sqdist ascending
   int nearestKSearch(const PointXYZI& q, int k, int* ids, float* sqdist) const;
   size_t size() const { return n_; }
@@ -83,7 +88,8 @@ class KdTreeFlann {
   size_t n_ = 0;
 };
 // brute-force kNN with FLANN's L2_Simple float accumulation; ties by (distance, index). Ground truth for the build.
-int knn_bruteforce(const CloudI& cloud, const PointXYZI& q, int k, int* ids, float* sqdist);
+int knn_bruteforce(const PointXYZI* cloud, size_t n, const PointXYZI& q, int k, int* ids, float* sqdist);
+inline int knn_bruteforce(const CloudI& cloud, const PointXYZI& q, int k, int* ids, float* sqdist) { return knn_bruteforce(cloud.data(), cloud.size(), q, k, ids, sqdist); }
 
 // ---- src/lidarOptimization.cpp + Ceres (Appendix A.5) ----
 enum LossKind { LOSS_TRIVIAL = 0, LOSS_HUBER = 1, LOSS_CAUCHY_TRUE = 2 };
@@ -103,6 +109,16 @@ struct LmSummary {
   int termination = 0;      // 0 max-iter, 1 param tol, 2 function tol, 3 gradient tol, 4 failure, 5 no residuals, 6 radius
   double H0[36]; double g0[6];  // J^T J and J^T r (unscaled) at the starting point, for stage parity
 };
+// What the trust-region loop needs from a problem with one 7-dof parameter block (local size 6).
+struct LmProgram {
+  virtual ~LmProgram() {}
+  virtual size_t num_residuals() const = 0;
+  // ProgramEvaluator::Evaluate: cost, corrected residuals (C), corrected local Jacobian (C x 6 row-major), gradient J^T r.
+  // residuals / jacobian / gradient may be null (cost-only evaluation of a candidate).  false = evaluation failure.
+  virtual bool evaluate(const double x[7], double* cost, std::vector<double>* residuals, std::vector<double>* jacobian, double gradient[6]) = 0;
+  virtual void plus(const double x[7], const double delta[6], double x_plus_delta[7]) = 0;  // LocalParameterization::Plus
+};
+void trust_region_lm(LmProgram& program, double x[7], LmSummary* summary = nullptr, int max_num_iterations = 4);
 // ceres::Solve(DENSE_QR, max_num_iterations=4) on one 7-dof block with PoseSE3Parameterization.
 void ceres_solve_pose(const std::vector<Residual>& blocks, LossKind loss, double x[7], LmSummary* summary = nullptr,
                       int max_num_iterations = 4);

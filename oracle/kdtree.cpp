@@ -42,8 +42,8 @@ struct KdTreeFlann::ResultSet {  // flann::KNNSimpleResultSet
   }
 };
 
-void KdTreeFlann::setInputCloud(const CloudI& cloud) {
-  n_ = cloud.size();
+void KdTreeFlann::setInputCloud(const PointXYZI* cloud, size_t n) {
+  n_ = n;
   pts_.resize(n_ * 3);
   for (size_t i = 0; i < n_; ++i) { pts_[3 * i] = cloud[i].x; pts_[3 * i + 1] = cloud[i].y; pts_[3 * i + 2] = cloud[i].z; }
   vind_.resize(n_);
@@ -202,14 +202,14 @@ int KdTreeFlann::nearestKSearch(const PointXYZI& q, int k, int* ids, float* sqdi
   return k;
 }
 
-int knn_bruteforce(const CloudI& cloud, const PointXYZI& q, int k, int* ids, float* sqdist) {
-  if (k > (int)cloud.size()) k = (int)cloud.size();
+int knn_bruteforce(const PointXYZI* cloud, size_t n_cloud, const PointXYZI& q, int k, int* ids, float* sqdist) {
+  if (k > (int)n_cloud) k = (int)n_cloud;
   if (k > 8) k = 8;
   float bd[8];
   int bi[8];
   int cnt = 0;
   const float vec[3] = {q.x, q.y, q.z};
-  for (int i = 0; i < (int)cloud.size(); ++i) {
+  for (int i = 0; i < (int)n_cloud; ++i) {
     const float p[3] = {cloud[i].x, cloud[i].y, cloud[i].z};
     float d = l2_simple(vec, p);
     if (cnt == k && !(d < bd[k - 1])) continue;  // ascending index scan: a later equal distance never displaces

@@ -18,15 +18,16 @@ struct cloud_point_index_idx {  // pcl/filters/voxel_grid.h
 };
 }  // namespace
 
-void voxel_grid_filter(const CloudI& in, float leaf, CloudI& out, bool total_order, bool* passthrough) {
+void voxel_grid_filter(const PointXYZI* in, size_t n_in, float leaf, CloudI& out, bool total_order, bool* passthrough) {
   if (passthrough) *passthrough = false;
   CloudI result;
-  if (in.empty()) { out.swap(result); return; }
+  if (n_in == 0) { out.swap(result); return; }
   const float inverse_leaf_size = 1.0f / leaf;  // Eigen::Array4f::Ones()/leaf_size_.array()
 
   // getMinMax3D
   float min_p[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, max_p[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-  for (const PointXYZI& p : in) {
+  for (size_t pi = 0; pi < n_in; ++pi) {
+    const PointXYZI& p = in[pi];
     min_p[0] = std::min(min_p[0], p.x); min_p[1] = std::min(min_p[1], p.y); min_p[2] = std::min(min_p[2], p.z);
     max_p[0] = std::max(max_p[0], p.x); max_p[1] = std::max(max_p[1], p.y); max_p[2] = std::max(max_p[2], p.z);
   }
@@ -36,7 +37,7 @@ void voxel_grid_filter(const CloudI& in, float leaf, CloudI& out, bool total_ord
   if ((dx * dy * dz) > static_cast<std::int64_t>(std::numeric_limits<std::int32_t>::max())) {
     // "Leaf size is too small for the input dataset. Integer indices would overflow." -> output = *input_ (Q13)
     if (passthrough) *passthrough = true;
-    result = in;
+    result.assign(in, in + n_in);
     out.swap(result);
     return;
   }
@@ -49,8 +50,8 @@ void voxel_grid_filter(const CloudI& in, float leaf, CloudI& out, bool total_ord
   divb_mul[0] = 1; divb_mul[1] = div_b[0]; divb_mul[2] = div_b[0] * div_b[1];
 
   std::vector<cloud_point_index_idx> index_vector;
-  index_vector.reserve(in.size());
-  for (size_t cp = 0; cp < in.size(); ++cp) {
+  index_vector.reserve(n_in);
+  for (size_t cp = 0; cp < n_in; ++cp) {
     int ijk0 = static_cast<int>(std::floor(in[cp].x * inverse_leaf_size) - static_cast<float>(min_b[0]));
     int ijk1 = static_cast<int>(std::floor(in[cp].y * inverse_leaf_size) - static_cast<float>(min_b[1]));
     int ijk2 = static_cast<int>(std::floor(in[cp].z * inverse_leaf_size) - static_cast<float>(min_b[2]));
@@ -77,10 +78,11 @@ void voxel_grid_filter(const CloudI& in, float leaf, CloudI& out, bool total_ord
   out.swap(result);
 }
 
-void crop_box_filter(const CloudI& in, const float mn[3], const float mx[3], CloudI& out) {
+void crop_box_filter(const PointXYZI* in, size_t n_in, const float mn[3], const float mx[3], CloudI& out) {
   CloudI result;
-  result.reserve(in.size());
-  for (const PointXYZI& p : in) {
+  result.reserve(n_in);
+  for (size_t pi = 0; pi < n_in; ++pi) {
+    const PointXYZI& p = in[pi];
     if ((p.x < mn[0] || p.y < mn[1] || p.z < mn[2]) || (p.x > mx[0] || p.y > mx[1] || p.z > mx[2])) continue;
     result.push_back(p);
   }

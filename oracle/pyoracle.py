@@ -160,55 +160,56 @@ class Odom:
     """OdomEstimationClass restatement (src/odomEstimationClass.cpp)."""
 
     def __init__(self, num_lines=64, scan_period=0.1, min_dis=2.0, max_dis=60.0, map_resolution=0.4, loss="cauchy",
-                 total_order=False, use_kdtree=True):
-        self.h = C.c_void_p(lib().fo_odom_create(int(num_lines), C.c_double(scan_period), C.c_double(min_dis), C.c_double(max_dis),
+                 total_order=False, use_kdtree=True, _lib=None):
+        self._L = _lib if _lib is not None else lib()
+        self.h = C.c_void_p(self._L.fo_odom_create(int(num_lines), C.c_double(scan_period), C.c_double(min_dis), C.c_double(max_dis),
                                                  C.c_double(map_resolution), loss.encode(), int(total_order), int(use_kdtree)))
 
     def __del__(self):
         if self.h:
-            lib().fo_odom_destroy(self.h); self.h = None
+            self._L.fo_odom_destroy(self.h); self.h = None
 
     def init_map(self, edge, surf):
         edge = np.ascontiguousarray(edge, POINT_I); surf = np.ascontiguousarray(surf, POINT_I)
-        lib().fo_odom_init_map(self.h, _p(edge), len(edge), _p(surf), len(surf))
+        self._L.fo_odom_init_map(self.h, _p(edge), len(edge), _p(surf), len(surf))
 
     def update(self, edge, surf, deskew=False):
         assert edge.dtype == POINT_IRT and surf.dtype == POINT_IRT
         pose = np.zeros(7)
-        lib().fo_odom_update(self.h, _p(edge), len(edge), _p(surf), len(surf), int(deskew), _p(pose))
+        self._L.fo_odom_update(self.h, _p(edge), len(edge), _p(surf), len(surf), int(deskew), _p(pose))
         return pose
 
     def update_xyzi(self, edge, surf, update_type=0):
         edge = np.ascontiguousarray(edge, POINT_I); surf = np.ascontiguousarray(surf, POINT_I)
         pose = np.zeros(7)
-        lib().fo_odom_update_xyzi(self.h, _p(edge), len(edge), _p(surf), len(surf), int(update_type), _p(pose))
+        self._L.fo_odom_update_xyzi(self.h, _p(edge), len(edge), _p(surf), len(surf), int(update_type), _p(pose))
         return pose
 
     def get(self):
         odom = np.zeros(16); last = np.zeros(16); v = np.zeros(3); oc = C.c_int()
-        lib().fo_odom_get(self.h, _p(odom), _p(last), _p(v), C.byref(oc))
+        self._L.fo_odom_get(self.h, _p(odom), _p(last), _p(v), C.byref(oc))
         return odom.reshape(4, 4), last.reshape(4, 4), v, oc.value
 
     def set_state(self, odom, last_odom, optimization_count):
         o = np.ascontiguousarray(odom, np.float64).reshape(16); l = np.ascontiguousarray(last_odom, np.float64).reshape(16)
-        lib().fo_odom_set_state(self.h, _p(o), _p(l), int(optimization_count))
+        self._L.fo_odom_set_state(self.h, _p(o), _p(l), int(optimization_count))
 
     def set_map(self, edge, surf):
         edge = np.ascontiguousarray(edge, POINT_I); surf = np.ascontiguousarray(surf, POINT_I)
-        lib().fo_odom_set_map(self.h, _p(edge), len(edge), _p(surf), len(surf))
+        self._L.fo_odom_set_map(self.h, _p(edge), len(edge), _p(surf), len(surf))
 
     def get_map(self):
         ne = C.c_int(); ns = C.c_int()
-        lib().fo_odom_map_sizes(self.h, C.byref(ne), C.byref(ns))
+        self._L.fo_odom_map_sizes(self.h, C.byref(ne), C.byref(ns))
         e = np.zeros(max(ne.value, 1), POINT_I); s = np.zeros(max(ns.value, 1), POINT_I)
-        lib().fo_odom_get_map(self.h, _p(e), len(e), _p(s), len(s))
+        self._L.fo_odom_get_map(self.h, _p(e), len(e), _p(s), len(s))
         return e[:ne.value], s[:ns.value]
 
     def knn_queries(self):
-        return lib().fo_odom_knn_queries(self.h)
+        return self._L.fo_odom_knn_queries(self.h)
 
     def debug(self):
-        L = lib()
+        L = self._L
 
         def fetch(what, dtype, per=1):
             n = L.fo_odom_debug(self.h, what, None, 0)

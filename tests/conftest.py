@@ -44,6 +44,15 @@ def po():
 
 
 @pytest.fixture(scope="session")
+def pr():
+    """The reference's own class sources compiled unmodified (oracle/_ref, built where /root/reference exists, shipped otherwise)."""
+    from oracle import pyref
+    if not pyref.available():
+        pytest.skip("oracle/_ref/libfloam_ref.so is not here and /root/reference is absent")
+    return pyref
+
+
+@pytest.fixture(scope="session")
 def synth():
     from floam_b200 import synth as s
     return s
@@ -60,10 +69,10 @@ def sequences(synth):
     """Lazily generated synthetic sequences, cached per (sensor, seed, frames, distort)."""
     cache = {}
 
-    def get(sensor, frames, seed=0, distort=False, sigma=0.02, n_az=None):
-        key = (sensor, frames, seed, distort, sigma, n_az)
+    def get(sensor, frames, seed=0, distort=False, sigma=0.02, n_az=None, speed=10.0):
+        key = (sensor, frames, seed, distort, sigma, n_az, speed)
         if key not in cache:
-            seq = synth.Sequence(sensor, seed=seed, distort=distort, sigma=sigma, n_az=n_az)
+            seq = synth.Sequence(sensor, seed=seed, distort=distort, sigma=sigma, n_az=n_az, speed=speed)
             scans, off = seq.scans(0, frames)
             cache[key] = (seq, scans, off)
         return cache[key]
