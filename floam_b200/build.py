@@ -11,7 +11,7 @@ ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 CUDA_LIB = os.path.join(LIB_DIR, "libfloam_b200.so")
-SYNTH_LIB = os.path.join(LIB_DIR, "libfloam_synth.so")
+SYNTH_LIB = os.path.join(_HERE, "synth", "libfloam_synth.so")   # the workload generator is not product code: kept out of lib/
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-Wall", "-Xcompiler", "-Wno-unknown-pragmas", "--expt-relaxed-constexpr",

@@ -30,7 +30,7 @@ class Params(C.Structure):
 # every symbol include/floam_b200.h declares (tests/test_abi.py checks the header against this list and the .so against both)
 SYMBOLS = [
     "floam_params_default", "floam_loss_from_string", "floam_status_string", "floam_version", "floam_create", "floam_destroy",
-    "floam_alloc_pinned", "floam_free_pinned", "floam_set_graphs", "floam_imu_push", "floam_imu_get", "floam_imu_size", "floam_deskew_align",
+    "floam_alloc_pinned", "floam_free_pinned", "floam_set_graphs", "floam_imu_push", "floam_imu_get", "floam_imu_size", "floam_imu_time_contained", "floam_deskew_align",
     "floam_feature_extract", "floam_odom_init_map", "floam_odom_update", "floam_odom_update_xyzi", "floam_odom_get", "floam_odom_map_sizes",
     "floam_odom_get_map", "floam_odom_set_state", "floam_odom_get_state", "floam_odom_set_map", "floam_process_scan", "floam_process_submit",
     "floam_process_wait", "floam_stage_scans", "floam_process_staged", "floam_mapping_update", "floam_mapping_get_map", "floam_voxel_grid",

@@ -79,6 +79,7 @@ void select_parity(floam_ctx* c, int p) {
   c->d_edge = c->d_edge_b[p]; c->d_surf = c->d_surf_b[p];
   c->d_ne = c->d_ne_b[p]; c->d_ns = c->d_ns_b[p];
   c->d_edge_src = c->d_edge_src_b[p]; c->d_surf_src = c->d_surf_src_b[p];
+  c->d_flags = c->d_flags_b[p];
   odom_select_buffers(c->odom, p);
 }
 
@@ -122,6 +123,7 @@ void enqueue_selector(floam_ctx* c, PointIRT* d_edge, const int* d_ne, PointIRT*
 // keyframe map update. FRONT(k+1) overlaps BACK(k); the buffers the two halves exchange exist twice (frame parity).
 void enqueue_front(floam_ctx* c, PointIRT* d_scan, const int* d_scan_n, int deskew, int slot, bool first, bool imu) {
   cudaStream_t s = c->front_stream;
+  cudaMemsetAsync(c->d_flags, 0, 4, s);   // error flags are per frame: a NaN point or an over-long ring in one scan does not poison the next
   // CenterTime + Compensate + IMU alignment folded into the frame (src/laserProcessingNode.cpp:100-116): in place on the uploaded scan
   if (imu) deskew_launch(c->imu, c->d_plan[slot], d_scan, d_scan_n, c->prm.max_scan_points, s);
   feature_extract_device(d_scan, d_scan_n, c->fprm, c->fws, c->d_edge, c->d_ne, c->d_surf, c->d_ns, c->d_edge_src, c->d_surf_src, c->d_flags, s);
@@ -313,12 +315,16 @@ int floam_create(const floam_params* params, int device, floam_ctx** out) {
   void* vmem_aux = A(voxel_workspace_bytes(aux_cap));
   void* vmem_front = A(voxel_workspace_bytes(ns));
   void* vmem_front_aux = A(voxel_workspace_bytes(ns));
-  c->imu.dev_cap = 1 << 20;
+  c->imu.dev_cap = 1 << 20;   // device ring of IMU samples (sliding window, imu.cuh); FLOAM_IMU_RING = smaller power of two for tests
+  if (const char* e = std::getenv("FLOAM_IMU_RING")) {
+    const int v = std::atoi(e);
+    if (v >= 256 && v <= (1 << 24) && (v & (v - 1)) == 0) c->imu.dev_cap = v;
+  }
   c->imu.d_samples = (ImuSample*)A((size_t)c->imu.dev_cap * sizeof(ImuSample));
   c->imu.d_plan = (DeskewPlan*)A(sizeof(DeskewPlan));
   for (int k = 0; k < 2; ++k) c->d_plan[k] = (DeskewPlan*)A(sizeof(DeskewPlan));
   if (!ok) return fail(FLOAM_ERR_CUDA);
-  c->d_ne_b[0] = ints; c->d_ns_b[0] = ints + 1; c->d_flags = ints + 2; c->d_stage_n = ints + 4; c->d_staged_n = ints + 8;
+  c->d_ne_b[0] = ints; c->d_ns_b[0] = ints + 1; c->d_flags_b[0] = ints + 2; c->d_flags_b[1] = ints + 3; c->d_stage_n = ints + 4; c->d_staged_n = ints + 8;
   c->d_ne_b[1] = ints + 16; c->d_ns_b[1] = ints + 17;
   if (cudaMemsetAsync(ints, 0, 128, c->stream) != cudaSuccess) return fail(FLOAM_ERR_CUDA);
   select_parity(c, 0);
@@ -415,9 +421,14 @@ int floam_imu_get(floam_ctx* c, double stamp, double q_xyzw[4], int* valid) {
   if (valid) *valid = ok ? 1 : 0;
   return FLOAM_OK;
 }
+int floam_imu_time_contained(floam_ctx* c, double stamp, int* contained) {
+  if (!c || !contained) return FLOAM_ERR_ARG;
+  *contained = imu_time_contained(c->imu, stamp) ? 1 : 0;
+  return FLOAM_OK;
+}
 int floam_imu_size(floam_ctx* c, int* n) {
   if (!c || !n) return FLOAM_ERR_ARG;
-  *n = (int)c->imu.host.size();
+  *n = (int)c->imu.total();   // every sample ever admitted, like data_.size() of the reference (older ones have left the window)
   return FLOAM_OK;
 }
 
@@ -554,7 +565,10 @@ int floam_odom_update_xyzi(floam_ctx* c, const floam_point_xyzi* edge, int ne, c
   return finish_update(c, pose_out);
 }
 
+// Refreshes mailbox 0 with the device state.  Mailbox 0 is also a slot of the submit/wait ring, and the pose state belongs to the
+// frames in flight: every caller is refused while submissions are pending (like the other stage entry points).
 static int sync_state(floam_ctx* c) {
+  if (c->inflight != 0) return FLOAM_ERR_ARG;
   if (set_device(c)) return FLOAM_ERR_CUDA;
   int rc = fetch_state(c, 0);
   if (rc) return rc;
@@ -1058,6 +1072,7 @@ int floam_replay_staged(floam_ctx* c, int first, int count, int deskew, double* 
   int rc = sync_state(c);
   if (rc) return rc;
   const int counter0 = c->h_state[0]->frame_counter;
+  FLOAM_CUDA_OK(cudaMemsetAsync(&c->odom.state->error_sticky, 0, 4, c->stream));
   FLOAM_CUDA_OK(cudaEventRecord(c->ev_replay_begin, c->front_stream));
   int last_slot = 0;
   const auto t_host0 = std::chrono::steady_clock::now();
@@ -1080,8 +1095,11 @@ int floam_replay_staged(floam_ctx* c, int first, int count, int deskew, double* 
     for (int k = 0; k < count; ++k)
       FLOAM_CUDA_OK(cudaMemcpy(poses_out + (size_t)k * 7, c->odom.traj + (size_t)((counter0 + k) % cap) * 7, 56, cudaMemcpyDeviceToHost));
   }
-  // status of the last frame's mailbox; earlier frames' sticky error flags are part of the same state
-  if (c->h_state[last_slot]->error_flags == 0 && c->h_state[(last_slot + 3) & 3]->error_flags != 0 && count > 1) return FLOAM_ERR_CAPACITY;
+  // flags are per frame; the device keeps the OR over the frames of this replay in error_sticky (mailed before the last frame's own
+  // flags are folded in, which status_from_flags covers): bits 0-1 map / grid capacity, bits 4-5 feature flags
+  const int sticky = c->h_state[last_slot]->error_sticky;
+  if (sticky & 0x10) return FLOAM_ERR_NONFINITE;
+  if (sticky & 0x23) return FLOAM_ERR_CAPACITY;
   return status_from_flags(c, last_slot);
 }
 

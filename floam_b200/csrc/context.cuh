@@ -51,7 +51,8 @@ struct floam_ctx {
   int *d_ne = nullptr, *d_ns = nullptr, *d_edge_src = nullptr, *d_surf_src = nullptr;
   floam::PointIRT *d_edge_b[2] = {nullptr, nullptr}, *d_surf_b[2] = {nullptr, nullptr};
   int *d_ne_b[2] = {nullptr, nullptr}, *d_ns_b[2] = {nullptr, nullptr}, *d_edge_src_b[2] = {nullptr, nullptr}, *d_surf_src_b[2] = {nullptr, nullptr};
-  int* d_flags = nullptr;
+  int* d_flags = nullptr;                       // feature-extraction flags word of the frame being enqueued (alias of d_flags_b[parity])
+  int* d_flags_b[2] = {nullptr, nullptr};       // one per frame parity, zeroed at the head of the frame's FRONT: flags are per frame
   floam::FeatureParams fprm;
   floam::FeatureWorkspace fws;
   floam::VoxelWorkspace vws;

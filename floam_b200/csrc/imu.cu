@@ -13,35 +13,45 @@ namespace floam {
 
 void imu_push(ImuDevice& imu, double stamp, const double q_xyzw[4]) {
   ImuSample s{stamp, {q_xyzw[0], q_xyzw[1], q_xyzw[2], q_xyzw[3]}};
-  if (imu.host.empty()) { imu.host.push_back(s); return; }
+  if (imu.total() == 0) { imu.first_stamp = stamp; imu.host.push_back(s); return; }
   const double tdiff = stamp - imu.host.back().stamp;
-  if (tdiff > 0.00001) imu.host.push_back(s);
+  if (!(tdiff > 0.00001)) return;
+  imu.host.push_back(s);
+  // sliding window: never hold more than dev_cap / 2 + a slack of dev_cap / 8 samples; drop the oldest in one go (amortised O(1))
+  const size_t keep = (size_t)imu.dev_cap / 2, slack = (size_t)imu.dev_cap / 8;
+  if (imu.dev_cap > 0 && imu.host.size() > keep + slack) {
+    const size_t drop = imu.host.size() - keep;
+    imu.host.erase(imu.host.begin(), imu.host.begin() + (long)drop);
+    imu.base += (long long)drop;
+  }
 }
 
-// index of the sample ImuHandler::Get returns for tStamp, or -1 when the validity rule (:57) fails
-static int imu_lookup(const std::vector<ImuSample>& v, double t) {
-  const int n = (int)v.size();
-  int lo = 0, hi = n;  // lower_bound: first stamp >= t
+// global number of the sample ImuHandler::Get returns for tStamp, or -1 when the validity rule (:57) fails
+static long long imu_lookup(const ImuDevice& imu, double t) {
+  const std::vector<ImuSample>& v = imu.host;
+  const long long n = (long long)v.size();
+  long long lo = 0, hi = n;  // lower_bound: first stamp >= t
   while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (v[mid].stamp < t) lo = mid + 1; else hi = mid;
+    const long long mid = (lo + hi) >> 1;
+    if (v[(size_t)mid].stamp < t) lo = mid + 1; else hi = mid;
   }
-  const int after = lo;
-  if (after == 0 || after == n) return -1;
-  const int before = after - 1;
+  const long long after = imu.base + lo;          // global numbers from here on
+  if (after == 0 || after == imu.total()) return -1;
+  if (lo == 0) return -1;                         // the sample before it left the window long ago (only for stamps > 20 min in the past)
+  const long long before = after - 1;
   if (before == 0) return -1;
   return before;
 }
 
 bool imu_get(const ImuDevice& imu, double stamp, double q[4]) {
-  const int i = imu_lookup(imu.host, stamp);
-  if (i < 0) return false;
-  for (int k = 0; k < 4; ++k) q[k] = imu.host[i].q[k];
+  const long long g = imu_lookup(imu, stamp);
+  if (g < 0) return false;
+  for (int k = 0; k < 4; ++k) q[k] = imu.host[(size_t)(g - imu.base)].q[k];
   return true;
 }
 
 bool imu_time_contained(const ImuDevice& imu, double t) {
-  return !imu.host.empty() && t >= imu.host.front().stamp && t <= imu.host.back().stamp;
+  return imu.total() > 0 && t >= imu.first_stamp && t <= imu.host.back().stamp;
 }
 
 static double stamp_to_sec(uint64_t stamp_us) {  // pcl_conversions::fromPCL + ros::Time::toSec
@@ -93,7 +103,8 @@ __global__ void __launch_bounds__(kThreads) deskew_align_kernel(PointIRT* __rest
   pdl_prologue();
   const int n = *d_n;
   const DeskewPlan plan = *d_plan;
-  const int n_samples = plan.n_samples;
+  const long long g_lo = plan.g_lo, g_hi = plan.g_hi;
+  const int mask = plan.ring_mask;
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
     float4* raw = reinterpret_cast<float4*>(pts + i);
     float4 a = raw[0], b = raw[1];  // b = intensity, ring|pad, time, pad
@@ -103,15 +114,15 @@ __global__ void __launch_bounds__(kThreads) deskew_align_kernel(PointIRT* __rest
     if (plan.can_compensate && plan.do_compensate) {
       const double t_cur = plan.t_scan_new + (double)t_new;
       // ImuHandler::Get: sample strictly before lower_bound(t_cur); invalid -> zero quaternion
-      int lo = 0, hi = n_samples;
+      long long lo = g_lo, hi = g_hi;   // global sample numbers; slot in the device ring = number & mask
       while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (__ldg(&samples[mid].stamp) < t_cur) lo = mid + 1; else hi = mid;
+        const long long mid = (lo + hi) >> 1;
+        if (__ldg(&samples[(int)(mid & mask)].stamp) < t_cur) lo = mid + 1; else hi = mid;
       }
       double qi[4] = {0.0, 0.0, 0.0, 0.0};
-      if (lo != 0 && lo != n_samples && lo - 1 != 0) {
+      if (lo != 0 && lo != g_hi && lo - 1 != 0 && lo > g_lo) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) qi[k] = __ldg(&samples[lo - 1].q[k]);
+        for (int k = 0; k < 4; ++k) qi[k] = __ldg(&samples[(int)((lo - 1) & mask)].q[k]);
       }
       double q_now[4], q_diff[4];
       m::quat_mul(qi, plan.extr, q_now);
@@ -135,14 +146,18 @@ __global__ void __launch_bounds__(kThreads) deskew_align_kernel(PointIRT* __rest
 }  // namespace
 
 int deskew_upload(ImuDevice& imu, DeskewPlan& plan, DeskewPlan* d_plan, cudaStream_t copy) {
-  const int total = (int)imu.host.size();
-  if (total > imu.dev_cap) return FLOAM_ERR_CAPACITY;
-  if (total > imu.dev_count) {
-    FLOAM_CUDA_OK(cudaMemcpyAsync(imu.d_samples + imu.dev_count, imu.host.data() + imu.dev_count, (size_t)(total - imu.dev_count) * sizeof(ImuSample),
-                                  cudaMemcpyHostToDevice, copy));
-    imu.dev_count = total;
+  const long long total = imu.total();
+  long long from = imu.dev_count > imu.base ? imu.dev_count : imu.base;   // samples dropped before they were uploaded are of no use any more
+  while (from < total) {   // ring upload: at most two pieces per call in practice
+    const int slot = (int)(from & (imu.dev_cap - 1));
+    const long long piece = std::min<long long>(total - from, imu.dev_cap - slot);
+    FLOAM_CUDA_OK(cudaMemcpyAsync(imu.d_samples + slot, imu.host.data() + (size_t)(from - imu.base), (size_t)piece * sizeof(ImuSample), cudaMemcpyHostToDevice, copy));
+    from += piece;
   }
-  plan.n_samples = total;
+  imu.dev_count = total;
+  plan.g_hi = total;
+  plan.g_lo = imu.base;   // the host window never exceeds 5/8 of the ring, so [g_lo, g_hi) is resident and stays so for 3/8 of a ring more
+  plan.ring_mask = imu.dev_cap - 1;
   FLOAM_CUDA_OK(cudaMemcpyAsync(d_plan, &plan, sizeof(DeskewPlan), cudaMemcpyHostToDevice, copy));  // pageable source: staged before the call returns
   return FLOAM_OK;
 }

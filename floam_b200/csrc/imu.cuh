@@ -14,12 +14,21 @@ struct ImuSample {   // device record
 };
 
 struct DeskewPlan;
+// The reference keeps every sample for ever (std::vector, :34).  Here the history is a sliding window: sample number g (counted from
+// the first one ever pushed) lives at host[g - base] and at d_samples[g & (dev_cap - 1)] (a ring; dev_cap is a power of two).  The
+// host drops the oldest samples once more than dev_cap / 2 are held, lookups search the newest dev_cap / 2 only, and an upload only
+// overwrites ring slots more than dev_cap samples old — so nothing a frame in flight can still read is touched (40+ minutes of
+// history at 400 Hz with the default 2^20 ring).  Validity rules that refer to "the first sample" (:57, :77) keep referring to the
+// first sample ever pushed: they use the global number / the remembered first stamp.
 struct ImuDevice {
-  std::vector<ImuSample> host;   // time-sorted, same admission rule as ImuHandler::AddMsg (:24-40)
+  std::vector<ImuSample> host;   // time-sorted, same admission rule as ImuHandler::AddMsg (:24-40); window [base, base + host.size())
+  long long base = 0;            // global number of host[0]
+  double first_stamp = 0.0;      // stamp of sample 0 (data_.front() of the reference)
   ImuSample* d_samples = nullptr;
-  int dev_count = 0;             // samples already uploaded
-  int dev_cap = 0;
+  long long dev_count = 0;       // samples already uploaded (global count)
+  int dev_cap = 0;               // ring size, power of two
   struct DeskewPlan* d_plan = nullptr;   // plan of the stand-alone entry point
+  long long total() const { return base + (long long)host.size(); }
 };
 
 // ImuHandler::AddMsg: keeps the sample iff it is the first or more than 10 us after the previous one
@@ -38,7 +47,8 @@ struct DeskewPlan {       // everything the per-point kernel needs, computed on 
   int can_compensate;     // dmapping::Compensate's return value
   int do_center, do_compensate, do_align;   // which of CenterTime / Compensate / alignment run (floam_deskew_flags)
   uint64_t stamp_us_new;
-  int n_samples;          // IMU samples resident on the device when the kernel runs
+  long long g_lo, g_hi;   // global sample numbers [g_lo, g_hi) the kernel may search (resident in the device ring when it runs)
+  int ring_mask;          // dev_cap - 1
 };
 // ros::Time / pcl stamp conversions + CenterTime + the host part of Compensate (TimeContained, qInit) and of the alignment
 void deskew_plan(const ImuDevice& imu, uint64_t stamp_us, float time_front, float time_back, const double extr_xyzw[4], int flags, DeskewPlan* plan);

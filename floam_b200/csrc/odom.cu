@@ -1272,12 +1272,19 @@ void odom_reset_state(OdomDevice& od, cudaStream_t s) {
   od.optimization_count = 2;
 }
 
-__global__ void mail_state_kernel(const PoseState* __restrict__ S, const int* __restrict__ d_flags, PoseState* h_state, int* h_flags) {
+__global__ void mail_state_kernel(PoseState* __restrict__ S, const int* __restrict__ d_flags, PoseState* h_state, int* h_flags) {
   pdl_prologue();
   const unsigned int* src = reinterpret_cast<const unsigned int*>(S);
   unsigned int* dst = reinterpret_cast<unsigned int*>(h_state);
   for (int i = threadIdx.x; i < (int)(sizeof(PoseState) / 4); i += blockDim.x) dst[i] = __ldcg(src + i);
-  if (threadIdx.x == 0) *h_flags = *d_flags;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int ff = *d_flags;
+    *h_flags = ff;
+    // the flags belong to the frame just mailed: the next frame starts clean (the OR over frames stays in error_sticky)
+    S->error_sticky |= S->error_flags | (ff << 4);
+    S->error_flags = 0;
+  }
   // no system fence: the host reads the mailbox only after an event recorded behind this kernel, and kernel completion flushes the stores
 }
 void odom_mail_state(OdomDevice& od, const int* d_flags, PoseState* h_state, int* h_flags, cudaStream_t s) {

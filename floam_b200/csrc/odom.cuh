@@ -27,7 +27,8 @@ struct PoseState {
   double lm_final_cost_last;
   unsigned int ticket;   // last-CTA-done counter for the reduction
   int outer_iterations;
-  int error_flags;       // bit 0: map capacity exceeded, bit 1: grid capacity exceeded
+  int error_flags;       // bit 0: map capacity exceeded, bit 1: grid capacity exceeded — of the CURRENT frame: cleared once mailed
+  int error_sticky;      // OR of every mailed frame's flags (bits 0-1 as above, bits 4-5 the feature-extraction flags word)
   int n_corr;            // accepted correspondences of the last association
   int n_corr_acc;        // accumulator of the running association
   int frame_counter;     // frames completed (index of the next trajectory record)
@@ -96,7 +97,7 @@ void odom_reset_state(OdomDevice& od, cudaStream_t s);
 void odom_record_pose(OdomDevice& od, cudaStream_t s);
 // End-of-frame mailbox: the state (and the feature-extraction flags word) written straight into pinned, device-mapped host memory by
 // a kernel — posted stores instead of two copy-engine nodes at the tail of the frame graph.
-void odom_mail_state(OdomDevice& od, const int* d_flags, PoseState* h_state, int* h_flags, cudaStream_t s);
+void odom_mail_state(OdomDevice& od, const int* d_flags, PoseState* h_state, int* h_flags, cudaStream_t s);   // also clears the frame's error flags
 
 // append (replace = 0) or overwrite (replace = 1) a map with a strided device cloud and rebuild its grid
 void local_map_load(OdomDevice& od, LocalMap& map, const void* d_pts, const int* d_n, int stride, int n_max, int replace, cudaStream_t s);

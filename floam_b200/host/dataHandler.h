@@ -3,13 +3,29 @@
 #ifndef FLOAM_B200_HOST_DATA_HANDLER_H_
 #define FLOAM_B200_HOST_DATA_HANDLER_H_
 #include <cstdio>
-#include "lidar.h"
+#ifdef FLOAM_B200_WITH_PCL   // include/dataHandler.h:4-12
+#include "ros/ros.h"
+#include <map>
+#include <algorithm>
+#include "sensor_msgs/Imu.h"
+#include "pcl_conversions/pcl_conversions.h"
+#include "math.h"
+using std::cout;
+using std::endl;
+#endif
+#include <lidar.h>       // through the include path (this directory first), so that lidar.h's #include_next finds the reference's
 
 #define SCAN_RATE 10.0
 namespace dmapping {
 
-inline Eigen::Quaterniond Imu2Orientation(const sensor_msgs::Imu& data) {
+inline Eigen::Quaterniond Imu2Orientation(const sensor_msgs::Imu& data) {  // :6-8
   return Eigen::Quaterniond(data.orientation.w, data.orientation.x, data.orientation.y, data.orientation.z);
+}
+inline Eigen::Vector3d Imu2AngularVelocity(const sensor_msgs::Imu& data) {  // :10-12
+  return Eigen::Vector3d(data.angular_velocity.x, data.angular_velocity.y, data.angular_velocity.z);
+}
+inline Eigen::Vector3d Imu2LinearAcceleration(const sensor_msgs::Imu& data) {  // :14-16
+  return Eigen::Vector3d(data.linear_acceleration.x, data.linear_acceleration.y, data.linear_acceleration.z);
 }
 
 class ImuHandler {
@@ -29,6 +45,12 @@ class ImuHandler {
     return valid != 0;
   }
   sensor_msgs::Imu Get(const double& tStamp) const { sensor_msgs::Imu data; Get(tStamp, data); return data; }  // :71-75
+  bool TimeContained(const double t) const {  // :76-81
+    if (fc_->ensure()) return false;
+    int contained = 0;
+    floam_imu_time_contained(fc_->ctx, t, &contained);
+    return contained != 0;
+  }
   std::size_t size() { int n = 0; if (!fc_->ensure()) floam_imu_size(fc_->ctx, &n); return (std::size_t)n; }
   floam_b200_host::FloamContext* context() const { return fc_; }
 
@@ -70,6 +92,14 @@ inline void CompensateVelocity(pcl::PointCloud<vel_point::PointXYZIRT>::Ptr inpu
   const double v[3] = {velocity(0), velocity(1), velocity(2)};
   floam_b200_host::report(floam_compensate_velocity(fc->ctx, reinterpret_cast<floam_point_xyzirt*>(input->points.data()), (int)input->points.size(), v),
                           "dmapping::CompensateVelocity");
+}
+
+// the reference's two-argument signature (include/dataHandler.h:64); served by one small process-wide context
+inline void CompensateVelocity(pcl::PointCloud<vel_point::PointXYZIRT>::Ptr input, const Eigen::Vector3d& velocity) {
+  static floam_b200_host::FloamContext shared;
+  static bool sized = false;
+  if (!sized) { shared.prm.max_map_points = 1 << 16; shared.prm.max_global_map_points = 0; shared.prm.max_grid_cells = 1 << 16; sized = true; }
+  CompensateVelocity(input, velocity, &shared);
 }
 
 }  // namespace dmapping

@@ -98,6 +98,7 @@ struct PointCloud2 {
 struct Imu {
   struct { struct { double t = 0; double toSec() const { return t; } } stamp; } header;
   struct { double x = 0, y = 0, z = 0, w = 0; } orientation;  // default message: all-zero quaternion
+  struct { double x = 0, y = 0, z = 0; } angular_velocity, linear_acceleration;
   typedef std::shared_ptr<const Imu> ConstPtr;
 };
 }  // namespace sensor_msgs

@@ -2,7 +2,20 @@
 #ifndef FLOAM_B200_HOST_LASER_MAPPING_CLASS_H_
 #define FLOAM_B200_HOST_LASER_MAPPING_CLASS_H_
 #include <cstdio>
-#include "lidar.h"
+#ifdef FLOAM_B200_WITH_PCL   // include/laserMappingClass.h:8-23
+#include <pcl/point_cloud.h>
+#include <pcl/point_types.h>
+#include <pcl/filters/filter.h>
+#include <pcl/filters/voxel_grid.h>
+#include <pcl/filters/passthrough.h>
+#include <pcl_ros/impl/transforms.hpp>
+#include <Eigen/Dense>
+#include <Eigen/Geometry>
+#include <string>
+#include <math.h>
+#include <vector>
+#endif
+#include <lidar.h>       // through the include path (this directory first), so that lidar.h's #include_next finds the reference's
 
 class LaserMappingClass {
  public:

@@ -3,7 +3,17 @@
 #ifndef FLOAM_B200_HOST_LASER_PROCESSING_CLASS_H_
 #define FLOAM_B200_HOST_LASER_PROCESSING_CLASS_H_
 #include <cstdio>
-#include "lidar.h"
+#ifdef FLOAM_B200_WITH_PCL   // what the reference's header includes (include/laserProcessingClass.h:6-16); the node relies on them
+#define PCL_NO_PRECOMPILE
+#include <pcl/point_cloud.h>
+#include <pcl/point_types.h>
+#include <pcl/filters/filter.h>
+#include <pcl/filters/voxel_grid.h>
+#include <pcl/filters/passthrough.h>
+#include <pcl/filters/extract_indices.h>
+#include <pcl/filters/crop_box.h>
+#endif
+#include <lidar.h>       // through the include path (this directory first), so that lidar.h's #include_next finds the reference's
 
 class LaserProcessingClass {
  public:

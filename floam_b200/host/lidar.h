@@ -1,22 +1,25 @@
-// Drop-in for the reference's include/lidar.h: vel_point::PointXYZIRT (:14-32), lidar::Lidar (:53-86), euler2Quaternion
-// (src/lidar.cpp:8-16).  PublishCloud / GetParamFromRos are ROS plumbing and stay in the reference's own header.
+// Drop-in for the reference's include/lidar.h.
+//  * Inside the catkin workspace (-DFLOAM_B200_WITH_PCL, this directory FIRST on the include path): the reference's own lidar.h is
+//    pulled in through #include_next, so vel_point::PointXYZIRT (:14-32), lidar::Lidar (:53-86), PublishCloud (:36-49) and
+//    GetParamFromRos stay the reference's (and src/lidar.cpp keeps providing euler2Quaternion and the setters); this header only
+//    adds the context plumbing the shims share.  tests/test_abi.py parses the three unmodified node sources against this mode.
+//  * Stand-alone (this repo's build container: no PCL / Eigen / ROS): the same types are defined here.
 #ifndef FLOAM_B200_HOST_LIDAR_H_
 #define FLOAM_B200_HOST_LIDAR_H_
 #include "floam_b200.h"
 #include "floam_compat.h"
 
+#ifdef FLOAM_B200_WITH_PCL
+#include_next <lidar.h>
+#else
 namespace vel_point {
-#ifndef FLOAM_B200_WITH_PCL
 struct alignas(16) PointXYZIRT {
   float x = 0, y = 0, z = 0, data3 = 1.0f;
   float intensity = 0;
   std::uint16_t ring = 0;
   float time = 0;
 };
-#endif
 }  // namespace vel_point
-static_assert(sizeof(vel_point::PointXYZIRT) == sizeof(floam_point_xyzirt), "PointXYZIRT must be byte-identical to the C ABI point");
-static_assert(sizeof(pcl::PointXYZI) == sizeof(floam_point_xyzi), "pcl::PointXYZI must be byte-identical to the C ABI point");
 
 namespace lidar {
 class Lidar {  // include/lidar.h:53-86, src/lidar.cpp:18-50
@@ -51,6 +54,10 @@ inline Eigen::Quaterniond euler2Quaternion(const double roll, const double pitch
   mul(ry, p, q);
   return Eigen::Quaterniond(q[3], q[0], q[1], q[2]);
 }
+#endif  // FLOAM_B200_WITH_PCL
+
+static_assert(sizeof(vel_point::PointXYZIRT) == sizeof(floam_point_xyzirt), "PointXYZIRT must be byte-identical to the C ABI point");
+static_assert(sizeof(pcl::PointXYZI) == sizeof(floam_point_xyzi), "pcl::PointXYZI must be byte-identical to the C ABI point");
 
 namespace floam_b200_host {
 // One floam_ctx per class instance by default; FloamContext::share() lets LaserProcessingClass and OdomEstimationClass of one

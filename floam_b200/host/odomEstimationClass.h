@@ -5,7 +5,28 @@
 #define FLOAM_B200_HOST_ODOM_ESTIMATION_CLASS_H_
 #include <cstdio>
 #include <string>
-#include "lidar.h"
+#ifdef FLOAM_B200_WITH_PCL   // the includes of the reference's header the node depends on (include/odomEstimationClass.h:8-40): PCL filters and
+#include <math.h>            // io for its dump-on-exit code, Dump / SavePosegraph / SaveOdom from utils.h; Ceres is no longer needed
+#include <vector>
+#include <sstream>
+#include <pcl/point_cloud.h>
+#include <pcl/point_types.h>
+#include <pcl/filters/filter.h>
+#include <pcl/filters/voxel_grid.h>
+#include <pcl/filters/passthrough.h>
+#include <pcl/filters/extract_indices.h>
+#include <pcl/filters/crop_box.h>
+#include <Eigen/Dense>
+#include <Eigen/Geometry>
+#include <ros/ros.h>
+#endif
+#include <lidar.h>       // through the include path (this directory first), so that lidar.h's #include_next finds the reference's
+#include <dataHandler.h>
+#ifdef FLOAM_B200_WITH_PCL
+#include "utils.h"
+using std::cout;
+using std::endl;
+#endif
 
 inline pcl::PointCloud<pcl::PointXYZI>::Ptr VelToIntensityCopy(const pcl::PointCloud<vel_point::PointXYZIRT>::Ptr VelCloud) {  // :308-318
   pcl::PointCloud<pcl::PointXYZI>::Ptr converted(new pcl::PointCloud<pcl::PointXYZI>());

@@ -48,6 +48,11 @@ enum floam_status {
   FLOAM_ERR_NONFINITE = 6    /* non-finite input coordinates (undefined in the reference, Q9) */
 };
 
+/* Error semantics of the frame path (floam_process_submit / _wait / _scan / _staged): FLOAM_ERR_NONFINITE and FLOAM_ERR_CAPACITY are
+ * reported for the frame that raised them and only for that frame (the pose of such a frame is still computed and returned; the
+ * reference has no error path at all and keeps running on NaN input, src/laserProcessingClass.cpp:74-75).  The next frame starts with
+ * clean flags.  floam_replay_staged reports the OR over the frames it replayed.  FLOAM_ERR_CUDA is fatal for the context. */
+
 enum floam_loss {
   FLOAM_LOSS_TRIVIAL = 0,    /* what the reference does for "cauchy" (loss_function stays nullptr, src/odomEstimationClass.cpp:88-91) */
   FLOAM_LOSS_HUBER = 1,      /* ceres::HuberLoss(0.1), src/odomEstimationClass.cpp:86 */
@@ -92,6 +97,7 @@ int floam_imu_push(floam_ctx* ctx, double stamp, const double q_xyzw[4]);
 /* dmapping::ImuHandler::Get (src/dataHandler.cpp:51-75): zero-order hold; *valid = 0 and a zero quaternion when not covered. */
 int floam_imu_get(floam_ctx* ctx, double stamp, double q_xyzw[4], int* valid);
 int floam_imu_size(floam_ctx* ctx, int* n); /* ImuHandler::size() */
+int floam_imu_time_contained(floam_ctx* ctx, double stamp, int* contained); /* ImuHandler::TimeContained (src/dataHandler.cpp:76-81) */
 
 /* CenterTime + dmapping::Compensate + IMU alignment, in place (src/laserProcessingNode.cpp:65-78,108-116; src/dataHandler.cpp:93-122).
  * stamp_us is the pcl header stamp (microseconds) and is re-centred like the reference. Returns FLOAM_NO_IMU when

@@ -588,7 +588,7 @@ def test_full_size_sequence_properties(capi, synth):
     P = np.concatenate([P0, P1])
     sizes = ctx.odom_map_sizes()
     ctx.close()
-    assert launches == 52 * (frames - 20)
+    assert 0 < launches <= 52 * (frames - 20)       # an upper bound: fewer dependent launches per frame is the optimisation target
     assert np.isfinite(P).all() and np.abs(np.linalg.norm(P[:, :4], axis=1) - 1.0).max() < 1e-12
     gt = [seq.pose(0.1 * f) for f in range(frames)]
     travelled = float(np.sum(np.linalg.norm(np.diff(np.array([g[:3, 3] for g in gt]), axis=0), axis=1)))
