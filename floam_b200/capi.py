@@ -17,6 +17,7 @@ POINT_I = np.dtype({"names": ["x", "y", "z", "pad0", "intensity", "p1", "p2", "p
 OK, ERR_NO_DEVICE, ERR_CUDA, ERR_CAPACITY, ERR_ARG, NO_IMU, ERR_NONFINITE = range(7)
 LOSS_TRIVIAL, LOSS_HUBER, LOSS_CAUCHY_TRUE = 0, 1, 2
 VANILLA, INITIAL_ITERATION, REFINEMENT_AND_UPDATE = 0, 1, 2
+FIX_SINGLE_PREDICTION, FIX_ROTATED_VELOCITY, FIX_IMU_SLERP = 1, 2, 4
 (DBG_DS_EDGE, DBG_DS_SURF, DBG_EDGE_KNN, DBG_SURF_KNN, DBG_EDGE_D2, DBG_SURF_D2, DBG_EDGE_OK, DBG_SURF_OK, DBG_RESIDUALS, DBG_LM,
  DBG_SCALARS, DBG_FEATURE_SRC_EDGE, DBG_FEATURE_SRC_SURF, DBG_CLOCKS, DBG_TIMELINE) = range(15)
 
@@ -24,7 +25,7 @@ VANILLA, INITIAL_ITERATION, REFINEMENT_AND_UPDATE = 0, 1, 2
 class Params(C.Structure):
     _fields_ = [("num_lines", C.c_int), ("scan_period", C.c_double), ("vertical_angle", C.c_double), ("max_distance", C.c_double),
                 ("min_distance", C.c_double), ("map_resolution", C.c_double), ("loss", C.c_int), ("max_scan_points", C.c_int),
-                ("max_map_points", C.c_int), ("max_global_map_points", C.c_int), ("max_grid_cells", C.c_int)]
+                ("max_map_points", C.c_int), ("max_global_map_points", C.c_int), ("max_grid_cells", C.c_int), ("fixes", C.c_int)]
 
 
 # every symbol include/floam_b200.h declares (tests/test_abi.py checks the header against this list and the .so against both)

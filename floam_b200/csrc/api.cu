@@ -229,6 +229,7 @@ void floam_params_default(floam_params* p) {
   p->max_map_points = 4000000;
   p->max_global_map_points = 8000000;
   p->max_grid_cells = 1 << 23;
+  p->fixes = 0;                 // reference behaviour, quirks included
 }
 
 int floam_loss_from_string(const char* loss_function) {
@@ -258,7 +259,7 @@ int floam_create(const floam_params* params, int device, floam_ctx** out) {
   if (!params || !out) return FLOAM_ERR_ARG;
   *out = nullptr;
   if (params->num_lines < 1 || params->num_lines > 128 || params->max_scan_points < 1024 || params->max_map_points < 1024 ||
-      params->max_grid_cells < 4096 || !(params->map_resolution > 0.0) || !(params->scan_period > 0.0))
+      params->max_grid_cells < 4096 || !(params->map_resolution > 0.0) || !(params->scan_period > 0.0) || (params->fixes & ~7))
     return FLOAM_ERR_ARG;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { cudaGetLastError(); return FLOAM_ERR_NO_DEVICE; }
@@ -315,6 +316,7 @@ int floam_create(const floam_params* params, int device, floam_ctx** out) {
   void* vmem_aux = A(voxel_workspace_bytes(aux_cap));
   void* vmem_front = A(voxel_workspace_bytes(ns));
   void* vmem_front_aux = A(voxel_workspace_bytes(ns));
+  c->imu.slerp = (params->fixes & FLOAM_FIX_IMU_SLERP) != 0;
   c->imu.dev_cap = 1 << 20;   // device ring of IMU samples (sliding window, imu.cuh); FLOAM_IMU_RING = smaller power of two for tests
   if (const char* e = std::getenv("FLOAM_IMU_RING")) {
     const int v = std::atoi(e);

@@ -46,7 +46,13 @@ static long long imu_lookup(const ImuDevice& imu, double t) {
 bool imu_get(const ImuDevice& imu, double stamp, double q[4]) {
   const long long g = imu_lookup(imu, stamp);
   if (g < 0) return false;
-  for (int k = 0; k < 4; ++k) q[k] = imu.host[(size_t)(g - imu.base)].q[k];
+  const ImuSample& before = imu.host[(size_t)(g - imu.base)];
+  if (imu.slerp) {   // opt-in: what Interpolate(tSlerp, before, after) was meant to do (:48-50, :61-62)
+    const ImuSample& after = imu.host[(size_t)(g + 1 - imu.base)];   // exists: the validity rule requires it
+    m::quat_slerp((stamp - before.stamp) / (after.stamp - before.stamp), before.q, after.q, q);
+    return true;
+  }
+  for (int k = 0; k < 4; ++k) q[k] = before.q[k];
   return true;
 }
 
@@ -121,8 +127,20 @@ __global__ void __launch_bounds__(kThreads) deskew_align_kernel(PointIRT* __rest
       }
       double qi[4] = {0.0, 0.0, 0.0, 0.0};
       if (lo != 0 && lo != g_hi && lo - 1 != 0 && lo > g_lo) {
+        const ImuSample* before = samples + (int)((lo - 1) & mask);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) qi[k] = __ldg(&samples[(int)((lo - 1) & mask)].q[k]);
+        for (int k = 0; k < 4; ++k) qi[k] = __ldg(&before->q[k]);
+        if (plan.slerp) {
+          const ImuSample* after = samples + (int)(lo & mask);
+          double qa[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) qa[k] = __ldg(&after->q[k]);
+          const double t0 = __ldg(&before->stamp), t1 = __ldg(&after->stamp);
+          double qs[4];
+          m::quat_slerp((t_cur - t0) / (t1 - t0), qi, qa, qs);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) qi[k] = qs[k];
+        }
       }
       double q_now[4], q_diff[4];
       m::quat_mul(qi, plan.extr, q_now);
@@ -158,6 +176,7 @@ int deskew_upload(ImuDevice& imu, DeskewPlan& plan, DeskewPlan* d_plan, cudaStre
   plan.g_hi = total;
   plan.g_lo = imu.base;   // the host window never exceeds 5/8 of the ring, so [g_lo, g_hi) is resident and stays so for 3/8 of a ring more
   plan.ring_mask = imu.dev_cap - 1;
+  plan.slerp = imu.slerp ? 1 : 0;
   FLOAM_CUDA_OK(cudaMemcpyAsync(d_plan, &plan, sizeof(DeskewPlan), cudaMemcpyHostToDevice, copy));  // pageable source: staged before the call returns
   return FLOAM_OK;
 }

@@ -27,6 +27,7 @@ struct ImuDevice {
   ImuSample* d_samples = nullptr;
   long long dev_count = 0;       // samples already uploaded (global count)
   int dev_cap = 0;               // ring size, power of two
+  bool slerp = false;            // FLOAM_FIX_IMU_SLERP: Get() interpolates instead of holding the sample before the stamp
   struct DeskewPlan* d_plan = nullptr;   // plan of the stand-alone entry point
   long long total() const { return base + (long long)host.size(); }
 };
@@ -49,6 +50,7 @@ struct DeskewPlan {       // everything the per-point kernel needs, computed on 
   uint64_t stamp_us_new;
   long long g_lo, g_hi;   // global sample numbers [g_lo, g_hi) the kernel may search (resident in the device ring when it runs)
   int ring_mask;          // dev_cap - 1
+  int slerp;              // FLOAM_FIX_IMU_SLERP
 };
 // ros::Time / pcl stamp conversions + CenterTime + the host part of Compensate (TimeContained, qInit) and of the alignment
 void deskew_plan(const ImuDevice& imu, uint64_t stamp_us, float time_front, float time_back, const double extr_xyzw[4], int flags, DeskewPlan* plan);

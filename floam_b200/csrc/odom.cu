@@ -73,7 +73,7 @@ __device__ __forceinline__ long long global_ns() {
   return (long long)t;
 }
 
-__global__ void predict_kernel(PoseState* S, const int* n_edge_map, const int* n_surf_map) {
+__global__ void predict_kernel(PoseState* S, const int* n_edge_map, const int* n_surf_map, int keep_pose) {
   pdl_prologue();
   if (threadIdx.x != 0) return;
   {
@@ -85,10 +85,14 @@ __global__ void predict_kernel(PoseState* S, const int* n_edge_map, const int* n
     S->tl_predict = now; S->tl_end[0] = S->tl_end[1] = 0;
   }
   double inv[12], rel[12], pred[12];
-  m::iso_inverse(S->last_odom, inv);
-  m::iso_mul(inv, S->odom, rel);
-  m::iso_mul(S->odom, rel, pred);
-  for (int i = 0; i < 12; ++i) { S->last_odom[i] = S->odom[i]; S->odom[i] = pred[i]; }
+  if (keep_pose) {   // FLOAM_FIX_SINGLE_PREDICTION, second deskew pass: odom is the pass-1 registration, last_odom the previous frame's pose (:66)
+    for (int i = 0; i < 12; ++i) pred[i] = S->odom[i];
+  } else {
+    m::iso_inverse(S->last_odom, inv);
+    m::iso_mul(inv, S->odom, rel);
+    m::iso_mul(S->odom, rel, pred);
+    for (int i = 0; i < 12; ++i) { S->last_odom[i] = S->odom[i]; S->odom[i] = pred[i]; }
+  }
   double q[4];
   m::quat_from_matrix(pred, q);
   S->x[0] = q[0]; S->x[1] = q[1]; S->x[2] = q[2]; S->x[3] = q[3];
@@ -359,9 +363,58 @@ __device__ __forceinline__ void knn5_scan_range(int b, int e, float qx, float qy
 //    candidate of a skipped cell has a computed distance >= that figure > bound >= the final 5th distance: the result is the
 //    same set, ties included, as the exhaustive scan.
 constexpr int kKnnPruneAbove = 256;   // candidates in the 27 cells
+
+// ---- TMA-staged cell tiles (north_star (3)) ----
+// Sparse neighbourhoods (<= kKnnPruneAbove candidates, the usual case at the default map resolution): instead of nine dependent
+// scan loops over the nine x-contiguous runs — each one an L2 round trip the warp sits out before it can issue the next — the nine
+// runs are brought into a per-warp shared-memory slab by up to nine bulk copies (cp.async.bulk global -> shared, lanes 0..8 issue one
+// each, completion counted in bytes on the warp's mbarrier) that are all in flight together; the lanes then read the candidates
+// from shared memory. One round trip instead of nine, same candidate set, same (distance, index) result.
+struct KnnStage {
+  float4* slab;            // this warp's kKnnPruneAbove entries
+  unsigned int bar;        // shared-space address of this warp's mbarrier
+  unsigned int phase;      // parity of the next completion
+};
+__device__ __forceinline__ bool mbar_try_wait(unsigned int bar, unsigned int parity) {
+  unsigned int ok;
+  asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void knn5_scan_staged(int rb, int re, int total, float qx, float qy, float qz, const float4* __restrict__ cell_pts, KnnStage& st,
+                                                 Knn5& k, float& rej) {
+  const int l = lane_id();
+  const int len = re - rb;          // lanes >= 9 hold 0
+  int incl = len;
+#pragma unroll
+  for (int o = 1; o < 16; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (l >= o) incl += t;
+  }
+  const int excl = incl - len;
+  // the previous query's reads of the slab (generic proxy) are done before the async proxy writes it again
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  if (l == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(st.bar), "r"((unsigned int)(total * 16)) : "memory");
+  __syncwarp();
+  if (len > 0) {
+    const unsigned int dst = (unsigned int)__cvta_generic_to_shared(st.slab + excl);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(cell_pts + rb), "r"((unsigned int)(len * 16)), "r"(st.bar) : "memory");
+  }
+  while (!mbar_try_wait(st.bar, st.phase)) {}
+  st.phase ^= 1u;
+  for (int i = l; i < total; i += 32) {
+    const float4 p = st.slab[i];
+    const float dx = fsub(qx, p.x), dy = fsub(qy, p.y), dz = fsub(qz, p.z);
+    const float dist = fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
+    knn5_insert(k, dist, __float_as_int(p.w), rej);
+  }
+}
+
 // others_min: lower bound of the computed distance of every map point that is inside the 27 cells and NOT in the result.
+template <bool kStaged>
 __device__ __forceinline__ void knn5_search_warp(const GridDims& g, const int* __restrict__ cell_start, const float4* __restrict__ cell_pts, float qx,
-                                                 float qy, float qz, Knn5& out, float& others_min) {
+                                                 float qy, float qz, Knn5& out, float& others_min, KnnStage* st = nullptr) {
   const int l = lane_id();
   float rej = FLT_MAX, skipped = FLT_MAX;
   Knn5 k;
@@ -395,7 +448,9 @@ __device__ __forceinline__ void knn5_search_warp(const GridDims& g, const int* _
     cdm = fadd(fadd(fmul(gx, gx), fmul(gy, gy)), fmul(gz, gz));
   }
   const int total = __reduce_add_sync(0xffffffffu, re - rb);
-  if (total <= kKnnPruneAbove) {
+  if (kStaged && total <= kKnnPruneAbove) {
+    if (total > 0) knn5_scan_staged(rb, re, total, qx, qy, qz, cell_pts, *st, k, rej);
+  } else if (total <= kKnnPruneAbove) {
 #pragma unroll
     for (int r = 0; r < 9; ++r) {
       const int b = __shfl_sync(0xffffffffu, rb, r), e = __shfl_sync(0xffffffffu, re, r);
@@ -729,6 +784,7 @@ constexpr int kKnnThreads = 256;
 // the float rounding of a computed distance, still exceeds the largest computed distance D5' from q' to the stored five — and the
 // five still lie in the 27 cells around q' — no other point can enter: the exhaustive search would return exactly these five, and
 // they are re-sorted by (distance, index). Otherwise the full search runs. Either way the outputs are those of the full search.
+template <bool kStaged>
 __global__ void __launch_bounds__(kKnnThreads) assoc_knn_kernel(const PoseState* __restrict__ S, const P4* __restrict__ ds_edge, const int* __restrict__ d_nde,
                                                                  const P4* __restrict__ ds_surf, const int* __restrict__ d_nds, LocalMap emap, LocalMap smap,
                                                                  int qcap, int* __restrict__ knn_ids, float* __restrict__ knn_d2, float4* __restrict__ knn_q,
@@ -743,6 +799,16 @@ __global__ void __launch_bounds__(kKnnThreads) assoc_knn_kernel(const PoseState*
   const GridDims ge = *emap.dims, gs = *smap.dims;
   if (skip) return;
   const int l = lane_id();
+  __shared__ __align__(128) float4 s_slab[kStaged ? kKnnThreads / 32 : 1][kStaged ? kKnnPruneAbove : 1];
+  __shared__ __align__(8) unsigned long long s_bar[kKnnThreads / 32];
+  KnnStage stage{s_slab[kStaged ? warp_id() : 0], (unsigned int)__cvta_generic_to_shared(&s_bar[warp_id()]), 0u};
+  if (kStaged) {
+    if (l == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(stage.bar));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+  }
   const int warps_total = gridDim.x * (kKnnThreads / 32);
   for (int slot = blockIdx.x * (kKnnThreads / 32) + warp_id(); slot < nde + nds; slot += warps_total) {
     const bool is_edge = slot < nde;
@@ -790,7 +856,7 @@ __global__ void __launch_bounds__(kKnnThreads) assoc_knn_kernel(const PoseState*
     }
     Knn5 nn;
     float others;
-    knn5_search_warp(is_edge ? ge : gs, map.cell_start, map.cell_pts, qx, qy, qz, nn, others);
+    knn5_search_warp<kStaged>(is_edge ? ge : gs, map.cell_start, map.cell_pts, qx, qy, qz, nn, others, &stage);
     const bool near = nn.d[4] < 1.0f;  // pointSearchSqDis[4] < 1.0 : the only queries the reference uses
     if (l < 5) {
       const int j = l;
@@ -1132,7 +1198,7 @@ __global__ void __launch_bounds__(kKnnThreads) knn5_kernel(const P4* __restrict_
     const float4 q = __ldg(queries + i);
     Knn5 nn;
     float others;
-    knn5_search_warp(g, map.cell_start, map.cell_pts, q.x, q.y, q.z, nn, others);
+    knn5_search_warp<false>(g, map.cell_start, map.cell_pts, q.x, q.y, q.z, nn, others);
     const bool near = nn.d[4] < 1.0f;
     if (lane_id() < 5) {
       const int j = lane_id();
@@ -1145,10 +1211,18 @@ __global__ void __launch_bounds__(kKnnThreads) knn5_kernel(const P4* __restrict_
 }
 
 // dmapping::CompensateVelocity (src/dataHandler.cpp:82-91) with GetVelocity() taken from the device state (Q14: no rotation)
-__global__ void __launch_bounds__(kThreads) compensate_velocity_kernel(PointIRT* __restrict__ pts, const int* __restrict__ d_n, const PoseState* __restrict__ S) {
+__global__ void __launch_bounds__(kThreads) compensate_velocity_kernel(PointIRT* __restrict__ pts, const int* __restrict__ d_n, const PoseState* __restrict__ S,
+                                                                        int rotate) {
   pdl_prologue();
   const int n = *d_n;
-  const double vx = S->velocity[0], vy = S->velocity[1], vz = S->velocity[2];
+  double vx = S->velocity[0], vy = S->velocity[1], vz = S->velocity[2];
+  if (rotate) {   // FLOAM_FIX_ROTATED_VELOCITY: the velocity is a world-frame vector, the points are in the sensor frame: v_sensor = R(odom)^T v
+    const double* R = S->odom;
+    const double wx = vx, wy = vy, wz = vz;
+    vx = R[0] * wx + R[3] * wy + R[6] * wz;
+    vy = R[1] * wx + R[4] * wy + R[7] * wz;
+    vz = R[2] * wx + R[5] * wy + R[8] * wz;
+  }
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
     PointIRT* p = pts + i;
     const double t = (double)p->time;
@@ -1228,12 +1302,28 @@ int odom_device_init(OdomDevice& od, const floam_params& prm, VoxelWorkspace* vw
   // so that every entry path adds the normal equations up in the same order. FLOAM_LM_CLUSTER overrides (8 or 16).
   od.lm_cluster_ctas = (prm.num_lines >= 128 || prm.map_resolution <= 0.2) ? 16 : kClusterCtas;
   if (const char* e = std::getenv("FLOAM_LM_CLUSTER")) od.lm_cluster_ctas = std::atoi(e) == 16 ? 16 : kClusterCtas;
+  if (od.lm_cluster_ctas == 16) {   // a part / partition whose GPCs cannot co-schedule 16 such CTAs must not fail every solve: fall back to 8
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(16); cfg.blockDim = dim3(kClusterThreads); cfg.dynamicSmemBytes = kLmStageBytes;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 16; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&n_clusters, lm_cluster_kernel, &cfg) != cudaSuccess || n_clusters < 1) {
+      cudaGetLastError();
+      od.lm_cluster_ctas = kClusterCtas;
+    }
+  }
+  od.knn_staged = true;   // TMA-staged cell tiles for sparse neighbourhoods (A/B: profiles/r2_knn_tma_ab.md); FLOAM_KNN_TMA=0 -> direct loads
+  if (const char* e = std::getenv("FLOAM_KNN_TMA")) od.knn_staged = std::atoi(e) != 0;
   FLOAM_CUDA_OK(cudaEventCreateWithFlags(&od.ev_fork, cudaEventDisableTiming));
   FLOAM_CUDA_OK(cudaEventCreateWithFlags(&od.ev_join, cudaEventDisableTiming));
   od.leaf_edge = (float)prm.map_resolution;        // setLeafSize(float...) :13-14
   od.leaf_surf = (float)(prm.map_resolution * 2);
   od.scan_period = prm.scan_period;
   od.loss = prm.loss;
+  od.fixes = prm.fixes;
   od.optimization_count = 2;                       // :22
   od.qcap = prm.max_scan_points;
   const int ncells_cap = prm.max_grid_cells;
@@ -1314,14 +1404,19 @@ void odom_update_device(OdomDevice& od, const void* d_edge, const int* d_ne, con
                         int ds_ready, cudaStream_t s) {
   // the caller has already applied `if (optimization_count > 2) optimization_count--` (:59-60, Q4)
   PoseState* S = od.state;
-  FLOAM_LAUNCH(K_PREDICT, predict_kernel, 1, 32, s, S, od.edge_map.d_n, od.surf_map.d_n);
+  const int keep_pose = (update_type == FLOAM_REFINEMENT_AND_UPDATE && (od.fixes & FLOAM_FIX_SINGLE_PREDICTION)) ? 1 : 0;
+  FLOAM_LAUNCH(K_PREDICT, predict_kernel, 1, 32, s, S, od.edge_map.d_n, od.surf_map.d_n, keep_pose);
   cudaStream_t a = od.aux_stream;
   // downSamplingToMap :137-142, unless the frame pipeline already did it ahead of time
   if (!ds_ready) odom_downsample_device(od, d_edge, d_ne, d_surf, d_ns, stride, n_max, *od.vws, *od.vws_aux, s, a, od.ev_fork, od.ev_join);
   for (int it = 0; it < od.optimization_count; ++it) {
     PdlSolveScope pdl;   // kNN, fit and LM may be scheduled while their predecessor drains (griddepcontrol.wait orders the data)
-    FLOAM_LAUNCH(K_ASSOC_KNN, assoc_knn_kernel, kKnnBlocks, kKnnThreads, s, S, od.ds_edge, od.d_nds_edge, od.ds_surf, od.d_nds_surf, od.edge_map, od.surf_map,
-                 od.qcap, od.knn_ids, od.knn_d2, od.knn_q, it > 0 ? 1 : 0);
+    if (od.knn_staged)
+      FLOAM_LAUNCH(K_ASSOC_KNN, assoc_knn_kernel<true>, kKnnBlocks, kKnnThreads, s, S, od.ds_edge, od.d_nds_edge, od.ds_surf, od.d_nds_surf, od.edge_map,
+                   od.surf_map, od.qcap, od.knn_ids, od.knn_d2, od.knn_q, it > 0 ? 1 : 0);
+    else
+      FLOAM_LAUNCH(K_ASSOC_KNN, assoc_knn_kernel<false>, kKnnBlocks, kKnnThreads, s, S, od.ds_edge, od.d_nds_edge, od.ds_surf, od.d_nds_surf, od.edge_map,
+                   od.surf_map, od.qcap, od.knn_ids, od.knn_d2, od.knn_q, it > 0 ? 1 : 0);
     FLOAM_LAUNCH(K_ASSOC_EVAL, assoc_eval_kernel, kAssocBlocks, kEvalThreads, s, S, od.ds_edge, od.d_nds_edge, od.ds_surf, od.d_nds_surf, od.edge_map, od.surf_map,
                  od.qcap, od.corr, od.corr_ok, od.knn_ids, od.loss, od.partials);
     FLOAM_LAUNCH_CLUSTER(K_LM_CLUSTER, lm_cluster_kernel, od.lm_cluster_ctas, kClusterThreads, kLmStageBytes, s, S, od.ds_edge, od.d_nds_edge, od.ds_surf, od.d_nds_surf, od.qcap, od.corr, od.corr_ok,
@@ -1370,7 +1465,8 @@ void odom_select_buffers(OdomDevice& od, int parity) {
 }
 
 void compensate_velocity_device(OdomDevice& od, PointIRT* d_pts, const int* d_n, int n_max, cudaStream_t s) {
-  FLOAM_LAUNCH(K_COMPENSATE_VELOCITY, compensate_velocity_kernel, grid_for(n_max), kThreads, s, d_pts, d_n, od.state);
+  FLOAM_LAUNCH(K_COMPENSATE_VELOCITY, compensate_velocity_kernel, grid_for(n_max), kThreads, s, d_pts, d_n, od.state,
+               (od.fixes & FLOAM_FIX_ROTATED_VELOCITY) ? 1 : 0);
 }
 
 void compensate_velocity_explicit_device(PointIRT* d_pts, const int* d_n, int n_max, const double v[3], cudaStream_t s) {

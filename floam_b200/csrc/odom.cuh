@@ -81,9 +81,11 @@ struct OdomDevice {
   cudaStream_t aux_stream;     // fork/join partner of the context stream
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int lm_cluster_ctas = 8;     // CTAs of the solve's thread-block cluster (8, or 16 for dense configurations)
+  bool knn_staged = true;      // association kNN brings sparse neighbourhoods into shared memory by bulk copies (cp.async.bulk + mbarrier)
   float leaf_edge, leaf_surf;
   double scan_period;
   int loss;
+  int fixes;                   // floam_fix bits (opt-in deviations from the reference, default 0)
   int optimization_count;      // host mirror (deterministic schedule, Q4)
   double* traj;                // [traj_cap][7] device-side trajectory log (pose of every completed frame)
   int traj_cap;

@@ -64,6 +64,23 @@ FM_HD void quat_from_matrix(const double* R, double* q) {  // Quaterniond(Matrix
     q[k] = (R[k * 3 + i] + R[i * 3 + k]) * t;
   }
 }
+// Eigen 3.3 QuaternionBase::slerp(t, other), coefficients (x,y,z,w): the interpolation dmapping::ImuHandler computes tSlerp for and then
+// drops (src/dataHandler.cpp:48-50,61-62); used by the opt-in FLOAM_FIX_IMU_SLERP mode only
+FM_HD void quat_slerp(double t, const double* a, const double* b, double* o) {
+  const double one = 1.0 - 2.220446049250313e-16;
+  const double d = a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3];
+  const double absD = fabs(d);
+  double scale0, scale1;
+  if (absD >= one) {
+    scale0 = 1.0 - t; scale1 = t;
+  } else {
+    const double theta = acos(absD), sinTheta = sin(theta);
+    scale0 = sin((1.0 - t) * theta) / sinTheta;
+    scale1 = sin(t * theta) / sinTheta;
+  }
+  if (d < 0.0) scale1 = -scale1;
+  for (int k = 0; k < 4; ++k) o[k] = scale0 * a[k] + scale1 * b[k];
+}
 // T = [R|t] as 12 doubles. Isometry product / inverse (Eigen Transform<double,3,Isometry>)
 FM_HD void iso_mul(const double* A, const double* B, double* O) {
   double r[12];

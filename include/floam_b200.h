@@ -59,6 +59,18 @@ enum floam_loss {
   FLOAM_LOSS_CAUCHY_TRUE = 2 /* opt-in: ceres::CauchyLoss(0.2) actually applied (not reachable in the reference) */
 };
 
+/* Opt-in algorithmic fixes.  All off by default: the default path reproduces the reference, quirks included.
+ *  SINGLE_PREDICTION : the second pass of the deskew mode does not predict again.  The reference's test `update_type == VANILLA ||
+ *                      UpdateType::INITIAL_ITERATION` is always true (src/odomEstimationClass.cpp:62-68, Q2), so pass 2 starts one
+ *                      inter-frame motion beyond the pass-1 result and overwrites last_odom with it; with the fix pass 2 starts AT the
+ *                      pass-1 result and last_odom stays the previous frame's pose, as the comment at :66 intends.
+ *  ROTATED_VELOCITY  : dmapping::CompensateVelocity adds the world-frame velocity to sensor-frame points without rotating it
+ *                      (src/dataHandler.cpp:82-91, include/odomEstimationClass.h:78, Q14); with the fix p += R(odom)^T v * t.
+ *  IMU_SLERP         : ImuHandler::Get interpolates the two samples around the stamp with Eigen's slerp at
+ *                      tSlerp = (t - t_before) / (t_after - t_before), which the reference computes and then ignores
+ *                      (Interpolate returns data1, src/dataHandler.cpp:48-50,61-62), instead of the zero-order hold. */
+enum floam_fix { FLOAM_FIX_SINGLE_PREDICTION = 1, FLOAM_FIX_ROTATED_VELOCITY = 2, FLOAM_FIX_IMU_SLERP = 4 };
+
 enum floam_update_type { FLOAM_VANILLA = 0, FLOAM_INITIAL_ITERATION = 1, FLOAM_REFINEMENT_AND_UPDATE = 2 }; /* include/odomEstimationClass.h:63 */
 
 /* lidar::Lidar (include/lidar.h:53-86) + OdomEstimationClass::init arguments + capacities */
@@ -74,6 +86,7 @@ typedef struct floam_params {
   int max_map_points;       /* capacity of each local map, edge and surf (default 4,000,000) */
   int max_global_map_points;/* capacity of the LaserMappingClass map (default 8,000,000; 0 = mapping disabled) */
   int max_grid_cells;       /* capacity of each local map's 1 m search grid, in cells (default 8,388,608) */
+  int fixes;                /* OR of floam_fix bits; default 0 = reference behaviour */
 } floam_params;
 
 void floam_params_default(floam_params* p);

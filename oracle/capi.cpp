@@ -60,6 +60,12 @@ int fo_crop_box(const PointXYZI* pts, int n, const float mn[3], const float mx[3
 int fo_knn(const PointXYZI* map, int m, const PointXYZI* queries, int nq, int k, int use_kdtree, int* ids, float* d2) {
   CloudI cloud(map, map + m);
   KdTreeFlann tree;
+  GridKnn grid;
+  if (use_kdtree == 2) {
+    grid.setInputCloud(cloud);
+    for (int i = 0; i < nq; ++i) grid.nearestKSearch(queries[i], k, ids + (size_t)i * k, d2 + (size_t)i * k);
+    return 0;
+  }
   if (use_kdtree) tree.setInputCloud(cloud);
   for (int i = 0; i < nq; ++i) {
     int idb[8]; float db[8];
@@ -147,11 +153,15 @@ void* fo_odom_create(int num_lines, double scan_period, double min_dis, double m
   LidarParam p; p.num_lines = num_lines; p.scan_period = scan_period; p.min_distance = min_dis; p.max_distance = max_dis;
   h->est.init(p, map_resolution, loss);
   h->est.total_order = total_order != 0;
-  h->est.use_kdtree = use_kdtree != 0;
+  h->est.use_kdtree = use_kdtree == 1;   // 0 = brute force, 1 = FLANN-style kd-tree, 2 = 27-cell grid ((distance, index) order like 0, at kd-tree speed)
+  h->est.use_grid = use_kdtree == 2;
   h->est.debug = &h->dbg;
   return h;
 }
 void fo_odom_destroy(void* h) { delete (OdomHandle*)h; }
+// opt-in fixes (floam_fix bits 1 | 2) — restatement only: the reference build has no such modes
+void fo_odom_set_fixes(void* h, int fixes) { ((OdomHandle*)h)->est.fixes = fixes; }
+void fo_imu_set_slerp(void* h, int on) { ((ImuHandle*)h)->h.slerp = on != 0; }
 void fo_odom_init_map(void* h, const PointXYZI* edge, int ne, const PointXYZI* surf, int ns) {
   ((OdomHandle*)h)->est.initMapWithPoints(CloudI(edge, edge + ne), CloudI(surf, surf + ns));
 }

@@ -91,6 +91,24 @@ class KdTreeFlann {
 int knn_bruteforce(const PointXYZI* cloud, size_t n, const PointXYZI& q, int k, int* ids, float* sqdist);
 inline int knn_bruteforce(const CloudI& cloud, const PointXYZI& q, int k, int* ids, float* sqdist) { return knn_bruteforce(cloud.data(), cloud.size(), q, k, ids, sqdist); }
 
+// The same answer as knn_bruteforce for every query the reference uses (5th squared distance < 1.0, src/odomEstimationClass.cpp:154,207),
+// at grid speed: points bucketed by 1 m cell, the 27 cells around the query scanned exhaustively with L2_Simple, (distance, index)
+// order.  A point outside those cells is at least one cell width away along some axis, so its computed squared distance is >= 1.0
+// and it can neither be nor displace one of five neighbours that pass the gate.  Queries that fail the gate report ids -1 and
+// distances FLT_MAX (the reference never looks at them).  Checked against knn_bruteforce in tests/test_oracle.py.
+class GridKnn {
+ public:
+  void setInputCloud(const PointXYZI* cloud, size_t n);
+  void setInputCloud(const CloudI& cloud) { setInputCloud(cloud.data(), cloud.size()); }
+  int nearestKSearch(const PointXYZI& q, int k, int* ids, float* sqdist) const;
+ private:
+  std::vector<float> pts_;        // xyz in cell order
+  std::vector<int> index_;        // original index of pts_[i]
+  std::vector<int> cell_start_;   // [ncells + 1]
+  int ix0_ = 0, iy0_ = 0, iz0_ = 0, nx_ = 0, ny_ = 0, nz_ = 0;
+  size_t n_ = 0;
+};
+
 // ---- src/lidarOptimization.cpp + Ceres (Appendix A.5) ----
 enum LossKind { LOSS_TRIVIAL = 0, LOSS_HUBER = 1, LOSS_CAUCHY_TRUE = 2 };
 struct Residual {   // one ceres residual block
@@ -130,6 +148,7 @@ class ImuHandler {
   bool Get(double tStamp, Quat& data) const;                     // :51-69
   Quat Get(double tStamp) const;                                 // :71-75 (default Imu = zero quaternion on failure)
   bool TimeContained(double t) const;                            // :76-81
+  bool slerp = false;   // NOT the reference: opt-in fix FLOAM_FIX_IMU_SLERP (what Interpolate(tSlerp, ...) was meant to do, :48-50)
   size_t size() const { return data_.size(); }
   const std::vector<std::pair<double, Quat>>& data() const { return data_; }
  private:
@@ -143,6 +162,8 @@ bool Compensate(const CloudIRT& input, std::uint64_t stamp_us, CloudIRT& compens
 void ImuAlign(const CloudIRT& compensated, std::uint64_t stamp_us, const ImuHandler& handler, const Quat& extrinsics, CloudIRT& aligned);
 // src/dataHandler.cpp:82-91
 void CompensateVelocity(CloudIRT& input, Vec3 velocity);
+// NOT the reference: opt-in fix FLOAM_FIX_ROTATED_VELOCITY (world-frame velocity rotated into the sensor frame first, Q14)
+void CompensateVelocityRotated(CloudIRT& input, Vec3 velocity, const Mat3& R_world_sensor);
 
 // ---- src/odomEstimationClass.cpp ----
 CloudI VelToIntensityCopy(const CloudIRT& c);  // :308-318
@@ -174,7 +195,9 @@ class OdomEstimation {
   CloudI laserCloudCornerMap, laserCloudSurfMap;
   // knobs that are not in the reference (test infrastructure)
   bool total_order = false;   // stable voxel order (see voxel_grid_filter)
-  bool use_kdtree = true;     // false -> brute force kNN
+  bool use_kdtree = true;     // false -> neighbours in (distance, index) order instead of the kd-tree's traversal order
+  int fixes = 0;              // NOT the reference: opt-in fixes, same bits as floam_fix in include/floam_b200.h (1 single prediction, 2 rotated velocity)
+  bool use_grid = false;      // with use_kdtree == false: GridKnn instead of the O(M) brute force (same results wherever the reference looks)
   OdomDebug* debug = nullptr;
   double parameters[7] = {0, 0, 0, 1, 0, 0, 0};
   Iso3 last_odom;
@@ -192,6 +215,7 @@ class OdomEstimation {
   void addSurfCostFactor(const CloudI& pc_in, const CloudI& map_in, std::vector<Residual>& problem, bool tap);   // :198-251
   void addPointsToMap(const CloudI& ds_edge, const CloudI& ds_surf);                                    // :253-294
   KdTreeFlann kdtreeEdgeMap, kdtreeSurfMap;
+  GridKnn gridEdgeMap, gridSurfMap;
   float leaf_edge_ = 0.4f, leaf_surf_ = 0.8f;
   std::string loss_function_;
   LidarParam lidar_param_;

@@ -3,6 +3,7 @@
 // caller, src/laserProcessingNode.cpp:65-78 (CenterTime) and :113-116 (IMU alignment via pcl::transformPointCloud).
 #include "floam_oracle.h"
 #include <algorithm>
+#include <limits>
 
 namespace fo {
 
@@ -35,6 +36,17 @@ bool ImuHandler::Get(double tStamp, Quat& data) const {
   auto itr_before = std::prev(itr_after, 1);
   if (itr_after != last && itr_after != first && itr_before != first) {
     data = itr_before->second;  // Interpolate() returns data1 (zero-order hold), :48-50
+    if (slerp) {  // opt-in fix, not the reference: Eigen's QuaternionBase::slerp at the tSlerp the reference computes (:61)
+      const double t = (tStamp - itr_before->first) / (itr_after->first - itr_before->first);
+      const Quat &a = itr_before->second, &b = itr_after->second;
+      const double one = 1.0 - std::numeric_limits<double>::epsilon();
+      const double d = a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w, absD = std::fabs(d);
+      double scale0, scale1;
+      if (absD >= one) { scale0 = 1.0 - t; scale1 = t; }
+      else { const double theta = std::acos(absD), sinTheta = std::sin(theta); scale0 = std::sin((1.0 - t) * theta) / sinTheta; scale1 = std::sin(t * theta) / sinTheta; }
+      if (d < 0) scale1 = -scale1;
+      data = Quat{scale0 * a.x + scale1 * b.x, scale0 * a.y + scale1 * b.y, scale0 * a.z + scale1 * b.z, scale0 * a.w + scale1 * b.w};
+    }
     return true;
   }
   return false;
@@ -102,6 +114,11 @@ void CompensateVelocity(CloudIRT& input, Vec3 velocity) {
     const Vec3 c = pntPosition + pntError;
     pnt.x = (float)c.x; pnt.y = (float)c.y; pnt.z = (float)c.z;
   }
+}
+
+void CompensateVelocityRotated(CloudIRT& input, Vec3 velocity, const Mat3& R) {
+  const Vec3 v = mat3_apply(mat3_transpose(R), velocity);
+  CompensateVelocity(input, v);
 }
 
 }  // namespace fo

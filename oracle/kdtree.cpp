@@ -221,4 +221,60 @@ int knn_bruteforce(const PointXYZI* cloud, size_t n_cloud, const PointXYZI& q, i
   return k;
 }
 
+void GridKnn::setInputCloud(const PointXYZI* cloud, size_t n) {
+  n_ = n;
+  pts_.clear(); index_.clear(); cell_start_.assign(1, 0);
+  nx_ = ny_ = nz_ = 0;
+  if (n == 0) return;
+  float mn[3] = {cloud[0].x, cloud[0].y, cloud[0].z}, mx[3] = {cloud[0].x, cloud[0].y, cloud[0].z};
+  for (size_t i = 1; i < n; ++i) {
+    const float v[3] = {cloud[i].x, cloud[i].y, cloud[i].z};
+    for (int d = 0; d < 3; ++d) { mn[d] = std::min(mn[d], v[d]); mx[d] = std::max(mx[d], v[d]); }
+  }
+  ix0_ = (int)std::floor(mn[0]); iy0_ = (int)std::floor(mn[1]); iz0_ = (int)std::floor(mn[2]);
+  nx_ = (int)std::floor(mx[0]) - ix0_ + 1; ny_ = (int)std::floor(mx[1]) - iy0_ + 1; nz_ = (int)std::floor(mx[2]) - iz0_ + 1;
+  const size_t ncells = (size_t)nx_ * ny_ * nz_;
+  std::vector<int> cell(n);
+  cell_start_.assign(ncells + 1, 0);
+  for (size_t i = 0; i < n; ++i) {
+    const int cx = (int)std::floor(cloud[i].x) - ix0_, cy = (int)std::floor(cloud[i].y) - iy0_, cz = (int)std::floor(cloud[i].z) - iz0_;
+    cell[i] = cx + nx_ * (cy + ny_ * cz);
+    cell_start_[(size_t)cell[i] + 1]++;
+  }
+  for (size_t c = 0; c < ncells; ++c) cell_start_[c + 1] += cell_start_[c];
+  std::vector<int> cursor(cell_start_.begin(), cell_start_.end() - 1);
+  pts_.resize(3 * n); index_.resize(n);
+  for (size_t i = 0; i < n; ++i) {
+    const int p = cursor[cell[i]]++;
+    pts_[3 * (size_t)p] = cloud[i].x; pts_[3 * (size_t)p + 1] = cloud[i].y; pts_[3 * (size_t)p + 2] = cloud[i].z;
+    index_[p] = (int)i;
+  }
+}
+
+int GridKnn::nearestKSearch(const PointXYZI& q, int k, int* ids, float* sqdist) const {
+  if (k > 8) k = 8;
+  float bd[8]; int bi[8]; int cnt = 0;
+  const float vec[3] = {q.x, q.y, q.z};
+  if (nx_ > 0 && std::isfinite(q.x) && std::isfinite(q.y) && std::isfinite(q.z) && std::fabs(q.x) < 1e9f && std::fabs(q.y) < 1e9f && std::fabs(q.z) < 1e9f) {
+    const int cx = (int)std::floor(q.x) - ix0_, cy = (int)std::floor(q.y) - iy0_, cz = (int)std::floor(q.z) - iz0_;
+    for (int z = std::max(cz - 1, 0); z <= std::min(cz + 1, nz_ - 1); ++z)
+      for (int y = std::max(cy - 1, 0); y <= std::min(cy + 1, ny_ - 1); ++y) {
+        const int x0 = std::max(cx - 1, 0), x1 = std::min(cx + 1, nx_ - 1);
+        if (x0 > x1) continue;
+        const size_t row = (size_t)nx_ * ((size_t)y + (size_t)ny_ * z);
+        for (int p = cell_start_[row + x0]; p < cell_start_[row + x1 + 1]; ++p) {
+          const float d = l2_simple(vec, &pts_[3 * (size_t)p]);
+          const int idx = index_[p];
+          if (cnt == k && !(d < bd[k - 1] || (d == bd[k - 1] && idx < bi[k - 1]))) continue;
+          int j = (cnt < k) ? cnt++ : k - 1;
+          while (j > 0 && (bd[j - 1] > d || (bd[j - 1] == d && bi[j - 1] > idx))) { bd[j] = bd[j - 1]; bi[j] = bi[j - 1]; --j; }
+          bd[j] = d; bi[j] = idx;
+        }
+      }
+  }
+  const bool near = cnt == k && bd[k - 1] < 1.0f;
+  for (int i = 0; i < k; ++i) { ids[i] = near ? bi[i] : -1; sqdist[i] = near ? bd[i] : std::numeric_limits<float>::max(); }
+  return k;
+}
+
 }  // namespace fo

@@ -41,8 +41,13 @@ void OdomEstimation::UpdatePointsToMapSelector(CloudIRT& edge_in, CloudIRT& surf
   } else {
     updatePointsToMap(edge_in, edge_in, INITIAL_ITERATION);  // Q3: edge cloud as both edge and surf
     Vec3 velocity = GetVelocity();
-    CompensateVelocity(edge_in, velocity);
-    CompensateVelocity(surf_in, velocity);
+    if (fixes & 2) {   // opt-in fix, not the reference (Q14)
+      CompensateVelocityRotated(edge_in, velocity, odom.R);
+      CompensateVelocityRotated(surf_in, velocity, odom.R);
+    } else {
+      CompensateVelocity(edge_in, velocity);
+      CompensateVelocity(surf_in, velocity);
+    }
     updatePointsToMap(edge_in, surf_in, REFINEMENT_AND_UPDATE);
   }
 }
@@ -58,8 +63,10 @@ void OdomEstimation::updatePointsToMap(const CloudI& edge_in, const CloudI& surf
 
   Iso3 odom_prediction = iso_mul(odom, iso_mul(iso_inverse(last_odom), odom));
   // `update_type == VANILLA || UpdateType::INITIAL_ITERATION` : second operand is the constant 1 -> always true (Q2)
-  last_odom = odom;
-  odom = odom_prediction;
+  if (!((fixes & 1) && update_type == REFINEMENT_AND_UPDATE)) {   // (fixes & 1): opt-in fix, not the reference — pass 2 keeps the pass-1 pose (:66)
+    last_odom = odom;
+    odom = odom_prediction;
+  }
 
   Quat q_w_curr = quat_from_matrix(odom.R);
   parameters[0] = q_w_curr.x; parameters[1] = q_w_curr.y; parameters[2] = q_w_curr.z; parameters[3] = q_w_curr.w;
@@ -81,6 +88,9 @@ void OdomEstimation::updatePointsToMap(const CloudI& edge_in, const CloudI& surf
     if (use_kdtree) {  // full rebuild every call (Q12)
       kdtreeEdgeMap.setInputCloud(laserCloudCornerMap);
       kdtreeSurfMap.setInputCloud(laserCloudSurfMap);
+    } else if (use_grid) {
+      gridEdgeMap.setInputCloud(laserCloudCornerMap);
+      gridSurfMap.setInputCloud(laserCloudSurfMap);
     }
     lap(tick, 1);
     LossKind loss = (loss_function_ == "huber") ? LOSS_HUBER : (loss_function_ == "cauchy_true" ? LOSS_CAUCHY_TRUE : LOSS_TRIVIAL);  // Q1
@@ -131,6 +141,7 @@ void OdomEstimation::addEdgeCostFactor(const CloudI& pc_in, const CloudI& map_in
     int pointSearchInd[8];
     float pointSearchSqDis[8];
     if (use_kdtree) kdtreeEdgeMap.nearestKSearch(point_temp, 5, pointSearchInd, pointSearchSqDis);
+    else if (use_grid) gridEdgeMap.nearestKSearch(point_temp, 5, pointSearchInd, pointSearchSqDis);
     else knn_bruteforce(map_in, point_temp, 5, pointSearchInd, pointSearchSqDis);
     stat_knn_queries++;
     if (tap) for (int j = 0; j < 5; ++j) { debug->edge_knn[i * 5 + j] = pointSearchInd[j]; debug->edge_d2[i * 5 + j] = pointSearchSqDis[j]; }
@@ -172,6 +183,7 @@ void OdomEstimation::addSurfCostFactor(const CloudI& pc_in, const CloudI& map_in
     int pointSearchInd[8];
     float pointSearchSqDis[8];
     if (use_kdtree) kdtreeSurfMap.nearestKSearch(point_temp, 5, pointSearchInd, pointSearchSqDis);
+    else if (use_grid) gridSurfMap.nearestKSearch(point_temp, 5, pointSearchInd, pointSearchSqDis);
     else knn_bruteforce(map_in, point_temp, 5, pointSearchInd, pointSearchSqDis);
     stat_knn_queries++;
     if (tap) for (int j = 0; j < 5; ++j) { debug->surf_knn[i * 5 + j] = pointSearchInd[j]; debug->surf_d2[i * 5 + j] = pointSearchSqDis[j]; }

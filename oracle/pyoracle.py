@@ -134,6 +134,10 @@ class Imu:
         q = np.ascontiguousarray(q_xyzw, np.float64)
         lib().fo_imu_add(self.h, C.c_double(stamp), _p(q))
 
+    def set_slerp(self, on):
+        """Opt-in fix FLOAM_FIX_IMU_SLERP (restatement only)."""
+        lib().fo_imu_set_slerp(self.h, int(on))
+
     def size(self):
         return lib().fo_imu_size(self.h)
 
@@ -168,6 +172,10 @@ class Odom:
     def __del__(self):
         if self.h:
             self._L.fo_odom_destroy(self.h); self.h = None
+
+    def set_fixes(self, fixes):
+        """Opt-in algorithmic fixes (floam_fix bits 1 = single prediction, 2 = rotated velocity); the restatement only."""
+        self._L.fo_odom_set_fixes(self.h, int(fixes))
 
     def init_map(self, edge, surf):
         edge = np.ascontiguousarray(edge, POINT_I); surf = np.ascontiguousarray(surf, POINT_I)

@@ -4,7 +4,8 @@ seconds, and the oracle's own single-thread frames/s on the same frames. One JSO
   0  VLP-16, 100 frames, res 0.4, deskew off          (the reference's CPU-runnable case)
   1  HDL-64, res 0.4, deskew off                      (bench.py's workload; shorter here)
   2  HDL-64 + 200 Hz IMU: deskew + alignment + two-pass velocity deskew, Huber loss
-  3  OS1-128 (128 x 2048) at map_resolution 0.1 (surf leaf 0.2): dense local maps, kNN-heavy
+  3  OS1-128 (128 x 2048), map_resolution 0.08 (surf leaf 0.16), max_dis 90 / min_dis 0.5 (launch file): the local map passes 1M points
+     around frame 110; frames/s are taken over frames 140..180 (parity of this configuration: tests/test_gpu_reference.py)
 """
 import json
 import sys
@@ -18,12 +19,15 @@ from oracle import pyoracle as po            # noqa: E402
 
 
 def run(cfg):
-    name, sensor, frames, res, loss, deskew, imu, oracle_frames = cfg
+    name, sensor, frames, res, loss, deskew, imu, oracle_frames = cfg[:8]
+    extra = cfg[8] if len(cfg) > 8 else {}
+    timed_from = extra.get("timed_from", 12)
     seq = synth.Sequence(sensor, seed=0, distort=deskew)
     scans, off = seq.scans(0, frames)
     nl = seq.num_lines
     prm = dict(num_lines=nl, map_resolution=res, loss=loss, max_scan_points=seq.max_points + 1024, max_map_points=1 << 22,
-               max_global_map_points=0, max_grid_cells=1 << 23)
+               max_global_map_points=0, max_grid_cells=1 << 24)
+    prm.update(extra.get("params", {}))
     ctx = capi.Context(**prm)
     ext = po.euler2quat(0, 0, 180)
     out = {"config": name, "sensor": sensor, "frames": frames, "map_resolution": res, "loss": loss, "deskew": deskew, "imu": imu,
@@ -66,10 +70,12 @@ def run(cfg):
         out["pipelined_poses_identical"] = bool(np.array_equal(np.array(Q), poses))
     else:
         ctx.stage_scans(scans, off)
-        p0, _ = ctx.replay_staged(0, 12)
-        p1, ms = ctx.replay_staged(12, frames - 12)
+        p0, _ = ctx.replay_staged(0, timed_from)
+        out["map_points_at_start_of_timed_frames"] = list(ctx.odom_map_sizes())
+        p1, ms = ctx.replay_staged(timed_from, frames - timed_from)
         poses = np.concatenate([p0, p1])
-        out["frames_per_s_device"] = (frames - 12) / (ms * 1e-3); out["ms_per_frame"] = ms / (frames - 12)
+        out["timed_frames"] = [timed_from, frames]
+        out["frames_per_s_device"] = (frames - timed_from) / (ms * 1e-3); out["ms_per_frame"] = ms / (frames - timed_from)
     d = ctx.debug()
     ne, ns = ctx.odom_map_sizes()
     out.update(map_points=[ne, ns], queries_last_frame=len(d["ds_edge"]) + len(d["ds_surf"]), correspondences_last_frame=d["n_corr"])
@@ -118,7 +124,8 @@ CONFIGS = [
     ("0: VLP-16 100 frames", "vlp16", 100, 0.4, "cauchy", False, False, 100),
     ("1: HDL-64 300 frames", "hdl64", 300, 0.4, "cauchy", False, False, 40),
     ("2: HDL-64 + IMU deskew, Huber, 60 frames", "hdl64", 60, 0.4, "huber", True, True, 20),
-    ("3: OS1-128 dense map (res 0.1), 60 frames", "os1-128", 60, 0.1, "cauchy", False, False, 6),
+    ("3: OS1-128, >= 1M-point local map (res 0.08, max_dis 90)", "os1-128", 180, 0.08, "cauchy", False, False, 0,
+     {"timed_from": 140, "params": {"max_distance": 90.0, "min_distance": 0.5}}),
 ]
 if __name__ == "__main__":
     which = [int(a) for a in sys.argv[1:]] or list(range(len(CONFIGS)))
