@@ -344,6 +344,36 @@ def run_multi_sequence(capi, device, rank, world, S, skip, n_timed, prm, solo_po
     return S * n_timed, wall, {"per_sequence_device_ms_per_frame": [round(m / n_timed, 4) for m in ms], "first_sequence_identical_to_solo_replay": same}
 
 
+def mapping_leg(capi, device, seq, scans, off, poses7, prm, n_frames=30):
+    """LaserMappingClass::updateCurrentPointsToMap / getMap (SURVEY 8 a28; src/laserMappingClass.cpp:148-200) at HDL-64 size, fed like the
+    mapping node: the filtered cloud (edge + surf features) and the odometry pose of the same frame.  Host buffers in, host wall clock
+    (upload + kernels + sync) per call, beside the reference class on one host thread with identical inputs."""
+    from floam_b200 import synth
+    po, kind = cpu_backend()
+    p = dict(prm); p["max_global_map_points"] = 1 << 22
+    ctx = capi.Context(device=device, **p)
+    ref = po.Mapping(map_resolution=ODOM["map_resolution"])
+    upd, get, cpu_upd, cpu_get, sizes = [], [], [], [], []
+    first = PREROLL
+    for f in range(first, first + n_frames):
+        e, sf = ctx.feature_extract(scans[off[f]:off[f + 1]])
+        cloud = synth.to_xyzi(np.concatenate([e, sf]))
+        T = synth.pose7_to_matrix(poses7[f])
+        t0 = time.perf_counter(); ctx.mapping_update(cloud, T); t1 = time.perf_counter()
+        m = ctx.mapping_get_map(); t2 = time.perf_counter()
+        with StdoutToStderr():
+            c0 = time.perf_counter(); ref.update(cloud, T); c1 = time.perf_counter()
+            rm = ref.get_map(); c2 = time.perf_counter()
+        upd.append((t1 - t0) * 1e3); get.append((t2 - t1) * 1e3); cpu_upd.append((c1 - c0) * 1e3); cpu_get.append((c2 - c1) * 1e3)
+        sizes.append((len(cloud), len(m), len(rm)))
+    ctx.close()
+    return {"frames": n_frames, "points_per_update": float(np.mean([s_[0] for s_ in sizes])), "map_points_end": sizes[-1][1],
+            "update_ms_p50": float(np.percentile(upd[3:], 50)), "get_map_ms_p50": float(np.percentile(get[3:], 50)),
+            "cpu_update_ms_p50": float(np.percentile(cpu_upd[3:], 50)), "cpu_get_map_ms_p50": float(np.percentile(cpu_get[3:], 50)), "cpu_kind": kind,
+            "map_sizes_equal_to_cpu": bool(all(s_[1] == s_[2] for s_ in sizes)),
+            "note": "floam_mapping_update / floam_mapping_get_map with host clouds (H2D of the cloud and D2H of the whole map inside the timings)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -442,32 +472,38 @@ def main():
     # ---- the same end-to-end call fed with the raw sensor_msgs/PointCloud2 bytes (22 B per point for the Velodyne XYZIRT layout
     #      instead of the 32-byte PCL struct): floam_process_submit_pc2 re-packs on the device, replacing pcl::fromROSMsg ----
     K2 = min(K, 200)
-    lay = [capi.pc2_layout(int(off[f + 1] - off[f]), 22) for f in range(PREROLL + W, PREROLL + W + K2)]
-    raw_off = np.zeros(K2 + 1, np.int64); raw_off[1:] = np.cumsum([L.row_step * L.height for L in lay])
+    first_pc2 = PREROLL   # the W warm-up frames go through the same call (its first use allocates the raw-message buffers)
+    lay = [capi.pc2_layout(int(off[f + 1] - off[f]), 22) for f in range(first_pc2, PREROLL + W + K2)]
+    raw_off = np.zeros(len(lay) + 1, np.int64); raw_off[1:] = np.cumsum([L.row_step * L.height for L in lay])
     raw_pin = capi.PinnedBuffer((int(raw_off[-1]) + 31) // 32 + 1)
     raw_all = raw_pin.array.view(np.uint8)
-    for k in range(K2):
-        f = PREROLL + W + k
+    for k in range(len(lay)):
+        f = first_pc2 + k
         raw_all[raw_off[k]:raw_off[k + 1]] = capi.pack_pointcloud2(pinned.array[off[f]:off[f + 1]], lay[k])
     ctx5 = capi.Context(device=local, **prm)
-    ctx5.stage_scans(scans[:off[PREROLL + W]], off[:PREROLL + W + 1])
-    ctx5.replay_staged(0, PREROLL + W)
+    ctx5.stage_scans(scans[:off[PREROLL]], off[:PREROLL + 1])
+    ctx5.replay_staged(0, PREROLL)
+
+    def run_pc2(k0, k1):
+        poses = np.zeros((k1 - k0, 7)); pending = []
+        for k in range(k0, k1):
+            if len(pending) == 3:
+                g = pending.pop(0); poses[g - k0] = ctx5.process_wait()
+            ctx5.process_submit_pc2(raw_all[raw_off[k]:raw_off[k + 1]], lay[k])
+            pending.append(k)
+        for g in pending:
+            poses[g - k0] = ctx5.process_wait()
+        return poses
+    run_pc2(0, W)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    poses_pc2 = np.zeros((K2, 7)); pending = []
     p0 = time.time()
-    for k in range(K2):
-        if len(pending) == 3:
-            g = pending.pop(0); poses_pc2[g] = ctx5.process_wait()
-        ctx5.process_submit_pc2(raw_all[raw_off[k]:raw_off[k + 1]], lay[k])
-        pending.append(k)
-    for g in pending:
-        poses_pc2[g] = ctx5.process_wait()
+    poses_pc2 = run_pc2(W, W + K2)
     torch.cuda.synchronize()
     p1 = time.time()
     pc2_frames, pc2_s = reduce_over_ranks(K2, p1 - p0, device="cuda")
-    pc2 = {"value": pc2_frames / pc2_s, "unit": UNIT, "h2d_bytes_per_step": float(raw_off[-1]) / K2, "d2h_bytes_per_step": 56 + 8, "steps": K2,
+    pc2 = {"value": pc2_frames / pc2_s, "unit": UNIT, "h2d_bytes_per_step": float(raw_off[-1] - raw_off[W]) / K2, "d2h_bytes_per_step": 56 + 8, "steps": K2,
            "poses_identical_to_device_replay": bool(np.array_equal(poses_pc2, poses_dev[:K2])),
            "call": "floam_process_submit_pc2 / floam_process_wait, raw PointCloud2 bytes in pinned host memory, three frames in flight"}
     ctx5.close()
@@ -521,6 +557,9 @@ def main():
         single.append((time.perf_counter() - t_s) * 1e3)
     ctx4.close()
     one.close()
+    mapping = None
+    if not args.no_cpu_baseline and world == 1:
+        mapping = mapping_leg(capi, local, seq, scans, off, np.concatenate([poses_pre, poses_warm, poses_dev]), prm)
     for k in stats:
         stats[k] /= TF
     # every kernel is bracketed by an event pair inside the frame graph; the pair itself costs a few microseconds, measured by an
@@ -561,7 +600,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 56 + 8,
                     "poses_identical_to_device_replay": identical,
                     "call": "floam_process_submit / floam_process_wait, 32-byte PointXYZIRT scans in pinned host memory, three frames in flight"},
-            "e2e_pointcloud2": pc2, "multi_sequence": multi,
+            "e2e_pointcloud2": pc2, "multi_sequence": multi, "laser_mapping": mapping,
             "gpu_launches": int(launches), "launches_per_frame": launches / K,
             "p50_ms_per_frame": float(np.percentile(lat, 50)), "p99_ms_per_frame": float(np.percentile(lat, 99)),
             "single_frame_latency_ms": {"p50": float(np.percentile(single, 50)), "p99": float(np.percentile(single, 99)), "frames": NL,

@@ -37,6 +37,7 @@ SYMBOLS = [
     "floam_process_wait", "floam_stage_scans", "floam_process_staged", "floam_mapping_update", "floam_mapping_get_map", "floam_voxel_grid",
     "floam_crop_box", "floam_knn5", "floam_debug_fetch", "floam_launch_count", "floam_last_frame_ms", "floam_replay_staged",
     "floam_set_kernel_timing", "floam_kernel_slots", "floam_kernel_name", "floam_kernel_timing", "floam_deskew_align_ex",
+    "floam_write_pcd_binary", "floam_save_posegraph", "floam_save_odom", "floam_save_balm", "floam_save_merged",
     "floam_compensate_velocity", "floam_process_submit_imu", "floam_process_scan_imu", "floam_unpack_pointcloud2", "floam_process_submit_pc2",
 ]
 
@@ -120,6 +121,36 @@ def default_params(**kw):
             v = lib().floam_loss_from_string(v.encode())
         setattr(p, k, v)
     return p
+
+
+def _dump_args(poses, stamps, clouds):
+    """clouds: list of POINT_I arrays -> (poses16, stamps, concatenated cloud, offsets)."""
+    P = np.ascontiguousarray(np.asarray(poses, np.float64).reshape(-1, 16))
+    st = np.ascontiguousarray(stamps, np.float64)
+    off = np.zeros(len(clouds) + 1, np.int64); off[1:] = np.cumsum([len(c) for c in clouds])
+    cat = np.ascontiguousarray(np.concatenate(clouds) if len(clouds) else np.zeros(0, POINT_I), POINT_I)
+    return P, st, cat, off
+
+
+def write_pcd_binary(path, pts):
+    pts = np.ascontiguousarray(pts, POINT_I)
+    _check(lib().floam_write_pcd_binary(str(path).encode(), _p(pts), len(pts)), "floam_write_pcd_binary")
+
+
+def save_posegraph(directory, poses, stamps, clouds):
+    """SavePosegraph (reference src/utils.cpp:3-79). Host I/O only: needs no context."""
+    P, st, cat, off = _dump_args(poses, stamps, clouds)
+    _check(lib().floam_save_posegraph(str(directory).encode(), _p(P), _p(st), _p(cat), _p(off), len(clouds)), "floam_save_posegraph")
+
+
+def save_odom(directory, poses, stamps, clouds):
+    P, st, cat, off = _dump_args(poses, stamps, clouds)
+    _check(lib().floam_save_odom(str(directory).encode(), _p(P), _p(st), _p(cat), _p(off), len(clouds)), "floam_save_odom")
+
+
+def save_balm(directory, poses, stamps, clouds):
+    P, st, cat, off = _dump_args(poses, stamps, clouds)
+    _check(lib().floam_save_balm(str(directory).encode(), _p(P), _p(st), _p(cat), _p(off), len(clouds)), "floam_save_balm")
 
 
 class PinnedBuffer:
@@ -367,6 +398,11 @@ class Context:
         ids = np.full((max(len(queries), 1), 5), -1, np.int32); d2 = np.zeros((max(len(queries), 1), 5), np.float32)
         _check(lib().floam_knn5(self.h, _p(map_pts), len(map_pts), _p(queries), len(queries), _p(ids), _p(d2)), "floam_knn5")
         return ids[:len(queries)], d2[:len(queries)]
+
+    def save_merged(self, directory, poses, clouds, downsample_size):
+        """SaveMerged (reference src/odomEstimationNode.cpp:66-92): transform + merge + VoxelGrid on the device, two PCD files."""
+        P, _, cat, off = _dump_args(poses, np.zeros(len(clouds)), clouds)
+        _check(lib().floam_save_merged(self.h, str(directory).encode(), _p(P), _p(cat), _p(off), len(clouds), C.c_double(downsample_size)), "floam_save_merged")
 
     # ---- taps / accounting ----
     def debug_fetch(self, what, dtype):

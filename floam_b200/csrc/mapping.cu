@@ -184,12 +184,31 @@ __global__ void __launch_bounds__(kThreads) reduce_kernel(const P4* __restrict__
     int hx, hy, hz;
     voxel_of(work[vals[j]], g, hx, hy, hz);
     float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+    // pcl::CentroidPoint: float sums in run order, then / n.  The ORDER of the additions is fixed, the loads are not: eight elements
+    // of the run are fetched at a time (index and head flag, then point and cell), so a long run (a ground voxel next to the sensor
+    // holds hundreds of returns) costs one round trip per eight points instead of three per point.
     int k = j;
-    do {  // pcl::CentroidPoint: float sums in run order, then / n
-      const float4 p = work[vals[k]];
-      sx = fadd(sx, p.x); sy = fadd(sy, p.y); sz = fadd(sz, p.z); si = fadd(si, p.w);
-      ++k;
-    } while (k < n && seg[k + 1] == seg[k] && work_cell[vals[k]] == c);
+    bool more = true;
+    while (more) {
+      int idx[8], sg[9];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) idx[u] = (k + u < n) ? __ldg(vals + k + u) : -1;
+#pragma unroll
+      for (int u = 0; u < 9; ++u) sg[u] = (k + u <= n) ? __ldg(seg + k + u) : 0;
+      float4 p[8];
+      unsigned int cc[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (idx[u] >= 0) { p[u] = work[idx[u]]; cc[u] = work_cell[idx[u]]; }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (!more) break;
+        const bool first = (k + u == j);   // the head itself always belongs to the run
+        if (!first && !(idx[u] >= 0 && sg[u + 1] == sg[u] && cc[u] == c)) { more = false; k += u; break; }
+        sx = fadd(sx, p[u].x); sy = fadd(sy, p[u].y); sz = fadd(sz, p[u].z); si = fadd(si, p[u].w);
+      }
+      if (more) k += 8;
+    }
     const float cnt = (float)(k - j);
     out[base + seg[j]] = make_float4(__fdiv_rn(sx, cnt), __fdiv_rn(sy, cnt), __fdiv_rn(sz, cnt), __fdiv_rn(si, cnt));
     out_cell[base + seg[j]] = c;

@@ -190,6 +190,21 @@ int floam_replay_staged(floam_ctx* ctx, int first, int count, int deskew, double
 int floam_mapping_update(floam_ctx* ctx, const floam_point_xyzi* pts, int n, const double pose_rowmajor[16]);
 int floam_mapping_get_map(floam_ctx* ctx, floam_point_xyzi* out, int cap, int* n);
 
+/* On-disk outputs the odometry node writes when it exits (src/odomEstimationNode.cpp:66-121,373-387; src/utils.cpp:3-106).  Scans come as
+ * one concatenated array of pcl::PointXYZI with offsets[n + 1], poses as row-major 4x4 matrices (Eigen::Affine3d::matrix()), stamps in
+ * seconds.  Files are byte-identical to the reference's: iostream text formats, PCL 1.8 binary PCD (FIELDS x y z intensity). */
+int floam_write_pcd_binary(const char* path, const floam_point_xyzi* pts, int n);               /* pcl::io::savePCDFileBinary<PointXYZI> */
+int floam_save_posegraph(const char* directory, const double* poses16, const double* stamps, const floam_point_xyzi* clouds, const int64_t* offsets,
+                         int n);                                                                 /* SavePosegraph: graph.g2o + %06d/{cloud.pcd,data} */
+int floam_save_odom(const char* directory, const double* poses16, const double* stamps, const floam_point_xyzi* clouds, const int64_t* offsets,
+                    int n);                                                                      /* SaveOdom: <sec>_<nsec>.pcd / .odom */
+int floam_save_balm(const char* directory, const double* poses16, const double* stamps, const floam_point_xyzi* clouds, const int64_t* offsets,
+                    int n);                                                                      /* SavePosesHomogeneousBALM: alidarPose.csv + full<i>.pcd (directory ends with '/') */
+/* SaveMerged: scans transformed by their poses (pcl::transformPointCloud with an Affine3d), merged, saved, voxel-downsampled, saved again;
+ * the transform and the VoxelGrid run on the device. directory ends with '/'. */
+int floam_save_merged(floam_ctx* ctx, const char* directory, const double* poses16, const floam_point_xyzi* clouds, const int64_t* offsets, int n,
+                      double downsample_size);
+
 /* pcl::VoxelGrid<PointXYZI>::filter and pcl::CropBox<PointXYZI>::filter as used at src/odomEstimationClass.cpp:137-142,278-292
  * (stage entry points; also what floam_b200/host/mini_pcl.h's filters call) */
 int floam_voxel_grid(floam_ctx* ctx, const floam_point_xyzi* pts, int n, float leaf, floam_point_xyzi* out, int cap, int* n_out);

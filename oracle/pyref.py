@@ -107,6 +107,30 @@ replay_sequence = _with_fresh_lib(_m.replay_sequence)
 replay_sequence_stages = _with_fresh_lib(_m.replay_sequence_stages)
 
 
+def _dump(fn, directory, poses, stamps, clouds, *extra):
+    import numpy as np
+    P = np.ascontiguousarray(np.asarray(poses, np.float64).reshape(-1, 16)); st = np.ascontiguousarray(stamps, np.float64)
+    off = np.zeros(len(clouds) + 1, np.int64); off[1:] = np.cumsum([len(c) for c in clouds])
+    cat = np.ascontiguousarray(np.concatenate(clouds) if len(clouds) else np.zeros(0, POINT_I), POINT_I)
+    getattr(lib(), fn)(str(directory).encode(), _m._p(P), _m._p(st), _m._p(cat), _m._p(off), len(clouds), *extra)
+
+
+def save_posegraph(directory, poses, stamps, clouds):      # SavePosegraph, src/utils.cpp:3-79 (the reference's code)
+    _dump("fo_save_posegraph", directory, poses, stamps, clouds)
+
+
+def save_odom(directory, poses, stamps, clouds):           # SaveOdom, src/utils.cpp:82-106
+    _dump("fo_save_odom", directory, poses, stamps, clouds)
+
+
+def save_balm(directory, poses, stamps, clouds):           # SavePosesHomogeneousBALM, src/odomEstimationNode.cpp:93-121
+    _dump("fo_save_balm", directory, poses, stamps, clouds)
+
+
+def save_merged(directory, poses, stamps, clouds, downsample_size, total_order=True):   # SaveMerged, src/odomEstimationNode.cpp:66-92
+    _dump("fo_save_merged", directory, poses, stamps, clouds, C.c_double(downsample_size), int(total_order))
+
+
 class Odom(_m.Odom):
     """OdomEstimationClass, the reference's code; each instance gets its own copy of the library (see fresh_lib)."""
 

@@ -49,6 +49,11 @@ void CenterTime(const pcl::PointCloud<vel_point::PointXYZIRT>::Ptr cloud);  // s
 template <typename T> void pcl::fromROSMsg(const sensor_msgs::PointCloud2&, pcl::PointCloud<T>&) { std::fprintf(stderr, "fromROSMsg: not part of the stand-in\n"); std::abort(); }
 template <typename T> void pcl::toROSMsg(const pcl::PointCloud<T>&, sensor_msgs::PointCloud2&) { std::fprintf(stderr, "toROSMsg: not part of the stand-in\n"); std::abort(); }
 template void pcl::fromROSMsg<vel_point::PointXYZIRT>(const sensor_msgs::PointCloud2&, pcl::PointCloud<vel_point::PointXYZIRT>&);
+template void pcl::toROSMsg<vel_point::PointXYZIRT>(const pcl::PointCloud<vel_point::PointXYZIRT>&, sensor_msgs::PointCloud2&);
+
+// dump-on-exit writers of the odometry node (src/odomEstimationNode.cpp:66-121; that file is built with -Dmain=... and its other symbols localised)
+void SaveMerged(const std::vector<pcl::PointCloud<pcl::PointXYZI>::Ptr> clouds, const std::vector<Eigen::Affine3d> poses, const std::string& directory, double downsample_size);
+void SavePosesHomogeneousBALM(const std::vector<pcl::PointCloud<pcl::PointXYZI>::Ptr> clouds, const std::vector<Eigen::Affine3d> poses, const std::string& directory, double downsample_size);
 
 namespace {
 typedef pcl::PointCloud<vel_point::PointXYZIRT> CloudIRT;
@@ -339,6 +344,49 @@ void fo_mapping_update(void* m, const void* pts, int n, const double pose16[16])
 }
 int fo_mapping_get_map(void* m, void* out, int cap) { return copy_out(*((LaserMappingClass*)m)->getMap(), out, cap); }
 
+}  // extern "C"
+
+// ---------- on-disk outputs (src/utils.cpp:3-106, src/odomEstimationNode.cpp:66-121) ----------
+namespace {
+struct DumpArgs {
+  std::vector<Eigen::Affine3d> poses;
+  std::vector<double> stamps;
+  std::vector<pcl::PointCloud<pcl::PointXYZI>::Ptr> clouds;
+};
+// poses16: row-major 4x4 per scan; stamps: seconds; clouds: concatenated 32-byte PointXYZI, offsets[n + 1]
+DumpArgs make_dump(const double* poses16, const double* stamps, const void* clouds, const long long* offsets, int n) {
+  DumpArgs d;
+  for (int i = 0; i < n; ++i) {
+    Eigen::Matrix4d M;
+    for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) M(r, c) = poses16[16 * i + 4 * r + c];
+    d.poses.push_back(Eigen::Affine3d(M));
+    d.stamps.push_back(stamps[i]);
+    pcl::PointCloud<pcl::PointXYZI>::Ptr c = make_i((const char*)clouds + 32 * offsets[i], (int)(offsets[i + 1] - offsets[i]));
+    pcl_conversions::toPCL(ros::Time(stamps[i]), c->header.stamp);   // the node stamps every stored cloud (src/odomEstimationNode.cpp:279)
+    d.clouds.push_back(c);
+  }
+  return d;
+}
+}  // namespace
+extern "C" {
+void fo_save_posegraph(const char* dir, const double* poses16, const double* stamps, const void* clouds, const long long* offsets, int n) {
+  DumpArgs d = make_dump(poses16, stamps, clouds, offsets, n);
+  SavePosegraph(dir, d.poses, d.stamps, d.clouds);
+}
+void fo_save_odom(const char* dir, const double* poses16, const double* stamps, const void* clouds, const long long* offsets, int n) {
+  DumpArgs d = make_dump(poses16, stamps, clouds, offsets, n);
+  SaveOdom(dir, d.poses, d.stamps, d.clouds);
+}
+void fo_save_balm(const char* dir, const double* poses16, const double* stamps, const void* clouds, const long long* offsets, int n) {
+  DumpArgs d = make_dump(poses16, stamps, clouds, offsets, n);
+  SavePosesHomogeneousBALM(d.clouds, d.poses, dir, 0.0);
+}
+void fo_save_merged(const char* dir, const double* poses16, const double* stamps, const void* clouds, const long long* offsets, int n, double downsample_size,
+                    int total_order) {
+  pcl::floam_stub::voxel_total_order() = total_order != 0;
+  DumpArgs d = make_dump(poses16, stamps, clouds, offsets, n);
+  SaveMerged(d.clouds, d.poses, dir, downsample_size);
+}
 }  // extern "C"
 
 // ---------- timed whole-sequence replay: featureExtraction + odometry per frame on one thread, the way the nodes call them ----------

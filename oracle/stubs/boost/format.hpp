@@ -1,38 +1,45 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY: stand-in for <boost/format.hpp> (include/utils.h:10,17-18; only "%0Nd"-style int fields are used).
+// ORACLE — TEST INFRASTRUCTURE ONLY: stand-in for <boost/format.hpp> (include/utils.h:10,17-18; src/utils.cpp:64,94).
+// Like Boost.Format, a printf-style directive only sets STREAM formatting state (fill, width, precision, fixed / dec) and the argument
+// is then written with operator<< — so "%lf" applied to an integer prints the integer, "%06d" zero-pads to six columns.
 #pragma once
+#include <cctype>
 #include <cstdio>
+#include <iomanip>
 #include <ostream>
+#include <sstream>
 #include <string>
 namespace boost {
 class format {
  public:
-  explicit format(const std::string& f) : fmt_(f) {}
+  explicit format(const std::string& f) : out_(f), cursor_(0) {}
   template <class T> format& operator%(const T& v) {
-    // substitute the first remaining %...d / %...s / %...f directive
-    size_t p = out_.empty() && !started_ ? 0 : 0;
-    (void)p;
-    if (!started_) { out_ = fmt_; started_ = true; }
     size_t a = out_.find('%', cursor_);
     if (a == std::string::npos) return *this;
     size_t b = a + 1;
-    while (b < out_.size() && !std::isalpha(static_cast<unsigned char>(out_[b]))) ++b;
-    std::string spec = out_.substr(a, b - a + 1);
-    char buf[128];
-    render(buf, sizeof(buf), spec, v);
-    out_.replace(a, b - a + 1, buf);
-    cursor_ = a + std::string(buf).size();
+    std::ostringstream os;
+    if (b < out_.size() && out_[b] == '0') { os.fill('0'); ++b; }
+    int width = 0;
+    while (b < out_.size() && std::isdigit(static_cast<unsigned char>(out_[b]))) width = width * 10 + (out_[b++] - '0');
+    if (b < out_.size() && out_[b] == '.') {
+      ++b; int prec = 0;
+      while (b < out_.size() && std::isdigit(static_cast<unsigned char>(out_[b]))) prec = prec * 10 + (out_[b++] - '0');
+      os.precision(prec);
+    }
+    while (b < out_.size() && (out_[b] == 'l' || out_[b] == 'h')) ++b;   // length modifiers are ignored
+    const char conv = b < out_.size() ? out_[b] : 's';
+    if (conv == 'f') os.setf(std::ios_base::fixed, std::ios_base::floatfield);
+    if (conv == 'e') os.setf(std::ios_base::scientific, std::ios_base::floatfield);
+    if (width) os.width(width);
+    os << v;
+    const std::string piece = os.str();
+    out_.replace(a, b - a + 1, piece);
+    cursor_ = a + piece.size();
     return *this;
   }
-  std::string str() const { return started_ ? out_ : fmt_; }
+  std::string str() const { return out_; }
  private:
-  static void render(char* buf, size_t n, const std::string& spec, int v) { std::snprintf(buf, n, spec.c_str(), v); }
-  static void render(char* buf, size_t n, const std::string& spec, long v) { std::string s = spec; s.insert(s.size() - 1, "l"); std::snprintf(buf, n, s.c_str(), v); }
-  static void render(char* buf, size_t n, const std::string& spec, unsigned long v) { std::string s = spec; s[s.size() - 1] = 'u'; s.insert(s.size() - 1, "l"); std::snprintf(buf, n, s.c_str(), v); }
-  static void render(char* buf, size_t n, const std::string& spec, double v) { std::snprintf(buf, n, spec.c_str(), v); }
-  static void render(char* buf, size_t n, const std::string&, const std::string& v) { std::snprintf(buf, n, "%s", v.c_str()); }
-  std::string fmt_, out_;
-  bool started_ = false;
-  size_t cursor_ = 0;
+  std::string out_;
+  size_t cursor_;
 };
 inline std::ostream& operator<<(std::ostream& os, const format& f) { return os << f.str(); }
 inline std::string str(const format& f) { return f.str(); }

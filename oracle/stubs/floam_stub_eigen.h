@@ -13,6 +13,8 @@
 #include <cstddef>
 #include <cstring>
 #include <memory>
+#include <ostream>
+#include <sstream>
 #include <type_traits>
 #include <vector>
 #include "../linalg.h"
@@ -164,6 +166,14 @@ struct DenseBase {
   DynView<S> topRows(int n) { return DynView<S>(&derived().at(0, 0), n, C, derived().row_stride(), derived().col_stride()); }
   DynView<S> bottomRows(int n) { return DynView<S>(&derived().at(R - n, 0), n, C, derived().row_stride(), derived().col_stride()); }
   PlainObject matrix() const { return eval(); }
+  // `m << a, b, c, ...;` fills coefficients row by row (Eigen's CommaInitializer)
+  struct CommaInit {
+    D& m; int k;
+    CommaInit& operator,(S v) { m.at(k / C, k % C) = v; ++k; return *this; }
+  };
+  CommaInit operator<<(S v) { derived().at(0, 0) = v; return CommaInit{derived(), 1}; }
+  struct DiagonalWrapper { PlainObject v; };
+  DiagonalWrapper asDiagonal() const { return DiagonalWrapper{eval()}; }
 
   template <class O> D& operator+=(const DenseBase<O, S, R, C>& o) {
     PlainObject t = o.eval();
@@ -256,6 +266,10 @@ class Matrix<S, Dynamic, Dynamic, Opt> {
   Matrix() : r_(0), c_(0) {}
   template <int R, int C, int O>
   Matrix(const Matrix<S, R, C, O>& o) : r_(R), c_(C), d_(R * C) { for (int j = 0; j < C; ++j) for (int i = 0; i < R; ++i) d_[j * R + i] = o.at(i, j); }
+  template <class W, class = decltype(W::v)>
+  Matrix(const W& diag) : r_(diag.v.size()), c_(diag.v.size()), d_((size_t)diag.v.size() * diag.v.size(), S(0)) {   // vec.asDiagonal()
+    for (int i = 0; i < r_; ++i) d_[i * r_ + i] = diag.v.lin_c(i);
+  }
   S operator()(int i, int j) const { return d_[j * r_ + i]; }
   S& operator()(int i, int j) { return d_[j * r_ + i]; }
   int rows() const { return r_; }
@@ -390,6 +404,31 @@ Matrix<S, R, C> operator*(const DenseBase<A, S, R, K>& a, const DenseBase<B, S, 
       r.at(i, j) = s;
     }
   return r;
+}
+
+// operator<<(ostream, matrix) with Eigen's default IOFormat: stream precision, columns aligned to the widest coefficient, coefficients
+// separated by one blank, rows by a newline (Eigen/src/Core/IO.h, print_matrix)
+template <class A, class S, int R, int C>
+std::ostream& operator<<(std::ostream& s, const DenseBase<A, S, R, C>& m) {
+  std::streamsize width = 0;
+  for (int j = 0; j < C; ++j)
+    for (int i = 0; i < R; ++i) {
+      std::stringstream sstr;
+      sstr.copyfmt(s);
+      sstr << m.derived().at(i, j);
+      width = std::max<std::streamsize>(width, (std::streamsize)sstr.str().length());
+    }
+  for (int i = 0; i < R; ++i) {
+    if (width) s.width(width);
+    s << m.derived().at(i, 0);
+    for (int j = 1; j < C; ++j) {
+      s << " ";
+      if (width) s.width(width);
+      s << m.derived().at(i, j);
+    }
+    if (i < R - 1) s << "\n";
+  }
+  return s;
 }
 
 typedef Matrix<double, 2, 1> Vector2d;
@@ -586,12 +625,28 @@ class Transform {
   Matrix<S, 3, 1> operator*(const DenseBase<V, S, 3, 1>& v) const { return linear() * v + translation(); }
   // Transform::inverse(Isometry): R^T, -R^T t.  (Affine mode would invert the linear part; the path never does that.)
   Transform inverse() const {
-    static_assert(Mode == Isometry, "inverse(): only the Isometry mode is used on the path");
     Transform r;
     r.m_.setIdentity();
-    const Matrix<S, 3, 3> Rt = linear().transpose();
-    r.linear() = Rt;
-    r.translation() = -(Rt * translation());
+    if (Mode == Isometry) {
+      const Matrix<S, 3, 3> Rt = linear().transpose();
+      r.linear() = Rt;
+      r.translation() = -(Rt * translation());
+    } else {   // Affine: general 3x3 inverse by cofactors (Eigen's compute_inverse_size3_helper), then -L^-1 t  (src/utils.cpp:35, off the hot path)
+      const Matrix<S, 3, 3> L = linear();
+      auto cof = [&](int i, int j) {
+        const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+        return L.at(i1, j1) * L.at(i2, j2) - L.at(i1, j2) * L.at(i2, j1);
+      };
+      const S c0 = cof(0, 0), c1 = cof(1, 0), c2 = cof(2, 0);
+      const S det = c0 * L.at(0, 0) + c1 * L.at(1, 0) + c2 * L.at(2, 0);
+      const S invdet = S(1) / det;
+      Matrix<S, 3, 3> Li;
+      Li.at(0, 0) = c0 * invdet; Li.at(0, 1) = c1 * invdet; Li.at(0, 2) = c2 * invdet;
+      Li.at(1, 0) = cof(0, 1) * invdet; Li.at(1, 1) = cof(1, 1) * invdet; Li.at(1, 2) = cof(2, 1) * invdet;
+      Li.at(2, 0) = cof(0, 2) * invdet; Li.at(2, 1) = cof(1, 2) * invdet; Li.at(2, 2) = cof(2, 2) * invdet;
+      r.linear() = Li;
+      r.translation() = -(Li * translation());
+    }
     return r;
   }
   template <class T>

@@ -3,6 +3,7 @@
 #include <pcl/point_cloud.h>
 #include <pcl/point_types.h>
 #include <cstdio>
+#include <fstream>   // the real pcd_io.h brings <fstream> in (src/utils.cpp uses std::ofstream without including it)
 #include <string>
 namespace pcl {
 namespace io {

@@ -1,5 +1,5 @@
 """Development aid: per-kernel-class device time for any synthetic configuration (graph-embedded event pairs, noop-calibrated).
-Usage: python tools/kernel_breakdown.py [sensor=hdl64] [map_resolution=0.4] [frames=40]"""
+Usage: python tools/kernel_breakdown.py [sensor=hdl64] [map_resolution=0.4] [frames=40] [max_dis=60] [min_dis=2]"""
 import sys
 import numpy as np
 sys.path.insert(0, ".")
@@ -7,10 +7,12 @@ from floam_b200 import capi, synth
 sensor = sys.argv[1] if len(sys.argv) > 1 else "hdl64"
 res = float(sys.argv[2]) if len(sys.argv) > 2 else 0.4
 frames = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+max_dis = float(sys.argv[4]) if len(sys.argv) > 4 else 60.0
+min_dis = float(sys.argv[5]) if len(sys.argv) > 5 else 2.0
 seq = synth.Sequence(sensor, seed=0)
 scans, off = seq.scans(0, frames)
 ctx = capi.Context(num_lines=seq.num_lines, loss="cauchy", map_resolution=res, max_scan_points=seq.max_points + 1024, max_map_points=1 << 22,
-                   max_global_map_points=0, max_grid_cells=1 << 23)
+                   max_global_map_points=0, max_grid_cells=1 << 24, max_distance=max_dis, min_distance=min_dis)
 ctx.stage_scans(scans, off)
 ctx.replay_staged(0, frames - 10)
 _, ms = ctx.replay_staged(frames - 10, 5)
