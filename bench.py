@@ -344,6 +344,29 @@ def run_multi_sequence(capi, device, rank, world, S, skip, n_timed, prm, solo_po
     return S * n_timed, wall, {"per_sequence_device_ms_per_frame": [round(m / n_timed, 4) for m in ms], "first_sequence_identical_to_solo_replay": same}
 
 
+def replica_identity(rank, poses):
+    """1 = this rank's first poses have the committed single-GPU CRC of its seed (tests/golden/replica_pose_crc.json, tools/replica_crc.py),
+    0 = they differ, -1 = no committed CRC for this seed.  Reduced over ranks with MIN."""
+    import zlib
+    import torch
+    import torch.distributed as dist
+    flag = -1
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "replica_pose_crc.json")) as f:
+            ref = json.load(f)
+        n = int(ref["frames"])
+        want = ref["seeds"].get(str(SEED_BASE + rank))
+        if want is not None and len(poses) >= n:
+            flag = 1 if (zlib.crc32(np.ascontiguousarray(poses[:n]).tobytes()) & 0xffffffff) == int(want) else 0
+    except (OSError, ValueError, KeyError):
+        flag = -1
+    if dist.is_available() and dist.is_initialized():
+        t = torch.tensor([flag], dtype=torch.int32, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        flag = int(t.item())
+    return {1: True, 0: False}.get(flag)
+
+
 def mapping_leg(capi, device, seq, scans, off, poses7, prm, n_frames=30):
     """LaserMappingClass::updateCurrentPointsToMap / getMap (SURVEY 8 a28; src/laserMappingClass.cpp:148-200) at HDL-64 size, fed like the
     mapping node: the filtered cloud (edge + surf features) and the odometry pose of the same frame.  Host buffers in, host wall clock
@@ -426,6 +449,8 @@ def main():
         dist.barrier()
     total_frames, max_s = reduce_over_ranks(K, ms_dev * 1e-3)
     value = total_frames / max_s
+    # replicas must be replicas: this rank's sequence (seed = rank) against the CRC of the same sequence replayed on ONE GPU (committed)
+    identity = replica_identity(rank, np.concatenate([poses_pre, poses_warm, poses_dev]))
     d = ctx.debug()
     ne_map, ns_map = ctx.odom_map_sizes()
     ctx.close()
@@ -601,6 +626,7 @@ def main():
                     "poses_identical_to_device_replay": identical,
                     "call": "floam_process_submit / floam_process_wait, 32-byte PointXYZIRT scans in pinned host memory, three frames in flight"},
             "e2e_pointcloud2": pc2, "multi_sequence": multi, "laser_mapping": mapping,
+            "replicas_identical_to_1gpu_run": identity,
             "gpu_launches": int(launches), "launches_per_frame": launches / K,
             "p50_ms_per_frame": float(np.percentile(lat, 50)), "p99_ms_per_frame": float(np.percentile(lat, 99)),
             "single_frame_latency_ms": {"p50": float(np.percentile(single, 50)), "p99": float(np.percentile(single, 99)), "frames": NL,
