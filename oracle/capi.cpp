@@ -1,4 +1,5 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see types.h).  parity unpinned.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see types.h).  Pinned: tests/test_reference_pin.py runs this restatement against the reference's own
+// sources compiled unmodified (oracle/_ref, `make ref`) on identical inputs — identical selections, bytes and poses.
 // Flat C interface over the restatement so tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 // --impl reference legs can drive it through ctypes.  Nothing under floam_b200/ or include/ may use this.
 #include "floam_oracle.h"

@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see types.h).  parity unpinned.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see types.h).  The cost functions / parameterisation are pinned the same way; the trust-region loop restates Ceres (un-vendored, absent here): unpinned.
 // Restates src/lidarOptimization.cpp:12-152 (EdgeAnalyticCostFunction, SurfNormAnalyticCostFunction,
 // PoseSE3Parameterization, getTransformFromSe3) and the Ceres 1.13/1.14 trust-region Levenberg-Marquardt loop
 // with DENSE_QR as configured at src/odomEstimationClass.cpp:83-108 (un-vendored; SURVEY.md Appendix A.5:

@@ -1,4 +1,5 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see types.h).  parity unpinned.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see types.h).  Pinned: tests/test_reference_pin.py runs this restatement against the reference's own
+// sources compiled unmodified (oracle/_ref, `make ref`) on identical inputs — identical selections, bytes and poses.
 // Restates src/laserProcessingClass.cpp:11-22 (RingExtractionVelodyne), :72-118 (featureExtraction),
 // :121-231 (featureExtractionFromSector).  Compile with -ffp-contract=off: the reference build has no FMA
 // (CMakeLists.txt:4-6, no -march) so the float 11-tap sum and the double squares are plain add/mul.

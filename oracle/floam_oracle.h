@@ -1,4 +1,5 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see types.h).  parity unpinned.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see types.h).  Pinned: tests/test_reference_pin.py runs this restatement against the reference's own
+// sources compiled unmodified (oracle/_ref, `make ref`) on identical inputs — identical selections, bytes and poses.
 //
 // Declarations of the CPU restatement.  Structure follows the reference classes 1:1 so it can be diffed by eye
 // (SURVEY.md §8c): LaserProcessing <-> src/laserProcessingClass.cpp, OdomEstimation <-> src/odomEstimationClass.cpp,

@@ -1,4 +1,5 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see types.h).  parity unpinned.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see types.h).  Pinned: tests/test_reference_pin.py runs this restatement against the reference's own
+// sources compiled unmodified (oracle/_ref, `make ref`) on identical inputs — identical selections, bytes and poses.
 // Restates src/dataHandler.cpp:24-122 (ImuHandler, CompensateVelocity, Compensate) and the IMU folding done by the
 // caller, src/laserProcessingNode.cpp:65-78 (CenterTime) and :113-116 (IMU alignment via pcl::transformPointCloud).
 #include "floam_oracle.h"

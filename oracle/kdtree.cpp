@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see types.h).  parity unpinned.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see types.h).  Restates FLANN (un-vendored): checked against the FLANN copy bundled with OpenCV (tests/test_oracle.py), otherwise unpinned.
 // Restates pcl::KdTreeFLANN<PointXYZI>::{setInputCloud,nearestKSearch} (PCL 1.8.1) over FLANN 1.9.1's
 // KDTreeSingleIndex<L2_Simple<float>> with KDTreeSingleIndexParams(15), KNNSimpleResultSet, eps=0, sorted=true
 // (un-vendored).  Reference call sites: src/odomEstimationClass.cpp:17-18,78-79,153,206.

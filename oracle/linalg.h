@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see types.h).  parity unpinned.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see types.h).  Restates Eigen 3.3 routines (un-vendored, absent here): parity unpinned for these library internals.
 //
 // Restatement of the Eigen 3.3.x routines the reference calls on the odometry path.
 // Eigen is not vendored in /root/reference and is absent from this image; the algorithms below follow the

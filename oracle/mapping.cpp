@@ -1,4 +1,5 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see types.h).  parity unpinned.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see types.h).  Pinned: tests/test_reference_pin.py runs this restatement against the reference's own
+// sources compiled unmodified (oracle/_ref, `make ref`) on identical inputs — identical selections, bytes and poses.
 // Restates src/laserMappingClass.cpp:7-32,106-200 (50 m cell grid that grows by slabs, float transform,
 // z-based intensity, per-cell in-place VoxelGrid over the 5x5x5 neighbourhood).
 #include "floam_oracle.h"

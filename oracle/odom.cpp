@@ -1,4 +1,5 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see types.h).  parity unpinned.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see types.h).  Pinned: tests/test_reference_pin.py runs this restatement against the reference's own
+// sources compiled unmodified (oracle/_ref, `make ref`) on identical inputs — identical selections, bytes and poses.
 // Restates src/odomEstimationClass.cpp:7-343 line by line (quirks Q1-Q4, Q10-Q12 of SURVEY.md §0 kept verbatim).
 #include "floam_oracle.h"
 

@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see types.h).  parity unpinned.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see types.h).  Restates PCL 1.8.1 filters (un-vendored, absent here): parity unpinned for these library internals.
 // Restates pcl::VoxelGrid<PointXYZI>::applyFilter and pcl::CropBox<PointXYZI>::applyFilter of PCL 1.8.1
 // (un-vendored dependency, pinned by README.md:31-33 -> ROS Melodic), as configured at
 // src/odomEstimationClass.cpp:13-14,137-142,270-292 and src/laserMappingClass.cpp:31,175-184

@@ -1,4 +1,5 @@
-"""ORACLE — TEST INFRASTRUCTURE ONLY.  parity unpinned (the reference ships no golden vectors).
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  Pinned against the reference's own class sources (oracle/_ref, tests/test_reference_pin.py); the
+third-party internals it restates (PCL / FLANN / Eigen / Ceres) are unpinned.
 
 ctypes driver for oracle/libfloam_oracle.so (the CPU restatement of the reference hot path).
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.

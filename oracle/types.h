@@ -1,4 +1,6 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY.  parity unpinned (the reference ships no golden vectors).
+// ORACLE — TEST INFRASTRUCTURE ONLY.  The reference ships no golden vectors; this restatement is pinned against the
+// reference's own class sources compiled unmodified into oracle/_ref (tests/test_reference_pin.py).  The PCL / FLANN / Eigen / Ceres
+// internals it restates are un-vendored and absent from this image: for those, parity is unpinned.
 //
 // CPU restatement of the dan11003/floam per-frame odometry hot path, dependency-free C++17.
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may use this
