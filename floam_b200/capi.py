@@ -34,7 +34,7 @@ SYMBOLS = [
     "floam_alloc_pinned", "floam_free_pinned", "floam_set_graphs", "floam_imu_push", "floam_imu_get", "floam_imu_size", "floam_imu_time_contained", "floam_deskew_align",
     "floam_feature_extract", "floam_odom_init_map", "floam_odom_update", "floam_odom_update_xyzi", "floam_odom_get", "floam_odom_map_sizes",
     "floam_odom_get_map", "floam_odom_set_state", "floam_odom_get_state", "floam_odom_set_map", "floam_process_scan", "floam_process_submit",
-    "floam_process_wait", "floam_stage_scans", "floam_process_staged", "floam_mapping_update", "floam_mapping_get_map", "floam_voxel_grid",
+    "floam_process_wait", "floam_stage_scans", "floam_process_staged", "floam_mapping_update", "floam_mapping_get_map", "floam_mapping_get_changed_cells", "floam_voxel_grid",
     "floam_crop_box", "floam_knn5", "floam_debug_fetch", "floam_launch_count", "floam_last_frame_ms", "floam_replay_staged",
     "floam_set_kernel_timing", "floam_kernel_slots", "floam_kernel_name", "floam_kernel_timing", "floam_deskew_align_ex",
     "floam_write_pcd_binary", "floam_save_posegraph", "floam_save_odom", "floam_save_balm", "floam_save_merged",
@@ -380,6 +380,14 @@ class Context:
         return out[:n.value]
 
     # ---- stage entry points ----
+    def mapping_get_changed_cells(self):
+        """Incremental getMap(): (points, cells[n,3]) of every 50 m cell changed since the previous call; clears the change marks."""
+        n = C.c_int()
+        _check(lib().floam_mapping_get_changed_cells(self.h, None, None, 0, C.byref(n)), "floam_mapping_get_changed_cells")
+        out = np.zeros(max(n.value, 1), POINT_I); cells = np.zeros((max(n.value, 1), 3), np.int32)
+        _check(lib().floam_mapping_get_changed_cells(self.h, _p(out), _p(cells), len(out), C.byref(n)), "floam_mapping_get_changed_cells")
+        return out[:n.value], cells[:n.value]
+
     def voxel_grid(self, pts, leaf):
         pts = np.ascontiguousarray(pts, POINT_I)
         out = np.zeros(max(len(pts), 1), POINT_I); n = C.c_int()

@@ -945,6 +945,36 @@ int floam_mapping_get_map(floam_ctx* c, floam_point_xyzi* out, int cap, int* n) 
   return download_p4(c, d_out, *n, out);
 }
 
+int floam_mapping_get_changed_cells(floam_ctx* c, floam_point_xyzi* out, int32_t* cells_xyz, int cap, int* n) {
+  if (!c || !n || (out && !cells_xyz)) return FLOAM_ERR_ARG;
+  if (!c->mapping.enabled) return FLOAM_ERR_ARG;
+  if (c->inflight != 0) return FLOAM_ERR_ARG;
+  if (set_device(c)) return FLOAM_ERR_CUDA;
+  P4* d_out = nullptr; unsigned int* d_cell = nullptr; int* d_n = nullptr;
+  int rc = mapping_get_dirty_device(c->mapping, &d_out, &d_cell, &d_n, c->stream);
+  if (rc) return rc;
+  FLOAM_CUDA_OK(cudaMemcpyAsync(c->h_ints + 24, d_n, 4, cudaMemcpyDeviceToHost, c->stream));
+  FLOAM_CUDA_OK(cudaStreamSynchronize(c->stream));
+  if ((rc = check_async("mapping_get_changed_cells"))) return rc;
+  const int need = c->h_ints[24];
+  *n = need;
+  if (!out) return FLOAM_OK;                  // size query: the change marks stay
+  if (need > cap) return FLOAM_ERR_CAPACITY;  // likewise
+  if (need > 0) {
+    std::vector<unsigned int> packed((size_t)need);
+    FLOAM_CUDA_OK(cudaMemcpy(packed.data(), d_cell, (size_t)need * 4, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < need; ++i) {
+      cells_xyz[3 * i] = (int)(packed[i] >> 20) - 512;
+      cells_xyz[3 * i + 1] = (int)((packed[i] >> 10) & 1023u) - 512;
+      cells_xyz[3 * i + 2] = (int)(packed[i] & 1023u) - 512;
+    }
+    if ((rc = download_p4(c, d_out, need, out))) return rc;
+  }
+  if ((rc = mapping_clear_dirty_device(c->mapping, c->stream))) return rc;
+  FLOAM_CUDA_OK(cudaStreamSynchronize(c->stream));
+  return FLOAM_OK;
+}
+
 // ---- debug taps ---------------------------------------------------------------------------------------------------
 int floam_debug_fetch(floam_ctx* c, int what, void* out, size_t cap_bytes, size_t* n_bytes) {
   if (!c || !n_bytes) return FLOAM_ERR_ARG;

@@ -81,7 +81,8 @@ __global__ void __launch_bounds__(kThreads) partition_kernel(const P4* __restric
 // pcl::transformPointCloud(pose.cast<float>()) + intensity rewrite + cell id (:158-171)
 __global__ void __launch_bounds__(kThreads) transform_new_kernel(const char* __restrict__ in, int stride, const int* __restrict__ d_nin, int* __restrict__ counts,
                                                                   BlockGeom g, int cap, P4* __restrict__ work, unsigned int* __restrict__ work_cell,
-                                                                  const unsigned int* __restrict__ allocated, int n_allocated) {
+                                                                  const unsigned int* __restrict__ allocated, int n_allocated,
+                                                                  unsigned char* __restrict__ dirty) {
   pdl_prologue();
   const int nin = *d_nin, base = counts[2];
   const bool fits = counts[1] + base + nin <= cap;
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__(kThreads) transform_new_kernel(const char* __r
         const unsigned int want = pack_cell(cx, cy, cz);
         int lo = 0, hi = n_allocated;   // sorted list of every cell some earlier block allocated
         while (lo < hi) { const int mid = (lo + hi) >> 1; if (allocated[mid] < want) lo = mid + 1; else hi = mid; }
-        if (lo < n_allocated && allocated[lo] == want) pc = want;
+        if (lo < n_allocated && allocated[lo] == want) { pc = want; dirty[lo] = 1; }   // appended to a cell outside the block: that cell changed too
       }
       if (pc == kNoCell) atomicAdd(&counts[4], 1);
       work[base + i] = make_float4(x, y, z, inten);
@@ -237,6 +238,40 @@ __global__ void __launch_bounds__(kThreads) gather_kernel(const P4* __restrict__
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) out[i] = pts[vals[i]];
 }
 
+// incremental getMap(): flag = 1 for every point whose cell carries a change mark
+__global__ void __launch_bounds__(kThreads) dirty_flags_kernel(const unsigned int* __restrict__ cell, const int* __restrict__ counts,
+                                                                const unsigned int* __restrict__ allocated, int n_allocated,
+                                                                const unsigned char* __restrict__ dirty, int* __restrict__ flags) {
+  pdl_prologue();
+  const int n = counts[0];
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+    const unsigned int want = cell[i];
+    int lo = 0, hi = n_allocated;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(allocated + mid) < want) lo = mid + 1; else hi = mid; }
+    flags[i] = (lo < n_allocated && __ldg(allocated + lo) == want && dirty[lo]) ? 1 : 0;
+  }
+}
+__global__ void __launch_bounds__(kThreads) dirty_scatter_kernel(const P4* __restrict__ pts, const unsigned int* __restrict__ cell, int* __restrict__ counts,
+                                                                  const int* __restrict__ pos, P4* __restrict__ out, unsigned int* __restrict__ out_cell) {
+  pdl_prologue();
+  const int n = counts[0];
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+    const int p = pos[i];
+    if (pos[i + 1] != p) { out[p] = pts[i]; out_cell[p] = cell[i]; }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) counts[11] = n > 0 ? pos[n] : 0;
+}
+__global__ void __launch_bounds__(kThreads) mark_dirty_kernel(const unsigned int* __restrict__ cells, int n_cells, const unsigned int* __restrict__ allocated,
+                                                               int n_allocated, unsigned char* __restrict__ dirty) {
+  pdl_prologue();
+  for (int k = blockIdx.x * kThreads + threadIdx.x; k < n_cells; k += gridDim.x * kThreads) {
+    const unsigned int want = cells[k];
+    int lo = 0, hi = n_allocated;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (allocated[mid] < want) lo = mid + 1; else hi = mid; }
+    if (lo < n_allocated && allocated[lo] == want) dirty[lo] = 1;
+  }
+}
+
 int bits_for(long long v) {
   int b = 1;
   while (b < 32 && (1ll << b) < v) ++b;
@@ -259,12 +294,17 @@ int mapping_device_init(MappingDevice& md, int cap, double map_resolution, Voxel
   md.d_counts = (int*)alloc(actx, 64);
   md.alloc_cap = 1 << 16;
   md.d_allocated = (unsigned int*)alloc(actx, (size_t)md.alloc_cap * 4);
+  md.d_dirty = (unsigned char*)alloc(actx, (size_t)md.alloc_cap);
+  if (md.d_dirty) FLOAM_CUDA_OK(cudaMemsetAsync(md.d_dirty, 0, (size_t)md.alloc_cap, s));
   md.d_nbits = md.d_counts ? md.d_counts + 8 : nullptr;
   if (!md.pts || !md.pts_alt || !md.work || !md.cell || !md.cell_alt || !md.work_cell || !md.d_counts || !md.d_allocated) return FLOAM_ERR_CUDA;
   FLOAM_CUDA_OK(cudaMemsetAsync(md.d_counts, 0, 64, s));
   for (int dx = -kRange; dx <= kRange; ++dx)   // LaserMappingClass::init allocates the block around the origin (:12-29)
     for (int dy = -kRange; dy <= kRange; ++dy)
       for (int dz = -kRange; dz <= kRange; ++dz) md.allocated.insert(pack_cell(dx, dy, dz));
+  md.allocated_prev.assign(md.allocated.begin(), md.allocated.end());   // the device list is valid from the start (sorted: std::set order)
+  FLOAM_CUDA_OK(cudaMemcpyAsync(md.d_allocated, md.allocated_prev.data(), md.allocated_prev.size() * 4, cudaMemcpyHostToDevice, s));
+  FLOAM_CUDA_OK(cudaStreamSynchronize(s));
   md.enabled = true;
   return FLOAM_OK;
 }
@@ -299,17 +339,31 @@ int mapping_update_device(MappingDevice& md, const void* d_in, int stride, const
       for (int dz = -kRange; dz <= kRange; ++dz) md.allocated.insert(pack_cell(g.cx + dx, g.cy + dy, g.cz + dz));
   if (md.allocated.size() != before) {
     if ((int)md.allocated.size() > md.alloc_cap) return FLOAM_ERR_CAPACITY;
+    // the sorted cell list is about to change, and with it the index of every cell in the dirty array: bring the device-side marks
+    // (cells that received appended points) back into the host set first; the next hand-out re-applies them
+    if (!md.allocated_prev.empty()) {
+      std::vector<unsigned char> marks(md.allocated_prev.size());
+      FLOAM_CUDA_OK(cudaMemcpyAsync(marks.data(), md.d_dirty, marks.size(), cudaMemcpyDeviceToHost, s));
+      FLOAM_CUDA_OK(cudaStreamSynchronize(s));
+      for (size_t i = 0; i < marks.size(); ++i) if (marks[i]) md.dirty_host.insert(md.allocated_prev[i]);
+      FLOAM_CUDA_OK(cudaMemsetAsync(md.d_dirty, 0, (size_t)md.alloc_cap, s));
+    }
+    md.allocated_prev.assign(md.allocated.begin(), md.allocated.end());
     std::vector<unsigned int> sorted(md.allocated.begin(), md.allocated.end());
     FLOAM_CUDA_OK(cudaMemcpyAsync(md.d_allocated, sorted.data(), sorted.size() * 4, cudaMemcpyHostToDevice, s));
     FLOAM_CUDA_OK(cudaStreamSynchronize(s));
   }
+  for (int dx = -kRange; dx <= kRange; ++dx)   // every cell of the block is re-filtered in place (:175-184): all of them count as changed
+    for (int dy = -kRange; dy <= kRange; ++dy)
+      for (int dz = -kRange; dz <= kRange; ++dz) md.dirty_host.insert(pack_cell(g.cx + dx, g.cy + dy, g.cz + dz));
   VoxelWorkspace& ws = *md.vws;
   int* counts = md.d_counts;
   const int gmap = grid_for(md.cap), gin = grid_for(n_max);
   FLOAM_LAUNCH(K_CLASSIFY_OLD, classify_old_kernel, gmap, kThreads, s, md.cell, counts, g, ws.flags);
   exclusive_scan_i32(ws.flags, ws.flags, counts, 0, md.cap, ws.scan, nullptr, s);
   FLOAM_LAUNCH(K_PARTITION, partition_kernel, gmap, kThreads, s, md.pts, md.cell, ws.flags, counts, md.pts_alt, md.cell_alt, md.work, md.work_cell);
-  FLOAM_LAUNCH(K_TRANSFORM_NEW, transform_new_kernel, gin, kThreads, s, (const char*)d_in, stride, d_n, counts, g, md.cap, md.work, md.work_cell, md.d_allocated, (int)md.allocated.size());
+  FLOAM_LAUNCH(K_TRANSFORM_NEW, transform_new_kernel, gin, kThreads, s, (const char*)d_in, stride, d_n, counts, g, md.cap, md.work, md.work_cell, md.d_allocated, (int)md.allocated.size(),
+               md.d_dirty);
   FLOAM_LAUNCH(K_KEYS1, keys1_kernel, gmap, kThreads, s, md.work, md.work_cell, counts, g, ws.keys, ws.vals);
   unsigned int* k1 = nullptr; int* v1 = nullptr;
   radix_sort_pairs(ws.keys, ws.vals, counts + 3, md.d_nbits, md.cap, ws.sort, nullptr, s, &k1, &v1);
@@ -338,6 +392,32 @@ int mapping_get_map_device(MappingDevice& md, P4** d_out, int** d_out_n, cudaStr
   FLOAM_LAUNCH(K_GATHER, gather_kernel, g, kThreads, s, md.pts, sv, md.d_counts, md.pts_alt);
   *d_out = md.pts_alt;
   *d_out_n = md.d_counts;
+  return FLOAM_OK;
+}
+
+int mapping_get_dirty_device(MappingDevice& md, P4** d_out, unsigned int** d_out_cell, int** d_out_n, cudaStream_t s) {
+  VoxelWorkspace& ws = *md.vws;
+  const int g = grid_for(md.cap);
+  const int n_alloc = (int)md.allocated.size();
+  if (!md.dirty_host.empty()) {   // the block cells of the updates since the last call (the host knows them without asking the device)
+    std::vector<unsigned int> cells(md.dirty_host.begin(), md.dirty_host.end());
+    if (cells.size() > (size_t)md.alloc_cap) return FLOAM_ERR_CAPACITY;
+    unsigned int* d_cells = reinterpret_cast<unsigned int*>(md.work_cell);   // idle between updates
+    FLOAM_CUDA_OK(cudaMemcpyAsync(d_cells, cells.data(), cells.size() * 4, cudaMemcpyHostToDevice, s));
+    FLOAM_LAUNCH(K_CLASSIFY_OLD, mark_dirty_kernel, grid_for((int)cells.size()), kThreads, s, d_cells, (int)cells.size(), md.d_allocated, n_alloc, md.d_dirty);
+    FLOAM_CUDA_OK(cudaStreamSynchronize(s));   // `cells` is a pageable temporary
+    md.dirty_host.clear();
+  }
+  FLOAM_LAUNCH(K_CLASSIFY_OLD, dirty_flags_kernel, g, kThreads, s, md.cell, md.d_counts, md.d_allocated, n_alloc, md.d_dirty, ws.flags);
+  exclusive_scan_i32(ws.flags, ws.flags, md.d_counts, 0, md.cap, ws.scan, nullptr, s);
+  FLOAM_LAUNCH(K_PARTITION, dirty_scatter_kernel, g, kThreads, s, md.pts, md.cell, md.d_counts, ws.flags, md.pts_alt, md.cell_alt);
+  *d_out = md.pts_alt;
+  *d_out_cell = md.cell_alt;
+  *d_out_n = md.d_counts + 11;
+  return FLOAM_OK;
+}
+int mapping_clear_dirty_device(MappingDevice& md, cudaStream_t s) {
+  FLOAM_CUDA_OK(cudaMemsetAsync(md.d_dirty, 0, (size_t)md.alloc_cap, s));
   return FLOAM_OK;
 }
 

@@ -3,6 +3,7 @@
 // See mapping.cu.
 #pragma once
 #include <set>
+#include <vector>
 
 #include "common.cuh"
 #include "voxel.cuh"
@@ -25,6 +26,11 @@ struct MappingDevice {
   std::set<unsigned int> allocated;   // cells some block has allocated so far (checkPoints), host mirror
   unsigned int* d_allocated = nullptr; // the same, sorted, on the device
   int alloc_cap = 0;
+  // incremental getMap(): one byte per allocated cell (same order as d_allocated), set when an update rewrites the cell or appends to it,
+  // cleared when mapping_get_dirty_device hands the cell's points out
+  unsigned char* d_dirty = nullptr;
+  std::vector<unsigned int> allocated_prev;   // the allocated list as the device currently holds it (sorted)
+  std::set<unsigned int> dirty_host;   // block cells of the updates since the last hand-out (marked on the device when the call runs)
   int cap = 0;
   float leaf = 0.4f;
   bool enabled = false;
@@ -35,5 +41,10 @@ int mapping_device_init(MappingDevice& md, int cap, double map_resolution, Voxel
 int mapping_update_device(MappingDevice& md, const void* d_in, int stride, const int* d_n, int n_max, const double pose16[16], cudaStream_t s);
 // getMap :188-200 : cells in (x, y, z) order, each cell in voxel order. Sorts into the alt buffers; *d_out_n = size.
 int mapping_get_map_device(MappingDevice& md, P4** d_out, int** d_out_n, cudaStream_t s);
+// Incremental getMap(): the points of every cell changed since the previous call (all of such a cell's points, map order kept, so the
+// caller can replace its copy of the cell), with their packed cell ids. *d_out / *d_out_cell / *d_out_n point into the ping-pong
+// buffers and stay valid until the next update. The change marks stay set until mapping_clear_dirty_device.
+int mapping_get_dirty_device(MappingDevice& md, P4** d_out, unsigned int** d_out_cell, int** d_out_n, cudaStream_t s);
+int mapping_clear_dirty_device(MappingDevice& md, cudaStream_t s);
 
 }  // namespace floam

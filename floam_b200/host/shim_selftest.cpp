@@ -61,7 +61,7 @@ int main() {
   odomEstimation.init(lidar_param, 0.4, "Cauchy");
   if (!shared.ctx) { std::printf("shim_selftest: no CUDA device, compile/link check only\n"); return 77; }
   laserMapping.init(0.4);
-  bool is_odom_inited = false;
+  bool is_odom_inited = false, incremental_ok = true;
   for (int f = 0; f < 5; ++f) {
     pcl::PointCloud<vel_point::PointXYZIRT>::Ptr pointcloud_in = make_scan(0.05 * f);
     pcl::PointCloud<vel_point::PointXYZIRT>::Ptr pointcloud_edge(new pcl::PointCloud<vel_point::PointXYZIRT>());
@@ -74,6 +74,11 @@ int main() {
       odomEstimation.UpdatePointsToMapSelector(pointcloud_edge, pointcloud_surf, false);
     }
     laserMapping.updateCurrentPointsToMap(VelToIntensityCopy(pointcloud_surf), odomEstimation.odom);
+    if (f != 2) {   // the node's per-frame getMap(): only changed cells cross PCIe; one frame skipped so that a hand-out spans two updates
+      pcl::PointCloud<pcl::PointXYZI>::Ptr inc = laserMapping.getMap(), full = laserMapping.getMapFull();
+      incremental_ok = incremental_ok && inc->points.size() == full->points.size() && !full->points.empty() &&
+                       std::memcmp(inc->points.data(), full->points.data(), full->points.size() * sizeof(pcl::PointXYZI)) == 0;
+    }
     std::printf("frame %d edge %zu surf %zu  t = %.4f %.4f %.4f  |v| = %.3f\n", f, pointcloud_edge->size(), pointcloud_surf->size(),
                 odomEstimation.odom.translation().x(), odomEstimation.odom.translation().y(), odomEstimation.odom.translation().z(),
                 odomEstimation.GetVelocity().norm());
@@ -83,7 +88,8 @@ int main() {
   pcl::PointCloud<pcl::PointXYZI>::Ptr global = laserMapping.getMap();
   std::printf("local map %zu points, global map %zu points\n", local->size(), global->size());
   const double x = odomEstimation.odom.translation().x();
-  if (!(std::fabs(x - 0.2) < 0.05) || local->size() == 0 || global->size() == 0) { std::printf("shim_selftest: FAILED\n"); return 1; }
+  std::printf("incremental getMap identical to the full download on every frame: %s\n", incremental_ok ? "yes" : "NO");
+  if (!(std::fabs(x - 0.2) < 0.05) || local->size() == 0 || global->size() == 0 || !incremental_ok) { std::printf("shim_selftest: FAILED\n"); return 1; }
   // the same five scans as PointCloud2 messages through the fused node adapter (own context): same kernels, same pose
   floam_b200_host::FloamContext fused;
   fused.prm = shared.prm;

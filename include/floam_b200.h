@@ -189,6 +189,12 @@ int floam_replay_staged(floam_ctx* ctx, int first, int count, int deskew, double
 /* LaserMappingClass::updateCurrentPointsToMap / getMap (src/laserMappingClass.cpp:148-200) */
 int floam_mapping_update(floam_ctx* ctx, const floam_point_xyzi* pts, int n, const double pose_rowmajor[16]);
 int floam_mapping_get_map(floam_ctx* ctx, floam_point_xyzi* out, int cap, int* n);
+/* Incremental getMap() (the node republishes the whole map every frame, src/laserMappingNode.cpp:85-92): the points of
+ * every 50 m cell that changed since the previous call — ALL points of such a cell, in the order getMap() lists them inside the cell —
+ * each with its cell coordinates (cells_xyz: 3 ints per point). A caller that keeps one cloud per cell replaces the changed cells and
+ * concatenates cells in (x, y, z) order to obtain exactly getMap()'s cloud (floam_b200/host/laserMappingClass.h does). out == NULL: only
+ * *n is returned and the change marks are kept. */
+int floam_mapping_get_changed_cells(floam_ctx* ctx, floam_point_xyzi* out, int32_t* cells_xyz, int cap, int* n);
 
 /* On-disk outputs the odometry node writes when it exits (src/odomEstimationNode.cpp:66-121,373-387; src/utils.cpp:3-106).  Scans come as
  * one concatenated array of pcl::PointXYZI with offsets[n + 1], poses as row-major 4x4 matrices (Eigen::Affine3d::matrix()), stamps in

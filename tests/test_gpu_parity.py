@@ -540,6 +540,37 @@ def test_mapping_parity(capi, po, synth, sequences):
     ctx.close()
 
 
+def test_mapping_incremental_get_map(capi, pr, synth, sequences):
+    # getMap() without re-downloading the whole map.  floam_mapping_get_changed_cells hands out the cells changed since
+    # the last call; a per-cell host copy, concatenated in (x, y, z) cell order, must equal both the full getMap() of the device and
+    # LaserMappingClass::getMap() of the reference build, frame by frame, while the 5x5x5 block crosses cell boundaries in both
+    # directions (so cells fall out of the block, stay untouched for a while, and are re-entered) and with several updates between calls.
+    seq, scans, off = sequences("vlp16", 12)
+    ctx = fresh(capi, 16, map_resolution=0.4); ref = pr.Mapping(map_resolution=0.4, total_order=True)   # contract voxel order
+    cells = {}
+    downloaded = []
+    route = [0.0, 4.0, 8.0, 8.2, 12.0, 12.0, 6.0, 2.0, 0.5, 9.0, 16.0, 16.1]       # seconds along the trajectory: forwards, back, forwards again
+    for f in range(12):
+        e, sf, _, _, _ = pr.feature_extract(scans[off[f]:off[f + 1]], 16, 2.0, 60.0)
+        pts = synth.to_xyzi(np.concatenate([e, sf]))
+        T = seq.pose(route[f])
+        ctx.mapping_update(pts, T); ref.update(pts, T)
+        if f in (3, 7):          # no getMap() after this frame: the next hand-out must cover two updates
+            continue
+        p, c = ctx.mapping_get_changed_cells()
+        downloaded.append(len(p))
+        for key in {tuple(k) for k in c.tolist()}:
+            cells[key] = p[(c == np.array(key, np.int32)).all(axis=1)]
+        assembled = np.concatenate([cells[k] for k in sorted(cells)]) if cells else np.zeros(0, capi.POINT_I)
+        full = ctx.mapping_get_map(); want = ref.get_map()
+        assert len(assembled) == len(full) == len(want), f
+        assert np.array_equal(xyzi(assembled), xyzi(full)) and np.array_equal(xyzi(full), xyzi(want)), f
+    p, c = ctx.mapping_get_changed_cells()
+    assert len(p) == 0                                         # nothing changed since the last hand-out
+    assert downloaded[-1] < len(ctx.mapping_get_map())          # once the trajectory has left cells behind, a hand-out is smaller than the map
+    ctx.close()
+
+
 def test_long_sequence_trajectory_error(capi, po, synth, sequences):
     # whole-sequence bar (BASELINE.json): trajectory within 1 cm ATE of the reference classes. Against the oracle run with the same
     # total-order contract the CUDA trajectory is identical to rounding; against the reference-faithful oracle (std::sort voxel order,
