@@ -1,5 +1,5 @@
-"""Regenerates profiles/r1_sass.txt.gz (full cuobjdump -sass of libfloam_b200.so) and profiles/r1_sass_summary.md (per-kernel
-instruction mix). Run after floam_b200/build.py; no GPU needed."""
+"""Regenerates profiles/r2_sass_summary.md (per-kernel instruction mix) from `cuobjdump -sass` of libfloam_b200.so; the full listing
+goes to gpurun_out/sass.txt.gz (scratch, not tracked). Run after floam_b200/build.py; no GPU needed."""
 import collections
 import gzip
 import os
@@ -11,7 +11,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "floam_b200", "lib", "libfloam_b200.so")
 sass = subprocess.check_output(["cuobjdump", "-sass", LIB], text=True)
 os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
-with gzip.open(os.path.join(ROOT, "profiles", "r1_sass.txt.gz"), "wt") as f:
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+with gzip.open(os.path.join(ROOT, "gpurun_out", "sass.txt.gz"), "wt") as f:
     f.write(sass)
 
 GROUPS = [("LDG", r"\bLDG"), ("STG", r"\bSTG"), ("ATOM/RED", r"\b(ATOMG|ATOMS|ATOM|RED)\b"), ("LDS/STS", r"\b(LDS|STS)"), ("LDL/STL", r"\b(LDL|STL)"),
@@ -39,11 +40,11 @@ for line in sass.splitlines():
                 counts[g] += 1
 if cur:
     rows.append((cur, n, counts))
-with open(os.path.join(ROOT, "profiles", "r1_sass_summary.md"), "w") as f:
+with open(os.path.join(ROOT, "profiles", "r2_sass_summary.md"), "w") as f:
     f.write("# SASS instruction mix per kernel (sm_100a), from `cuobjdump -sass floam_b200/lib/libfloam_b200.so`\n\n")
-    f.write("Full listing: `r1_sass.txt.gz` (regenerate both with `python tools/sass_summary.py`). Static instruction counts.\n")
-    f.write("No tensor-core instructions appear anywhere (nothing on this path is a dense contraction); the one TMA instruction is the bulk copy\nof the count table in `radix_scatter_kernel` (`UBLKCP`). The kNN gathers are\n")
-    f.write("short runs read through `LDG` (see DESIGN.md section 4). Float arithmetic of the bit-exact stages is `FADD`/`FMUL` (never `FFMA`).\n\n")
+    f.write("Regenerate with `python tools/sass_summary.py` (the full listing lands in gpurun_out/sass.txt.gz, untracked). Static instruction counts.\n")
+    f.write("No tensor-core instructions appear anywhere (nothing on this path is a dense contraction). TMA bulk copies (`UBLKCP`): the count table\nof `radix_scatter_kernel` and the per-warp candidate slabs of the staged kNN (`assoc_knn_kernel<true>`; DESIGN.md section 4).\n")
+    f.write("Float arithmetic of the bit-exact stages is `FADD`/`FMUL` (never `FFMA`).\n\n")
     f.write("| kernel | instructions | " + " | ".join(g for g, _ in GROUPS) + " |\n|---|---|" + "---|" * len(GROUPS) + "\n")
     for name, n, c in sorted(rows, key=lambda r: -r[1]):
         f.write("| %s | %d | " % (name, n) + " | ".join(str(c.get(g, 0)) for g, _ in GROUPS) + " |\n")
