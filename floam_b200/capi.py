@@ -31,7 +31,7 @@ class Params(C.Structure):
 # every symbol include/floam_b200.h declares (tests/test_abi.py checks the header against this list and the .so against both)
 SYMBOLS = [
     "floam_params_default", "floam_loss_from_string", "floam_status_string", "floam_version", "floam_create", "floam_destroy",
-    "floam_alloc_pinned", "floam_free_pinned", "floam_set_graphs", "floam_imu_push", "floam_imu_get", "floam_imu_size", "floam_imu_time_contained", "floam_deskew_align",
+    "floam_alloc_pinned", "floam_free_pinned", "floam_set_graphs", "floam_set_map_merge", "floam_voxel_grid_update", "floam_imu_push", "floam_imu_get", "floam_imu_size", "floam_imu_time_contained", "floam_deskew_align",
     "floam_feature_extract", "floam_odom_init_map", "floam_odom_update", "floam_odom_update_xyzi", "floam_odom_get", "floam_odom_map_sizes",
     "floam_odom_get_map", "floam_odom_set_state", "floam_odom_get_state", "floam_odom_set_map", "floam_process_scan", "floam_process_submit",
     "floam_process_wait", "floam_stage_scans", "floam_process_staged", "floam_mapping_update", "floam_mapping_get_map", "floam_mapping_get_changed_cells", "floam_voxel_grid",
@@ -197,6 +197,10 @@ class Context:
 
     def set_graphs(self, enabled):
         _check(lib().floam_set_graphs(self.h, int(enabled)), "floam_set_graphs")
+
+    def set_map_merge(self, mode):
+        """Keyframe map update: 0 = full re-sort, 1 = by map size (default), 2 = sort only the out-of-place points and merge. Same maps."""
+        _check(lib().floam_set_map_merge(self.h, int(mode)), "floam_set_map_merge")
 
     # ---- IMU ----
     def imu_push(self, stamp, q_xyzw):
@@ -392,6 +396,17 @@ class Context:
         pts = np.ascontiguousarray(pts, POINT_I)
         out = np.zeros(max(len(pts), 1), POINT_I); n = C.c_int()
         _check(lib().floam_voxel_grid(self.h, _p(pts), len(pts), C.c_float(leaf), _p(out), len(out), C.byref(n)), "floam_voxel_grid")
+        return out[:n.value]
+
+    def voxel_grid_update(self, map_pts, new_pts, leaf, mn=None, mx=None):
+        """VoxelGrid(CropBox(map_pts + new_pts)) through the keyframe update's merge path (floam_voxel_grid_update)."""
+        map_pts = np.ascontiguousarray(map_pts, POINT_I); new_pts = np.ascontiguousarray(new_pts, POINT_I)
+        out = np.zeros(max(len(map_pts) + len(new_pts), 1), POINT_I); n = C.c_int()
+        if mn is not None:
+            mn = np.ascontiguousarray(mn, np.float32); mx = np.ascontiguousarray(mx, np.float32)
+        _check(lib().floam_voxel_grid_update(self.h, _p(map_pts), len(map_pts), _p(new_pts), len(new_pts), C.c_float(leaf),
+                                             _p(mn) if mn is not None else None, _p(mx) if mx is not None else None, _p(out), len(out), C.byref(n)),
+               "floam_voxel_grid_update")
         return out[:n.value]
 
     def crop_box(self, pts, mn, mx):

@@ -102,6 +102,13 @@ void pose_out_from_state(const PoseState* S, double pose[7]) {
 
 int next_outer(int count) { return count > 2 ? count - 1 : count; }
 
+// Size hints for the keyframe map filters (they only pick a kernel variant, odom_map_update_merges): the local map sizes the last
+// mailed update started from.
+void note_map_sizes(floam_ctx* c, const PoseState* S) {
+  c->odom.edge_map_hint = S->map_points[0];
+  c->odom.surf_map_hint = S->map_points[1];
+}
+
 // OdomEstimationClass::UpdatePointsToMapSelector (src/odomEstimationClass.cpp:34-50) on device-resident feature clouds
 void enqueue_selector(floam_ctx* c, PointIRT* d_edge, const int* d_ne, PointIRT* d_surf, const int* d_ns, int n_max, int deskew, bool ds_ready = false) {
   OdomDevice& od = c->odom;
@@ -187,6 +194,7 @@ int launch_frame(floam_ctx* c, int deskew, int ring, bool imu) {
   const bool timing = c->timer.enabled;
   select_parity(c, slot);
   const int outer = first ? 0 : next_outer(od.optimization_count);
+  const int variant = first ? 0 : (odom_map_update_merges(od, 0) ? 16 : 0) + (odom_map_update_merges(od, 1) ? 32 : 0);   // which map filters the BACK is captured with
   const int flags = (first ? 0 : 1) + (imu ? 2 : 0) + (timing ? 4 : 0);
   // FRONT(k) may not overwrite the parity's buffers before BACK(k-2) has finished with them
   if (c->back_valid[slot]) FLOAM_CUDA_OK(cudaStreamWaitEvent(c->front_stream, c->ev_back_done[slot], 0));
@@ -196,7 +204,7 @@ int launch_frame(floam_ctx* c, int deskew, int ring, bool imu) {
   FLOAM_CUDA_OK(cudaEventRecord(c->ev_front_done[slot], c->front_stream));
   FLOAM_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_front_done[slot], 0));
   const int saved_count = od.optimization_count;
-  rc = launch_half(c, floam_graph_key{flags, outer, first ? 0 : (deskew ? 1 : 0), ring}, c->stream, [&]() { enqueue_back(c, deskew, ring, first); });
+  rc = launch_half(c, floam_graph_key{flags + variant, outer, first ? 0 : (deskew ? 1 : 0), ring}, c->stream, [&]() { enqueue_back(c, deskew, ring, first); });
   if (rc) return rc;
   FLOAM_CUDA_OK(cudaEventRecord(c->ev_back_done[slot], c->stream));
   c->back_valid[slot] = true;
@@ -532,6 +540,7 @@ static int finish_update(floam_ctx* c, double pose_out[7]) {
   FLOAM_CUDA_OK(cudaStreamSynchronize(c->stream));
   if ((rc = check_async("odom_update"))) return rc;
   cudaEventElapsedTime(&c->last_frame_ms, c->ev_begin[0], c->ev_end[0]);
+  note_map_sizes(c, c->h_state[0]);
   if (pose_out) pose_out_from_state(c->h_state[0], pose_out);
   return status_from_flags(c, 0);
 }
@@ -575,6 +584,7 @@ static int sync_state(floam_ctx* c) {
   int rc = fetch_state(c, 0);
   if (rc) return rc;
   FLOAM_CUDA_OK(cudaStreamSynchronize(c->stream));
+  note_map_sizes(c, c->h_state[0]);
   return FLOAM_OK;
 }
 
@@ -797,6 +807,7 @@ int floam_process_wait(floam_ctx* c, double pose_out[7]) {
   cudaEventElapsedTime(&c->last_frame_ms, c->ev_begin[slot], c->ev_end[slot]);
   c->wait_slot = (slot + 1) & 3;
   c->inflight--;
+  note_map_sizes(c, c->h_state[slot]);
   if (pose_out) pose_out_from_state(c->h_state[slot], pose_out);
   return status_from_flags(c, slot);
 }
@@ -838,6 +849,7 @@ int floam_process_staged(floam_ctx* c, int frame, int deskew, double pose_out[7]
   FLOAM_CUDA_OK(cudaStreamSynchronize(c->stream));
   if ((rc = check_async("process_staged"))) return rc;
   cudaEventElapsedTime(&c->last_frame_ms, c->ev_begin[slot], c->ev_end[slot]);
+  note_map_sizes(c, c->h_state[slot]);
   if (pose_out) pose_out_from_state(c->h_state[slot], pose_out);
   return status_from_flags(c, slot);
 }
@@ -855,6 +867,34 @@ int floam_voxel_grid(floam_ctx* c, const floam_point_xyzi* pts, int n, float lea
   FLOAM_CUDA_OK(cudaMemcpyAsync(c->h_ints + 20, c->d_stage_n + 1, 4, cudaMemcpyDeviceToHost, c->stream));
   FLOAM_CUDA_OK(cudaStreamSynchronize(c->stream));
   if ((rc = check_async("voxel_grid"))) return rc;
+  *n_out = c->h_ints[20];
+  if (*n_out > cap) return FLOAM_ERR_CAPACITY;
+  return out ? download_p4(c, c->d_stage_out, *n_out, out) : FLOAM_OK;
+}
+
+int floam_voxel_grid_update(floam_ctx* c, const floam_point_xyzi* map_pts, int n_map, const floam_point_xyzi* new_pts, int n_new, float leaf,
+                            const float min_xyz[3], const float max_xyz[3], floam_point_xyzi* out, int cap, int* n_out) {
+  if (!c || (!map_pts && n_map > 0) || (!new_pts && n_new > 0) || !n_out || n_map < 0 || n_new < 0 || !(leaf > 0.f) || (min_xyz == nullptr) != (max_xyz == nullptr))
+    return FLOAM_ERR_ARG;
+  if ((long long)n_map + n_new > c->stage_cap) return FLOAM_ERR_CAPACITY;
+  if (c->inflight != 0) return FLOAM_ERR_ARG;
+  if (set_device(c)) return FLOAM_ERR_CUDA;
+  int rc = upload_cloud(c, map_pts, n_map, c->d_stage_in, c->d_stage_n, 0);
+  if (rc) return rc;
+  if (n_new > 0) FLOAM_CUDA_OK(cudaMemcpyAsync((char*)c->d_stage_in + (size_t)n_map * 32, new_pts, (size_t)n_new * 32, cudaMemcpyHostToDevice, c->stream));
+  c->h_ints[1] = n_new;
+  FLOAM_CUDA_OK(cudaMemcpyAsync(c->d_stage_n + 2, &c->h_ints[1], 4, cudaMemcpyHostToDevice, c->stream));
+  if (min_xyz) {
+    float* hb = (float*)(c->h_doubles);
+    for (int a = 0; a < 3; ++a) { hb[a] = min_xyz[a]; hb[3 + a] = max_xyz[a]; }
+    FLOAM_CUDA_OK(cudaMemcpyAsync(c->d_stage_bounds, hb, 24, cudaMemcpyHostToDevice, c->stream));
+  }
+  FLOAM_CUDA_OK(cudaMemsetAsync(c->d_stage_n + 1, 0, 4, c->stream));
+  voxel_grid_merge_device(c->d_stage_in, 32, c->d_stage_n, std::max(n_map + n_new, 1), leaf, c->d_stage_out, c->d_stage_n + 1, c->vws, nullptr, c->stream,
+                          min_xyz ? c->d_stage_bounds : nullptr, c->d_stage_n + 2, c->stage_cap);
+  FLOAM_CUDA_OK(cudaMemcpyAsync(c->h_ints + 20, c->d_stage_n + 1, 4, cudaMemcpyDeviceToHost, c->stream));
+  FLOAM_CUDA_OK(cudaStreamSynchronize(c->stream));
+  if ((rc = check_async("voxel_grid_update"))) return rc;
   *n_out = c->h_ints[20];
   if (*n_out > cap) return FLOAM_ERR_CAPACITY;
   return out ? download_p4(c, c->d_stage_out, *n_out, out) : FLOAM_OK;
@@ -1110,6 +1150,12 @@ int floam_replay_staged(floam_ctx* c, int first, int count, int deskew, double* 
   const auto t_host0 = std::chrono::steady_clock::now();
   for (int f = first; f < first + count; ++f) {
     last_slot = c->submit_slot;
+    if (f - first >= 4) {
+      // this mailbox last carried frame f - 4: once it has arrived the host is at most four frames ahead of the device (three stay
+      // queued, the device never waits) and knows the map sizes of a recent frame when it picks the next frame's graph
+      FLOAM_CUDA_OK(cudaEventSynchronize(c->ev_end[last_slot]));
+      note_map_sizes(c, c->h_state[last_slot]);
+    }
     if ((rc = enqueue_staged_frame(c, f, deskew))) return rc;
   }
   FLOAM_CUDA_OK(cudaEventRecord(c->ev_replay_end, c->stream));
@@ -1167,6 +1213,17 @@ int floam_kernel_timing(floam_ctx* c, int slot, double* total_ms, int64_t* launc
 int floam_set_graphs(floam_ctx* c, int enabled) {
   if (!c) return FLOAM_ERR_ARG;
   c->use_graphs = enabled != 0;
+  return FLOAM_OK;
+}
+
+int floam_set_map_merge(floam_ctx* c, int mode) {
+  if (!c || c->inflight != 0 || mode < 0 || mode > 2) return FLOAM_ERR_ARG;
+  if (set_device(c)) return FLOAM_ERR_CUDA;
+  FLOAM_CUDA_OK(cudaDeviceSynchronize());
+  c->odom.map_merge_mode = mode;
+  for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second.exec);   // the captured launch sequences bake the choice in
+  c->graphs.clear();
+  c->timer.persist = 0; c->timer.used = 0;
   return FLOAM_OK;
 }
 

@@ -68,6 +68,8 @@ enum KernelSlot {
   K_RECORD_POSE,
   K_MAIL_STATE,
   K_UNPACK_PC2,
+  K_VOXEL_CLASSIFY,
+  K_VOXEL_MERGE,
   K_NOOP,
   K_NUM_SLOTS
 };

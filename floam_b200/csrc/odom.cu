@@ -76,6 +76,7 @@ __device__ __forceinline__ long long global_ns() {
 __global__ void predict_kernel(PoseState* S, const int* n_edge_map, const int* n_surf_map, int keep_pose) {
   pdl_prologue();
   if (threadIdx.x != 0) return;
+  S->map_points[0] = *n_edge_map; S->map_points[1] = *n_surf_map;
   {
     const long long now = global_ns();
     if (S->tl_predict != 0 && S->tl_end[0] != 0) {
@@ -1317,6 +1318,9 @@ int odom_device_init(OdomDevice& od, const floam_params& prm, VoxelWorkspace* vw
   }
   od.knn_staged = true;   // TMA-staged cell tiles for sparse neighbourhoods (A/B: profiles/r2_knn_tma_ab.md); FLOAM_KNN_TMA=0 -> direct loads
   if (const char* e = std::getenv("FLOAM_KNN_TMA")) od.knn_staged = std::atoi(e) != 0;
+  od.map_merge_mode = 1;
+  if (const char* e = std::getenv("FLOAM_MAP_MERGE")) od.map_merge_mode = std::max(0, std::min(2, std::atoi(e)));
+  if (const char* e = std::getenv("FLOAM_MAP_MERGE_MIN")) od.map_merge_min_points = std::atoi(e);
   FLOAM_CUDA_OK(cudaEventCreateWithFlags(&od.ev_fork, cudaEventDisableTiming));
   FLOAM_CUDA_OK(cudaEventCreateWithFlags(&od.ev_join, cudaEventDisableTiming));
   od.leaf_edge = (float)prm.map_resolution;        // setLeafSize(float...) :13-14
@@ -1400,6 +1404,11 @@ void odom_init_map_device(OdomDevice& od, const void* d_edge, const int* d_ne, c
   local_map_load(od, od.surf_map, d_surf, d_ns, stride, n_max, replace, s);
 }
 
+bool odom_map_update_merges(const OdomDevice& od, int k) {
+  const int hint = k == 0 ? od.surf_map_hint : od.edge_map_hint;
+  return od.map_merge_mode == 2 || (od.map_merge_mode == 1 && hint >= od.map_merge_min_points);
+}
+
 void odom_update_device(OdomDevice& od, const void* d_edge, const int* d_ne, const void* d_surf, const int* d_ns, int stride, int n_max, int update_type,
                         int ds_ready, cudaStream_t s) {
   // the caller has already applied `if (optimization_count > 2) optimization_count--` (:59-60, Q4)
@@ -1440,7 +1449,10 @@ void odom_update_device(OdomDevice& od, const void* d_edge, const int* d_ne, con
     // (:270-287) is folded into the VoxelGrid (:289-292), and its last kernel leaves the bounding box of the new map for the search
     // grid. The filter gathers from mp.pts through the sorted index into mp.tmp; the grid's scatter kernel copies the cloud home.
     const VoxelAppend app{dss[k], S->x, &S->error_flags};
-    voxel_grid_device(mp.pts, 16, mp.d_n, mp.cap, leaf[k], mp.tmp, mp.d_n, ws, skip, st, S->crop_bounds, nds[k], mp.cap, &app, mp.bbox);
+    // The map is the previous filter's output, i.e. already in voxel order but for a few re-voxelised centroids: by default only the
+    // new points and the out-of-place ones are sorted and merged in (voxel_grid_merge_device); identical result either way.
+    if (odom_map_update_merges(od, k)) voxel_grid_merge_device(mp.pts, 16, mp.d_n, mp.cap, leaf[k], mp.tmp, mp.d_n, ws, skip, st, S->crop_bounds, nds[k], mp.cap, &app, mp.bbox);
+    else voxel_grid_device(mp.pts, 16, mp.d_n, mp.cap, leaf[k], mp.tmp, mp.d_n, ws, skip, st, S->crop_bounds, nds[k], mp.cap, &app, mp.bbox);
     rebuild_grid(od, mp, skip, st, &ws, true, &S->tl_end[k]);
   }
   cudaEventRecord(od.ev_join, a);

@@ -32,6 +32,7 @@ struct PoseState {
   int n_corr;            // accepted correspondences of the last association
   int n_corr_acc;        // accumulator of the running association
   int frame_counter;     // frames completed (index of the next trajectory record)
+  int map_points[2];     // edge / surf local map sizes at the start of the last update (the host's size hints come from here)
   // development aid (FLOAM_DBG_TIMELINE): globaltimer stamps of the BACK half — predict start, finish start, start of the two grid
   // scatters (its last kernels) — and their running sums: [0] BACK duration, [1] gap between consecutive BACKs, [2] solve part, [3] frames
   long long tl_predict, tl_finish, tl_end[2], tl_sum[4];
@@ -61,6 +62,10 @@ struct LocalMap {
 
 constexpr int kLmTerms = 29;  // 21 H (upper triangle) + 6 g + cost + number of correspondences
 
+struct OdomDevice;
+// which filter the next keyframe update of the surf (k = 0) / edge (k = 1) map will be enqueued with: part of the frame graph's key
+bool odom_map_update_merges(const OdomDevice& od, int k);
+
 struct OdomDevice {
   PoseState* state;
   LocalMap edge_map, surf_map;
@@ -81,6 +86,12 @@ struct OdomDevice {
   cudaStream_t aux_stream;     // fork/join partner of the context stream
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int lm_cluster_ctas = 8;     // CTAs of the solve's thread-block cluster (8, or 16 for dense configurations)
+  // Keyframe map update: full re-sort of map + new points, or classify + sort of the out-of-place points + merge (voxel.cu). Same
+  // maps; the merge wins from ~250k map points on (tools/probes/map_merge_sweep.py), the re-sort below. 0 = re-sort, 1 = by the
+  // host's size hint (default), 2 = merge always. FLOAM_MAP_MERGE / floam_set_map_merge.
+  int map_merge_mode = 1;
+  int map_merge_min_points = 250000;            // FLOAM_MAP_MERGE_MIN
+  int edge_map_hint = -1, surf_map_hint = -1;   // host-side guesses of the map sizes the next keyframe update will filter (-1: unknown)
   bool knn_staged = true;      // association kNN brings sparse neighbourhoods into shared memory by bulk copies (cp.async.bulk + mbarrier)
   float leaf_edge, leaf_surf;
   double scan_period;

@@ -60,6 +60,8 @@ static const char* const kSlotNames[K_NUM_SLOTS] = {
   "record_pose",
   "mail_state",
   "unpack_pc2",
+  "voxel_classify",
+  "voxel_merge",
   "noop"
 };
 const char* kernel_slot_name(int slot) { return (slot >= 0 && slot < K_NUM_SLOTS) ? kSlotNames[slot] : "?"; }

@@ -11,7 +11,10 @@ struct VoxelWorkspace {
   unsigned int* bbox;   // 6 order-preserving-encoded floats: min xyz, max xyz
   int* d_nbits;         // key width of the current grid
   int* d_passthrough;   // Q13: leaf too small for the extent -> output = input
-  int* d_counts;        // [0] points of the running filter's input, [1] points its crop box kept
+  int* d_counts;        // [0] points of the running filter's input, [1] points its crop box kept, [2] MAIN / [3] SIDE points (merge path)
+  unsigned int* main_keys;   // [n_max] merge path: keys / indices of the points that are already in order
+  int* main_vals;
+  unsigned long long* merge_state;   // look-back states of voxel_classify_kernel, two words per 4096-point tile
   SortWorkspace sort;
   ScanWorkspace scan;
   int n_max;
@@ -39,6 +42,12 @@ struct VoxelAppend {
 void voxel_grid_device(const void* d_in, int stride_bytes, const int* d_n, int n_max, float leaf, P4* d_out, int* d_nout, VoxelWorkspace& ws,
                        const int* d_skip, cudaStream_t s, const float* d_crop = nullptr, const int* d_extra = nullptr, int cap = 0,
                        const VoxelAppend* append = nullptr, unsigned int* out_bbox = nullptr);
+
+// The same filter for an input that is mostly in voxel order already (a local map + the new frame's points, addPointsToMap): only
+// the out-of-place points are sorted and then merged into the rest (voxel.cu). Identical output for ANY input.
+void voxel_grid_merge_device(const void* d_in, int stride_bytes, const int* d_n, int n_max, float leaf, P4* d_out, int* d_nout, VoxelWorkspace& ws,
+                             const int* d_skip, cudaStream_t s, const float* d_crop = nullptr, const int* d_extra = nullptr, int cap = 0,
+                             const VoxelAppend* append = nullptr, unsigned int* out_bbox = nullptr);
 
 // pcl::CropBox<PointXYZI>::filter, identity transform, negative=false, inclusive float bounds read from device memory
 // (d_bounds: min xyz, max xyz). Order-preserving compaction.

@@ -103,6 +103,11 @@ void* floam_alloc_pinned(size_t bytes);
 void floam_free_pinned(void* p);
 /* per-frame launch sequences are replayed as CUDA graphs by default; 0 launches the kernels one by one (debugging / profiling) */
 int floam_set_graphs(floam_ctx* ctx, int enabled);
+/* addPointsToMap's CropBox + VoxelGrid (src/odomEstimationClass.cpp:270-292) either re-sorts map + new points, or sorts only the new
+ * and the out-of-place points and merges them into the map, which is in voxel order already (faster from ~250k map points on).
+ * Identical maps either way. mode 0 = always re-sort, 1 = by map size (default), 2 = always merge; for A/B measurements and tests.
+ * No frame may be in flight. Process default: environment FLOAM_MAP_MERGE (and FLOAM_MAP_MERGE_MIN = the size threshold). */
+int floam_set_map_merge(floam_ctx* ctx, int mode);
 
 /* Quaternions cross this ABI in Eigen coefficient order (x, y, z, w), like parameters[0..3] of the reference. */
 /* dmapping::ImuHandler::AddMsg (src/dataHandler.cpp:24-40): drops samples <= 10 us after the previous one. */
@@ -215,6 +220,11 @@ int floam_save_merged(floam_ctx* ctx, const char* directory, const double* poses
  * (stage entry points; also what floam_b200/host/mini_pcl.h's filters call) */
 int floam_voxel_grid(floam_ctx* ctx, const floam_point_xyzi* pts, int n, float leaf, floam_point_xyzi* out, int cap, int* n_out);
 int floam_crop_box(floam_ctx* ctx, const floam_point_xyzi* pts, int n, const float min_xyz[3], const float max_xyz[3], floam_point_xyzi* out, int cap, int* n_out);
+/* The filter step of addPointsToMap (:270-292) on its own: VoxelGrid(CropBox(map_pts followed by new_pts)), through the merge path
+ * the keyframe update uses (map_pts is expected to be mostly in voxel order; any input gives the exact filter result).
+ * min_xyz / max_xyz both NULL: no crop box. */
+int floam_voxel_grid_update(floam_ctx* ctx, const floam_point_xyzi* map_pts, int n_map, const floam_point_xyzi* new_pts, int n_new, float leaf,
+                            const float min_xyz[3], const float max_xyz[3], floam_point_xyzi* out, int cap, int* n_out);
 /* pcl::KdTreeFLANN::setInputCloud + nearestKSearch(k=5) (src/odomEstimationClass.cpp:78-79,153,206): exact ids for every
  * query whose 5th neighbour is closer than 1 m (the only ones the reference uses); others report ids = -1. */
 int floam_knn5(floam_ctx* ctx, const floam_point_xyzi* map, int m, const floam_point_xyzi* queries, int nq, int* ids, float* sqdist);

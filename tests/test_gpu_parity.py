@@ -178,6 +178,75 @@ def test_voxel_grid_idempotent_full_size(capi, sequences, ctxs, synth):
     assert np.array_equal(order, np.arange(len(a)))             # output sorted by (kz, ky, kx)
 
 
+def voxel_order(pts, leaf):
+    inv = np.float32(1.0) / np.float32(leaf)
+    k = [np.floor(pts[a].astype(np.float32) * inv).astype(np.int64) for a in ("x", "y", "z")]
+    return np.lexsort((k[0], k[1], k[2]))          # stable: ascending (kz, ky, kx), input order inside a voxel
+
+
+def test_voxel_grid_update_merge_path(capi, po, ctxs):
+    # The keyframe update's filter (src/odomEstimationClass.cpp:270-292) sorts only what is out of place and merges it into the map
+    # (voxel_classify / voxel_merge, csrc/voxel.cu). Whatever the classification decides, the result must be the filter of the
+    # concatenated cloud: maps in voxel order, maps with many points per voxel, out-of-place points moved up and down (a run that
+    # descends, a high outlier in front of its voxel mates), unsorted maps, empty sides, the crop box, Q13 pass-through, > 1 tile maps.
+    ctx = ctxs(16)
+    rng = np.random.default_rng(4242)
+
+    def check(old, new, leaf, crop=None, tag=""):
+        both = np.concatenate([old, new])
+        want = both
+        mn = mx = None
+        if crop is not None:
+            mn, mx = crop
+            want = po.crop_box(both, mn, mx)
+        want, _ = po.voxel_grid(want, leaf, total_order=True)
+        got = ctx.voxel_grid_update(old, new, leaf, mn, mx)
+        assert len(got) == len(want) and np.array_equal(xyzi(got), xyzi(want)), tag
+
+    empty = np.zeros(0, capi.POINT_I)
+    check(empty, empty, 0.4, tag="empty")
+    check(empty, cloud(capi, rng, 3000), 0.4, tag="no map")
+    check(cloud(capi, rng, 1), empty, 0.4, tag="one point")
+    for trial, (m, q, leaf, ext) in enumerate([(20000, 5000, 0.4, 40.0), (60000, 6000, 0.8, 60.0), (4096, 4096, 0.4, 10.0), (150000, 47000, 0.2, 40.0),
+                                               (9000, 300, 3.0, 5.0), (700000, 50000, 0.4, 100.0)]):
+        raw = cloud(capi, rng, m, lo=(-ext, -ext, -ext / 8), hi=(ext, ext, ext / 8))
+        new = cloud(capi, rng, q, lo=(-ext, -ext, -ext / 8), hi=(ext, ext, ext / 8))
+        filt = ctx.voxel_grid(raw, leaf)                       # a real map: one centroid per voxel, voxel order
+        check(filt, new, leaf, tag=("filtered map", trial))
+        check(filt, empty, leaf, tag=("nothing new", trial))
+        box = (np.array([-ext / 2, -ext / 3, -ext], np.float32), np.array([ext / 3, ext / 2, ext], np.float32))
+        check(filt, new, leaf, crop=box, tag=("crop box", trial))
+        dense = raw[voxel_order(raw, leaf)]                    # many points per voxel, in order: ties between the map and the new points
+        check(dense, new, leaf, tag=("dense sorted map", trial))
+        moved = dense.copy()                                   # out-of-place points: blocks moved towards the front and the back, single swaps
+        a, b, c = m // 5, m // 2, (4 * m) // 5
+        w = max(1, min(50, m // 10))
+        moved[a:a + w], moved[c:c + w] = dense[c:c + w].copy(), dense[a:a + w].copy()
+        for i in rng.integers(0, m - 1, 20):
+            moved[i], moved[i + 1] = moved[i + 1].copy(), moved[i].copy()
+        moved[b] = dense[m - 1]                                # one high outlier in the middle
+        check(moved, new, leaf, crop=box if trial % 2 else None, tag=("out-of-place points", trial))
+        check(raw, new, leaf, tag=("unsorted map", trial))
+    far = cloud(capi, rng, 3000, lo=(-500, -500, -500), hi=(500, 500, 500))
+    check(far[:2000], far[2000:], 0.1, tag="Q13 pass-through")
+
+
+def test_map_update_identical_with_and_without_merge(capi, synth, sequences):
+    # the same sequence with the keyframe update's merge path forced on and off (full re-sort of map + new points): same poses, same maps
+    seq, scans, off = sequences("hdl64", 14)
+    got = []
+    for merge in (True, False):
+        ctx = fresh(capi, 64, loss="cauchy"); ctx.set_map_merge(2 if merge else 0)
+        poses = np.array([ctx.process_scan(scans[off[f]:off[f + 1]], False) for f in range(14)])
+        ctx.set_kernel_timing(True); ctx.process_scan(scans[off[13]:off[14]], False); t = ctx.kernel_timing(); ctx.set_kernel_timing(False)
+        assert ("voxel_merge" in t) == merge
+        got.append((poses, ctx.odom_get_map()))
+        ctx.close()
+    assert np.array_equal(got[0][0], got[1][0])
+    for k in range(2):
+        assert np.array_equal(xyzi(got[0][1][k]), xyzi(got[1][1][k]))
+
+
 @pytest.mark.parametrize("n", [0, 1, 4097, 300000])
 def test_crop_box_bit_exact(capi, po, ctxs, n):
     pts = cloud(capi, np.random.default_rng(n + 3), n)
@@ -332,8 +401,10 @@ def test_empty_feature_clouds(capi, po, synth, sequences):
 
 
 # ------------------------------------------------------------------------------------------------ sequences -------------
-def run_both(capi, po, synth, scans, off, nl, loss, deskew, frames, total_order=True, use_kdtree=False, **kw):
+def run_both(capi, po, synth, scans, off, nl, loss, deskew, frames, total_order=True, use_kdtree=False, map_merge=None, **kw):
     ctx = fresh(capi, nl, loss=loss, **kw)
+    if map_merge is not None:
+        ctx.set_map_merge(map_merge)
     orc = po.Odom(num_lines=nl, loss=loss, total_order=total_order, use_kdtree=use_kdtree, map_resolution=kw.get("map_resolution", 0.4))
     P, O = [], []
     for f in range(frames):
@@ -356,6 +427,17 @@ def test_sequence_pose_parity(capi, po, synth, sequences, sensor, loss, deskew, 
     ge, gs = ctx.odom_get_map(); oe, os_ = orc.get_map()
     assert len(ge) == len(oe) and len(gs) == len(os_)
     assert np.allclose(xyzi(ge), xyzi(oe), atol=1e-5) and np.allclose(xyzi(gs), xyzi(os_), atol=1e-5)
+    ctx.close()
+
+
+@pytest.mark.parametrize("sensor,loss,deskew,frames", [("vlp16", "huber", True, 12), ("hdl64", "cauchy", False, 10)])
+def test_sequence_pose_parity_with_the_merge_update_forced(capi, po, synth, sequences, sensor, loss, deskew, frames):
+    # small maps take the full re-sort by default; here every keyframe update goes through classify + partial sort + merge (floam_set_map_merge 2)
+    seq, scans, off = sequences(sensor, frames, distort=deskew)
+    ctx, orc, P, O = run_both(capi, po, synth, scans, off, LINES[sensor], loss, deskew, frames, map_merge=2)
+    assert np.abs(P - O).max() < 1e-8
+    ge, gs = ctx.odom_get_map(); oe, os_ = orc.get_map()
+    assert np.array_equal(xyzi(ge), xyzi(oe)) and np.array_equal(xyzi(gs), xyzi(os_))
     ctx.close()
 
 
