@@ -261,14 +261,32 @@ __global__ void __launch_bounds__(kThreads) grid_count_kernel(const P4* __restri
     if (overflow) atomicOr(&S->error_flags, 2);
   }
   if (g.ncells == 0) return;
+  // the scan's per-tile sums come for free here; they are gathered per CTA in shared memory first (a map spans a handful of 4096-cell
+  // tiles, and every warp of the grid adding to the same few global words was most of this kernel on dense maps)
+  constexpr int kTileBins = 2048;
+  __shared__ int s_tiles[kTileBins];
+  const int ntiles = (g.ncells + kScanTile - 1) / kScanTile;
+  const bool binned = ntiles <= kTileBins;
+  if (binned) {
+    for (int t = threadIdx.x; t < ntiles; t += kThreads) s_tiles[t] = 0;
+    __syncthreads();
+  }
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
     const float4 p = __ldg(pts + i);
     const int c = cell_of(g, p.x, p.y, p.z);
-    atomicAdd(&cell_count[c], 1);
-    // the scan's per-tile sums come for free here (one atomic per group of lanes that hit the same tile)
+    // one atomic per group of lanes that hit the same cell: the cloud is in voxel order, so neighbouring lanes mostly share a 1 m
+    // cell (dense maps: a dozen voxels per cell edge) and per-point atomics would queue on one address
+    const unsigned int active = __activemask();
+    const unsigned int same = __match_any_sync(active, c);
+    if (lane_id() == __ffs(same) - 1) atomicAdd(&cell_count[c], __popc(same));
     const int t = c >> 12;
-    const unsigned int peers = __match_any_sync(__activemask(), t);
-    if (lane_id() == __ffs(peers) - 1) atomicAdd(&tile_sums[t], __popc(peers));
+    const unsigned int peers = __match_any_sync(active, t);
+    if (lane_id() == __ffs(peers) - 1) atomicAdd(binned ? &s_tiles[t] : &tile_sums[t], __popc(peers));
+  }
+  if (binned) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < ntiles; t += kThreads)
+      if (s_tiles[t]) atomicAdd(&tile_sums[t], s_tiles[t]);
   }
 }
 
@@ -296,7 +314,13 @@ __global__ void __launch_bounds__(kThreads) grid_scatter_kernel(const P4* __rest
     if (home) home[i] = p;
     if (g.ncells == 0) continue;
     const int c = cell_of(g, p.x, p.y, p.z);
-    const int pos = cell_start[c] + atomicSub(&cell_count[c], 1) - 1;
+    // lanes of the same cell take their slots from one atomic (see grid_count_kernel)
+    const unsigned int same = __match_any_sync(__activemask(), c);
+    const int leader = __ffs(same) - 1;
+    int top = 0;
+    if (lane_id() == leader) top = atomicSub(&cell_count[c], __popc(same));
+    top = __shfl_sync(same, top, leader);
+    const int pos = cell_start[c] + top - 1 - __popc(same & ((1u << lane_id()) - 1u));
     cell_pts[pos] = make_float4(p.x, p.y, p.z, __int_as_float(i));
   }
 }
