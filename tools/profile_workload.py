@@ -1,7 +1,7 @@
 """Profiling workload (for ncu): a short run that launches EVERY kernel class of the library at HDL-64 size —
 the fused frame path from raw PointCloud2 bytes with the IMU steps folded in (unpack_pc2, deskew_align, ring_*, sector,
 feature_*, voxel_*, radix_*, grid_*, predict, assoc_*, lm_cluster, mail_state), the stage entry points (crop_*, repack, knn5,
-compensate_velocity) and LaserMappingClass (mapping.cu kernels).  FLOAM_KNN_TMA=0/1 selects the kNN variant for the A/B.
+compensate_velocity, the merge update's voxel_classify / voxel_merge) and LaserMappingClass (mapping.cu kernels).  FLOAM_KNN_TMA=0/1 selects the kNN variant for the A/B.
 Usage: python tools/profile_workload.py [frames=24]"""
 import sys
 
@@ -34,6 +34,8 @@ m = ctx.mapping_get_map()
 em, sm = ctx.odom_get_map()
 c = ctx.crop_box(sm, [-30, -30, -5], [30, 30, 5])
 v = ctx.voxel_grid(sm, 0.8)
+u = ctx.voxel_grid_update(v, sm[:2000], 0.8)          # the large-map keyframe filter: voxel_classify + voxel_merge
+changed, cells = ctx.mapping_get_changed_cells()
 ids, d2 = ctx.knn5(sm, sm[:2000])
 pts = seq.scan(0); ctx.compensate_velocity(pts, [1.0, 0.0, 0.0])
 print("profile workload ok: %d frames, pose[-1] %s, maps %d/%d, global map %d, crop %d, voxel %d" % (frames, np.round(poses[-1], 4), len(em), len(sm), len(m), len(c), len(v)))
