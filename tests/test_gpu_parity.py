@@ -247,6 +247,29 @@ def test_map_update_identical_with_and_without_merge(capi, synth, sequences):
         assert np.array_equal(xyzi(got[0][1][k]), xyzi(got[1][1][k]))
 
 
+def test_map_update_switches_to_merge_as_the_map_grows(capi, synth, sequences, monkeypatch):
+    # default mode: each map's keyframe update takes the merge path once the host's size hint passes the threshold (250k points; lowered
+    # here so that the switch happens in the middle of a short replay). Frames in flight, hints a few frames old: same poses and maps as
+    # the run that never merges, and both variants must actually have run.
+    seq, scans, off = sequences("hdl64", 40)
+    monkeypatch.setenv("FLOAM_MAP_MERGE_MIN", "9000")
+    auto = fresh(capi, 64, loss="cauchy")
+    monkeypatch.delenv("FLOAM_MAP_MERGE_MIN")
+    never = fresh(capi, 64, loss="cauchy"); never.set_map_merge(0)
+    out = []
+    for ctx in (auto, never):
+        ctx.stage_scans(scans, off)
+        ctx.set_kernel_timing(True)
+        poses, _ = ctx.replay_staged(0, 40)
+        t = ctx.kernel_timing(); ctx.set_kernel_timing(False)
+        out.append((poses, ctx.odom_get_map(), t.get("voxel_merge", (0, 0))[1]))
+        ctx.close()
+    assert np.array_equal(out[0][0], out[1][0])
+    for k in range(2):
+        assert np.array_equal(xyzi(out[0][1][k]), xyzi(out[1][1][k]))
+    assert 0 < out[0][2] < 2 * 39 and out[1][2] == 0        # some, not all, of the 39 x 2 map updates merged
+
+
 @pytest.mark.parametrize("n", [0, 1, 4097, 300000])
 def test_crop_box_bit_exact(capi, po, ctxs, n):
     pts = cloud(capi, np.random.default_rng(n + 3), n)
