@@ -1,5 +1,5 @@
 """First-contact GPU diagnostic: runs every stage of the CUDA path against the oracle and prints what differs.
-(Development aid; the judged checks live in tests/.)  Usage: python tools/gpu_diag.py [sensor] [frames]"""
+(Development aid; the judged checks live in tests/.)  Usage: python tools/probes/gpu_diag.py [sensor] [frames]"""
 import sys
 import time
 import traceback
