@@ -128,4 +128,10 @@ def test_unmodified_reference_nodes_parse_against_the_shims(node):
 def test_no_prebuilt_binaries_are_tracked():
     tracked = subprocess.check_output(["git", "ls-files"], cwd=ROOT, text=True).split()
     bad = [f for f in tracked if f.endswith((".so", ".o", ".a")) or f.startswith("floam_b200/lib/") or f.startswith("oracle/_ref/")]
+    for f in tracked:       # ELF executables under any name (a compiled probe was committed once)
+        path = os.path.join(ROOT, f)
+        if os.path.isfile(path):
+            with open(path, "rb") as fh:
+                if fh.read(4) == b"\x7fELF":
+                    bad.append(f)
     assert not bad, bad
