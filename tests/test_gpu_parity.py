@@ -231,6 +231,49 @@ def test_voxel_grid_update_merge_path(capi, po, ctxs):
     check(far[:2000], far[2000:], 0.1, tag="Q13 pass-through")
 
 
+def test_voxel_grid_update_randomised_structures(capi, po, ctxs):
+    # many small adversarial maps for the merge update: sizes around the 4096-point tile (the descent test looks one point ahead, across
+    # tiles), a handful of voxels only (long runs of equal keys on both sides of the merge), descending and alternating voxel orders,
+    # new points that fall into the map's voxels or into none, duplicates of map points among the new ones
+    ctx = ctxs(16)
+    rng = np.random.default_rng(777)
+    leaf = 0.5
+    for trial in range(60):
+        m = int(rng.choice([1, 2, 5, 63, 4095, 4096, 4097, 8191, 8192, 8193, 12288, 20000]))
+        q = int(rng.choice([0, 1, 7, 100, 4096, 5000]))
+        nvox = int(rng.choice([1, 2, 3, 17, 400, 100000]))
+        side = max(1, int(round(nvox ** (1 / 3))))
+        def pts_in_grid(n):
+            p = np.zeros(n, capi.POINT_I)
+            cell = rng.integers(0, side, (n, 3))
+            jitter = rng.uniform(0.02, leaf - 0.02, (n, 3))
+            xyz = (cell * leaf + jitter - side * leaf / 2).astype(np.float32)
+            p["x"], p["y"], p["z"] = xyz[:, 0], xyz[:, 1], xyz[:, 2]
+            p["intensity"] = rng.random(n); p["pad0"] = 1
+            return p
+        old = pts_in_grid(m)
+        order = voxel_order(old, leaf)
+        kind = trial % 5
+        if kind == 0:
+            old = old[order]                                 # in voxel order, many points per voxel
+        elif kind == 1:
+            old = old[order[::-1]]                           # strictly the wrong way round: every point starts a descent
+        elif kind == 2:
+            half = old[order]; old = np.concatenate([half[1::2], half[0::2]])     # two interleaved ascending runs
+        elif kind == 3:
+            old = old[order]
+            for i in rng.integers(0, max(1, m - 1), 8):      # a few neighbours swapped
+                j = min(m - 1, i + 1)
+                old[i], old[j] = old[j].copy(), old[i].copy()
+        new = pts_in_grid(q)
+        if q > 3 and m > 3:
+            new[:3] = old[:3]                                # exact duplicates of map points
+        both = np.concatenate([old, new])
+        want, _ = po.voxel_grid(both, leaf, total_order=True)
+        got = ctx.voxel_grid_update(old, new, leaf)
+        assert len(got) == len(want) and np.array_equal(xyzi(got), xyzi(want)), (trial, m, q, nvox, kind)
+
+
 def test_map_update_identical_with_and_without_merge(capi, synth, sequences):
     # the same sequence with the keyframe update's merge path forced on and off (full re-sort of map + new points): same poses, same maps
     seq, scans, off = sequences("hdl64", 14)
