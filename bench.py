@@ -457,11 +457,21 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     ctx.launch_count(reset=True)
+    tl0 = ctx.debug_fetch(capi.DBG_TIMELINE, np.int64)
     wall0 = time.time()
     poses_dev, ms_dev = ctx.replay_staged(PREROLL + W, K)
     torch.cuda.synchronize()
     wall1 = time.time()
     launches = ctx.launch_count()
+    # the pose-dependent chain of the timed frames from the stamps its kernels leave on the device (globaltimer ns, sums kept in the state):
+    # this path is bound by that chain, not by bandwidth, so this is the breakdown the roofline fraction cannot give
+    tl1 = ctx.debug_fetch(capi.DBG_TIMELINE, np.int64)
+    n_tl = max(1, int(tl1[3] - tl0[3]))
+    chain = {"frames": n_tl, "pose_dependent_half_us": float(tl1[0] - tl0[0]) / n_tl / 1e3, "solve_part_us": float(tl1[2] - tl0[2]) / n_tl / 1e3,
+             "map_update_part_us": float((tl1[0] - tl0[0]) - (tl1[2] - tl0[2])) / n_tl / 1e3,
+             "rest_of_frame_us": 1e3 * ms_dev / K - float(tl1[0] - tl0[0]) / n_tl / 1e3,
+             "note": "device globaltimer stamps (predict start, write-back, start of the last kernels of the map update); rest = this rank's frame time minus the half: "
+                     "its last kernels, the branch join, mail_state, the graph-to-graph boundary"}
     if world > 1:
         dist.barrier()
     total_frames, max_s = reduce_over_ranks(K, ms_dev * 1e-3)
@@ -649,7 +659,7 @@ def main():
             "single_frame_latency_ms": {"p50": float(np.percentile(single, 50)), "p99": float(np.percentile(single, 99)), "frames": NL,
                                         "note": "floam_process_scan with nothing else in flight: upload + FRONT + BACK + pose read-back, host wall clock"},
             "knn_queries_per_s": float(stats["Q"] * 2 * value / world),
-            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "roofline": roofline, "chain": chain, "cpu_baseline": cpu, "clocks": clocks,
             "frame_stats": {k: round(v, 1) for k, v in stats.items()}, "map_points_timed_region": {"start": map_points_start, "end": [ne_map, ns_map]},
             "last_frame": {"n_corr": d["n_corr"], "outer_iterations": d["outer_iterations"], "keyframe": d["keyframe"]},
             "wall_s_timed_region": wall1 - wall0, "gen_s": t_gen}
