@@ -36,12 +36,10 @@ constexpr int kAssocBlocks = kNumSMs / 2;   // 74 CTAs x 128 threads, grid-strid
 constexpr int kKnnBlocks = kNumSMs * 4;     // 592 CTAs x 8 warps, one warp per query, grid-stride
 static_assert(kAssocBlocks <= 1024, "partials rows");
 
-inline int grid_for(int n_max) {
+// the kernels stride; two CTAs per SM unless the input is known to be large (see voxel.cu, grid_for)
+inline int grid_for(int n_max, int ctas_per_sm = 2) {
   int g = (n_max + kThreads - 1) / kThreads;
-  // the kernels stride; empty CTAs of a capacity-sized grid are not free. Two CTAs of 256 threads per SM: measured against four, one
-  // sequence runs as fast (5.43k frames/s either way) and four sequences sharing the GPU gain 6.5 % (9.6k -> 10.2k): fewer resident CTAs
-  // of one sequence's kernels in the way of the others'. One per SM: 10.6k, but a single sequence loses 1-4 %.
-  const int cap = kNumSMs * 2;
+  const int cap = kNumSMs * ctas_per_sm;
   return g < 1 ? 1 : (g > cap ? cap : g);
 }
 
@@ -1278,9 +1276,9 @@ int* dims_ncells_ptr(GridDims* dims) { return reinterpret_cast<int*>(reinterpret
 // from_tmp: the cloud sits in map.tmp (output of the keyframe filter, which has also accumulated its bounding box); the scatter kernel
 // copies it home into map.pts on the way
 void rebuild_grid(OdomDevice& od, LocalMap& map, const int* d_skip, cudaStream_t s, VoxelWorkspace* ws = nullptr, bool from_tmp = false,
-                  long long* stamp = nullptr) {
+                  long long* stamp = nullptr, bool large = false) {
   if (!ws) ws = od.vws;
-  const int g = grid_for(map.cap);
+  const int g = grid_for(map.cap, large ? 4 : 2);
   const P4* src = from_tmp ? map.tmp : map.pts;
   if (!from_tmp) FLOAM_LAUNCH(K_GRID_BBOX, grid_bbox_kernel, g, kThreads, s, map.pts, map.d_n, map.bbox, d_skip);
   FLOAM_LAUNCH(K_GRID_COUNT, grid_count_kernel, g, kThreads, s, src, map.d_n, map.bbox, map.dims, map.ncells_cap, od.state, map.cell_count, map.tile_sums,
@@ -1476,11 +1474,14 @@ void odom_update_device(OdomDevice& od, const void* d_edge, const int* d_ne, con
     // (:270-287) is folded into the VoxelGrid (:289-292), and its last kernel leaves the bounding box of the new map for the search
     // grid. The filter gathers from mp.pts through the sorted index into mp.tmp; the grid's scatter kernel copies the cloud home.
     const VoxelAppend app{dss[k], S->x, &S->error_flags};
-    // The map is the previous filter's output, i.e. already in voxel order but for a few re-voxelised centroids: by default only the
-    // new points and the out-of-place ones are sorted and merged in (voxel_grid_merge_device); identical result either way.
-    if (odom_map_update_merges(od, k)) voxel_grid_merge_device(mp.pts, 16, mp.d_n, mp.cap, leaf[k], mp.tmp, mp.d_n, ws, skip, st, S->crop_bounds, nds[k], mp.cap, &app, mp.bbox);
+    // The map is the previous filter's output, i.e. already in voxel order but for a few re-voxelised centroids: once it is large only
+    // the new points and the out-of-place ones are sorted and merged in (voxel_grid_merge_device); identical result either way.
+    const bool large = odom_map_update_merges(od, k);   // the size hint that picks the merge path also widens the grids
+    ws.large_input = large;
+    if (large) voxel_grid_merge_device(mp.pts, 16, mp.d_n, mp.cap, leaf[k], mp.tmp, mp.d_n, ws, skip, st, S->crop_bounds, nds[k], mp.cap, &app, mp.bbox);
     else voxel_grid_device(mp.pts, 16, mp.d_n, mp.cap, leaf[k], mp.tmp, mp.d_n, ws, skip, st, S->crop_bounds, nds[k], mp.cap, &app, mp.bbox);
-    rebuild_grid(od, mp, skip, st, &ws, true, &S->tl_end[k]);
+    rebuild_grid(od, mp, skip, st, &ws, true, &S->tl_end[k], large);
+    ws.large_input = false;
   }
   cudaEventRecord(od.ev_join, a);
   cudaStreamWaitEvent(s, od.ev_join, 0);

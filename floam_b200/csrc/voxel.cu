@@ -659,12 +659,13 @@ __global__ void __launch_bounds__(kThreads) repack_kernel(const char* __restrict
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) out[i] = load_xyzi(in, 32, i);
 }
 
-inline int grid_for(int n_max) {
+// The kernels stride; empty CTAs of a capacity-sized grid are not free. Default two CTAs of 256 threads per SM: measured against four,
+// one sequence runs as fast (5.43k frames/s either way) and four sequences sharing the GPU gain 6.5 % (9.6k -> 10.2k): fewer resident
+// CTAs of one sequence's kernels in the way of the others'. Large inputs (the >= 250k-point maps that also take the merge path) keep
+// four per SM: at configs[3] two cost 6.5 % (0.653 -> 0.696 ms per frame).
+inline int grid_for(int n_max, int ctas_per_sm = 2) {
   int g = (n_max + kThreads - 1) / kThreads;
-  // the kernels stride; empty CTAs of a capacity-sized grid are not free. Two CTAs of 256 threads per SM: measured against four, one
-  // sequence runs as fast (5.43k frames/s either way) and four sequences sharing the GPU gain 6.5 % (9.6k -> 10.2k): fewer resident CTAs
-  // of one sequence's kernels in the way of the others'. One per SM: 10.6k, but a single sequence loses 1-4 %.
-  const int cap = kNumSMs * 2;
+  const int cap = kNumSMs * ctas_per_sm;
   return g < 1 ? 1 : (g > cap ? cap : g);
 }
 
@@ -714,7 +715,7 @@ void voxel_grid_device(const void* d_in, int stride_bytes, const int* d_n, int n
   const VoxelAppend app = append ? *append : VoxelAppend{nullptr, nullptr, nullptr};
   if (n_max > ws.n_max) n_max = ws.n_max;
   const char* in = (const char*)d_in;
-  const int g = grid_for(n_max);
+  const int g = grid_for(n_max, ws.large_input ? 4 : 2);
   int gt = (n_max + kScanTile - 1) / kScanTile;
   if (gt > g_rank_grid_limit) gt = g_rank_grid_limit;   // voxel_rank_kernel loops over tiles; all of its CTAs must be able to be resident together
   int* counts = ws.d_counts;   // [0] input points, [1] points kept by the crop
@@ -735,7 +736,7 @@ void voxel_grid_merge_device(const void* d_in, int stride_bytes, const int* d_n,
   const VoxelAppend app = append ? *append : VoxelAppend{nullptr, nullptr, nullptr};
   if (n_max > ws.n_max) n_max = ws.n_max;
   const char* in = (const char*)d_in;
-  const int g = grid_for(n_max);
+  const int g = grid_for(n_max, ws.large_input ? 4 : 2);
   int gt = (n_max + kScanTile - 1) / kScanTile, gc = gt;
   if (gt > g_rank_grid_limit) gt = g_rank_grid_limit;         // the look-back kernels loop over tiles; all CTAs of a grid must be able to be
   if (gc > g_classify_grid_limit) gc = g_classify_grid_limit; // resident together (a waiting tile depends on lower-numbered ones)

@@ -18,6 +18,7 @@ struct VoxelWorkspace {
   SortWorkspace sort;
   ScanWorkspace scan;
   int n_max;
+  bool large_input = false;   // host-side hint for the grids of the next filter call: hundreds of thousands of points expected (four CTAs per SM instead of two)
 };
 size_t voxel_workspace_bytes(int n_max);
 void voxel_workspace_bind(VoxelWorkspace& ws, void* mem, int n_max);
