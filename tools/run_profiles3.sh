@@ -9,7 +9,7 @@ $NCU --metrics gpu__time_duration.sum -s 1200 -c 160 --csv --log-file gpurun_out
 echo "bench launch list: $(wc -l < gpurun_out/${TAG}_launches_ncu.csv) lines"
 W="python tools/profile_workload.py 24"
 $W > gpurun_out/${TAG}_plain.log 2>&1 || { echo "plain workload failed"; tail -5 gpurun_out/${TAG}_plain.log; exit 1; }
-$NCU --set full --import-source on -k regex:"voxel_classify|voxel_merge|voxel_rank|grid_count|grid_scatter|dirty" -s 180 -c 40 -f -o gpurun_out/${TAG}_late $W > gpurun_out/${TAG}_late.log 2>&1
+$NCU --set full --import-source on -k regex:"voxel_classify|voxel_merge|voxel_rank|grid_count|grid_scatter|dirty|sector_kernel" -s 200 -c 44 -f -o gpurun_out/${TAG}_late $W > gpurun_out/${TAG}_late.log 2>&1
 ncu -i gpurun_out/${TAG}_late.ncu-rep --page raw --csv > gpurun_out/${TAG}_late_raw.csv 2>/dev/null
 rm -f gpurun_out/${TAG}_late.ncu-rep
 echo "late kernels: $(wc -l < gpurun_out/${TAG}_late_raw.csv) csv lines"
